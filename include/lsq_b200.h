@@ -1,0 +1,142 @@
+/*
+ * lsq_b200 -- C ABI of the B200 (sm_100a) implementation of apple/ml-quant's binary-quantized
+ * inference path.  Plain pointers and sizes only; every pointer named d_* is a DEVICE pointer, every
+ * call is asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 on success and a
+ * negative code otherwise (text via lsq_last_error(), thread local).  No call allocates: outputs and
+ * workspaces are caller provided (sizes from the *_bytes queries).  The library is re-entrant and
+ * keeps no mutable global state, so replicas driven from several host threads (nn.DataParallel,
+ * quant/common/initialization.py:125-127 in the reference) may call it concurrently.
+ *
+ * The reference has no native boundary (it is pure PyTorch); each entry point below replaces the
+ * ATen operator sequence of the cited reference lines (paths relative to the reference root).
+ *
+ * Conventions
+ *   rows x len : a quantizer "row" is index 0 of the reference's 4-D tensor flattened over the rest
+ *                (weights: one row per output channel; activations: one row per sample).
+ *   sign(0) = +1 (quant/binary/ste.py:16-18).  alpha <= 0 means "no clamp"; otherwise the input is
+ *   clamped to [-alpha, alpha] first (quant/binary/quantization.py:22-24).
+ *   scale table: float[nscales][rows], row-major.
+ *   planes: the +-1 factors b_j of x_q = sum_j s_j b_j, b_j = sign(x - sum_{i<j} s_i b_i)
+ *           (quantization.py:89-92, :113-115, :139-146); ls-T uses s_2 = s_1.
+ */
+#ifndef LSQ_B200_H_
+#define LSQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LSQ_API __attribute__((visibility("default")))
+#else
+#define LSQ_API
+#endif
+
+#define LSQ_ABI_VERSION 1
+#define LSQ_MAX_PLANES 8
+
+enum lsq_status {
+  LSQ_OK = 0,
+  LSQ_ERR_ARG = -1,        /* invalid argument (shape, null pointer, unsupported option) */
+  LSQ_ERR_WORKSPACE = -2,  /* workspace too small */
+  LSQ_ERR_CUDA = -3,       /* a CUDA runtime call failed; see lsq_last_error() */
+  LSQ_ERR_UNSUPPORTED = -4 /* shape outside what the tensor-core kernel handles */
+};
+
+LSQ_API int lsq_abi_version(void);
+LSQ_API const char* lsq_last_error(void);
+
+/* ---- row quantizer primitives ------------------------------------------------------------- */
+
+/* Workspace (bytes) for lsq_row_absmean / lsq_encode_act on `rows` rows of `len` elements.
+ * Must be zero-filled once before first use; the kernels leave it zeroed. */
+LSQ_API size_t lsq_reduce_workspace_bytes(int64_t rows, int64_t len);
+
+/* out[r] = mean_j |res(x[r][j])|, res = x after clamping and after folding `nscales` planes:
+ *   res_0 = clamp(x), res_i = res_{i-1} - s_i[r] * sign(res_{i-1}).
+ * nscales = 0 is the ls-1 / gf first scale  mean|x|  (quantization.py:53-55, :135-137);
+ * nscales = 1 with s_1 = v1 is the ls-2 second scale (quantization.py:84-85);
+ * nscales = i is the gf scale v_{i+1} (quantization.py:135-138). */
+LSQ_API int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float alpha,
+                    const float* d_scales, int nscales, float* d_out,
+                    void* d_ws, size_t ws_bytes, void* stream);
+
+/* Least-squares optimal v1 for the 2-bit (ternary = 0) or ternary (= 1) quantizer: replaces
+ * opt_v1 / compute_mask / cost_function (quant/binary/optimal.py:16-155).  Only every `skip`-th
+ * element of a row enters the solve (optimal.py:134).  d_diag (optional, int32[rows][4]) receives
+ * {global passes, collected elements, candidates found, flags}.  One CTA per row. */
+LSQ_API int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
+                 float* d_v1, int32_t* d_diag, void* stream);
+
+/* Dense fake-quant tensor  out = sum_j s_j b_j  in the reference's fp32 operation order
+ * (quantization.py:56, :89-92, :113-115, :139-146).  ternary = 1: two planes, both scaled by s_1. */
+LSQ_API int lsq_fakequant(const float* d_x, int64_t rows, int64_t len, float alpha,
+                  const float* d_scales, int nplanes, int ternary, float* d_out, void* stream);
+
+/* STE backward: gin = gout where -1 <= x <= 1, else 0 (quant/binary/ste.py:50-66). */
+LSQ_API int lsq_ste_backward(const float* d_x, const float* d_gout, float* d_gin, int64_t n, void* stream);
+
+/* ---- activation bit planes for the binary convolution ------------------------------------- */
+
+/* Geometry of the packed activation planes consumed by lsq_bconv2d_*.  Positions are stored in a
+ * "virtual raster": per sample (Hv + ph) rows of pitch P = Wv + ph, the extra row / columns being the
+ * zero padding shared between neighbouring rows and samples, so that a convolution tap is a uniform
+ * shift of the position index.  For stride 2 the input is split into its 4 parity phases
+ * (Hv = ceil(H/2)), each a stride-1 problem.  One position holds cw = ceil(C/32) 32-bit words,
+ * channel c at bit (c & 31) of word (c >> 5).  Fill with lsq_act_geometry(). */
+typedef struct lsq_act_geom {
+  int32_t n, c, h, w;         /* activation tensor [n, c, h, w] (NCHW fp32) */
+  int32_t kh, kw, stride, pad;
+  int32_t ho, wo;             /* convolution output size */
+  int32_t cw;                 /* words per position */
+  int32_t nphase;             /* 1 (stride 1) or 4 (stride 2) */
+  int32_t hv, wv, ph;         /* phase extent and shared padding (in phase coordinates) */
+  int32_t pitch, rows_per_sample, lead;
+  int64_t vtot;               /* positions per (plane, phase), including slack */
+} lsq_act_geom;
+
+LSQ_API int lsq_act_geometry(int n, int c, int h, int w, int kh, int kw, int stride, int pad,
+                     lsq_act_geom* out);
+/* bytes of the plane buffer for `nplanes` planes */
+LSQ_API size_t lsq_act_planes_bytes(const lsq_act_geom* g, int nplanes);
+
+/* One pass over x [n,c,h,w]: clamp, fold the given nscales (= nplanes-1, or nplanes when the last
+ * scale is known too) scales, write `nplanes` bit planes in the geometry's layout and, when
+ * d_last_scale != NULL, the per-sample mean |res_{nplanes-1}| (the next scale: v1 for ls-1, v2 for
+ * ls-2, v_k for gf-k).  Replaces binarize / residual / mean chains of quantization.py:35-148 on
+ * the QuantConv2d input (binary_conv.py:163). */
+LSQ_API int lsq_encode_act(const float* d_x, const lsq_act_geom* g, float alpha,
+                   const float* d_scales, int nscales, int nplanes,
+                   uint32_t* d_planes, float* d_last_scale,
+                   void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- weights --------------------------------------------------------------------------------- */
+
+/* Packed sign(W) for ls-1 weights [cout, cin, kh, kw] (weight_quantization.py:32-33 without the
+ * scale, which moves to the conv epilogue).  Two images in one buffer:
+ *   bits : uint32[cout][kh*kw][cw]                    (CUDA-core kernel)
+ *   i8   : the tcgen05 shared-memory operand image (K-major, no swizzle), see lsq_bconv_tc.cu */
+LSQ_API size_t lsq_wpack_bytes(int cout, int cin, int kh, int kw);
+LSQ_API int lsq_pack_weights(const float* d_w, int cout, int cin, int kh, int kw, void* d_wpack, void* stream);
+
+/* ---- binary convolution ---------------------------------------------------------------------- */
+
+/* y[n,co,:,:] = w_scale[co] * sum_j act_scales[j][n] * conv(plane_j, sign(W))[n,co] + bias[co]
+ * (QuantConv2d.forward, quant/binary/binary_conv.py:161-173, for ls-1 weights and any k-plane
+ * activation scheme; zero padding contributes 0).  d_bias may be NULL.  impl: 0 = auto,
+ * 1 = CUDA-core XNOR/popcount kernel, 2 = tcgen05 INT8 tensor-core kernel (LSQ_ERR_UNSUPPORTED when
+ * the shape does not fit it). */
+LSQ_API int lsq_bconv2d_fwd(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes,
+                    const float* d_act_scales, const void* d_wpack, const float* d_w_scale,
+                    const float* d_bias, int cout, float* d_y, int impl, void* stream);
+
+/* 1 if the tensor-core kernel handles this problem */
+LSQ_API int lsq_bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSQ_B200_H_ */

@@ -1,0 +1,73 @@
+"""ctypes binding of liblsq_b200.so (include/lsq_b200.h).  No torch types cross the boundary: only
+device pointers, sizes and the current CUDA stream handle.  Missing library -> loud failure."""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liblsq_b200.so')
+_lock = threading.Lock()
+_lib = None
+
+MAX_PLANES = 8
+
+EXPORTS = [
+    'lsq_abi_version', 'lsq_last_error', 'lsq_reduce_workspace_bytes', 'lsq_row_absmean', 'lsq_solve_v1',
+    'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry', 'lsq_act_planes_bytes', 'lsq_encode_act',
+    'lsq_wpack_bytes', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
+]
+
+
+class ActGeom(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ('n', 'c', 'h', 'w', 'kh', 'kw', 'stride', 'pad', 'ho', 'wo', 'cw', 'nphase', 'hv', 'wv', 'ph',
+                 'pitch', 'rows_per_sample', 'lead')] + [('vtot', C.c_int64)]
+
+
+class LsqError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise LsqError(
+                    f'{LIB_PATH} is missing: the CUDA library is the only implementation of this path '
+                    '(there is no CPU fallback). Build it with `python -m ml_quant_b200.build`.')
+            L = C.CDLL(LIB_PATH)
+            vp, f32, i64, i32, sz = C.c_void_p, C.c_float, C.c_int64, C.c_int, C.c_size_t
+            gp = C.POINTER(ActGeom)
+            L.lsq_abi_version.restype = i32
+            L.lsq_last_error.restype = C.c_char_p
+            L.lsq_reduce_workspace_bytes.restype = sz
+            L.lsq_reduce_workspace_bytes.argtypes = [i64, i64]
+            L.lsq_row_absmean.argtypes = [vp, i64, i64, f32, vp, i32, vp, vp, sz, vp]
+            L.lsq_solve_v1.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp, vp]
+            L.lsq_fakequant.argtypes = [vp, i64, i64, f32, vp, i32, i32, vp, vp]
+            L.lsq_ste_backward.argtypes = [vp, vp, vp, i64, vp]
+            L.lsq_act_geometry.argtypes = [i32] * 8 + [gp]
+            L.lsq_act_planes_bytes.restype = sz
+            L.lsq_act_planes_bytes.argtypes = [gp, i32]
+            L.lsq_encode_act.argtypes = [vp, gp, f32, vp, i32, i32, vp, vp, vp, sz, vp]
+            L.lsq_wpack_bytes.restype = sz
+            L.lsq_wpack_bytes.argtypes = [i32] * 4
+            L.lsq_pack_weights.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+            L.lsq_bconv2d_fwd.argtypes = [vp, gp, i32, vp, vp, vp, vp, i32, vp, i32, vp]
+            L.lsq_bconv2d_tc_supported.argtypes = [gp, i32, i32]
+            for name in ('lsq_row_absmean', 'lsq_solve_v1', 'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry',
+                         'lsq_encode_act', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported'):
+                getattr(L, name).restype = i32
+            if L.lsq_abi_version() != 1:
+                raise LsqError('liblsq_b200.so ABI version mismatch')
+            _lib = L
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().lsq_last_error().decode('utf-8', 'replace')
+        raise LsqError(f'{what} failed ({status}): {msg}')

@@ -1,0 +1,178 @@
+"""QuantConv2d: convolution on scaled-binary weights and activations.
+
+Mirror of quant/binary/binary_conv.py (constructor and factories :55-159, forward :161-173): same
+constructor signature, attributes (``x_approximate``, ``w_approximate``, ``clamping_fn``,
+``quantized_parameters``), scheme validation and state_dict keys.
+
+Forward has two routes, both on the GPU:
+  * packed  -- inference with ls-1 weights and a 1..4-plane activation code (ls-1, ls-2, ls-T, gf-k):
+               clamp + scale solve + bit-plane encode (csrc/lsq_solve.cu, lsq_quant.cu), then a binary
+               convolution with integer accumulation and the scales, bias applied in the epilogue
+               (csrc/lsq_bconv_tc.cu on tcgen05 tensor cores, csrc/lsq_bconv.cu otherwise).  The dense
+               fake-quant tensors of the reference are never materialised.  sign(W) is packed once and
+               cached until the weight changes.
+  * generic -- everything else (gradients required, other weight schemes, grouped / dilated convs):
+               the reference's composition x_approximate(clamp(x)), w_approximate(W), F.conv2d with the
+               quantizers running as CUDA kernels.
+"""
+from collections import defaultdict
+from functools import partial
+import re
+from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from . import activation_quantization, quantization, weight_quantization
+
+_PACKED_MAX_PLANES = 4
+
+
+class QuantConv2d(nn.Conv2d):
+    """Conv2d(w_quant(w), x_quant(clamp(x)))."""
+
+    def __init__(self, x_quant: str, w_quant: str, in_channels: int, out_channels: int,
+                 kernel_size: Union[int, Tuple[int, int]], clamp: Optional[Dict] = None,
+                 moving_average_mode: str = 'off', moving_average_momentum: float = 0.99, **kwargs: Any):
+        super().__init__(in_channels, out_channels, kernel_size, **kwargs)
+        clamp = {'kind': 'identity'} if clamp is None else clamp
+        self.x_approximate = self._get_x_quantizer(x_quant, moving_average_mode, moving_average_momentum)
+        self.w_approximate = self._get_w_quantizer(w_quant, out_channels)
+        self.clamping_fn = self._get_clamper(**clamp)
+        self.quantized_parameters: Dict[str, List[torch.Tensor]] = defaultdict(list)
+        if self.bias is not None:
+            self.quantized_parameters['fp'].append(self.bias)
+        self.quantized_parameters[w_quant].append(self.weight)
+        # host-side description used by the packed route
+        self.x_quant, self.w_quant = x_quant, w_quant
+        self.clamp_alpha: Optional[float] = float(clamp.get('alpha', 2)) if clamp['kind'] == 'symmetric' else None
+        self.packed_impl = 0            # 0 auto, 1 CUDA-core kernel, 2 tensor-core kernel (tests / profiling)
+        self.allow_packed = True
+        self._wpack_cache: Dict[int, Tuple[Tuple[int, int], torch.Tensor]] = {}
+        self._planes_cache: Dict[int, torch.Tensor] = {}
+
+    # ---- factories (same static methods as the reference) -----------------------------------
+    @staticmethod
+    def _validate_scheme(scheme: str) -> None:
+        if scheme not in {'fp', 'ls-1', 'ls-T', 'ls-2'} and not re.fullmatch(r'gf-\d+', scheme):
+            raise ValueError(f'Scheme {scheme} is invalid. Please see docs for valid schemes.')
+
+    @staticmethod
+    def _get_x_quantizer(scheme: str, moving_average_mode: str = 'off',
+                         moving_average_momentum: float = 0.99) -> nn.Module:
+        QuantConv2d._validate_scheme(scheme)
+        aq = activation_quantization
+        if scheme == 'fp':
+            return quantization.QuantizerFP()
+        if scheme.startswith('gf'):
+            return aq.ActivationQuantizerGF(int(scheme.split('-')[1]), moving_average_mode, moving_average_momentum)
+        cls = {'ls-1': aq.ActivationQuantizerLS1, 'ls-2': aq.ActivationQuantizerLS2,
+               'ls-T': aq.ActivationQuantizerLST}[scheme]
+        return cls(moving_average_mode, moving_average_momentum)
+
+    @staticmethod
+    def _get_w_quantizer(scheme: str, size: int) -> nn.Module:
+        QuantConv2d._validate_scheme(scheme)
+        wq = weight_quantization
+        if scheme == 'fp':
+            return quantization.QuantizerFP()
+        if scheme.startswith('gf'):
+            return wq.WeightQuantizerGF(size, int(scheme.split('-')[1]))
+        return {'ls-1': wq.WeightQuantizerLS1, 'ls-2': wq.WeightQuantizerLS2,
+                'ls-T': wq.WeightQuantizerLST}[scheme](size)
+
+    @staticmethod
+    def _get_clamper(kind: str, alpha: float = 2) -> Callable[[torch.Tensor], torch.Tensor]:
+        table: Dict[str, Callable[[torch.Tensor], torch.Tensor]] = {
+            'identity': quantization.clamp_identity,
+            'symmetric': partial(quantization.clamp_symmetric, alpha=alpha),
+        }
+        if kind not in table:
+            raise ValueError(f'{kind} is not a valid clamping function.')
+        return table[kind]
+
+    # ---- packed route ---------------------------------------------------------------------------
+    def _num_planes(self) -> int:
+        s = self.x_quant
+        return {'ls-1': 1, 'ls-2': 2, 'ls-T': 2}.get(s) or (int(s.split('-')[1]) if s.startswith('gf') else 0)
+
+    def _packed_geometry(self, x: torch.Tensor):
+        """Geometry when the packed route applies to this call, else None."""
+        if not (self.allow_packed and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+            return None
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            return None
+        if self.w_quant != 'ls-1' or not 1 <= self._num_planes() <= _PACKED_MAX_PLANES:
+            return None
+        if self.groups != 1 or tuple(self.dilation) != (1, 1) or self.padding_mode != 'zeros':
+            return None
+        if isinstance(self.padding, str) or self.stride[0] != self.stride[1] or self.padding[0] != self.padding[1]:
+            return None
+        xa = self.x_approximate
+        if xa.training and xa.moving_average_mode != activation_quantization.MovingAverageMode.off:
+            return None          # the moving average is being tracked: keep the reference's control flow
+        n, c, h, w = x.shape
+        return ops.act_geometry(n, c, h, w, self.kernel_size[0], self.kernel_size[1], self.stride[0], self.padding[0])
+
+    def packed_weights(self) -> torch.Tensor:
+        """sign(W) operand images, repacked only when the weight tensor changes."""
+        w = self.weight
+        dev = w.device.index or 0
+        key = (w.data_ptr(), w._version)
+        hit = self._wpack_cache.get(dev)
+        if hit is None or hit[0] != key:
+            hit = (key, ops.pack_weights(w))
+            self._wpack_cache[dev] = hit
+        return hit[1]
+
+    def _weight_scale(self) -> torch.Tensor:
+        wa = self.w_approximate
+        if wa.training:
+            # train-mode call under no_grad (e.g. calibration): solve and cache like the reference
+            wa.v1.copy_(ops.row_absmean(self.weight.detach().reshape(self.out_channels, -1)))
+        return wa.v1
+
+    def quantize_input(self, x: torch.Tensor, g) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Packed activation code of x: (bit planes, scale table [planes, batch])."""
+        xa, alpha, npl = self.x_approximate, self.clamp_alpha, self._num_planes()
+        n = x.shape[0]
+        dev = x.device.index or 0
+        buf = self._planes_cache.get(dev)
+        rows = x.reshape(n, -1)
+        tern = self.x_quant == 'ls-T'
+        if xa.uses_stored_scales():
+            scales = [s.contiguous() for s in xa.stored_scales(n)]
+            known = scales[:1] if tern else scales
+            planes, _ = ops.encode_act(x, g, known[:npl], npl, alpha, False, buf)
+            table = scales + scales if tern else scales
+        elif self.x_quant == 'ls-1':
+            planes, v1 = ops.encode_act(x, g, [], 1, alpha, True, buf)
+            table = [v1]
+        elif self.x_quant in ('ls-2', 'ls-T'):
+            v1 = ops.solve_v1(rows, tern, 3, alpha)
+            planes, v2 = ops.encode_act(x, g, [v1], 2, alpha, not tern, buf)
+            table = [v1, v1] if tern else [v1, v2]
+        else:
+            scales: List[torch.Tensor] = []
+            for _ in range(npl - 1):
+                scales.append(ops.row_absmean(rows, scales, alpha))
+            planes, last = ops.encode_act(x, g, scales, npl, alpha, True, buf)
+            table = scales + [last]
+        self._planes_cache[dev] = planes
+        return planes, torch.stack(table)
+
+    def _forward_packed(self, x: torch.Tensor, g) -> torch.Tensor:
+        x = x.contiguous()
+        planes, table = self.quantize_input(x, g)
+        return ops.bconv2d(planes, g, self._num_planes(), table, self.packed_weights(), self._weight_scale(),
+                           self.bias, self.out_channels, self.packed_impl)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
+        g = self._packed_geometry(x)
+        if g is not None:
+            return self._forward_packed(x, g)
+        x_q = self.x_approximate(self.clamping_fn(x))
+        w_q = self.w_approximate(self.weight)
+        return F.conv2d(x_q, w_q, self.bias, self.stride, self.padding, self.dilation, self.groups)

@@ -1,0 +1,83 @@
+// Shared helpers for the lsq_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/lsq_b200.h"
+
+namespace lsq {
+
+void set_error(const char* fmt, ...);
+
+#define LSQ_CHECK_ARG(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      lsq::set_error(__VA_ARGS__);               \
+      return LSQ_ERR_ARG;                        \
+    }                                            \
+  } while (0)
+
+#define LSQ_CUDA_LAUNCH_CHECK(what)                                                   \
+  do {                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess) {                                                         \
+      lsq::set_error("%s: %s", what, cudaGetErrorString(e__));                        \
+      return LSQ_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+// sign with sign(0) = +1, as a float (+-1).  quant/binary/ste.py:16-18
+__device__ __forceinline__ float sign_pm1(float x) { return x >= 0.0f ? 1.0f : -1.0f; }
+
+// clamp(x, -alpha, alpha) when alpha > 0.  quant/binary/quantization.py:22-24
+__device__ __forceinline__ float clamp_sym(float x, float alpha) {
+  return alpha > 0.0f ? fminf(fmaxf(x, -alpha), alpha) : x;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Deterministic block-wide sum (fixed tree).  `red` holds >= 32 doubles.  Result valid in all threads.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double t = (lane < nw) ? red[lane] : 0.0;
+  t = warp_sum(t);
+  return t;
+}
+
+// Geometry helpers shared by the encoder and the convolution kernels (see lsq_b200.h).
+struct ActGeom {
+  int n, c, h, w, kh, kw, stride, pad, ho, wo, cw, nphase, hv, wv, ph, pitch, rps, lead;
+  long long vtot;
+};
+__host__ __device__ inline ActGeom to_dev(const lsq_act_geom& g) {
+  ActGeom d;
+  d.n = g.n; d.c = g.c; d.h = g.h; d.w = g.w; d.kh = g.kh; d.kw = g.kw; d.stride = g.stride;
+  d.pad = g.pad; d.ho = g.ho; d.wo = g.wo; d.cw = g.cw; d.nphase = g.nphase; d.hv = g.hv;
+  d.wv = g.wv; d.ph = g.ph; d.pitch = g.pitch; d.rps = g.rows_per_sample; d.lead = g.lead;
+  d.vtot = g.vtot;
+  return d;
+}
+// virtual position of phase coordinate (a, b) of sample s; a in [-ph, hv), b in [-ph, wv+ph)
+__host__ __device__ inline long long vpos(const ActGeom& g, int s, int a, int b) {
+  return (long long)g.lead + ((long long)s * g.rps + g.ph + a) * g.pitch + b;
+}
+
+}  // namespace lsq

@@ -1,0 +1,329 @@
+// Row quantizer primitives and the activation bit-plane encoder (HBM-bound, CUDA cores).
+//
+//  lsq_row_absmean  : per-row mean |residual|      (quantization.py:53-55, :84-85, :135-138)
+//  lsq_fakequant    : dense sum_j s_j b_j          (quantization.py:56, :89-92, :113-115, :139-146)
+//  lsq_ste_backward : straight-through gradient    (ste.py:50-66)
+//  lsq_encode_act   : NCHW fp32 -> bit planes in the convolution's virtual raster + next scale
+//
+// All reductions are fp64 with a fixed summation tree (per-thread order, warp shuffles, per-block
+// partials summed in block order by the last block to finish), so results are run-to-run and
+// batch-size invariant.
+#include <stdarg.h>
+#include <string.h>
+#include "lsq_common.cuh"
+
+namespace lsq {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int kRowThreads = 256;
+constexpr int kRowChunk = 4096;   // elements per block in row kernels
+constexpr int kEncThreads = 128;  // pixels per block in the encoder
+
+struct ScaleTab {  // up to LSQ_MAX_PLANES per-row scales, passed by value
+  const float* p[LSQ_MAX_PLANES];
+};
+
+// residual after folding `ns` scales:  res_i = res_{i-1} - s_i * sign(res_{i-1})   (fp32, no FMA)
+template <int MAXS>
+__device__ __forceinline__ float fold_residual(float v, const float (&s)[MAXS], int ns) {
+#pragma unroll
+  for (int i = 0; i < MAXS; ++i)
+    if (i < ns) v = __fsub_rn(v, __fmul_rn(s[i], sign_pm1(v)));
+  return v;
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+row_absmean_kernel(const float* __restrict__ x, long long len, float alpha, const float* __restrict__ scales,
+                   long long rows, int ns, float* __restrict__ out, double* __restrict__ partial,
+                   unsigned* __restrict__ counter) {
+  __shared__ double red[32];
+  __shared__ bool last;
+  const long long r = blockIdx.y;
+  const float* xr = x + r * len;
+  float s[LSQ_MAX_PLANES];
+#pragma unroll
+  for (int i = 0; i < LSQ_MAX_PLANES; ++i) s[i] = (i < ns) ? scales[(long long)i * rows + r] : 0.0f;
+  const long long beg = (long long)blockIdx.x * kRowChunk;
+  const long long end = min(beg + (long long)kRowChunk, len);
+  double acc = 0.0;
+  for (long long e = beg + threadIdx.x; e < end; e += kRowThreads) {
+    float v = clamp_sym(__ldg(xr + e), alpha);
+    acc += (double)fabsf(fold_residual(v, s, ns));
+  }
+  double tot = block_sum(acc, red);
+  const unsigned nblk = gridDim.x;
+  if (threadIdx.x == 0) {
+    partial[r * nblk + blockIdx.x] = tot;
+    __threadfence();
+    last = (atomicAdd(&counter[r], 1u) == nblk - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b = 0; b < nblk; ++b) t += __ldcg(&partial[r * nblk + b]);
+    out[r] = (float)(t / (double)len);
+    counter[r] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+fakequant_kernel(const float* __restrict__ x, long long len, float alpha, const float* __restrict__ scales,
+                 long long rows, int npl, int ternary, float* __restrict__ out) {
+  const long long r = blockIdx.y;
+  float s[LSQ_MAX_PLANES];
+#pragma unroll
+  for (int i = 0; i < LSQ_MAX_PLANES; ++i) {
+    int src = ternary ? 0 : i;
+    s[i] = (i < npl) ? scales[(long long)src * rows + r] : 0.0f;
+  }
+  const float* xr = x + r * len;
+  float* o = out + r * len;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (long long)gridDim.x * blockDim.x) {
+    const float v = clamp_sym(__ldg(xr + e), alpha);
+    float acc = 0.0f;
+    if (ternary) {
+      // v1 * (b1 + b2), quantization.py:115
+      float b1 = sign_pm1(v);
+      float b2 = sign_pm1(__fsub_rn(v, __fmul_rn(s[0], b1)));
+      acc = __fmul_rn(s[0], __fadd_rn(b1, b2));
+    } else {
+#pragma unroll
+      for (int i = 0; i < LSQ_MAX_PLANES; ++i)
+        if (i < npl) {
+          float b = sign_pm1(__fsub_rn(v, acc));  // i == 0: acc = 0 -> sign(v)
+          float t = __fmul_rn(s[i], b);
+          acc = (i == 0) ? t : __fadd_rn(acc, t);
+        }
+    }
+    o[e] = acc;
+  }
+}
+
+__global__ void ste_backward_kernel(const float* __restrict__ x, const float* __restrict__ go,
+                                    float* __restrict__ gi, long long n) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float v = x[e];
+    gi[e] = (v > 1.0f || v < -1.0f) ? 0.0f : go[e];
+  }
+}
+
+// One thread per pixel, looping over channels: loads are coalesced along W (NCHW input), the
+// channel bits of a pixel accumulate in a register word and leave as one 32-bit store per 32 channels
+// into the position-major plane layout (adjacent stores of a thread fill the same sector, L2 merges).
+template <int NPL>
+__global__ void __launch_bounds__(kEncThreads)
+encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const float* __restrict__ scales,
+                  int ns, uint32_t* __restrict__ planes, double* __restrict__ partial,
+                  unsigned* __restrict__ counter, float* __restrict__ last_scale) {
+  __shared__ double red[32];
+  __shared__ bool last;
+  const int s = blockIdx.y;
+  const int hw = g.h * g.w;
+  const int p = blockIdx.x * kEncThreads + threadIdx.x;
+  const bool valid = p < hw;
+  float sc[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) sc[i] = (i < ns) ? scales[(long long)i * g.n + s] : 0.0f;
+  double acc_sum = 0.0;
+  if (valid) {
+    const int yi = p / g.w, xi = p - yi * g.w;
+    int phase = 0, a = yi, b = xi;
+    if (g.nphase == 4) {
+      phase = ((yi & 1) << 1) | (xi & 1);
+      a = yi >> 1;
+      b = xi >> 1;
+    }
+    const long long v = vpos(g, s, a, b);
+    const float* xp = x + (long long)s * g.c * hw + p;
+    for (int cg = 0; cg < g.cw; ++cg) {
+      uint32_t word[NPL];
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) word[j] = 0u;
+      float gsum = 0.0f;
+      const int cbase = cg * 32;
+      const int cn = min(32, g.c - cbase);
+#pragma unroll 8
+      for (int cc = 0; cc < cn; ++cc) {
+        const float val = clamp_sym(__ldg(xp + (long long)(cbase + cc) * hw), alpha);
+        float acc = 0.0f, res = val;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const float bj = sign_pm1(j == 0 ? val : __fsub_rn(val, acc));
+          word[j] |= (bj > 0.0f ? 1u : 0u) << cc;
+          if (j < ns) {
+            const float t = __fmul_rn(sc[j], bj);
+            acc = (j == 0) ? t : __fadd_rn(acc, t);
+            res = __fsub_rn(res, __fmul_rn(sc[j], sign_pm1(res)));
+          }
+        }
+        gsum += fabsf(res);
+      }
+      acc_sum += (double)gsum;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j)
+        planes[(((long long)j * g.nphase + phase) * g.vtot + v) * g.cw + cg] = word[j];
+    }
+  }
+  if (last_scale == nullptr) return;
+  double tot = block_sum(acc_sum, red);
+  const unsigned nblk = gridDim.x;
+  if (threadIdx.x == 0) {
+    partial[(long long)s * nblk + blockIdx.x] = tot;
+    __threadfence();
+    last = (atomicAdd(&counter[s], 1u) == nblk - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b = 0; b < nblk; ++b) t += __ldcg(&partial[(long long)s * nblk + b]);
+    last_scale[s] = (float)(t / ((double)g.c * (double)hw));
+    counter[s] = 0u;
+  }
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace lsq
+
+using namespace lsq;
+
+extern "C" {
+
+int lsq_abi_version(void) { return LSQ_ABI_VERSION; }
+const char* lsq_last_error(void) { return lsq::g_err; }
+
+size_t lsq_reduce_workspace_bytes(int64_t rows, int64_t len) {
+  if (rows <= 0 || len <= 0) return 256;
+  size_t nblk = (size_t)((len + kEncThreads - 1) / kEncThreads) + 1;
+  return align_up((size_t)rows * 4, 256) + (size_t)rows * nblk * 8 + 256;
+}
+
+int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales,
+                    int nscales, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+  LSQ_CHECK_ARG(d_x && d_out && d_ws, "lsq_row_absmean: null pointer");
+  LSQ_CHECK_ARG(rows > 0 && len > 0 && rows <= 65535, "lsq_row_absmean: bad shape rows=%lld len=%lld", (long long)rows, (long long)len);
+  LSQ_CHECK_ARG(nscales >= 0 && nscales <= LSQ_MAX_PLANES && (nscales == 0 || d_scales), "lsq_row_absmean: bad nscales %d", nscales);
+  if (ws_bytes < lsq_reduce_workspace_bytes(rows, len)) {
+    set_error("lsq_row_absmean: workspace %zu < %zu", ws_bytes, lsq_reduce_workspace_bytes(rows, len));
+    return LSQ_ERR_WORKSPACE;
+  }
+  unsigned* counter = (unsigned*)d_ws;
+  double* partial = (double*)((char*)d_ws + align_up((size_t)rows * 4, 256));
+  dim3 grid((unsigned)((len + kRowChunk - 1) / kRowChunk), (unsigned)rows);
+  row_absmean_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nscales,
+                                                                     d_out, partial, counter);
+  LSQ_CUDA_LAUNCH_CHECK("row_absmean_kernel");
+  return LSQ_OK;
+}
+
+int lsq_fakequant(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales, int nplanes,
+                  int ternary, float* d_out, void* stream) {
+  LSQ_CHECK_ARG(d_x && d_out && d_scales, "lsq_fakequant: null pointer");
+  LSQ_CHECK_ARG(rows > 0 && len > 0 && rows <= 65535, "lsq_fakequant: bad shape");
+  LSQ_CHECK_ARG(nplanes >= 1 && nplanes <= LSQ_MAX_PLANES, "lsq_fakequant: bad nplanes %d", nplanes);
+  LSQ_CHECK_ARG(!ternary || nplanes == 2, "lsq_fakequant: ternary needs nplanes == 2");
+  unsigned gx = (unsigned)((len + kRowThreads * 4 - 1) / (kRowThreads * 4));
+  if (gx > 4096) gx = 4096;
+  dim3 grid(gx, (unsigned)rows);
+  fakequant_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nplanes, ternary, d_out);
+  LSQ_CUDA_LAUNCH_CHECK("fakequant_kernel");
+  return LSQ_OK;
+}
+
+int lsq_ste_backward(const float* d_x, const float* d_gout, float* d_gin, int64_t n, void* stream) {
+  LSQ_CHECK_ARG(d_x && d_gout && d_gin && n >= 0, "lsq_ste_backward: bad argument");
+  if (n == 0) return LSQ_OK;
+  unsigned grid = (unsigned)((n + 1023) / 1024);
+  if (grid > 148 * 16) grid = 148 * 16;
+  ste_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_gout, d_gin, n);
+  LSQ_CUDA_LAUNCH_CHECK("ste_backward_kernel");
+  return LSQ_OK;
+}
+
+int lsq_act_geometry(int n, int c, int h, int w, int kh, int kw, int stride, int pad, lsq_act_geom* g) {
+  LSQ_CHECK_ARG(g != nullptr, "lsq_act_geometry: null output");
+  LSQ_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && kh > 0 && kw > 0 && pad >= 0, "lsq_act_geometry: bad shape");
+  if (stride != 1 && stride != 2) {
+    set_error("lsq_act_geometry: stride %d not supported by the packed path", stride);
+    return LSQ_ERR_UNSUPPORTED;
+  }
+  if (h + 2 * pad < kh || w + 2 * pad < kw) {
+    set_error("lsq_act_geometry: kernel larger than padded input");
+    return LSQ_ERR_ARG;
+  }
+  memset(g, 0, sizeof(*g));
+  g->n = n; g->c = c; g->h = h; g->w = w; g->kh = kh; g->kw = kw; g->stride = stride; g->pad = pad;
+  g->ho = (h + 2 * pad - kh) / stride + 1;
+  g->wo = (w + 2 * pad - kw) / stride + 1;
+  g->cw = (c + 31) / 32;
+  g->nphase = stride == 1 ? 1 : 4;
+  g->hv = (h + stride - 1) / stride;
+  g->wv = (w + stride - 1) / stride;
+  // shared zero padding, in phase coordinates: taps reach floor((d - pad)/stride) for d in [0, k)
+  auto fdiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+  int ph = (pad + stride - 1) / stride;
+  int after_h = (g->ho - 1 + fdiv(kh - 1 - pad, stride)) - (g->hv - 1);
+  int after_w = (g->wo - 1 + fdiv(kw - 1 - pad, stride)) - (g->wv - 1);
+  if (after_h > ph) ph = after_h;
+  if (after_w > ph) ph = after_w;
+  g->ph = ph;
+  if (g->ho > g->hv || g->wo > g->wv + ph) {
+    set_error("lsq_act_geometry: output larger than the input raster (kernel %dx%d pad %d)", kh, kw, pad);
+    return LSQ_ERR_UNSUPPORTED;
+  }
+  g->pitch = g->wv + ph;
+  g->rows_per_sample = g->hv + ph;
+  g->lead = ph;
+  int64_t v = (int64_t)g->lead + ((int64_t)n * g->rows_per_sample + ph) * g->pitch + ph;
+  v += 2 * ((int64_t)ph * g->pitch + ph) + 256 + 64;
+  g->vtot = (v + 31) / 32 * 32;
+  return LSQ_OK;
+}
+
+size_t lsq_act_planes_bytes(const lsq_act_geom* g, int nplanes) {
+  if (!g || nplanes <= 0) return 0;
+  return (size_t)nplanes * g->nphase * (size_t)g->vtot * g->cw * sizeof(uint32_t);
+}
+
+int lsq_encode_act(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
+                   int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
+                   void* stream) {
+  LSQ_CHECK_ARG(d_x && g && d_planes, "lsq_encode_act: null pointer");
+  LSQ_CHECK_ARG(nplanes >= 1 && nplanes <= 4, "lsq_encode_act: nplanes %d not in [1,4]", nplanes);
+  LSQ_CHECK_ARG(nscales >= 0 && nscales <= nplanes && (nscales == 0 || d_scales), "lsq_encode_act: bad nscales %d", nscales);
+  LSQ_CHECK_ARG(g->n <= 65535, "lsq_encode_act: batch too large");
+  const int hw = g->h * g->w;
+  double* partial = nullptr;
+  unsigned* counter = nullptr;
+  if (d_last_scale) {
+    size_t need = lsq_reduce_workspace_bytes(g->n, (int64_t)g->c * hw);
+    if (!d_ws || ws_bytes < need) {
+      set_error("lsq_encode_act: workspace %zu < %zu", ws_bytes, need);
+      return LSQ_ERR_WORKSPACE;
+    }
+    counter = (unsigned*)d_ws;
+    partial = (double*)((char*)d_ws + align_up((size_t)g->n * 4, 256));
+  }
+  ActGeom dg = to_dev(*g);
+  dim3 grid((unsigned)((hw + kEncThreads - 1) / kEncThreads), (unsigned)g->n);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nplanes) {
+    case 1: encode_act_kernel<1><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale); break;
+    case 2: encode_act_kernel<2><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale); break;
+    case 3: encode_act_kernel<3><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale); break;
+    default: encode_act_kernel<4><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale); break;
+  }
+  LSQ_CUDA_LAUNCH_CHECK("encode_act_kernel");
+  return LSQ_OK;
+}
+
+}  // extern "C"

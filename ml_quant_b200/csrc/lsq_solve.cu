@@ -1,0 +1,608 @@
+// Least-squares optimal v1 for the 2-bit / ternary quantizer: one CTA per row, no global sort.
+//
+// Replaces opt_v1 -> compute_mask -> cost_function (quant/binary/optimal.py:16-155), which sorts
+// every row, forms fp32 prefix means, picks the positions i with  a_i <= thr(i) <= a_{i+1}  for
+// thr = hi_i/2 (and (lo_i+hi_i)/2 for 2 bits) and evaluates an fp32 cost on a [rows, cand, n] tensor.
+//
+// Here (tests/solver_model.py is the executable specification of this file):
+//   1. one pass histograms the float bit patterns of a = |clamp(x)|[::skip] (monotone keys) into
+//      8192 bins (count + fp32 sum) and accumulates S = sum a, Q = sum a^2 in fp64;
+//   2. prefix counts / sums at bin edges bound both threshold functions over each bin, which flags
+//      the few bins that can hold a candidate (a conservative test, 1e-4 margin on the fp32 sums);
+//   3. a second pass collects only the flagged elements (<= 8192) into shared memory together with
+//      the exact fp64 sum of everything below each flagged range; they are sorted (bitonic) and
+//      every element gets the reference's own fp32 candidate test on (float) prefix sums, so the
+//      candidate set is the reference's;
+//   4. the cost of a candidate is the closed form of optimal.py:31-38 in fp64; the
+//      first minimum in ascending order wins, as torch.argmin does.
+//   Rows with n <= 8192 skip 1-2 (everything is "collected").  Ranges too large to collect are
+//   refined in child windows with a finer bin shift; at shift 0 a bin is a run of equal values and
+//   is evaluated directly.  No host synchronisation (the reference does .tolist(), optimal.py:147).
+#include "lsq_common.cuh"
+
+namespace lsq {
+
+constexpr int kSolveThreads = 1024;
+constexpr int kBins = 8192;
+constexpr int kBinsPerThread = kBins / kSolveThreads;
+constexpr int kCap = 8192;
+constexpr int kMaxRanges = 4;
+constexpr int kMaxFlag = 64;
+constexpr int kStack = 16;
+constexpr int kTopShift = 18;
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+
+struct Range {
+  uint32_t blo, bhi;      // bins (inclusive)
+  uint32_t cnt_below;     // sorted position of the first element of the range
+  uint32_t count;
+  unsigned long long klo, khi;  // key bounds [klo, khi)
+  double sum_below;       // exact fp64 sum of all elements below the range
+  uint32_t next_key;      // smallest key above the range (or the row maximum)
+  uint32_t list_start;    // offset in the collected list
+};
+
+struct SolveSmem {
+  uint32_t hist[kBins];
+  float bsum[kBins];
+  uint32_t keys[kCap];
+  double red[32];
+  double wsum[32];
+  uint32_t wcnt[32];
+  uint32_t wfirst[32];
+  // flagged bins of the current window
+  int nflag;
+  uint32_t fmin, fmax;
+  uint16_t fbin[kMaxFlag];
+  uint32_t fexcl[kMaxFlag];
+  uint32_t fnext[kMaxFlag];
+  double fsumb[kMaxFlag];
+  // ranges to collect
+  int ncollect;
+  Range rng[kMaxRanges];
+  double seg_base[kMaxRanges];
+  // window stack
+  int nstack;
+  uint32_t st_klo[kStack];
+  int st_shift[kStack];
+  // per-window scalars
+  uint32_t cnt_below;
+  uint32_t min_above;
+  uint32_t kmin, kmax;
+  uint32_t nlist;
+  int direct_eval;  // shift == 0: evaluate flagged bins from the histogram
+  int flags;
+  // best candidate
+  double best_cost[32];
+  uint32_t best_pos[32];
+  uint32_t best_key[32];
+  uint32_t ncand;
+};
+
+__device__ __forceinline__ float key_val(uint32_t k) { return __uint_as_float(k); }
+
+struct Best {
+  double cost;
+  uint32_t pos, key;
+  __device__ void offer(double c, uint32_t p, uint32_t k) {
+    if (c < cost || (c == cost && p < pos)) { cost = c; pos = p; key = k; }
+  }
+};
+
+// fp32 emulation of optimal.py:56-80 at sorted position i = k-1 (1 <= i <= n-2)
+template <bool TERN>
+__device__ __forceinline__ bool is_candidate(float a_i, float a_next, uint32_t k, double s_i, uint32_t n, float tot) {
+  const float cum = (float)s_i;
+  const float m2 = __fdiv_rn(__fsub_rn(tot, cum), (float)(n - k));
+  const float half = __fmul_rn(0.5f, m2);
+  bool ok = (a_i <= half) && (half <= a_next);
+  if (!TERN) {
+    const float m1 = __fdiv_rn(cum, (float)k);
+    const float mid = __fmul_rn(0.5f, __fadd_rn(m1, m2));
+    ok = ok || ((a_i <= mid) && (mid <= a_next));
+  }
+  return ok;
+}
+
+// closed form of cost^2 (optimal.py:31-38) for candidate value c with k elements <= c
+template <bool TERN>
+__device__ __forceinline__ double closed_cost2(double c, double k, double s_i, double n, double s_tot, double q_tot) {
+  const double sabs = (s_tot - s_i - (n - k) * c) + (k * c - s_i);
+  const double sq = q_tot - 2.0 * c * s_tot + n * c * c;
+  if (TERN) return sq - 2.0 * c * sabs + n * c * c;
+  return sq - sabs * sabs / n;
+}
+
+template <bool TERN>
+__device__ __forceinline__ void try_position(Best& best, uint32_t& ncand, uint32_t key_i, uint32_t key_next,
+                                             uint32_t i, double s_i, uint32_t n, double s_tot, double q_tot) {
+  if (i < 1 || i + 2 > n) return;
+  const float a_i = key_val(key_i);
+  if (is_candidate<TERN>(a_i, key_val(key_next), i + 1, s_i, n, (float)s_tot)) {
+    ++ncand;
+    best.offer(closed_cost2<TERN>((double)a_i, (double)(i + 1), s_i, (double)n, s_tot, q_tot), i, key_i);
+  }
+}
+
+__device__ __forceinline__ void bitonic_sort(uint32_t* keys, uint32_t lp) {
+  for (uint32_t k = 2; k <= lp; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (lp >> 1); t += blockDim.x) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const uint32_t p = i | j;
+        const uint32_t a = keys[i], b = keys[p];
+        const bool up = ((i & k) == 0);
+        if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Evaluate the sorted list keys[0..L) made of `nseg` segments (ranges in ascending key order).
+template <bool TERN>
+__device__ void evaluate_list(SolveSmem& sm, uint32_t L, int nseg, uint32_t n, double s_tot, double q_tot,
+                              Best& best, uint32_t& ncand) {
+  const uint32_t per = (L + blockDim.x - 1) / blockDim.x;
+  const uint32_t j0 = min(threadIdx.x * per, L), j1 = min(j0 + per, L);
+  double loc = 0.0;
+  for (uint32_t j = j0; j < j1; ++j) loc += (double)key_val(sm.keys[j]);
+  // exclusive block scan of loc (fixed order)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double inc = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) sm.wsum[wid] = inc;
+  __syncthreads();
+  double off = 0.0;
+  for (int w = 0; w < wid; ++w) off += sm.wsum[w];
+  double run = off + inc - loc;  // exclusive prefix at j0
+  // publish the exclusive prefix at each segment start
+  for (int g = 0; g < nseg; ++g) {
+    const uint32_t st = sm.rng[g].list_start;
+    if (st >= j0 && st < j1) {
+      double r = run;
+      for (uint32_t j = j0; j < st; ++j) r += (double)key_val(sm.keys[j]);
+      sm.seg_base[g] = r;
+    }
+  }
+  __syncthreads();
+  for (uint32_t j = j0; j < j1; ++j) {
+    const uint32_t kj = sm.keys[j];
+    run += (double)key_val(kj);
+    int g = 0;
+    while (g + 1 < nseg && j >= sm.rng[g + 1].list_start) ++g;
+    const Range& R = sm.rng[g];
+    const uint32_t seg_end = R.list_start + R.count;
+    const uint32_t i = R.cnt_below + (j - R.list_start);
+    const double s_i = R.sum_below + (run - sm.seg_base[g]);
+    const uint32_t knext = (j + 1 < seg_end) ? sm.keys[j + 1] : R.next_key;
+    try_position<TERN>(best, ncand, kj, knext, i, s_i, n, s_tot, q_tot);
+  }
+  __syncthreads();
+}
+
+template <bool TERN>
+__global__ void __launch_bounds__(kSolveThreads, 1)
+solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
+                int* __restrict__ diag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
+  const long long row = blockIdx.x;
+  const float* xr = x + row * len;
+  const uint32_t n = (uint32_t)((len + skip - 1) / skip);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  Best best{1e300, 0xFFFFFFFFu, 0u};
+  uint32_t ncand = 0;
+  int passes = 0;
+  uint32_t collected = 0;
+
+  if (tid == 0) {
+    sm.kmin = kNoKey; sm.kmax = 0u; sm.nstack = 0; sm.flags = 0; sm.ncand = 0u; sm.nlist = 0u;
+  }
+  __syncthreads();
+  if (n < 3) {
+    if (tid == 0) {
+      v1_out[row] = 0.0f;
+      if (diag) { diag[row * 4 + 0] = 0; diag[row * 4 + 1] = 0; diag[row * 4 + 2] = 0; diag[row * 4 + 3] = 0; }
+    }
+    return;
+  }
+
+  double s_tot = 0.0, q_tot = 0.0;
+  if (n <= (uint32_t)kCap) {
+    // ---- small row: everything is the collected list -------------------------------------
+    uint32_t lp = 2;
+    while (lp < n) lp <<= 1;
+    double ls = 0.0, lq = 0.0;
+    uint32_t kmn = kNoKey, kmx = 0u;
+    for (uint32_t e = tid; e < lp; e += blockDim.x) {
+      uint32_t k = kNoKey;
+      if (e < n) {
+        const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
+        k = __float_as_uint(a);
+        ls += (double)a; lq += (double)a * (double)a;
+        kmn = min(kmn, k); kmx = max(kmx, k);
+      }
+      sm.keys[e] = k;
+    }
+    s_tot = block_sum(ls, sm.red);
+    q_tot = block_sum(lq, sm.red);
+    kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
+    if (lane == 0) { atomicMin(&sm.kmin, kmn); atomicMax(&sm.kmax, kmx); }
+    __syncthreads();
+    passes = 1;
+    bitonic_sort(sm.keys, lp);
+    if (tid == 0) {
+      sm.rng[0].cnt_below = 0; sm.rng[0].count = n; sm.rng[0].sum_below = 0.0;
+      sm.rng[0].next_key = sm.kmax; sm.rng[0].list_start = 0;
+    }
+    __syncthreads();
+    collected = n;
+    evaluate_list<TERN>(sm, n, 1, n, s_tot, q_tot, best, ncand);
+  } else {
+    // ---- large row: histogram windows -------------------------------------------------------
+    if (tid == 0) { sm.st_klo[0] = 0u; sm.st_shift[0] = kTopShift; sm.nstack = 1; }
+    __syncthreads();
+    bool first = true;
+    while (true) {
+      __syncthreads();
+      if (sm.nstack == 0) break;
+      const uint32_t klo = sm.st_klo[sm.nstack - 1];
+      const int shift = sm.st_shift[sm.nstack - 1];
+      const unsigned long long khi = (unsigned long long)klo + ((unsigned long long)kBins << shift);
+      __syncthreads();
+      if (tid == 0) {
+        --sm.nstack;
+        sm.cnt_below = 0u; sm.min_above = kNoKey; sm.nflag = 0; sm.fmin = kNoKey; sm.fmax = 0u;
+        sm.ncollect = 0; sm.nlist = 0u; sm.direct_eval = 0;
+      }
+      for (int b = tid; b < kBins; b += blockDim.x) { sm.hist[b] = 0u; sm.bsum[b] = 0.0f; }
+      __syncthreads();
+      // -- histogram pass
+      {
+        double ls = 0.0, lq = 0.0, lb = 0.0;
+        uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey;
+        for (uint32_t e = tid; e < n; e += blockDim.x) {
+          const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
+          const uint32_t k = __float_as_uint(a);
+          if (first) { ls += (double)a; lq += (double)a * (double)a; kmn = min(kmn, k); kmx = max(kmx, k); }
+          if (k < klo) { ++cb; lb += (double)a; }
+          else if ((unsigned long long)k >= khi) { mab = min(mab, k); }
+          else {
+            const uint32_t b = (k - klo) >> shift;
+            atomicAdd(&sm.hist[b], 1u);
+            atomicAdd(&sm.bsum[b], a);
+          }
+        }
+        ++passes;
+        if (first) {
+          s_tot = block_sum(ls, sm.red);
+          q_tot = block_sum(lq, sm.red);
+          kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
+          if (lane == 0) { atomicMin(&sm.kmin, kmn); atomicMax(&sm.kmax, kmx); }
+        }
+        const double sum_below_w = block_sum(lb, sm.red);
+        cb = (uint32_t)__reduce_add_sync(0xffffffffu, cb);
+        mab = warp_min_u32(mab);
+        if (lane == 0) { atomicAdd(&sm.cnt_below, cb); atomicMin(&sm.min_above, mab); }
+        __syncthreads();
+        const uint32_t kmax = sm.kmax;
+        const uint32_t min_above = (sm.min_above == kNoKey) ? kmax : sm.min_above;
+        const uint32_t cnt_below_w = sm.cnt_below;
+
+        // -- scan bins: thread owns bins [8*tid, 8*tid+8)
+        uint32_t c[kBinsPerThread];
+        double s[kBinsPerThread];
+        uint32_t ct = 0; double stt = 0.0; uint32_t fn = kNoKey;
+#pragma unroll
+        for (int j = 0; j < kBinsPerThread; ++j) {
+          const uint32_t b = tid * kBinsPerThread + j;
+          c[j] = sm.hist[b];
+          s[j] = (shift == 0) ? (double)c[j] * (double)key_val(klo + b) : (double)sm.bsum[b];
+          if (c[j] == 0u) s[j] = 0.0;
+          ct += c[j]; stt += s[j];
+          if (c[j] != 0u && fn == kNoKey) fn = b;
+        }
+        uint32_t ci = ct; double si = stt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t tc = __shfl_up_sync(0xffffffffu, ci, o);
+          double ts = __shfl_up_sync(0xffffffffu, si, o);
+          if (lane >= o) { ci += tc; si += ts; }
+        }
+        // suffix-min of the first non-empty bin over lanes > lane
+        uint32_t sfx = fn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t t = __shfl_down_sync(0xffffffffu, sfx, o);
+          if (lane + o < 32) sfx = min(sfx, t);
+        }
+        uint32_t nxt_in_warp = __shfl_down_sync(0xffffffffu, sfx, 1);
+        if (lane == 31) nxt_in_warp = kNoKey;
+        __syncthreads();
+        if (lane == 31) { sm.wcnt[wid] = ci; sm.wsum[wid] = si; }
+        if (lane == 0) sm.wfirst[wid] = sfx;
+        __syncthreads();
+        uint32_t coff = 0; double soff = 0.0;
+        for (int w = 0; w < wid; ++w) { coff += sm.wcnt[w]; soff += sm.wsum[w]; }
+        uint32_t nxt_after = nxt_in_warp;
+        for (int w = wid + 1; w < 32 && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
+        uint32_t excl = cnt_below_w + coff + ci - ct;
+        double pref = sum_below_w + soff + si - stt;
+
+        // -- flag bins that can hold a candidate
+        const double marg = (shift == 0) ? 0.0 : 1e-4;
+        const double eps = 1e-6;
+        const double dn = (double)n;
+        const double vmax = (double)key_val(kmax);
+#pragma unroll
+        for (int j = 0; j < kBinsPerThread; ++j) {
+          if (c[j] == 0u) continue;
+          const uint32_t b = tid * kBinsPerThread + j;
+          uint32_t nb = kNoKey;
+#pragma unroll
+          for (int j2 = kBinsPerThread - 1; j2 > j; --j2)
+            if (c[j2] != 0u) nb = tid * kBinsPerThread + j2;
+          if (nb == kNoKey) nb = nxt_after;
+          const uint32_t k0 = max(excl, 1u), k1 = min(excl + c[j], n - 1);
+          if (k0 <= k1) {
+            const unsigned long long elo_k = min((unsigned long long)klo + ((unsigned long long)b << shift), 0x7F800000ull);
+            const unsigned long long ehi_k = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, (unsigned long long)kmax);
+            const double edge_lo = (double)key_val((uint32_t)elo_k);
+            const double edge_hi = fmax((double)key_val((uint32_t)ehi_k), edge_lo);
+            double lo0, hi0, lo1, hi1;
+            if (excl >= 1u) { lo0 = pref * (1.0 - marg); hi0 = pref * (1.0 + marg); }
+            else { lo0 = pref * (1.0 - marg) + edge_lo; hi0 = pref * (1.0 + marg) + edge_hi; }
+            if (excl + c[j] <= n - 1) { lo1 = (pref + s[j]) * (1.0 - marg); hi1 = (pref + s[j]) * (1.0 + marg); }
+            else { lo1 = hi1 = s_tot - vmax; }
+            double nxt_hi;
+            if (nb != kNoKey) {
+              const unsigned long long nh = min((unsigned long long)klo + ((unsigned long long)(nb + 1) << shift) - 1ull, (unsigned long long)kmax);
+              const unsigned long long nl = min((unsigned long long)klo + ((unsigned long long)nb << shift), 0x7F800000ull);
+              nxt_hi = fmax((double)key_val((uint32_t)nh), (double)key_val((uint32_t)nl));
+            } else {
+              nxt_hi = (double)key_val(min_above);
+            }
+            // thresholds at the first (k0) and last (k1) split of the bin, over the admissible sums
+            const double h0a = 0.5 * (s_tot - lo0) / (dn - k0), h0b = 0.5 * (s_tot - hi0) / (dn - k0);
+            const double h1a = 0.5 * (s_tot - lo1) / (dn - k1), h1b = 0.5 * (s_tot - hi1) / (dn - k1);
+            const double half_min = fmin(h0a, h0b), half_max = fmax(h1a, h1b);
+            bool hit = (half_max * (1.0 + eps) >= edge_lo) &&
+                       (half_min * (1.0 - eps) <= edge_hi || half_max * (1.0 - eps) <= nxt_hi);
+            if (!TERN) {
+              const double m0a = h0a + 0.5 * lo0 / k0, m0b = h0b + 0.5 * hi0 / k0;
+              const double m1a = h1a + 0.5 * lo1 / k1, m1b = h1b + 0.5 * hi1 / k1;
+              const double mid_min = fmin(m0a, m0b), mid_max = fmax(m1a, m1b);
+              hit = hit || ((mid_max * (1.0 + eps) >= edge_lo) &&
+                            (mid_min * (1.0 - eps) <= edge_hi || mid_max * (1.0 - eps) <= nxt_hi));
+            }
+            if (hit) {
+              const int slot = atomicAdd(&sm.nflag, 1);
+              atomicMin(&sm.fmin, b); atomicMax(&sm.fmax, b);
+              if (slot < kMaxFlag) {
+                sm.fbin[slot] = (uint16_t)b; sm.fexcl[slot] = excl; sm.fsumb[slot] = pref;
+                sm.fnext[slot] = (nb != kNoKey) ? (uint32_t)min((unsigned long long)klo + ((unsigned long long)nb << shift), 0xFFFFFFFEull) : min_above;
+              } else if (shift == 0) {
+                // flag list overflow at the finest level: evaluate this run of equal values here
+                const uint32_t kv = klo + b;
+                const uint32_t knx = (nb != kNoKey) ? klo + nb : min_above;
+                for (uint32_t jj = 0; jj < c[j]; ++jj)
+                  try_position<TERN>(best, ncand, kv, (jj + 1 < c[j]) ? kv : knx, excl + jj,
+                                     pref + (double)(jj + 1) * (double)key_val(kv), n, s_tot, q_tot);
+              }
+            }
+          }
+          excl += c[j]; pref += s[j];
+        }
+        __syncthreads();
+
+        // -- thread 0: turn flagged bins into ranges, decide collect / refine
+        if (tid == 0 && sm.nflag > 0) {
+          const int nf = min(sm.nflag, kMaxFlag);
+          if (shift == 0) {
+            sm.direct_eval = nf;
+          } else {
+            int nr = 0;
+            Range* R = sm.rng;
+            if (sm.nflag > kMaxFlag) {
+              uint32_t cbw = cnt_below_w, cnt = 0;
+              for (uint32_t b = 0; b < sm.fmin; ++b) cbw += sm.hist[b];
+              for (uint32_t b = sm.fmin; b <= sm.fmax; ++b) cnt += sm.hist[b];
+              R[0].blo = sm.fmin; R[0].bhi = sm.fmax; R[0].cnt_below = cbw; R[0].count = cnt;
+              nr = 1;
+            } else {
+              // insertion sort of slots by bin
+              int ord[kMaxFlag];
+              for (int i = 0; i < nf; ++i) {
+                int j = i;
+                while (j > 0 && sm.fbin[ord[j - 1]] > sm.fbin[i]) { ord[j] = ord[j - 1]; --j; }
+                ord[j] = i;
+              }
+              // consecutive non-empty flagged bins form one range; keep at most kMaxRanges by merging
+              uint32_t r_blo[kMaxFlag], r_bhi[kMaxFlag], r_cb[kMaxFlag], r_end[kMaxFlag];
+              for (int i = 0; i < nf; ++i) {
+                const int sl = ord[i];
+                const uint32_t b = sm.fbin[sl], ex = sm.fexcl[sl], en = ex + sm.hist[b];
+                if (nr > 0 && r_end[nr - 1] == ex) { r_bhi[nr - 1] = b; r_end[nr - 1] = en; }
+                else { r_blo[nr] = b; r_bhi[nr] = b; r_cb[nr] = ex; r_end[nr] = en; ++nr; }
+              }
+              while (nr > kMaxRanges) {
+                int gbest = 0; uint32_t gap = kNoKey;
+                for (int g = 0; g + 1 < nr; ++g) {
+                  const uint32_t d = r_blo[g + 1] - r_bhi[g];
+                  if (d < gap) { gap = d; gbest = g; }
+                }
+                r_bhi[gbest] = r_bhi[gbest + 1]; r_end[gbest] = r_end[gbest + 1];
+                for (int g = gbest + 1; g + 1 < nr; ++g) {
+                  r_blo[g] = r_blo[g + 1]; r_bhi[g] = r_bhi[g + 1]; r_cb[g] = r_cb[g + 1]; r_end[g] = r_end[g + 1];
+                }
+                --nr;
+              }
+              for (int g = 0; g < nr; ++g) {
+                R[g].blo = r_blo[g]; R[g].bhi = r_bhi[g]; R[g].cnt_below = r_cb[g]; R[g].count = r_end[g] - r_cb[g];
+              }
+            }
+            // collect what fits, refine the rest
+            uint32_t budget = kCap, lstart = 0;
+            int nc = 0;
+            for (int g = 0; g < nr; ++g) {
+              Range r = R[g];
+              if (r.count <= budget) {
+                budget -= r.count;
+                r.klo = (unsigned long long)klo + ((unsigned long long)r.blo << shift);
+                r.khi = (unsigned long long)klo + ((unsigned long long)(r.bhi + 1) << shift);
+                r.list_start = lstart; lstart += r.count;
+                R[nc++] = r;
+              } else {
+                const unsigned long long span = (unsigned long long)(r.bhi - r.blo + 1) << shift;
+                int lg = 0;
+                while ((1ull << lg) < span) ++lg;
+                int nshift = lg - 13;
+                if (nshift < 0) nshift = 0;
+                if (nshift >= shift) nshift = shift - 1;
+                const unsigned long long wspan = (unsigned long long)kBins << nshift;
+                for (unsigned long long o = 0; o < span; o += wspan) {
+                  if (sm.nstack < kStack) {
+                    sm.st_klo[sm.nstack] = (uint32_t)((unsigned long long)klo + ((unsigned long long)r.blo << shift) + o);
+                    sm.st_shift[sm.nstack] = nshift;
+                    ++sm.nstack;
+                  } else {
+                    sm.flags |= 1;  // window stack overflow: result may miss candidates
+                  }
+                }
+              }
+            }
+            sm.ncollect = nc;
+          }
+        }
+        __syncthreads();
+
+        // -- shift 0: runs of equal values straight from the histogram
+        if (sm.direct_eval > 0) {
+          const int nf = sm.direct_eval;
+          for (int sl = 0; sl < nf; ++sl) {
+            const uint32_t b = sm.fbin[sl], cnt = sm.hist[b], kv = klo + b;
+            const double base = sm.fsumb[sl], v = (double)key_val(kv);
+            for (uint32_t jj = tid; jj < cnt; jj += blockDim.x)
+              try_position<TERN>(best, ncand, kv, (jj + 1 < cnt) ? kv : sm.fnext[sl], sm.fexcl[sl] + jj,
+                                 base + (double)(jj + 1) * v, n, s_tot, q_tot);
+          }
+        }
+
+        // -- collection pass
+        const int nc = sm.ncollect;
+        if (nc > 0) {
+          double sb[kMaxRanges];
+          uint32_t ma[kMaxRanges];
+#pragma unroll
+          for (int g = 0; g < kMaxRanges; ++g) { sb[g] = 0.0; ma[g] = kNoKey; }
+          for (uint32_t e = tid; e < n; e += blockDim.x) {
+            const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
+            const uint32_t k = __float_as_uint(a);
+#pragma unroll
+            for (int g = 0; g < kMaxRanges; ++g) {
+              if (g < nc) {
+                if ((unsigned long long)k < sm.rng[g].klo) sb[g] += (double)a;
+                else if ((unsigned long long)k < sm.rng[g].khi) {
+                  const uint32_t slot = atomicAdd(&sm.nlist, 1u);
+                  if (slot < (uint32_t)kCap) sm.keys[slot] = k;
+                } else ma[g] = min(ma[g], k);
+              }
+            }
+          }
+          ++passes;
+#pragma unroll
+          for (int g = 0; g < kMaxRanges; ++g) {
+            if (g < nc) {
+              const double t = block_sum(sb[g], sm.red);
+              uint32_t m = warp_min_u32(ma[g]);
+              __syncthreads();
+              if (tid == 0) { sm.rng[g].sum_below = t; sm.rng[g].next_key = kNoKey; }
+              __syncthreads();
+              if (lane == 0) atomicMin(&sm.rng[g].next_key, m);
+            }
+          }
+          __syncthreads();
+          const uint32_t L = min(sm.nlist, (uint32_t)kCap);
+          if (tid == 0) {
+            for (int g = 0; g < nc; ++g)
+              if (sm.rng[g].next_key == kNoKey) sm.rng[g].next_key = sm.kmax;
+            if (sm.nlist > (uint32_t)kCap) sm.flags |= 2;
+          }
+          uint32_t lp = 2;
+          while (lp < L) lp <<= 1;
+          for (uint32_t e = L + tid; e < lp; e += blockDim.x) sm.keys[e] = kNoKey;
+          __syncthreads();
+          collected += L;
+          bitonic_sort(sm.keys, lp);
+          evaluate_list<TERN>(sm, L, nc, n, s_tot, q_tot, best, ncand);
+        }
+      }
+      first = false;
+    }
+  }
+
+  // ---- reduce the best candidate over the block ------------------------------------------------
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, best.cost, o);
+    const uint32_t op = __shfl_xor_sync(0xffffffffu, best.pos, o);
+    const uint32_t ok = __shfl_xor_sync(0xffffffffu, best.key, o);
+    best.offer(oc, op, ok);
+  }
+  ncand = (uint32_t)__reduce_add_sync(0xffffffffu, ncand);
+  if (lane == 0) {
+    sm.best_cost[wid] = best.cost; sm.best_pos[wid] = best.pos; sm.best_key[wid] = best.key;
+    atomicAdd(&sm.ncand, ncand);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    Best b{1e300, 0xFFFFFFFFu, 0u};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) b.offer(sm.best_cost[w], sm.best_pos[w], sm.best_key[w]);
+    uint32_t nc_tot = sm.ncand;
+    if (TERN) {
+      // optimal.py:86-118: when min > mean/2 the value mean/2 (not a data element) is appended last
+      const float mean = (float)(s_tot / (double)n);
+      const float half_mean = __fmul_rn(0.5f, mean);
+      if (key_val(sm.kmin) > half_mean) {
+        ++nc_tot;
+        b.offer(closed_cost2<true>((double)half_mean, 0.0, 0.0, (double)n, s_tot, q_tot), n, __float_as_uint(half_mean));
+      }
+    }
+    v1_out[row] = (nc_tot > 0) ? key_val(b.key) : 0.0f;
+    if (diag) {
+      diag[row * 4 + 0] = passes; diag[row * 4 + 1] = (int)collected; diag[row * 4 + 2] = (int)nc_tot;
+      diag[row * 4 + 3] = sm.flags;
+    }
+  }
+}
+
+}  // namespace lsq
+
+using namespace lsq;
+
+extern "C" int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
+                            float* d_v1, int32_t* d_diag, void* stream) {
+  LSQ_CHECK_ARG(d_x && d_v1, "lsq_solve_v1: null pointer");
+  LSQ_CHECK_ARG(rows > 0 && len > 0 && skip >= 1, "lsq_solve_v1: bad shape rows=%lld len=%lld skip=%d", (long long)rows, (long long)len, skip);
+  LSQ_CHECK_ARG((len + skip - 1) / skip < (1ll << 31), "lsq_solve_v1: row too long");
+  const size_t smem = sizeof(SolveSmem);
+  cudaError_t e;
+  if (ternary) e = cudaFuncSetAttribute(solve_v1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else e = cudaFuncSetAttribute(solve_v1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("lsq_solve_v1: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return LSQ_ERR_CUDA;
+  }
+  dim3 grid((unsigned)rows);
+  if (ternary) solve_v1_kernel<true><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag);
+  else solve_v1_kernel<false><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag);
+  LSQ_CUDA_LAUNCH_CHECK("solve_v1_kernel");
+  return LSQ_OK;
+}

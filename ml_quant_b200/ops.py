@@ -1,0 +1,178 @@
+"""Host-side launchers: torch tensors in, C-ABI calls on the current CUDA stream, torch tensors out.
+
+Torch is plumbing here (device memory, streams); every value is computed by liblsq_b200.so.
+All entry points require contiguous fp32 CUDA tensors and raise otherwise -- there is no CPU path.
+"""
+import ctypes as C
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _C
+
+_tls = threading.local()
+
+
+def require_cuda(x: torch.Tensor, what: str = 'tensor') -> None:
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise _C.LsqError(
+            f'ml_quant_b200: {what} must be a CUDA tensor -- the quantizer runs only as sm_100a CUDA kernels '
+            '(no CPU fallback; the CPU restatement used for testing lives in oracle/).')
+    if x.dtype != torch.float32:
+        raise _C.LsqError(f'ml_quant_b200: {what} must be float32, got {x.dtype}')
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch, cached per (thread, device, stream); kernels leave it zeroed."""
+    cache = getattr(_tls, 'ws', None)
+    if cache is None:
+        cache = _tls.ws = {}
+    key = (device.index, _stream())
+    buf = cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        cache[key] = buf
+    return buf
+
+
+def scale_table(scales: Sequence[torch.Tensor], rows: int, device) -> Optional[torch.Tensor]:
+    if len(scales) == 0:
+        return None
+    tab = torch.stack([s.detach().reshape(-1).to(device=device, dtype=torch.float32) for s in scales]).contiguous()
+    if tab.shape[1] != rows:
+        raise ValueError(f'scale vectors must have {rows} entries, got {tab.shape[1]}')
+    return tab
+
+
+def _alpha(alpha: Optional[float]) -> float:
+    return float(alpha) if alpha is not None and alpha > 0 else 0.0
+
+
+def row_absmean(x2d: torch.Tensor, scales: Sequence[torch.Tensor] = (), alpha: Optional[float] = None) -> torch.Tensor:
+    """mean |residual| per row after folding ``scales`` (include/lsq_b200.h: lsq_row_absmean)."""
+    require_cuda(x2d)
+    x2d = x2d.contiguous()
+    rows, length = x2d.shape
+    out = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    tab = scale_table(scales, rows, x2d.device)
+    L = _C.lib()
+    need = L.lsq_reduce_workspace_bytes(rows, length)
+    ws = workspace(x2d.device, need)
+    with torch.cuda.device(x2d.device):
+        _C.check(L.lsq_row_absmean(x2d.data_ptr(), rows, length, _alpha(alpha), _ptr(tab), len(scales),
+                                   out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), 'lsq_row_absmean')
+    return out
+
+
+def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[float] = None,
+             diag: bool = False):
+    """Optimal v1 per row (lsq_solve_v1); returns [rows] (and the int32 [rows,4] diagnostics)."""
+    require_cuda(x2d)
+    x2d = x2d.contiguous()
+    rows, length = x2d.shape
+    out = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    dg = torch.zeros(rows, 4, dtype=torch.int32, device=x2d.device) if diag else None
+    with torch.cuda.device(x2d.device):
+        _C.check(_C.lib().lsq_solve_v1(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
+                                       out.data_ptr(), _ptr(dg), _stream()), 'lsq_solve_v1')
+    return (out, dg) if diag else out
+
+
+def fakequant(x2d: torch.Tensor, scales: Sequence[torch.Tensor], ternary: bool = False,
+              alpha: Optional[float] = None) -> torch.Tensor:
+    """Dense sum_j s_j b_j in the reference's operation order (lsq_fakequant)."""
+    require_cuda(x2d)
+    x2d = x2d.contiguous()
+    rows, length = x2d.shape
+    nplanes = 2 if ternary else len(scales)
+    tab = scale_table(scales, rows, x2d.device)
+    out = torch.empty_like(x2d)
+    with torch.cuda.device(x2d.device):
+        _C.check(_C.lib().lsq_fakequant(x2d.data_ptr(), rows, length, _alpha(alpha), tab.data_ptr(), nplanes,
+                                        int(bool(ternary)), out.data_ptr(), _stream()), 'lsq_fakequant')
+    return out
+
+
+def ste_backward(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    require_cuda(x)
+    x = x.contiguous()
+    grad_out = grad_out.contiguous().to(torch.float32)
+    gin = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().lsq_ste_backward(x.data_ptr(), grad_out.data_ptr(), gin.data_ptr(), x.numel(), _stream()),
+                 'lsq_ste_backward')
+    return gin
+
+
+def act_geometry(n: int, c: int, h: int, w: int, kh: int, kw: int, stride: int, pad: int) -> Optional[_C.ActGeom]:
+    """Packed-plane geometry, or None when the packed path does not cover the shape."""
+    g = _C.ActGeom()
+    st = _C.lib().lsq_act_geometry(n, c, h, w, kh, kw, stride, pad, C.byref(g))
+    if st == -4:
+        return None
+    _C.check(st, 'lsq_act_geometry')
+    return g
+
+
+def encode_act(x: torch.Tensor, g: _C.ActGeom, scales: Sequence[torch.Tensor], nplanes: int,
+               alpha: Optional[float] = None, want_next_scale: bool = False,
+               planes: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """x [n,c,h,w] -> bit planes (int32 buffer) and optionally the next per-sample scale (lsq_encode_act)."""
+    require_cuda(x)
+    x = x.contiguous()
+    L = _C.lib()
+    nbytes = L.lsq_act_planes_bytes(C.byref(g), nplanes)
+    if planes is None or planes.numel() * 4 < nbytes:
+        planes = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=x.device)
+    tab = scale_table(scales, g.n, x.device)
+    nxt = torch.empty(g.n, dtype=torch.float32, device=x.device) if want_next_scale else None
+    need = L.lsq_reduce_workspace_bytes(g.n, g.c * g.h * g.w)
+    ws = workspace(x.device, need)
+    with torch.cuda.device(x.device):
+        _C.check(L.lsq_encode_act(x.data_ptr(), C.byref(g), _alpha(alpha), _ptr(tab), len(scales), nplanes,
+                                  planes.data_ptr(), _ptr(nxt), ws.data_ptr(), ws.numel(), _stream()), 'lsq_encode_act')
+    return planes, nxt
+
+
+def pack_weights(w: torch.Tensor) -> torch.Tensor:
+    """sign(W) images for the convolution kernels (lsq_pack_weights)."""
+    require_cuda(w, 'weight')
+    w = w.detach().contiguous()
+    cout, cin, kh, kw = w.shape
+    L = _C.lib()
+    nbytes = L.lsq_wpack_bytes(cout, cin, kh, kw)
+    buf = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=w.device)
+    off = (-buf.data_ptr()) % 1024
+    view = buf[off:off + nbytes]
+    with torch.cuda.device(w.device):
+        _C.check(L.lsq_pack_weights(w.data_ptr(), cout, cin, kh, kw, view.data_ptr(), _stream()), 'lsq_pack_weights')
+    return view
+
+
+def bconv2d(planes: torch.Tensor, g: _C.ActGeom, nplanes: int, act_scales: torch.Tensor, wpack: torch.Tensor,
+            w_scale: torch.Tensor, bias: Optional[torch.Tensor], cout: int, impl: int = 0,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Binary convolution forward (lsq_bconv2d_fwd): act_scales is the [nplanes, n] table."""
+    if out is None:
+        out = torch.empty(g.n, cout, g.ho, g.wo, dtype=torch.float32, device=planes.device)
+    act_scales = act_scales.contiguous()
+    w_scale = w_scale.detach().contiguous()
+    b = None if bias is None else bias.detach().contiguous()
+    with torch.cuda.device(planes.device):
+        _C.check(_C.lib().lsq_bconv2d_fwd(planes.data_ptr(), C.byref(g), nplanes, act_scales.data_ptr(),
+                                          wpack.data_ptr(), w_scale.data_ptr(), _ptr(b), cout, out.data_ptr(),
+                                          int(impl), _stream()), 'lsq_bconv2d_fwd')
+    return out
+
+
+def tc_supported(g: _C.ActGeom, nplanes: int, cout: int) -> bool:
+    return bool(_C.lib().lsq_bconv2d_tc_supported(C.byref(g), nplanes, cout))

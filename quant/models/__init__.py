@@ -1,0 +1,1 @@
+"""Drop-in for the reference package quant.models."""
