@@ -13,6 +13,35 @@ from . import _C
 
 _tls = threading.local()
 
+# ---- instrumentation (bench.py): launches of OUR kernels and optional per-launch CUDA-event timing ----
+LAUNCHES = {}          # kernel name -> number of launches since reset_counters()
+PROFILE = None         # None, or a list receiving (name, start_event, end_event, alg_bytes, alg_ops)
+
+
+def reset_counters() -> None:
+    LAUNCHES.clear()
+
+
+class _launch:
+    """Context manager around one C-ABI kernel launch: counts it, optionally brackets it with events."""
+
+    def __init__(self, name: str, alg_bytes: float = 0.0, alg_ops: float = 0.0):
+        self.name, self.b, self.o = name, alg_bytes, alg_ops
+
+    def __enter__(self):
+        LAUNCHES[self.name] = LAUNCHES.get(self.name, 0) + 1
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, self.e0, self.e1, self.b, self.o))
+        return False
+
 
 def require_cuda(x: torch.Tensor, what: str = 'tensor') -> None:
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
@@ -67,7 +96,7 @@ def row_absmean(x2d: torch.Tensor, scales: Sequence[torch.Tensor] = (), alpha: O
     L = _C.lib()
     need = L.lsq_reduce_workspace_bytes(rows, length)
     ws = workspace(x2d.device, need)
-    with torch.cuda.device(x2d.device):
+    with torch.cuda.device(x2d.device), _launch('row_absmean', 4.0 * rows * length):
         _C.check(L.lsq_row_absmean(x2d.data_ptr(), rows, length, _alpha(alpha), _ptr(tab), len(scales),
                                    out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), 'lsq_row_absmean')
     return out
@@ -81,7 +110,7 @@ def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[fl
     rows, length = x2d.shape
     out = torch.empty(rows, dtype=torch.float32, device=x2d.device)
     dg = torch.zeros(rows, 4, dtype=torch.int32, device=x2d.device) if diag else None
-    with torch.cuda.device(x2d.device):
+    with torch.cuda.device(x2d.device), _launch('solve_v1', 4.0 * rows * length):
         _C.check(_C.lib().lsq_solve_v1(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
                                        out.data_ptr(), _ptr(dg), _stream()), 'lsq_solve_v1')
     return (out, dg) if diag else out
@@ -96,7 +125,7 @@ def fakequant(x2d: torch.Tensor, scales: Sequence[torch.Tensor], ternary: bool =
     nplanes = 2 if ternary else len(scales)
     tab = scale_table(scales, rows, x2d.device)
     out = torch.empty_like(x2d)
-    with torch.cuda.device(x2d.device):
+    with torch.cuda.device(x2d.device), _launch('fakequant', 8.0 * rows * length):
         _C.check(_C.lib().lsq_fakequant(x2d.data_ptr(), rows, length, _alpha(alpha), tab.data_ptr(), nplanes,
                                         int(bool(ternary)), out.data_ptr(), _stream()), 'lsq_fakequant')
     return out
@@ -107,7 +136,7 @@ def ste_backward(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
     x = x.contiguous()
     grad_out = grad_out.contiguous().to(torch.float32)
     gin = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _launch('ste_backward', 12.0 * x.numel()):
         _C.check(_C.lib().lsq_ste_backward(x.data_ptr(), grad_out.data_ptr(), gin.data_ptr(), x.numel(), _stream()),
                  'lsq_ste_backward')
     return gin
@@ -137,7 +166,7 @@ def encode_act(x: torch.Tensor, g: _C.ActGeom, scales: Sequence[torch.Tensor], n
     nxt = torch.empty(g.n, dtype=torch.float32, device=x.device) if want_next_scale else None
     need = L.lsq_reduce_workspace_bytes(g.n, g.c * g.h * g.w)
     ws = workspace(x.device, need)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _launch('encode_act', x.numel() * (4.0 + nplanes / 8.0)):
         _C.check(L.lsq_encode_act(x.data_ptr(), C.byref(g), _alpha(alpha), _ptr(tab), len(scales), nplanes,
                                   planes.data_ptr(), _ptr(nxt), ws.data_ptr(), ws.numel(), _stream()), 'lsq_encode_act')
     return planes, nxt
@@ -153,7 +182,7 @@ def pack_weights(w: torch.Tensor) -> torch.Tensor:
     buf = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=w.device)
     off = (-buf.data_ptr()) % 1024
     view = buf[off:off + nbytes]
-    with torch.cuda.device(w.device):
+    with torch.cuda.device(w.device), _launch('pack_weights', 5.0 * w.numel()):
         _C.check(L.lsq_pack_weights(w.data_ptr(), cout, cin, kh, kw, view.data_ptr(), _stream()), 'lsq_pack_weights')
     return view
 
@@ -167,7 +196,10 @@ def bconv2d(planes: torch.Tensor, g: _C.ActGeom, nplanes: int, act_scales: torch
     act_scales = act_scales.contiguous()
     w_scale = w_scale.detach().contiguous()
     b = None if bias is None else bias.detach().contiguous()
-    with torch.cuda.device(planes.device):
+    n_out = g.n * cout * g.ho * g.wo
+    macs = float(n_out) * g.c * g.kh * g.kw * nplanes
+    name = 'bconv_tc' if (impl == 2 or (impl == 0 and tc_supported(g, nplanes, cout))) else 'bconv_simple'
+    with torch.cuda.device(planes.device), _launch(name, 4.0 * n_out + nplanes * g.n * g.c * g.h * g.w / 8.0, 2.0 * macs):
         _C.check(_C.lib().lsq_bconv2d_fwd(planes.data_ptr(), C.byref(g), nplanes, act_scales.data_ptr(),
                                           wpack.data_ptr(), w_scale.data_ptr(), _ptr(b), cout, out.data_ptr(),
                                           int(impl), _stream()), 'lsq_bconv2d_fwd')

@@ -1,0 +1,137 @@
+"""Inference runtime around the hot path: model construction / calibration for benchmarks and tests,
+whole-forward CUDA-graph capture, a double-buffered host->device pipeline (the "public API" call a
+user makes with host batches) and batch sharding over the GPUs of one node (one process per GPU,
+weights replicated, one NCCL all_gather of logits -- SURVEY.md section 8e).
+"""
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import configs
+from .binary.binary_conv import QuantConv2d
+from .nets import QLeNet5, QResNet
+
+
+def build_model(config: str, device: Optional[torch.device] = None, seed: int = 0) -> nn.Module:
+    """Random-init network of the named shipped config (there are no checkpoints offline)."""
+    torch.manual_seed(seed)
+    arch = configs.arch(config)
+    if 'lenet' in config:
+        model: nn.Module = QLeNet5(loss_fn=F.nll_loss, **arch)
+    else:
+        model = QResNet(loss_fn=F.cross_entropy, **arch)
+    return model.to(device) if device is not None else model
+
+
+@torch.no_grad()
+def calibrate(model: nn.Module, input_shape, batches: int = 2, batch: int = 32, seed: int = 100) -> nn.Module:
+    """Populate what a checkpoint would carry: weight scales (w_approximate.v*) and BatchNorm running
+    statistics, by ``batches`` train-mode forwards on seeded N(0,1) inputs.
+    A freshly constructed model in eval() has v1 = 0 and outputs only biases."""
+    dev = next(model.parameters()).device
+    model.train()
+    for i in range(batches):
+        g = torch.Generator(device='cpu').manual_seed(seed + i)
+        model(torch.randn(batch, *input_shape, generator=g).to(dev))
+    return model.eval()
+
+
+class GraphedForward:
+    """model(x) for a fixed input shape as one CUDA graph: no per-layer launch gaps, no host work."""
+
+    def __init__(self, model: nn.Module, example: torch.Tensor, warmup: int = 2):
+        self.model = model
+        self.static_in = example.clone()
+        side = torch.cuda.Stream(device=example.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self.model(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = self.model(self.static_in)
+
+    def __call__(self, x: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x is not None and x.data_ptr() != self.static_in.data_ptr():
+            self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
+class HostPipeline:
+    """Classify host batches: pinned host memory -> GPU (copy stream) -> forward -> logits to host.
+
+    The upload of batch i+1 overlaps the forward of batch i (two device input buffers)."""
+
+    def __init__(self, model: nn.Module, batch_shape, device: torch.device, use_graph: bool = True):
+        self.device = device
+        self.bufs = [torch.empty(batch_shape, device=device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.freed = [torch.cuda.Event() for _ in range(2)]
+        self.model = model
+        self.fwd = [GraphedForward(model, b) if use_graph else None for b in self.bufs]
+        n_out = self._run(0).shape
+        self.host_out = torch.empty(n_out, pin_memory=True)
+        for e in self.freed:
+            e.record()
+
+    def _run(self, i: int) -> torch.Tensor:
+        if self.fwd[i] is not None:
+            return self.fwd[i]()
+        with torch.no_grad():
+            return self.model(self.bufs[i])
+
+    def upload(self, i: int, host_batch: torch.Tensor) -> None:
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.freed[i])
+            self.bufs[i].copy_(host_batch, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+
+    def infer(self, i: int) -> torch.Tensor:
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready[i])
+        out = self._run(i)
+        self.freed[i].record(cur)
+        self.host_out.copy_(out, non_blocking=True)
+        return self.host_out
+
+    def run(self, host_batches) -> torch.Tensor:
+        """host_batches: sequence of pinned tensors; returns the logits of the last one (on host)."""
+        n = len(host_batches)
+        self.upload(0, host_batches[0])
+        for k in range(n):
+            if k + 1 < n:
+                self.upload((k + 1) & 1, host_batches[k + 1])
+            self.infer(k & 1)
+        torch.cuda.current_stream().synchronize()
+        return self.host_out
+
+
+def gather_logits(local: torch.Tensor, world: int) -> torch.Tensor:
+    """The path's only collective: all ranks' logits (one NCCL all_gather over NVLink)."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    local = local.contiguous()
+    if dist.get_backend() == 'nccl':
+        out = torch.empty(world * local.shape[0], *local.shape[1:], dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local)
+        return out
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local)
+    return torch.cat(parts)
+
+
+def shard_bounds(total: int, world: int, rank: int):
+    """Contiguous batch split (samples are independent units: per-sample scales, eval BatchNorm)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def quant_layers(model: nn.Module):
+    return [m for m in model.modules() if isinstance(m, QuantConv2d)]

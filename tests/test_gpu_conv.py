@@ -1,0 +1,221 @@
+"""GPU parity of the binary convolution and of whole networks against golden vectors / the oracle."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import lsq_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _planes_from_gpu(planes, g, npl):
+    """Unpack the GPU plane buffer back to bool [npl, n, c, h, w] for bit-exact comparison."""
+    buf = planes.cpu()[: npl * g.nphase * g.vtot * g.cw].view(npl, g.nphase, g.vtot, g.cw)
+    out = torch.zeros(npl, g.n, g.c, g.h, g.w, dtype=torch.bool)
+    s = g.stride
+    yy, xx = torch.meshgrid(torch.arange(g.h), torch.arange(g.w), indexing='ij')
+    phase = ((yy % s) * 2 + (xx % s)) if s == 2 else torch.zeros_like(yy)
+    for n in range(g.n):
+        v = g.lead + (n * g.rows_per_sample + g.ph + yy // s) * g.pitch + xx // s
+        words = buf[:, phase, v]                       # [npl, h, w, cw]
+        for c in range(g.c):
+            out[:, n, c] = ((words[..., c >> 5] >> (c & 31)) & 1).bool()
+    return out
+
+
+def _run_layer(rec, impl):
+    from quant.binary.binary_conv import QuantConv2d
+    from ml_quant_b200 import ops
+    s, st = rec['spec'], rec['state']
+    clamp = None if s['alpha'] is None else {'kind': 'symmetric', 'alpha': s['alpha']}
+    m = QuantConv2d(s['x_quant'], s['w_quant'], s['cin'], s['cout'], s['k'], clamp, stride=s['stride'],
+                    padding=s['padding'], bias=s['bias'])
+    m.load_state_dict(st, strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize('impl', [1, 2])
+def test_layers_with_injected_scales(golden_layers, impl):
+    """Encode + binary conv with the reference's activation scales: planes bit-exact, y within 1e-5 max|y|."""
+    from ml_quant_b200 import ops
+    ran = 0
+    for rec in golden_layers:
+        s, st = rec['spec'], rec['state']
+        if s['w_quant'] != 'ls-1' or s['x_quant'] == 'fp':
+            continue
+        m = _run_layer(rec, impl)
+        x = rec['x']
+        n, c, h, w = x.shape
+        g = ops.act_geometry(n, c, h, w, s['k'], s['k'], s['stride'], s['padding'])
+        npl = m._num_planes()
+        if impl == 2 and not ops.tc_supported(g, npl, s['cout']):
+            continue
+        sc = rec['x_scales']
+        tern = s['x_quant'] == 'ls-T'
+        known = sc[:1] if tern else sc
+        planes, _ = ops.encode_act(x.to(DEV), g, [v.to(DEV) for v in known[:npl]], npl, s['alpha'], False)
+        xin = x if s['alpha'] is None else x.clamp(-s['alpha'], s['alpha'])
+        ref_planes = torch.stack(O.bit_planes(xin, s['x_quant'], sc))
+        assert torch.equal(_planes_from_gpu(planes, g, npl), ref_planes), s
+        table = torch.stack(sc + sc if tern else sc).to(DEV)
+        y = ops.bconv2d(planes, g, npl, table, m.packed_weights(), m.w_approximate.v1, m.bias, s['cout'], impl)
+        err = float((y.cpu() - rec['y']).abs().max() / rec['y'].abs().max())
+        assert err < 1e-5, (s, err)
+        ran += 1
+    assert ran >= 3
+
+
+def test_tensor_core_and_cuda_core_kernels_agree():
+    """Same integer accumulators -> outputs equal to fp32 rounding of the epilogue (<= 1e-6 max|y|)."""
+    from ml_quant_b200 import ops
+    torch.manual_seed(11)
+    for (n, cin, cout, h, w, st, npl) in [(3, 64, 64, 56, 56, 1, 2), (2, 128, 256, 28, 28, 2, 2), (2, 512, 512, 7, 7, 1, 1),
+                                          (5, 256, 128, 15, 13, 1, 2), (2, 64, 128, 17, 19, 2, 1)]:
+        x = torch.randn(n, cin, h, w, device=DEV)
+        wt = torch.randn(cout, cin, 3, 3, device=DEV)
+        g = ops.act_geometry(n, cin, h, w, 3, 3, st, 1)
+        assert ops.tc_supported(g, npl, cout)
+        v1 = torch.rand(n, device=DEV) + 0.5
+        planes, v2 = ops.encode_act(x, g, [v1] if npl == 2 else [], npl, None, True)
+        table = torch.stack([v1, v2]) if npl == 2 else v2[None]
+        wp = ops.pack_weights(wt)
+        ws, b = torch.rand(cout, device=DEV), torch.randn(cout, device=DEV)
+        y1 = ops.bconv2d(planes, g, npl, table, wp, ws, b, cout, 1)
+        y2 = ops.bconv2d(planes, g, npl, table, wp, ws, b, cout, 2)
+        assert float((y1 - y2).abs().max() / y1.abs().max()) < 1e-6
+
+
+def test_module_end_to_end_layers(golden_layers):
+    """QuantConv2d.forward with its own solve.  Scales that are means agree to 1e-6 and the output to
+    1e-5 max|y|; for ls-2 / ls-T the output is compared after checking the staged solver contract."""
+    torch.backends.cudnn.allow_tf32 = False
+    from ml_quant_b200 import ops
+    for rec in golden_layers:
+        s = rec['spec']
+        m = _run_layer(rec, 0)
+        with torch.no_grad():
+            y = m(rec['x'].to(DEV)).cpu()
+        scale = rec['y'].abs().max()
+        err = float((y - rec['y']).abs().max() / scale)
+        if s['x_quant'] in ('ls-2', 'ls-T'):
+            xin = rec['x'] if s['alpha'] is None else rec['x'].clamp(-s['alpha'], s['alpha'])
+            rows = xin.reshape(xin.shape[0], -1)
+            v1 = ops.solve_v1(rows.to(DEV), s['x_quant'] == 'ls-T', 3).cpu()
+            if torch.equal(v1, rec['x_scales'][0]):
+                assert err < 1e-5, (s, err)
+            else:                                   # a different but equally good candidate
+                c_my = O.exact_cost(rows, v1, s['x_quant'] == 'ls-T', 3)
+                c_or = O.exact_cost(rows, rec['x_scales'][0], s['x_quant'] == 'ls-T', 3)
+                assert bool((c_my <= c_or * (1 + 1e-5)).all()) and err < 5e-2, (s, err)
+        else:
+            assert err < 1e-5, (s, err)
+
+
+def test_packed_and_generic_routes_agree():
+    torch.backends.cudnn.allow_tf32 = False
+    from quant.binary.binary_conv import QuantConv2d
+    torch.manual_seed(2)
+    for xs in ('ls-1', 'ls-2', 'ls-T', 'gf-2', 'gf-3'):
+        m = QuantConv2d(xs, 'ls-1', 64, 64, 3, {'kind': 'symmetric', 'alpha': 2.0}, padding=1).to(DEV)
+        x = torch.randn(3, 64, 20, 20, device=DEV) * 1.5
+        with torch.no_grad():
+            m.train()
+            m(x)
+            m.eval()
+            a = m(x)
+            m.allow_packed = False
+            b = m(x)
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-5, xs
+
+
+def test_fp_and_structured_kats():
+    # reference tests/binary/test_binary_conv.py:18-67
+    from quant.binary.binary_conv import QuantConv2d
+    torch.manual_seed(1234)
+    x = torch.randn(8, 3, 40, 40, device=DEV, requires_grad=True)
+    ref = nn.Conv2d(3, 30, 5).to(DEV)
+    mine = QuantConv2d('fp', 'fp', 3, 30, 5).to(DEV)
+    mine.weight, mine.bias = nn.Parameter(ref.weight), nn.Parameter(ref.bias)
+    assert torch.equal(ref(x), mine(x))
+    x = torch.zeros(1, 3, 8, 8)
+    x[0, :, :4, 4:] = -1
+    x[0, :, 4:, :4] = 2
+    x[0, :, 4:, 4:] = -3
+    conv = QuantConv2d('fp', 'ls-1', 3, 1, (4, 4), stride=4, bias=False).to(DEV)
+    y = conv(x.to(DEV)).squeeze()
+    assert y.shape == (2, 2) and y[0, 0] == 0
+    assert torch.isclose(y[1, 0], -2 * y[0, 1]) and torch.isclose(y[1, 1], 3 * y[0, 1])
+    conv = QuantConv2d('ls-1', 'ls-1', 3, 16, (2, 2)).to(DEV)
+    y = conv(torch.randn(4, 3, 8, 8, device=DEV))
+    assert bool((y.abs().amax(dim=(2, 3)) <= 12 + conv.bias.abs() + 1e-5).all())
+
+
+def test_training_step_runs_and_ste_gradients_flow():
+    from quant.binary.binary_conv import QuantConv2d
+    torch.manual_seed(0)
+    m = QuantConv2d('ls-2', 'ls-1', 8, 8, 3, {'kind': 'symmetric', 'alpha': 2.0}, padding=1).to(DEV).train()
+    x = torch.randn(4, 8, 10, 10, device=DEV, requires_grad=True)
+    m(x).square().mean().backward()
+    assert x.grad is not None and float(x.grad.abs().sum()) > 0 and float(m.weight.grad.abs().sum()) > 0
+    assert float(m.w_approximate.v1.abs().sum()) > 0
+
+
+def test_nets_against_golden(golden_nets):
+    """Whole networks with the reference's state_dict.  MNIST (fp activations, ls-1 weights) and the
+    ls-1 activation ResNet have no ill-posed solve: 1e-4 of max|logit| (sign flips of near-zero BN
+    outputs are the only discrete effect).  ls-2 / ls-T: logits within 5e-2 and same top-1."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from ml_quant_b200.nets import QLeNet5, QResNet
+    for name, rec in golden_nets.items():
+        cls, loss = (QLeNet5, F.nll_loss) if name.startswith('mnist') else (QResNet, F.cross_entropy)
+        m = cls(loss_fn=loss, **rec['arch'])
+        m.load_state_dict(rec['state'])
+        m = m.to(DEV).eval()
+        with torch.no_grad():
+            y = m(rec['x'].to(DEV)).cpu()
+        err = float((y - rec['y']).abs().max() / rec['y'].abs().max())
+        if name in ('mnist_ls1w_fpa',):
+            assert err < 1e-5, (name, err)
+        elif name == 'imagenet_ls1':
+            assert err < 2e-3, (name, err)
+        else:
+            assert err < 5e-2, (name, err)
+            assert torch.equal(y.argmax(1), rec['y'].argmax(1)), name
+
+
+def test_full_size_resnet18_against_live_oracle():
+    """BASELINE network at full width and resolution (batch 4): GPU forward vs the oracle on the CPU."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from ml_quant_b200 import configs, runtime
+    model = runtime.build_model('imagenet_resnet18_ls1w_ls1a', torch.device(DEV))
+    runtime.calibrate(model, (3, 224, 224), batches=1, batch=8)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(4, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        y = model(x.to(DEV)).cpu()
+    y_ref = O.resnet_forward(sd, configs.arch('imagenet_resnet18_ls1w_ls1a'), x)
+    err = float((y - y_ref).abs().max() / y_ref.abs().max())
+    assert err < 5e-3, err
+    # batch sharding is result preserving (per-sample scales, eval BN): bit-identical halves
+    with torch.no_grad():
+        a = model(x[:2].to(DEV)).cpu()
+    assert torch.equal(a, y[:2])
+
+
+def test_cuda_graph_and_host_pipeline_match_eager():
+    from ml_quant_b200 import runtime
+    model = runtime.build_model('cifar100_resnet18_ls1w_ls2a', torch.device(DEV))
+    runtime.calibrate(model, (3, 32, 32), batches=1, batch=16)
+    x = torch.randn(8, 3, 32, 32)
+    with torch.no_grad():
+        eager = model(x.to(DEV)).cpu()
+    fwd = runtime.GraphedForward(model, x.to(DEV))
+    assert torch.equal(fwd().cpu(), eager)
+    pipe = runtime.HostPipeline(model, (8, 3, 32, 32), torch.device(DEV))
+    hx = x.pin_memory()
+    assert torch.equal(pipe.run([hx, hx, hx]).clone(), eager)

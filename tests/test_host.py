@@ -1,0 +1,176 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol of include/lsq_b200.h,
+geometry arithmetic, host logic of the reference-API mirror (construction, validation, state_dict
+layout, moving average), loud failure on CPU tensors, and the multi-process sharding helpers (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    from ml_quant_b200 import _C
+    hdr = open(os.path.join(ROOT, 'include', 'lsq_b200.h')).read()
+    declared = set(re.findall(r'LSQ_API\s+[\w\s\*]+?\b(lsq_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_C.EXPORTS), declared ^ set(_C.EXPORTS)
+    L = _C.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.lsq_abi_version() == 1
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from ml_quant_b200 import _C
+    L = _C.lib()
+    assert L.lsq_row_absmean(None, 1, 1, 0.0, None, 0, None, None, 0, None) == -1
+    assert b'null pointer' in L.lsq_last_error()
+    g = _C.ActGeom()
+    assert L.lsq_act_geometry(1, 64, 8, 8, 3, 3, 3, 1, ctypes.byref(g)) == -4     # stride 3: not packed
+
+
+@pytest.mark.parametrize('shape', [(512, 64, 56, 56, 3, 1, 1), (4, 64, 56, 56, 3, 2, 1), (2, 128, 7, 9, 3, 2, 1),
+                                   (4, 20, 12, 12, 5, 1, 0), (3, 16, 9, 9, 3, 2, 1), (2, 32, 5, 5, 1, 1, 0)])
+def test_geometry_positions_are_unique_and_padding_is_shared(shape):
+    """Every (sample, phase row, phase col) maps to its own position; every tap of every valid output
+    lands either on a valid position of the right phase or on a padding position."""
+    from ml_quant_b200 import ops
+    n, c, h, w, k, s, p = shape
+    n = min(n, 3)
+    g = ops.act_geometry(n, c, h, w, k, k, s, p)
+    assert g.ho == (h + 2 * p - k) // s + 1 and g.wo == (w + 2 * p - k) // s + 1
+
+    def vpos(smp, a, b):
+        return g.lead + (smp * g.rows_per_sample + g.ph + a) * g.pitch + b
+
+    owner = {}
+    for smp in range(n):
+        for yi in range(h):
+            for xi in range(w):
+                ph = ((yi % s) * 2 + (xi % s)) if s == 2 else 0
+                key = (ph, vpos(smp, yi // s, xi // s))
+                assert key not in owner
+                owner[key] = (smp, yi, xi)
+    assert max(v for _, v in owner) < g.vtot
+    for smp in range(n):
+        for yo in range(g.ho):
+            for xo in range(g.wo):
+                q = vpos(smp, yo, xo)
+                for dy in range(k):
+                    for dx in range(k):
+                        ey, ex = dy - p, dx - p
+                        qy, qx = ey // s, ex // s
+                        ph = ((ey - qy * s) * 2 + (ex - qx * s)) if s == 2 else 0
+                        yi, xi = yo * s + ey, xo * s + ex
+                        hit = owner.get((ph, q + qy * g.pitch + qx))
+                        if 0 <= yi < h and 0 <= xi < w:
+                            assert hit == (smp, yi, xi)
+                        else:
+                            assert hit is None
+
+
+def test_quantconv_construction_and_validation():
+    # reference tests/binary/test_binary_conv.py:70-107
+    import itertools
+    from quant.binary.binary_conv import QuantConv2d
+    clamp = {'alpha': 2, 'kind': 'symmetric'}
+    c = QuantConv2d('ls-2', 'ls-1', 3, 1, (4, 4), clamp=clamp, stride=4, bias=False)
+    assert len(c.quantized_parameters['fp']) == 0 and len(c.quantized_parameters['ls-1']) == 1
+    assert set(c.quantized_parameters.keys()) - {'fp', 'ls-1'} == set() and len(list(c.parameters())) == 1
+    c = QuantConv2d('ls-2', 'ls-2', 3, 1, (4, 4), clamp=clamp, stride=4)
+    assert len(c.quantized_parameters['fp']) == 1 and len(c.quantized_parameters['ls-2']) == 1
+    schemes = ['fp', 'ls-1', 'ls-2', 'ls-T', 'gf-2', 'gf-3']
+    for xs, ws in itertools.product(schemes, schemes):
+        QuantConv2d(xs, ws, 3, 1, (4, 4))
+    for bad in [('ls', 'ls-1'), ('l2', 'ls-1'), ('ls-1', 'ls-3'), ('ls-1', 'l2')]:
+        with pytest.raises(ValueError):
+            QuantConv2d(bad[0], bad[1], 3, 1, (4, 4))
+    with pytest.raises(ValueError):
+        QuantConv2d('ls-1', 'ls-2', 3, 1, (4, 4), clamp={'kind': 'sym'})
+
+
+def test_fp_quantconv_equals_conv2d_on_cpu():
+    # reference tests/binary/test_binary_conv.py:18-38 -- the fp/fp route has no quantizer in it
+    from quant.binary.binary_conv import QuantConv2d
+    torch.manual_seed(1234)
+    x = torch.randn(2, 3, 20, 20, requires_grad=True)
+    x2 = x.clone().detach().requires_grad_(True)
+    ref = nn.Conv2d(3, 8, 5)
+    mine = QuantConv2d('fp', 'fp', 3, 8, 5)
+    mine.weight, mine.bias = nn.Parameter(ref.weight), nn.Parameter(ref.bias)
+    a, b = ref(x), mine(x2)
+    a.sum().backward()
+    b.sum().backward()
+    assert torch.equal(a, b) and torch.equal(x.grad, x2.grad)
+
+
+def test_cpu_tensors_fail_loudly():
+    from ml_quant_b200._C import LsqError
+    from quant.binary import quantization
+    from quant.binary.binary_conv import QuantConv2d
+    with pytest.raises(LsqError, match='no CPU fallback'):
+        quantization.quantizer_ls_2(torch.randn(2, 3, 4, 4))
+    with pytest.raises(LsqError):
+        QuantConv2d('ls-1', 'ls-1', 3, 4, 3).eval()(torch.randn(1, 3, 8, 8))
+
+
+def test_state_dict_layout_matches_reference(golden_nets):
+    from ml_quant_b200.nets import QLeNet5, QResNet
+    for name, rec in golden_nets.items():
+        cls, loss = (QLeNet5, F.nll_loss) if name.startswith('mnist') else (QResNet, F.cross_entropy)
+        m = cls(loss_fn=loss, **rec['arch'])
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        ref = {k: tuple(v.shape) for k, v in rec['state'].items()}
+        assert list(mine.items()) == list(ref.items()), name
+        m.load_state_dict(rec['state'], strict=True)
+
+
+def test_moving_average_closed_form():
+    # reference tests/utils/test_moving_average.py, tests/binary/test_activation_quantization.py (2.0 / 4.0 / 2.2)
+    from ml_quant_b200.utils.moving_average import MovingAverage
+    ma = MovingAverage(torch.tensor([0.9]))
+    ma.train()
+    assert ma(torch.tensor([2.0])).item() == 2.0
+    assert ma(torch.tensor([4.0])).item() == pytest.approx(0.9 * 2 + 0.1 * 4)
+    assert ma.num_batches_tracked.item() == 2
+    ma.eval()
+    assert ma(torch.tensor([100.0])).item() == pytest.approx(2.2)
+    assert set(ma.state_dict()) == {'num_batches_tracked', 'momentum', 'moving_average'}
+
+
+def test_shard_bounds_cover_the_batch():
+    from ml_quant_b200.runtime import shard_bounds
+    for total, world in [(4096, 8), (10, 4), (7, 8)]:
+        spans = [shard_bounds(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def test_gather_logits_two_ranks_gloo(tmp_path):
+    """N>1 host logic on CPU: contiguous batch shards, one all_gather restores the full batch order."""
+    code = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from ml_quant_b200.runtime import gather_logits, shard_bounds
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+full = torch.arange(8 * 5, dtype=torch.float32).view(8, 5)
+lo, hi = shard_bounds(8, w, r)
+out = gather_logits(full[lo:hi] * 1.0, w)
+assert torch.equal(out, full), (r, out)
+dist.destroy_process_group()
+print("rank", r, "ok")
+'''
+    f = tmp_path / 'w.py'
+    f.write_text(code)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29577', str(f), ROOT],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count('ok') == 2
