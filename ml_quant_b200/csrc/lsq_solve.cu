@@ -9,13 +9,15 @@
 //      8192 bins (count + fp32 sum) and accumulates S = sum a, Q = sum a^2 in fp64;
 //   2. prefix counts / sums at bin edges bound both threshold functions over each bin, which flags
 //      the few bins that can hold a candidate (a conservative test, 1e-4 margin on the fp32 sums);
-//   3. a second pass collects only the flagged elements (<= 8192) into shared memory together with
-//      the exact fp64 sum of everything below each flagged range; they are sorted (bitonic) and
-//      every element gets the reference's own fp32 candidate test on (float) prefix sums, so the
-//      candidate set is the reference's;
+//   3. a second pass collects only the flagged elements (<= 8192, list A) into shared memory together
+//      with the exact fp64 sum of everything below each flagged range; each range is then refined once
+//      more IN SHARED MEMORY with 8192 finer bins whose sums are exact integers (mantissa sums per
+//      exponent), which leaves a few dozen elements (list B); those are sorted (bitonic) and every one
+//      gets the reference's own fp32 candidate test on (float) prefix sums, so the candidate set is the
+//      reference's;
 //   4. the cost of a candidate is the closed form of optimal.py:31-38 in fp64; the
 //      first minimum in ascending order wins, as torch.argmin does.
-//   Rows with n <= 8192 skip 1-2 (everything is "collected").  Ranges too large to collect are
+//   Rows with n <= 8192 skip 1-2 (the whole row is list A).  Ranges too large to collect are
 //   refined in child windows with a finer bin shift; at shift 0 a bin is a run of equal values and
 //   is evaluated directly.  No host synchronisation (the reference does .tolist(), optimal.py:147).
 #include "lsq_common.cuh"
@@ -25,61 +27,71 @@ namespace lsq {
 constexpr int kSolveThreads = 1024;
 constexpr int kBins = 8192;
 constexpr int kBinsPerThread = kBins / kSolveThreads;
-constexpr int kCap = 8192;
+constexpr int kCap = 8192;      // list A: elements of the flagged ranges of a global window
+constexpr int kFineCap = 2048;  // list B: elements that are sorted and evaluated one by one
 constexpr int kMaxRanges = 4;
 constexpr int kMaxFlag = 64;
-constexpr int kStack = 16;
+constexpr int kStack = 24;
 constexpr int kTopShift = 18;
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 
-struct Range {
-  uint32_t blo, bhi;      // bins (inclusive)
-  uint32_t cnt_below;     // sorted position of the first element of the range
-  uint32_t count;
-  unsigned long long klo, khi;  // key bounds [klo, khi)
-  double sum_below;       // exact fp64 sum of all elements below the range
-  uint32_t next_key;      // smallest key above the range (or the row maximum)
-  uint32_t list_start;    // offset in the collected list
+// A contiguous run of the sorted row: keys in [klo, khi), preceded by cnt_below elements whose
+// exact sum is sum_below, followed by next_key (smallest key >= khi, or the row maximum).
+struct Span {
+  unsigned long long klo, khi;
+  double sum_below;
+  uint32_t cnt_below, next_key;
+};
+struct Window {       // a Span to histogram with bins of 2^shift keys starting at klo
+  Span base;          // elements are taken from base (global row: the whole key space)
+  uint32_t klo;
+  int shift;
+  int from_list;      // 0: elements come from the global row, 1: from list A restricted to base
+};
+struct Range {        // flagged bins [blo, bhi] of the current window
+  uint32_t blo, bhi, cnt_below, count;
+  Span span;
+  uint32_t list_start;
 };
 
 struct SolveSmem {
   uint32_t hist[kBins];
-  float bsum[kBins];
-  uint32_t keys[kCap];
+  union { float f[kBins]; uint32_t lo[kBins]; } bsum;   // global windows: fp32 sums; list windows: sum(m & 0xFFF)
+  uint32_t bhi[kBins];                                   // list windows: sum(m >> 12)
+  uint32_t list_a[kCap];
+  uint32_t list_b[kFineCap];
   double red[32];
   double wsum[32];
   uint32_t wcnt[32];
   uint32_t wfirst[32];
-  // flagged bins of the current window
   int nflag;
   uint32_t fmin, fmax;
   uint16_t fbin[kMaxFlag];
   uint32_t fexcl[kMaxFlag];
   uint32_t fnext[kMaxFlag];
   double fsumb[kMaxFlag];
-  // ranges to collect
-  int ncollect;
+  int ford[kMaxFlag];
+  int nrange;
   Range rng[kMaxRanges];
   double seg_base[kMaxRanges];
-  // window stack
   int nstack;
-  uint32_t st_klo[kStack];
-  int st_shift[kStack];
-  // per-window scalars
-  uint32_t cnt_below;
-  uint32_t min_above;
-  uint32_t kmin, kmax;
-  uint32_t nlist;
-  int direct_eval;  // shift == 0: evaluate flagged bins from the histogram
-  int flags;
-  // best candidate
+  Window stack[kStack];
+  Window cur;
+  uint32_t cnt_below, min_above, kmin, kmax, nlist_a, nlist_b;
+  int direct_eval, flags, action;   // action: 0 none, 1 collect ranges into a list
   double best_cost[32];
-  uint32_t best_pos[32];
-  uint32_t best_key[32];
-  uint32_t ncand;
+  uint32_t best_pos[32], best_key[32], ncand;
 };
 
 __device__ __forceinline__ float key_val(uint32_t k) { return __uint_as_float(k); }
+
+// exact value sum of `cnt` keys sharing one exponent: lo = sum(m & 0xFFF), hi = sum(m >> 12)
+__device__ __forceinline__ double exact_bin_sum(uint32_t any_key, uint32_t cnt, uint32_t lo, uint32_t hi) {
+  const int e = (int)(any_key >> 23);
+  const double msum = (double)hi * 4096.0 + (double)lo;
+  if (e == 0) return ldexp(msum, -149);
+  return ldexp((double)cnt * 8388608.0 + msum, e - 150);
+}
 
 struct Best {
   double cost;
@@ -139,15 +151,14 @@ __device__ __forceinline__ void bitonic_sort(uint32_t* keys, uint32_t lp) {
   }
 }
 
-// Evaluate the sorted list keys[0..L) made of `nseg` segments (ranges in ascending key order).
+// Evaluate the sorted list keys[0..L) made of the `nseg` ranges sm.rng[] (ascending key order).
 template <bool TERN>
-__device__ void evaluate_list(SolveSmem& sm, uint32_t L, int nseg, uint32_t n, double s_tot, double q_tot,
-                              Best& best, uint32_t& ncand) {
+__device__ void evaluate_list(SolveSmem& sm, const uint32_t* keys, uint32_t L, int nseg, uint32_t n, double s_tot,
+                              double q_tot, Best& best, uint32_t& ncand) {
   const uint32_t per = (L + blockDim.x - 1) / blockDim.x;
   const uint32_t j0 = min(threadIdx.x * per, L), j1 = min(j0 + per, L);
   double loc = 0.0;
-  for (uint32_t j = j0; j < j1; ++j) loc += (double)key_val(sm.keys[j]);
-  // exclusive block scan of loc (fixed order)
+  for (uint32_t j = j0; j < j1; ++j) loc += (double)key_val(keys[j]);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double inc = loc;
 #pragma unroll
@@ -161,26 +172,25 @@ __device__ void evaluate_list(SolveSmem& sm, uint32_t L, int nseg, uint32_t n, d
   double off = 0.0;
   for (int w = 0; w < wid; ++w) off += sm.wsum[w];
   double run = off + inc - loc;  // exclusive prefix at j0
-  // publish the exclusive prefix at each segment start
   for (int g = 0; g < nseg; ++g) {
     const uint32_t st = sm.rng[g].list_start;
     if (st >= j0 && st < j1) {
       double r = run;
-      for (uint32_t j = j0; j < st; ++j) r += (double)key_val(sm.keys[j]);
+      for (uint32_t j = j0; j < st; ++j) r += (double)key_val(keys[j]);
       sm.seg_base[g] = r;
     }
   }
   __syncthreads();
   for (uint32_t j = j0; j < j1; ++j) {
-    const uint32_t kj = sm.keys[j];
+    const uint32_t kj = keys[j];
     run += (double)key_val(kj);
     int g = 0;
     while (g + 1 < nseg && j >= sm.rng[g + 1].list_start) ++g;
     const Range& R = sm.rng[g];
     const uint32_t seg_end = R.list_start + R.count;
-    const uint32_t i = R.cnt_below + (j - R.list_start);
-    const double s_i = R.sum_below + (run - sm.seg_base[g]);
-    const uint32_t knext = (j + 1 < seg_end) ? sm.keys[j + 1] : R.next_key;
+    const uint32_t i = R.span.cnt_below + (j - R.list_start);
+    const double s_i = R.span.sum_below + (run - sm.seg_base[g]);
+    const uint32_t knext = (j + 1 < seg_end) ? keys[j + 1] : R.span.next_key;
     try_position<TERN>(best, ncand, kj, knext, i, s_i, n, s_tot, q_tot);
   }
   __syncthreads();
@@ -202,7 +212,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
   uint32_t collected = 0;
 
   if (tid == 0) {
-    sm.kmin = kNoKey; sm.kmax = 0u; sm.nstack = 0; sm.flags = 0; sm.ncand = 0u; sm.nlist = 0u;
+    sm.kmin = kNoKey; sm.kmax = 0u; sm.nstack = 0; sm.flags = 0; sm.ncand = 0u; sm.nlist_a = 0u; sm.nlist_b = 0u;
   }
   __syncthreads();
   if (n < 3) {
@@ -214,21 +224,17 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
   }
 
   double s_tot = 0.0, q_tot = 0.0;
+  bool first = true;          // row totals not yet known
   if (n <= (uint32_t)kCap) {
-    // ---- small row: everything is the collected list -------------------------------------
-    uint32_t lp = 2;
-    while (lp < n) lp <<= 1;
+    // ---- small row: list A is the whole row --------------------------------------------------
     double ls = 0.0, lq = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u;
-    for (uint32_t e = tid; e < lp; e += blockDim.x) {
-      uint32_t k = kNoKey;
-      if (e < n) {
-        const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
-        k = __float_as_uint(a);
-        ls += (double)a; lq += (double)a * (double)a;
-        kmn = min(kmn, k); kmx = max(kmx, k);
-      }
-      sm.keys[e] = k;
+    for (uint32_t e = tid; e < n; e += blockDim.x) {
+      const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
+      const uint32_t k = __float_as_uint(a);
+      ls += (double)a; lq += (double)a * (double)a;
+      kmn = min(kmn, k); kmx = max(kmx, k);
+      sm.list_a[e] = k;
     }
     s_tot = block_sum(ls, sm.red);
     q_tot = block_sum(lq, sm.red);
@@ -236,314 +242,385 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     if (lane == 0) { atomicMin(&sm.kmin, kmn); atomicMax(&sm.kmax, kmx); }
     __syncthreads();
     passes = 1;
-    bitonic_sort(sm.keys, lp);
+    first = false;
     if (tid == 0) {
-      sm.rng[0].cnt_below = 0; sm.rng[0].count = n; sm.rng[0].sum_below = 0.0;
-      sm.rng[0].next_key = sm.kmax; sm.rng[0].list_start = 0;
+      sm.nlist_a = n;
+      Window w;
+      w.base.klo = 0ull; w.base.khi = 1ull << 32; w.base.sum_below = 0.0; w.base.cnt_below = 0u; w.base.next_key = sm.kmax;
+      w.klo = 0u; w.shift = kTopShift; w.from_list = 1;
+      sm.stack[0] = w; sm.nstack = 1;
+    }
+  } else if (tid == 0) {
+    Window w;
+    w.base.klo = 0ull; w.base.khi = 1ull << 32; w.base.sum_below = 0.0; w.base.cnt_below = 0u; w.base.next_key = 0u;
+    w.klo = 0u; w.shift = kTopShift; w.from_list = 0;
+    sm.stack[0] = w; sm.nstack = 1;
+  }
+  __syncthreads();
+
+  while (true) {
+    __syncthreads();
+    if (sm.nstack == 0) break;
+    if (tid == 0) {
+      sm.cur = sm.stack[--sm.nstack];
+      sm.cnt_below = 0u; sm.min_above = kNoKey; sm.nflag = 0; sm.fmin = kNoKey; sm.fmax = 0u;
+      sm.nrange = 0; sm.direct_eval = 0; sm.action = 0;
+    }
+    for (int b = tid; b < kBins; b += blockDim.x) { sm.hist[b] = 0u; sm.bsum.lo[b] = 0u; sm.bhi[b] = 0u; }
+    __syncthreads();
+    const Window W = sm.cur;
+    const uint32_t klo = W.klo;
+    const int shift = W.shift;
+    const bool from_list = W.from_list != 0;
+    const unsigned long long khi = min((unsigned long long)klo + ((unsigned long long)kBins << shift), W.base.khi);
+
+    // ---- histogram pass over the window's source ---------------------------------------------
+    double ls = 0.0, lq = 0.0, lb = 0.0;
+    uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey;
+    if (!from_list) {
+      for (uint32_t e = tid; e < n; e += blockDim.x) {
+        const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
+        const uint32_t k = __float_as_uint(a);
+        if (first) { ls += (double)a; lq += (double)a * (double)a; kmn = min(kmn, k); kmx = max(kmx, k); }
+        if (k < klo) { ++cb; lb += (double)a; }
+        else if ((unsigned long long)k >= khi) { mab = min(mab, k); }
+        else {
+          const uint32_t b = (k - klo) >> shift;
+          atomicAdd(&sm.hist[b], 1u);
+          atomicAdd(&sm.bsum.f[b], a);
+        }
+      }
+      ++passes;
+    } else {
+      const uint32_t la = sm.nlist_a;
+      for (uint32_t e = tid; e < la; e += blockDim.x) {
+        const uint32_t k = sm.list_a[e];
+        if ((unsigned long long)k < W.base.klo || (unsigned long long)k >= W.base.khi) continue;
+        if (k < klo) { ++cb; lb += (double)key_val(k); }
+        else if ((unsigned long long)k >= khi) { mab = min(mab, k); }
+        else {
+          const uint32_t b = (k - klo) >> shift;
+          const uint32_t m = k & 0x7FFFFFu;
+          atomicAdd(&sm.hist[b], 1u);
+          atomicAdd(&sm.bsum.lo[b], m & 0xFFFu);
+          atomicAdd(&sm.bhi[b], m >> 12);
+        }
+      }
+    }
+    if (first) {
+      s_tot = block_sum(ls, sm.red);
+      q_tot = block_sum(lq, sm.red);
+      kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
+      if (lane == 0) { atomicMin(&sm.kmin, kmn); atomicMax(&sm.kmax, kmx); }
+      first = false;
+    }
+    // sum of everything below the window.  Global rows: per-thread order is fixed -> deterministic.
+    // List windows normally start at their base span (nothing below, lb = 0); only the rare child of a
+    // list window sums list elements here, in list order.
+    const double sum_below_w = W.base.sum_below + block_sum(lb, sm.red);
+    cb = (uint32_t)__reduce_add_sync(0xffffffffu, cb);
+    mab = warp_min_u32(mab);
+    if (lane == 0) { atomicAdd(&sm.cnt_below, cb); atomicMin(&sm.min_above, mab); }
+    __syncthreads();
+    const uint32_t kmax = sm.kmax;
+    const uint32_t base_next = (W.base.next_key != 0u) ? W.base.next_key : kmax;   // top window: maximum not known at push time
+    const uint32_t min_above = (sm.min_above != kNoKey) ? sm.min_above : base_next;
+    const uint32_t cnt_below_w = W.base.cnt_below + sm.cnt_below;
+
+    // ---- scan bins: thread owns bins [8*tid, 8*tid+8) ---------------------------------------------
+    uint32_t c[kBinsPerThread];
+    double s[kBinsPerThread];
+    uint32_t ct = 0; double stt = 0.0; uint32_t fn = kNoKey;
+#pragma unroll
+    for (int j = 0; j < kBinsPerThread; ++j) {
+      const uint32_t b = tid * kBinsPerThread + j;
+      c[j] = sm.hist[b];
+      if (c[j] == 0u) s[j] = 0.0;
+      else if (shift == 0) s[j] = (double)c[j] * (double)key_val(klo + b);
+      else if (from_list) s[j] = exact_bin_sum(klo + (b << shift), c[j], sm.bsum.lo[b], sm.bhi[b]);
+      else s[j] = (double)sm.bsum.f[b];
+      ct += c[j]; stt += s[j];
+      if (c[j] != 0u && fn == kNoKey) fn = b;
+    }
+    uint32_t ci = ct; double si = stt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t tc = __shfl_up_sync(0xffffffffu, ci, o);
+      double ts = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) { ci += tc; si += ts; }
+    }
+    uint32_t sfx = fn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_down_sync(0xffffffffu, sfx, o);
+      if (lane + o < 32) sfx = min(sfx, t);
+    }
+    uint32_t nxt_in_warp = __shfl_down_sync(0xffffffffu, sfx, 1);
+    if (lane == 31) nxt_in_warp = kNoKey;
+    __syncthreads();
+    if (lane == 31) { sm.wcnt[wid] = ci; sm.wsum[wid] = si; }
+    if (lane == 0) sm.wfirst[wid] = sfx;
+    __syncthreads();
+    uint32_t coff = 0; double soff = 0.0;
+    for (int w = 0; w < wid; ++w) { coff += sm.wcnt[w]; soff += sm.wsum[w]; }
+    uint32_t nxt_after = nxt_in_warp;
+    for (int w = wid + 1; w < 32 && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
+    uint32_t excl = cnt_below_w + coff + ci - ct;
+    double pref = sum_below_w + soff + si - stt;
+
+    // ---- flag bins that can hold a candidate ------------------------------------------------------
+    const double marg = (shift == 0) ? 0.0 : (from_list ? 1e-12 : 1e-4);
+    const double eps = 1e-6;
+    const double dn = (double)n;
+    const double vmax = (double)key_val(kmax);
+#pragma unroll
+    for (int j = 0; j < kBinsPerThread; ++j) {
+      if (c[j] == 0u) continue;
+      const uint32_t b = tid * kBinsPerThread + j;
+      uint32_t nb = kNoKey;
+#pragma unroll
+      for (int j2 = kBinsPerThread - 1; j2 > j; --j2)
+        if (c[j2] != 0u) nb = tid * kBinsPerThread + j2;
+      if (nb == kNoKey) nb = nxt_after;
+      const uint32_t k0 = max(excl, 1u), k1 = min(excl + c[j], n - 1);
+      if (k0 <= k1) {
+        const unsigned long long elo_k = min((unsigned long long)klo + ((unsigned long long)b << shift), 0x7F800000ull);
+        const unsigned long long ehi_k = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, (unsigned long long)kmax);
+        const double edge_lo = (double)key_val((uint32_t)elo_k);
+        const double edge_hi = fmax((double)key_val((uint32_t)ehi_k), edge_lo);
+        double lo0, hi0, lo1, hi1;
+        if (excl >= 1u) { lo0 = pref * (1.0 - marg); hi0 = pref * (1.0 + marg); }
+        else { lo0 = pref * (1.0 - marg) + edge_lo; hi0 = pref * (1.0 + marg) + edge_hi; }
+        if (excl + c[j] <= n - 1) { lo1 = (pref + s[j]) * (1.0 - marg); hi1 = (pref + s[j]) * (1.0 + marg); }
+        else { lo1 = hi1 = s_tot - vmax; }
+        double nxt_hi;
+        if (nb != kNoKey) {
+          const unsigned long long nh = min((unsigned long long)klo + ((unsigned long long)(nb + 1) << shift) - 1ull, (unsigned long long)kmax);
+          const unsigned long long nl = min((unsigned long long)klo + ((unsigned long long)nb << shift), 0x7F800000ull);
+          nxt_hi = fmax((double)key_val((uint32_t)nh), (double)key_val((uint32_t)nl));
+        } else {
+          nxt_hi = (double)key_val(min_above);
+        }
+        const double h0a = 0.5 * (s_tot - lo0) / (dn - k0), h0b = 0.5 * (s_tot - hi0) / (dn - k0);
+        const double h1a = 0.5 * (s_tot - lo1) / (dn - k1), h1b = 0.5 * (s_tot - hi1) / (dn - k1);
+        const double half_min = fmin(h0a, h0b), half_max = fmax(h1a, h1b);
+        bool hit = (half_max * (1.0 + eps) >= edge_lo) &&
+                   (half_min * (1.0 - eps) <= edge_hi || half_max * (1.0 - eps) <= nxt_hi);
+        if (!TERN) {
+          const double m0a = h0a + 0.5 * lo0 / k0, m0b = h0b + 0.5 * hi0 / k0;
+          const double m1a = h1a + 0.5 * lo1 / k1, m1b = h1b + 0.5 * hi1 / k1;
+          const double mid_min = fmin(m0a, m0b), mid_max = fmax(m1a, m1b);
+          hit = hit || ((mid_max * (1.0 + eps) >= edge_lo) &&
+                        (mid_min * (1.0 - eps) <= edge_hi || mid_max * (1.0 - eps) <= nxt_hi));
+        }
+        if (hit) {
+          const int slot = atomicAdd(&sm.nflag, 1);
+          atomicMin(&sm.fmin, b); atomicMax(&sm.fmax, b);
+          if (slot < kMaxFlag) {
+            sm.fbin[slot] = (uint16_t)b; sm.fexcl[slot] = excl; sm.fsumb[slot] = pref;
+            sm.fnext[slot] = (nb != kNoKey) ? (uint32_t)min((unsigned long long)klo + ((unsigned long long)nb << shift), 0xFFFFFFFEull) : min_above;
+          } else if (shift == 0) {
+            const uint32_t kv = klo + b;
+            const uint32_t knx = (nb != kNoKey) ? klo + nb : min_above;
+            for (uint32_t jj = 0; jj < c[j]; ++jj)
+              try_position<TERN>(best, ncand, kv, (jj + 1 < c[j]) ? kv : knx, excl + jj,
+                                 pref + (double)(jj + 1) * (double)key_val(kv), n, s_tot, q_tot);
+          }
+        }
+      }
+      excl += c[j]; pref += s[j];
     }
     __syncthreads();
-    collected = n;
-    evaluate_list<TERN>(sm, n, 1, n, s_tot, q_tot, best, ncand);
-  } else {
-    // ---- large row: histogram windows -------------------------------------------------------
-    if (tid == 0) { sm.st_klo[0] = 0u; sm.st_shift[0] = kTopShift; sm.nstack = 1; }
-    __syncthreads();
-    bool first = true;
-    while (true) {
-      __syncthreads();
-      if (sm.nstack == 0) break;
-      const uint32_t klo = sm.st_klo[sm.nstack - 1];
-      const int shift = sm.st_shift[sm.nstack - 1];
-      const unsigned long long khi = (unsigned long long)klo + ((unsigned long long)kBins << shift);
-      __syncthreads();
-      if (tid == 0) {
-        --sm.nstack;
-        sm.cnt_below = 0u; sm.min_above = kNoKey; sm.nflag = 0; sm.fmin = kNoKey; sm.fmax = 0u;
-        sm.ncollect = 0; sm.nlist = 0u; sm.direct_eval = 0;
+
+    // ---- thread 0: flagged bins -> ranges -> collect / refine ---------------------------------------
+    if (tid == 0 && sm.nflag > 0) {
+      const int nf = min(sm.nflag, kMaxFlag);
+      if (shift == 0) {
+        sm.direct_eval = nf;
+      } else {
+        int nr = 0;
+        Range* R = sm.rng;
+        if (sm.nflag > kMaxFlag) {
+          uint32_t cbw = cnt_below_w, cnt = 0;
+          for (uint32_t b = 0; b < sm.fmin; ++b) cbw += sm.hist[b];
+          for (uint32_t b = sm.fmin; b <= sm.fmax; ++b) cnt += sm.hist[b];
+          R[0].blo = sm.fmin; R[0].bhi = sm.fmax; R[0].cnt_below = cbw; R[0].count = cnt;
+          nr = 1;
+        } else {
+          int* ord = sm.ford;
+          for (int i = 0; i < nf; ++i) {
+            int j = i;
+            while (j > 0 && sm.fbin[ord[j - 1]] > sm.fbin[i]) { ord[j] = ord[j - 1]; --j; }
+            ord[j] = i;
+          }
+          // consecutive non-empty flagged bins form one range (kept in place in fexcl/fnext as scratch)
+          uint32_t r_end = 0;
+          for (int i = 0; i < nf; ++i) {
+            const int sl = ord[i];
+            const uint32_t b = sm.fbin[sl], ex = sm.fexcl[sl], en = ex + sm.hist[b];
+            if (nr > 0 && r_end == ex && nr <= kMaxRanges) { R[nr - 1].bhi = b; R[nr - 1].count = en - R[nr - 1].cnt_below; }
+            else if (nr < kMaxRanges) { R[nr].blo = b; R[nr].bhi = b; R[nr].cnt_below = ex; R[nr].count = en - ex; ++nr; }
+            else {
+              // more than kMaxRanges runs: extend the last range over the gap (it then also holds unflagged bins)
+              R[nr - 1].bhi = b; R[nr - 1].count = en - R[nr - 1].cnt_below;
+            }
+            r_end = en;
+          }
+        }
+        // collect what fits into the destination list, refine the rest in child windows
+        const uint32_t cap = from_list ? (uint32_t)kFineCap : (uint32_t)kCap;
+        uint32_t budget = cap, lstart = 0;
+        int nc = 0;
+        for (int g = 0; g < nr; ++g) {
+          Range r = R[g];
+          r.span.klo = (unsigned long long)klo + ((unsigned long long)r.blo << shift);
+          r.span.khi = min((unsigned long long)klo + ((unsigned long long)(r.bhi + 1) << shift), W.base.khi);
+          r.span.cnt_below = r.cnt_below; r.span.sum_below = 0.0; r.span.next_key = kNoKey;
+          if (r.count <= budget) {
+            budget -= r.count;
+            r.list_start = lstart; lstart += r.count;
+            R[nc++] = r;
+          } else {
+            const unsigned long long span = r.span.khi - r.span.klo;
+            int lg = 0;
+            while ((1ull << lg) < span) ++lg;
+            int nshift = lg - 13;
+            if (nshift < 0) nshift = 0;
+            if (nshift >= shift) nshift = shift - 1;
+            const unsigned long long wspan = (unsigned long long)kBins << nshift;
+            for (unsigned long long o = 0; o < span; o += wspan) {
+              if (sm.nstack < kStack) {
+                Window ch;
+                ch.base = W.base; ch.klo = (uint32_t)(r.span.klo + o); ch.shift = nshift; ch.from_list = W.from_list;
+                sm.stack[sm.nstack++] = ch;
+              } else {
+                sm.flags |= 1;
+              }
+            }
+          }
+        }
+        sm.nrange = nc;
+        sm.action = nc > 0 ? 1 : 0;
       }
-      for (int b = tid; b < kBins; b += blockDim.x) { sm.hist[b] = 0u; sm.bsum[b] = 0.0f; }
+    }
+    __syncthreads();
+
+    // ---- shift 0: runs of equal values straight from the histogram --------------------------------
+    if (sm.direct_eval > 0) {
+      const int nf = sm.direct_eval;
+      for (int sl = 0; sl < nf; ++sl) {
+        const uint32_t b = sm.fbin[sl], cnt = sm.hist[b], kv = klo + b;
+        const double base = sm.fsumb[sl], v = (double)key_val(kv);
+        for (uint32_t jj = tid; jj < cnt; jj += blockDim.x)
+          try_position<TERN>(best, ncand, kv, (jj + 1 < cnt) ? kv : sm.fnext[sl], sm.fexcl[sl] + jj,
+                             base + (double)(jj + 1) * v, n, s_tot, q_tot);
+      }
+    }
+
+    // ---- collection ----------------------------------------------------------------------------------
+    if (sm.action == 1) {
+      const int nc = sm.nrange;
+      double sb[kMaxRanges];
+      uint32_t ma[kMaxRanges];
+#pragma unroll
+      for (int g = 0; g < kMaxRanges; ++g) { sb[g] = 0.0; ma[g] = kNoKey; }
+      if (tid == 0) { if (from_list) sm.nlist_b = 0u; else sm.nlist_a = 0u; }
       __syncthreads();
-      // -- histogram pass
-      {
-        double ls = 0.0, lq = 0.0, lb = 0.0;
-        uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey;
+      if (!from_list) {
         for (uint32_t e = tid; e < n; e += blockDim.x) {
           const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
           const uint32_t k = __float_as_uint(a);
-          if (first) { ls += (double)a; lq += (double)a * (double)a; kmn = min(kmn, k); kmx = max(kmx, k); }
-          if (k < klo) { ++cb; lb += (double)a; }
-          else if ((unsigned long long)k >= khi) { mab = min(mab, k); }
-          else {
-            const uint32_t b = (k - klo) >> shift;
-            atomicAdd(&sm.hist[b], 1u);
-            atomicAdd(&sm.bsum[b], a);
-          }
-        }
-        ++passes;
-        if (first) {
-          s_tot = block_sum(ls, sm.red);
-          q_tot = block_sum(lq, sm.red);
-          kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
-          if (lane == 0) { atomicMin(&sm.kmin, kmn); atomicMax(&sm.kmax, kmx); }
-        }
-        const double sum_below_w = block_sum(lb, sm.red);
-        cb = (uint32_t)__reduce_add_sync(0xffffffffu, cb);
-        mab = warp_min_u32(mab);
-        if (lane == 0) { atomicAdd(&sm.cnt_below, cb); atomicMin(&sm.min_above, mab); }
-        __syncthreads();
-        const uint32_t kmax = sm.kmax;
-        const uint32_t min_above = (sm.min_above == kNoKey) ? kmax : sm.min_above;
-        const uint32_t cnt_below_w = sm.cnt_below;
-
-        // -- scan bins: thread owns bins [8*tid, 8*tid+8)
-        uint32_t c[kBinsPerThread];
-        double s[kBinsPerThread];
-        uint32_t ct = 0; double stt = 0.0; uint32_t fn = kNoKey;
-#pragma unroll
-        for (int j = 0; j < kBinsPerThread; ++j) {
-          const uint32_t b = tid * kBinsPerThread + j;
-          c[j] = sm.hist[b];
-          s[j] = (shift == 0) ? (double)c[j] * (double)key_val(klo + b) : (double)sm.bsum[b];
-          if (c[j] == 0u) s[j] = 0.0;
-          ct += c[j]; stt += s[j];
-          if (c[j] != 0u && fn == kNoKey) fn = b;
-        }
-        uint32_t ci = ct; double si = stt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          uint32_t tc = __shfl_up_sync(0xffffffffu, ci, o);
-          double ts = __shfl_up_sync(0xffffffffu, si, o);
-          if (lane >= o) { ci += tc; si += ts; }
-        }
-        // suffix-min of the first non-empty bin over lanes > lane
-        uint32_t sfx = fn;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          uint32_t t = __shfl_down_sync(0xffffffffu, sfx, o);
-          if (lane + o < 32) sfx = min(sfx, t);
-        }
-        uint32_t nxt_in_warp = __shfl_down_sync(0xffffffffu, sfx, 1);
-        if (lane == 31) nxt_in_warp = kNoKey;
-        __syncthreads();
-        if (lane == 31) { sm.wcnt[wid] = ci; sm.wsum[wid] = si; }
-        if (lane == 0) sm.wfirst[wid] = sfx;
-        __syncthreads();
-        uint32_t coff = 0; double soff = 0.0;
-        for (int w = 0; w < wid; ++w) { coff += sm.wcnt[w]; soff += sm.wsum[w]; }
-        uint32_t nxt_after = nxt_in_warp;
-        for (int w = wid + 1; w < 32 && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
-        uint32_t excl = cnt_below_w + coff + ci - ct;
-        double pref = sum_below_w + soff + si - stt;
-
-        // -- flag bins that can hold a candidate
-        const double marg = (shift == 0) ? 0.0 : 1e-4;
-        const double eps = 1e-6;
-        const double dn = (double)n;
-        const double vmax = (double)key_val(kmax);
-#pragma unroll
-        for (int j = 0; j < kBinsPerThread; ++j) {
-          if (c[j] == 0u) continue;
-          const uint32_t b = tid * kBinsPerThread + j;
-          uint32_t nb = kNoKey;
-#pragma unroll
-          for (int j2 = kBinsPerThread - 1; j2 > j; --j2)
-            if (c[j2] != 0u) nb = tid * kBinsPerThread + j2;
-          if (nb == kNoKey) nb = nxt_after;
-          const uint32_t k0 = max(excl, 1u), k1 = min(excl + c[j], n - 1);
-          if (k0 <= k1) {
-            const unsigned long long elo_k = min((unsigned long long)klo + ((unsigned long long)b << shift), 0x7F800000ull);
-            const unsigned long long ehi_k = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, (unsigned long long)kmax);
-            const double edge_lo = (double)key_val((uint32_t)elo_k);
-            const double edge_hi = fmax((double)key_val((uint32_t)ehi_k), edge_lo);
-            double lo0, hi0, lo1, hi1;
-            if (excl >= 1u) { lo0 = pref * (1.0 - marg); hi0 = pref * (1.0 + marg); }
-            else { lo0 = pref * (1.0 - marg) + edge_lo; hi0 = pref * (1.0 + marg) + edge_hi; }
-            if (excl + c[j] <= n - 1) { lo1 = (pref + s[j]) * (1.0 - marg); hi1 = (pref + s[j]) * (1.0 + marg); }
-            else { lo1 = hi1 = s_tot - vmax; }
-            double nxt_hi;
-            if (nb != kNoKey) {
-              const unsigned long long nh = min((unsigned long long)klo + ((unsigned long long)(nb + 1) << shift) - 1ull, (unsigned long long)kmax);
-              const unsigned long long nl = min((unsigned long long)klo + ((unsigned long long)nb << shift), 0x7F800000ull);
-              nxt_hi = fmax((double)key_val((uint32_t)nh), (double)key_val((uint32_t)nl));
-            } else {
-              nxt_hi = (double)key_val(min_above);
-            }
-            // thresholds at the first (k0) and last (k1) split of the bin, over the admissible sums
-            const double h0a = 0.5 * (s_tot - lo0) / (dn - k0), h0b = 0.5 * (s_tot - hi0) / (dn - k0);
-            const double h1a = 0.5 * (s_tot - lo1) / (dn - k1), h1b = 0.5 * (s_tot - hi1) / (dn - k1);
-            const double half_min = fmin(h0a, h0b), half_max = fmax(h1a, h1b);
-            bool hit = (half_max * (1.0 + eps) >= edge_lo) &&
-                       (half_min * (1.0 - eps) <= edge_hi || half_max * (1.0 - eps) <= nxt_hi);
-            if (!TERN) {
-              const double m0a = h0a + 0.5 * lo0 / k0, m0b = h0b + 0.5 * hi0 / k0;
-              const double m1a = h1a + 0.5 * lo1 / k1, m1b = h1b + 0.5 * hi1 / k1;
-              const double mid_min = fmin(m0a, m0b), mid_max = fmax(m1a, m1b);
-              hit = hit || ((mid_max * (1.0 + eps) >= edge_lo) &&
-                            (mid_min * (1.0 - eps) <= edge_hi || mid_max * (1.0 - eps) <= nxt_hi));
-            }
-            if (hit) {
-              const int slot = atomicAdd(&sm.nflag, 1);
-              atomicMin(&sm.fmin, b); atomicMax(&sm.fmax, b);
-              if (slot < kMaxFlag) {
-                sm.fbin[slot] = (uint16_t)b; sm.fexcl[slot] = excl; sm.fsumb[slot] = pref;
-                sm.fnext[slot] = (nb != kNoKey) ? (uint32_t)min((unsigned long long)klo + ((unsigned long long)nb << shift), 0xFFFFFFFEull) : min_above;
-              } else if (shift == 0) {
-                // flag list overflow at the finest level: evaluate this run of equal values here
-                const uint32_t kv = klo + b;
-                const uint32_t knx = (nb != kNoKey) ? klo + nb : min_above;
-                for (uint32_t jj = 0; jj < c[j]; ++jj)
-                  try_position<TERN>(best, ncand, kv, (jj + 1 < c[j]) ? kv : knx, excl + jj,
-                                     pref + (double)(jj + 1) * (double)key_val(kv), n, s_tot, q_tot);
-              }
-            }
-          }
-          excl += c[j]; pref += s[j];
-        }
-        __syncthreads();
-
-        // -- thread 0: turn flagged bins into ranges, decide collect / refine
-        if (tid == 0 && sm.nflag > 0) {
-          const int nf = min(sm.nflag, kMaxFlag);
-          if (shift == 0) {
-            sm.direct_eval = nf;
-          } else {
-            int nr = 0;
-            Range* R = sm.rng;
-            if (sm.nflag > kMaxFlag) {
-              uint32_t cbw = cnt_below_w, cnt = 0;
-              for (uint32_t b = 0; b < sm.fmin; ++b) cbw += sm.hist[b];
-              for (uint32_t b = sm.fmin; b <= sm.fmax; ++b) cnt += sm.hist[b];
-              R[0].blo = sm.fmin; R[0].bhi = sm.fmax; R[0].cnt_below = cbw; R[0].count = cnt;
-              nr = 1;
-            } else {
-              // insertion sort of slots by bin
-              int ord[kMaxFlag];
-              for (int i = 0; i < nf; ++i) {
-                int j = i;
-                while (j > 0 && sm.fbin[ord[j - 1]] > sm.fbin[i]) { ord[j] = ord[j - 1]; --j; }
-                ord[j] = i;
-              }
-              // consecutive non-empty flagged bins form one range; keep at most kMaxRanges by merging
-              uint32_t r_blo[kMaxFlag], r_bhi[kMaxFlag], r_cb[kMaxFlag], r_end[kMaxFlag];
-              for (int i = 0; i < nf; ++i) {
-                const int sl = ord[i];
-                const uint32_t b = sm.fbin[sl], ex = sm.fexcl[sl], en = ex + sm.hist[b];
-                if (nr > 0 && r_end[nr - 1] == ex) { r_bhi[nr - 1] = b; r_end[nr - 1] = en; }
-                else { r_blo[nr] = b; r_bhi[nr] = b; r_cb[nr] = ex; r_end[nr] = en; ++nr; }
-              }
-              while (nr > kMaxRanges) {
-                int gbest = 0; uint32_t gap = kNoKey;
-                for (int g = 0; g + 1 < nr; ++g) {
-                  const uint32_t d = r_blo[g + 1] - r_bhi[g];
-                  if (d < gap) { gap = d; gbest = g; }
-                }
-                r_bhi[gbest] = r_bhi[gbest + 1]; r_end[gbest] = r_end[gbest + 1];
-                for (int g = gbest + 1; g + 1 < nr; ++g) {
-                  r_blo[g] = r_blo[g + 1]; r_bhi[g] = r_bhi[g + 1]; r_cb[g] = r_cb[g + 1]; r_end[g] = r_end[g + 1];
-                }
-                --nr;
-              }
-              for (int g = 0; g < nr; ++g) {
-                R[g].blo = r_blo[g]; R[g].bhi = r_bhi[g]; R[g].cnt_below = r_cb[g]; R[g].count = r_end[g] - r_cb[g];
-              }
-            }
-            // collect what fits, refine the rest
-            uint32_t budget = kCap, lstart = 0;
-            int nc = 0;
-            for (int g = 0; g < nr; ++g) {
-              Range r = R[g];
-              if (r.count <= budget) {
-                budget -= r.count;
-                r.klo = (unsigned long long)klo + ((unsigned long long)r.blo << shift);
-                r.khi = (unsigned long long)klo + ((unsigned long long)(r.bhi + 1) << shift);
-                r.list_start = lstart; lstart += r.count;
-                R[nc++] = r;
-              } else {
-                const unsigned long long span = (unsigned long long)(r.bhi - r.blo + 1) << shift;
-                int lg = 0;
-                while ((1ull << lg) < span) ++lg;
-                int nshift = lg - 13;
-                if (nshift < 0) nshift = 0;
-                if (nshift >= shift) nshift = shift - 1;
-                const unsigned long long wspan = (unsigned long long)kBins << nshift;
-                for (unsigned long long o = 0; o < span; o += wspan) {
-                  if (sm.nstack < kStack) {
-                    sm.st_klo[sm.nstack] = (uint32_t)((unsigned long long)klo + ((unsigned long long)r.blo << shift) + o);
-                    sm.st_shift[sm.nstack] = nshift;
-                    ++sm.nstack;
-                  } else {
-                    sm.flags |= 1;  // window stack overflow: result may miss candidates
-                  }
-                }
-              }
-            }
-            sm.ncollect = nc;
-          }
-        }
-        __syncthreads();
-
-        // -- shift 0: runs of equal values straight from the histogram
-        if (sm.direct_eval > 0) {
-          const int nf = sm.direct_eval;
-          for (int sl = 0; sl < nf; ++sl) {
-            const uint32_t b = sm.fbin[sl], cnt = sm.hist[b], kv = klo + b;
-            const double base = sm.fsumb[sl], v = (double)key_val(kv);
-            for (uint32_t jj = tid; jj < cnt; jj += blockDim.x)
-              try_position<TERN>(best, ncand, kv, (jj + 1 < cnt) ? kv : sm.fnext[sl], sm.fexcl[sl] + jj,
-                                 base + (double)(jj + 1) * v, n, s_tot, q_tot);
-          }
-        }
-
-        // -- collection pass
-        const int nc = sm.ncollect;
-        if (nc > 0) {
-          double sb[kMaxRanges];
-          uint32_t ma[kMaxRanges];
-#pragma unroll
-          for (int g = 0; g < kMaxRanges; ++g) { sb[g] = 0.0; ma[g] = kNoKey; }
-          for (uint32_t e = tid; e < n; e += blockDim.x) {
-            const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
-            const uint32_t k = __float_as_uint(a);
-#pragma unroll
-            for (int g = 0; g < kMaxRanges; ++g) {
-              if (g < nc) {
-                if ((unsigned long long)k < sm.rng[g].klo) sb[g] += (double)a;
-                else if ((unsigned long long)k < sm.rng[g].khi) {
-                  const uint32_t slot = atomicAdd(&sm.nlist, 1u);
-                  if (slot < (uint32_t)kCap) sm.keys[slot] = k;
-                } else ma[g] = min(ma[g], k);
-              }
-            }
-          }
-          ++passes;
 #pragma unroll
           for (int g = 0; g < kMaxRanges; ++g) {
             if (g < nc) {
-              const double t = block_sum(sb[g], sm.red);
-              uint32_t m = warp_min_u32(ma[g]);
-              __syncthreads();
-              if (tid == 0) { sm.rng[g].sum_below = t; sm.rng[g].next_key = kNoKey; }
-              __syncthreads();
-              if (lane == 0) atomicMin(&sm.rng[g].next_key, m);
+              if ((unsigned long long)k < sm.rng[g].span.klo) sb[g] += (double)a;
+              else if ((unsigned long long)k < sm.rng[g].span.khi) {
+                const uint32_t slot = atomicAdd(&sm.nlist_a, 1u);
+                if (slot < (uint32_t)kCap) sm.list_a[slot] = k;
+              } else ma[g] = min(ma[g], k);
             }
           }
-          __syncthreads();
-          const uint32_t L = min(sm.nlist, (uint32_t)kCap);
-          if (tid == 0) {
-            for (int g = 0; g < nc; ++g)
-              if (sm.rng[g].next_key == kNoKey) sm.rng[g].next_key = sm.kmax;
-            if (sm.nlist > (uint32_t)kCap) sm.flags |= 2;
+        }
+        ++passes;
+      } else {
+        const uint32_t la = sm.nlist_a;
+        for (uint32_t e = tid; e < la; e += blockDim.x) {
+          const uint32_t k = sm.list_a[e];
+          if ((unsigned long long)k < W.base.klo || (unsigned long long)k >= W.base.khi) continue;
+#pragma unroll
+          for (int g = 0; g < kMaxRanges; ++g) {
+            if (g < nc) {
+              if ((unsigned long long)k >= sm.rng[g].span.klo && (unsigned long long)k < sm.rng[g].span.khi) {
+                const uint32_t slot = atomicAdd(&sm.nlist_b, 1u);
+                if (slot < (uint32_t)kFineCap) sm.list_b[slot] = k;
+              } else if ((unsigned long long)k >= sm.rng[g].span.khi) ma[g] = min(ma[g], k);
+            }
           }
-          uint32_t lp = 2;
-          while (lp < L) lp <<= 1;
-          for (uint32_t e = L + tid; e < lp; e += blockDim.x) sm.keys[e] = kNoKey;
-          __syncthreads();
-          collected += L;
-          bitonic_sort(sm.keys, lp);
-          evaluate_list<TERN>(sm, L, nc, n, s_tot, q_tot, best, ncand);
         }
       }
-      first = false;
+#pragma unroll
+      for (int g = 0; g < kMaxRanges; ++g) {
+        if (g < nc) {
+          const double t = from_list ? 0.0 : block_sum(sb[g], sm.red);
+          uint32_t m = warp_min_u32(ma[g]);
+          __syncthreads();
+          if (tid == 0) { sm.rng[g].span.sum_below = W.base.sum_below + t; sm.rng[g].span.next_key = kNoKey; }
+          __syncthreads();
+          if (lane == 0) atomicMin(&sm.rng[g].span.next_key, m);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int g = 0; g < nc; ++g)
+          if (sm.rng[g].span.next_key == kNoKey) sm.rng[g].span.next_key = base_next;
+      }
+      __syncthreads();
+      if (!from_list) {
+        // ranges of the global row are now in list A: refine each one in shared memory
+        const uint32_t L = min(sm.nlist_a, (uint32_t)kCap);
+        if (tid == 0) {
+          if (sm.nlist_a > (uint32_t)kCap) { sm.flags |= 2; sm.nlist_a = kCap; }
+          for (int g = nc - 1; g >= 0; --g) {
+            const Range& r = sm.rng[g];
+            const unsigned long long span = r.span.khi - r.span.klo;
+            int lg = 0;
+            while ((1ull << lg) < span) ++lg;
+            int nshift = lg - 13;
+            if (nshift < 0) nshift = 0;
+            if (sm.nstack < kStack) {
+              Window ch;
+              ch.base = r.span; ch.klo = (uint32_t)r.span.klo; ch.shift = nshift; ch.from_list = 1;
+              sm.stack[sm.nstack++] = ch;
+            } else {
+              sm.flags |= 1;
+            }
+          }
+        }
+        collected += L;
+      } else {
+        // list B holds the few elements that can be candidates: exact sums below each range come from
+        // the bins of this window (integers), then sort and test every element
+        const uint32_t L = min(sm.nlist_b, (uint32_t)kFineCap);
+        if (tid == 0 && sm.nlist_b > (uint32_t)kFineCap) sm.flags |= 2;
+        // sum below range g = window prefix at bin blo: recompute with one warp-free pass per range
+        for (int g = 0; g < nc; ++g) {
+          double part = 0.0;
+          const uint32_t blo = sm.rng[g].blo;
+          for (uint32_t b = tid; b < blo; b += blockDim.x) {
+            const uint32_t cc = sm.hist[b];
+            if (cc) part += exact_bin_sum(klo + (b << shift), cc, sm.bsum.lo[b], sm.bhi[b]);
+          }
+          const double t = block_sum(part, sm.red);
+          __syncthreads();
+          if (tid == 0) sm.rng[g].span.sum_below = sum_below_w + t;
+        }
+        uint32_t lp = 2;
+        while (lp < L) lp <<= 1;
+        for (uint32_t e = L + tid; e < lp; e += blockDim.x) sm.list_b[e] = kNoKey;
+        __syncthreads();
+        bitonic_sort(sm.list_b, lp);
+        evaluate_list<TERN>(sm, sm.list_b, L, nc, n, s_tot, q_tot, best, ncand);
+      }
     }
   }
 

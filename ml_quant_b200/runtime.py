@@ -14,6 +14,22 @@ from .binary.binary_conv import QuantConv2d
 from .nets import QLeNet5, QResNet
 
 
+def strict_fp32() -> None:
+    """IEEE fp32 for the full-precision layers around the hot path (stem, shortcuts, classifier):
+    torch defaults cuDNN convolutions to TF32, which alone moves logits by ~1e-3."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for mod, attr in ((getattr(torch.backends.cudnn, 'conv', None), 'fp32_precision'),
+                      (getattr(torch.backends.cudnn, 'rnn', None), 'fp32_precision'),
+                      (torch.backends.cudnn, 'fp32_precision'),
+                      (getattr(torch.backends.cuda, 'matmul', None), 'fp32_precision')):
+        if mod is not None and hasattr(mod, attr):
+            try:
+                setattr(mod, attr, 'ieee')
+            except Exception:  # noqa: BLE001
+                pass
+
+
 def build_model(config: str, device: Optional[torch.device] = None, seed: int = 0) -> nn.Module:
     """Random-init network of the named shipped config (there are no checkpoints offline)."""
     torch.manual_seed(seed)

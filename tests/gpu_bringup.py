@@ -22,6 +22,11 @@ from ml_quant_b200.binary.binary_conv import QuantConv2d  # noqa: E402
 DEV = 'cuda:0'
 
 
+def runtime_strict():
+    from ml_quant_b200.runtime import strict_fp32
+    strict_fp32()
+
+
 def report(name, ok, extra=''):
     print(f"{'PASS' if ok else 'FAIL'} {name} {extra}", flush=True)
 
@@ -149,8 +154,7 @@ def stage_conv(impl):
 
 def stage_module():
     """QuantConv2d end to end (own scales) against the oracle forward."""
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    runtime_strict()
     for xs, cin, cout, st in [('ls-2', 64, 64, 1), ('ls-1', 64, 128, 2), ('ls-T', 64, 64, 1), ('gf-2', 64, 64, 1)]:
         torch.manual_seed(3)
         m = QuantConv2d(xs, 'ls-1', cin, cout, 3, {'kind': 'symmetric', 'alpha': 3.0}, stride=st, padding=1)
@@ -168,8 +172,26 @@ def stage_module():
         report(f'module {xs} {cin}->{cout} s{st}', e1 < 1e-3, f'packed err={e1:.2e} generic err={e2:.2e}')
 
 
+def stage_solve_timing():
+    for c, hw in [(64, 56), (128, 28), (256, 14), (512, 7)]:
+        x = torch.randn(512, c * hw * hw, device=DEV).clamp_(-3, 3)
+        for tern in (False, True):
+            for _ in range(2):
+                ops.solve_v1(x, tern, 3)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                v, dg = ops.solve_v1(x, tern, 3, diag=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(f'INFO solve 512x{c*hw*hw} tern={int(tern)}: {ms:.3f} ms  ({x.numel()*4/ms/1e6:.0f} GB/s of fp32 input) passes max {int(dg[:,0].max())} '
+                  f'collected mean {float(dg[:,1].float().mean()):.0f} cands mean {float(dg[:,2].float().mean()):.1f} flags {int(dg[:,3].max())}', flush=True)
+
+
 STAGES = {'quant': stage_quant, 'solve': stage_solve, 'conv1': lambda: stage_conv(1), 'conv2': lambda: stage_conv(2),
-          'module': stage_module}
+          'module': stage_module, 'solve_timing': stage_solve_timing}
 
 if __name__ == '__main__':
     todo = sys.argv[1:]

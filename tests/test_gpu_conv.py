@@ -10,6 +10,11 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
+def runtime_strict():
+    from ml_quant_b200.runtime import strict_fp32
+    strict_fp32()
+
+
 def _planes_from_gpu(planes, g, npl):
     """Unpack the GPU plane buffer back to bool [npl, n, c, h, w] for bit-exact comparison."""
     buf = planes.cpu()[: npl * g.nphase * g.vtot * g.cw].view(npl, g.nphase, g.vtot, g.cw)
@@ -90,7 +95,7 @@ def test_tensor_core_and_cuda_core_kernels_agree():
 def test_module_end_to_end_layers(golden_layers):
     """QuantConv2d.forward with its own solve.  Scales that are means agree to 1e-6 and the output to
     1e-5 max|y|; for ls-2 / ls-T the output is compared after checking the staged solver contract."""
-    torch.backends.cudnn.allow_tf32 = False
+    runtime_strict()
     from ml_quant_b200 import ops
     for rec in golden_layers:
         s = rec['spec']
@@ -114,7 +119,7 @@ def test_module_end_to_end_layers(golden_layers):
 
 
 def test_packed_and_generic_routes_agree():
-    torch.backends.cudnn.allow_tf32 = False
+    runtime_strict()
     from quant.binary.binary_conv import QuantConv2d
     torch.manual_seed(2)
     for xs in ('ls-1', 'ls-2', 'ls-T', 'gf-2', 'gf-3'):
@@ -166,8 +171,7 @@ def test_nets_against_golden(golden_nets):
     """Whole networks with the reference's state_dict.  MNIST (fp activations, ls-1 weights) and the
     ls-1 activation ResNet have no ill-posed solve: 1e-4 of max|logit| (sign flips of near-zero BN
     outputs are the only discrete effect).  ls-2 / ls-T: logits within 5e-2 and same top-1."""
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    runtime_strict()
     from ml_quant_b200.nets import QLeNet5, QResNet
     for name, rec in golden_nets.items():
         cls, loss = (QLeNet5, F.nll_loss) if name.startswith('mnist') else (QResNet, F.cross_entropy)
@@ -188,8 +192,7 @@ def test_nets_against_golden(golden_nets):
 
 def test_full_size_resnet18_against_live_oracle():
     """BASELINE network at full width and resolution (batch 4): GPU forward vs the oracle on the CPU."""
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    runtime_strict()
     from ml_quant_b200 import configs, runtime
     model = runtime.build_model('imagenet_resnet18_ls1w_ls1a', torch.device(DEV))
     runtime.calibrate(model, (3, 224, 224), batches=1, batch=8)
