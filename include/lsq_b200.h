@@ -66,8 +66,9 @@ LSQ_API int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float a
 
 /* Least-squares optimal v1 for the 2-bit (ternary = 0) or ternary (= 1) quantizer: replaces
  * opt_v1 / compute_mask / cost_function (quant/binary/optimal.py:16-155).  Only every `skip`-th
- * element of a row enters the solve (optimal.py:134).  d_diag (optional, int32[rows][4]) receives
- * {global passes, collected elements, candidates found, flags}.  One CTA per row. */
+ * element of a row enters the solve (optimal.py:134).  d_diag (optional, int32[rows][16]) receives
+ * {global passes, collected elements, candidates found, flags, 12 per-phase cycle counters}.
+ * One CTA per row. */
 LSQ_API int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
                  float* d_v1, int32_t* d_diag, void* stream);
 

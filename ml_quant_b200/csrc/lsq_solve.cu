@@ -6,9 +6,10 @@
 //
 // Here (tests/solver_model.py is the executable specification of this file):
 //   1. one pass histograms the float bit patterns of a = |clamp(x)|[::skip] (monotone keys) into
-//      8192 bins (count + fp32 sum) and accumulates S = sum a, Q = sum a^2 in fp64;
+//      8192 bins (count + integer sum of the top 14 mantissa bits: native shared-memory atomics, order
+//      independent) and accumulates S = sum a, Q = sum a^2 in fp64;
 //   2. prefix counts / sums at bin edges bound both threshold functions over each bin, which flags
-//      the few bins that can hold a candidate (a conservative test, 1e-4 margin on the fp32 sums);
+//      the few bins that can hold a candidate (a conservative fp32 test, 1e-4 margin on the sums);
 //   3. a second pass collects only the flagged elements (<= 8192, list A) into shared memory together
 //      with the exact fp64 sum of everything below each flagged range; each range is then refined once
 //      more IN SHARED MEMORY with 8192 finer bins whose sums are exact integers (mantissa sums per
@@ -27,6 +28,8 @@ namespace lsq {
 constexpr int kSolveThreads = 1024;
 constexpr int kBins = 8192;
 constexpr int kBinsPerThread = kBins / kSolveThreads;
+constexpr int kListBins = 1024;   // bins of a shared-memory refinement window (one per thread)
+constexpr int kListBinsLog2 = 10;
 constexpr int kCap = 8192;      // list A: elements of the flagged ranges of a global window
 constexpr int kFineCap = 2048;  // list B: elements that are sorted and evaluated one by one
 constexpr int kMaxRanges = 4;
@@ -34,6 +37,8 @@ constexpr int kMaxFlag = 64;
 constexpr int kStack = 24;
 constexpr int kTopShift = 18;
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+constexpr int kLoadBatch = 8;
+constexpr uint32_t kMaxExactN = 262144;  // sum(m >> 9) of a bin fits 32 bits up to this many elements
 
 // A contiguous run of the sorted row: keys in [klo, khi), preceded by cnt_below elements whose
 // exact sum is sum_below, followed by next_key (smallest key >= khi, or the row maximum).
@@ -56,8 +61,8 @@ struct Range {        // flagged bins [blo, bhi] of the current window
 
 struct SolveSmem {
   uint32_t hist[kBins];
-  union { float f[kBins]; uint32_t lo[kBins]; } bsum;   // global windows: fp32 sums; list windows: sum(m & 0xFFF)
-  uint32_t bhi[kBins];                                   // list windows: sum(m >> 12)
+  union { float f[kBins]; uint32_t lo[kBins]; } bsum;   // global windows: sum(m >> 9); list windows: sum(m & 0xFFF)
+  uint32_t bhi[kListBins];                               // list windows: sum(m >> 12)
   uint32_t list_a[kCap];
   uint32_t list_b[kFineCap];
   double red[32];
@@ -89,6 +94,15 @@ __device__ __forceinline__ float key_val(uint32_t k) { return __uint_as_float(k)
 __device__ __forceinline__ double exact_bin_sum(uint32_t any_key, uint32_t cnt, uint32_t lo, uint32_t hi) {
   const int e = (int)(any_key >> 23);
   const double msum = (double)hi * 4096.0 + (double)lo;
+  if (e == 0) return ldexp(msum, -149);
+  return ldexp((double)cnt * 8388608.0 + msum, e - 150);
+}
+
+// value sum of `cnt` keys sharing one exponent from s9 = sum(m >> 9): midpoint of the possible range,
+// relative error < 2^8 / 2^23 = 3.1e-5
+__device__ __forceinline__ double approx_bin_sum(uint32_t any_key, uint32_t cnt, uint32_t s9) {
+  const int e = (int)(any_key >> 23);
+  const double msum = (double)s9 * 512.0 + 256.0 * (double)cnt;
   if (e == 0) return ldexp(msum, -149);
   return ldexp((double)cnt * 8388608.0 + msum, e - 150);
 }
@@ -210,6 +224,9 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
   uint32_t ncand = 0;
   int passes = 0;
   uint32_t collected = 0;
+  long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#define LSQ_TICK(i) do { if (diag && tid == 0) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; } } while (0)
 
   if (tid == 0) {
     sm.kmin = kNoKey; sm.kmax = 0u; sm.nstack = 0; sm.flags = 0; sm.ncand = 0u; sm.nlist_a = 0u; sm.nlist_b = 0u;
@@ -218,7 +235,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
   if (n < 3) {
     if (tid == 0) {
       v1_out[row] = 0.0f;
-      if (diag) { diag[row * 4 + 0] = 0; diag[row * 4 + 1] = 0; diag[row * 4 + 2] = 0; diag[row * 4 + 3] = 0; }
+      if (diag) for (int i = 0; i < 16; ++i) diag[row * 16 + i] = 0;
     }
     return;
   }
@@ -247,7 +264,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       sm.nlist_a = n;
       Window w;
       w.base.klo = 0ull; w.base.khi = 1ull << 32; w.base.sum_below = 0.0; w.base.cnt_below = 0u; w.base.next_key = sm.kmax;
-      w.klo = 0u; w.shift = kTopShift; w.from_list = 1;
+      w.klo = 0u; w.shift = 31 - kListBinsLog2; w.from_list = 1;
       sm.stack[0] = w; sm.nstack = 1;
     }
   } else if (tid == 0) {
@@ -266,28 +283,47 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       sm.cnt_below = 0u; sm.min_above = kNoKey; sm.nflag = 0; sm.fmin = kNoKey; sm.fmax = 0u;
       sm.nrange = 0; sm.direct_eval = 0; sm.action = 0;
     }
-    for (int b = tid; b < kBins; b += blockDim.x) { sm.hist[b] = 0u; sm.bsum.lo[b] = 0u; sm.bhi[b] = 0u; }
+    for (int b = tid; b < kBins; b += blockDim.x) { sm.hist[b] = 0u; sm.bsum.lo[b] = 0u; }
+    if (tid < kListBins) sm.bhi[tid] = 0u;
     __syncthreads();
+    LSQ_TICK(0);   // pop + zero
     const Window W = sm.cur;
     const uint32_t klo = W.klo;
     const int shift = W.shift;
     const bool from_list = W.from_list != 0;
-    const unsigned long long khi = min((unsigned long long)klo + ((unsigned long long)kBins << shift), W.base.khi);
+    const int nbins = from_list ? kListBins : kBins;
+    const unsigned long long khi = min((unsigned long long)klo + ((unsigned long long)nbins << shift), W.base.khi);
+    // how bin sums are known: 2 = exact integers (list windows), 1 = mantissa sums truncated to 14 bits
+    // (global windows, relative error < 3.1e-5), 0 = counts only (rows too long for 32-bit sums)
+    const int sum_mode = from_list ? 2 : (n <= kMaxExactN ? 1 : 0);
+    const uint32_t khi_incl = (uint32_t)min(khi - 1ull, 0xFFFFFFFFull);
+    const uint32_t base_lo = (uint32_t)W.base.klo, base_hi_incl = (uint32_t)min(W.base.khi - 1ull, 0xFFFFFFFFull);
 
     // ---- histogram pass over the window's source ---------------------------------------------
     double ls = 0.0, lq = 0.0, lb = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey;
     if (!from_list) {
-      for (uint32_t e = tid; e < n; e += blockDim.x) {
-        const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
-        const uint32_t k = __float_as_uint(a);
-        if (first) { ls += (double)a; lq += (double)a * (double)a; kmn = min(kmn, k); kmx = max(kmx, k); }
-        if (k < klo) { ++cb; lb += (double)a; }
-        else if ((unsigned long long)k >= khi) { mab = min(mab, k); }
-        else {
-          const uint32_t b = (k - klo) >> shift;
-          atomicAdd(&sm.hist[b], 1u);
-          atomicAdd(&sm.bsum.f[b], a);
+      // kLoadBatch independent loads in flight per thread (the pass is latency bound otherwise)
+      for (uint32_t e0 = tid; e0 < n; e0 += blockDim.x * kLoadBatch) {
+        float v[kLoadBatch];
+#pragma unroll
+        for (int u = 0; u < kLoadBatch; ++u) {
+          const uint32_t e = e0 + u * blockDim.x;
+          v[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < kLoadBatch; ++u) {
+          if (e0 + u * blockDim.x >= n) break;
+          const float a = fabsf(clamp_sym(v[u], alpha));
+          const uint32_t k = __float_as_uint(a);
+          if (first) { ls += (double)a; lq += (double)a * (double)a; kmn = min(kmn, k); kmx = max(kmx, k); }
+          if (k < klo) { ++cb; lb += (double)a; }
+          else if (k > khi_incl) { mab = min(mab, k); }
+          else {
+            const uint32_t b = (k - klo) >> shift;
+            atomicAdd(&sm.hist[b], 1u);
+            if (sum_mode == 1) atomicAdd(&sm.bsum.lo[b], (k & 0x7FFFFFu) >> 9);
+          }
         }
       }
       ++passes;
@@ -295,9 +331,9 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       const uint32_t la = sm.nlist_a;
       for (uint32_t e = tid; e < la; e += blockDim.x) {
         const uint32_t k = sm.list_a[e];
-        if ((unsigned long long)k < W.base.klo || (unsigned long long)k >= W.base.khi) continue;
+        if (k < base_lo || k > base_hi_incl) continue;
         if (k < klo) { ++cb; lb += (double)key_val(k); }
-        else if ((unsigned long long)k >= khi) { mab = min(mab, k); }
+        else if (k > khi_incl) { mab = min(mab, k); }
         else {
           const uint32_t b = (k - klo) >> shift;
           const uint32_t m = k & 0x7FFFFFu;
@@ -307,6 +343,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
         }
       }
     }
+    if (from_list) LSQ_TICK(2); else LSQ_TICK(1);   // histogram pass (global / list)
     if (first) {
       s_tot = block_sum(ls, sm.red);
       q_tot = block_sum(lq, sm.red);
@@ -327,18 +364,25 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     const uint32_t min_above = (sm.min_above != kNoKey) ? sm.min_above : base_next;
     const uint32_t cnt_below_w = W.base.cnt_below + sm.cnt_below;
 
+    LSQ_TICK(3);   // reductions
     // ---- scan bins: thread owns bins [8*tid, 8*tid+8) ---------------------------------------------
     uint32_t c[kBinsPerThread];
     double s[kBinsPerThread];
     uint32_t ct = 0; double stt = 0.0; uint32_t fn = kNoKey;
+    const int bpt = from_list ? 1 : kBinsPerThread;
 #pragma unroll
     for (int j = 0; j < kBinsPerThread; ++j) {
-      const uint32_t b = tid * kBinsPerThread + j;
+      const uint32_t b = tid * bpt + j;
+      if (j >= bpt) { c[j] = 0u; s[j] = 0.0; continue; }
       c[j] = sm.hist[b];
       if (c[j] == 0u) s[j] = 0.0;
       else if (shift == 0) s[j] = (double)c[j] * (double)key_val(klo + b);
-      else if (from_list) s[j] = exact_bin_sum(klo + (b << shift), c[j], sm.bsum.lo[b], sm.bhi[b]);
-      else s[j] = (double)sm.bsum.f[b];
+      else if (sum_mode == 2) s[j] = exact_bin_sum(klo + (b << shift), c[j], sm.bsum.lo[b], sm.bhi[b]);
+      else if (sum_mode == 1) s[j] = approx_bin_sum(klo + (b << shift), c[j], sm.bsum.lo[b]);
+      else {
+        const unsigned long long e1 = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, 0x7F800000ull);
+        s[j] = 0.5 * (double)c[j] * ((double)key_val(klo + (b << shift)) + (double)key_val((uint32_t)e1));
+      }
       ct += c[j]; stt += s[j];
       if (c[j] != 0u && fn == kNoKey) fn = b;
     }
@@ -369,49 +413,54 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     double pref = sum_below_w + soff + si - stt;
 
     // ---- flag bins that can hold a candidate ------------------------------------------------------
-    const double marg = (shift == 0) ? 0.0 : (from_list ? 1e-12 : 1e-4);
-    const double eps = 1e-6;
-    const double dn = (double)n;
-    const double vmax = (double)key_val(kmax);
+    // relative uncertainty of the prefix sums (see sum_mode) and of the fp32 threshold arithmetic below
+    const float marg = (shift == 0 || sum_mode == 2) ? 0.0f : (sum_mode == 1 ? 1e-4f : 0.02f);
+    const float eps = 4e-6f;
 #pragma unroll
     for (int j = 0; j < kBinsPerThread; ++j) {
       if (c[j] == 0u) continue;
-      const uint32_t b = tid * kBinsPerThread + j;
+      const uint32_t b = tid * bpt + j;
       uint32_t nb = kNoKey;
 #pragma unroll
       for (int j2 = kBinsPerThread - 1; j2 > j; --j2)
-        if (c[j2] != 0u) nb = tid * kBinsPerThread + j2;
+        if (c[j2] != 0u) nb = tid * bpt + j2;
       if (nb == kNoKey) nb = nxt_after;
       const uint32_t k0 = max(excl, 1u), k1 = min(excl + c[j], n - 1);
       if (k0 <= k1) {
         const unsigned long long elo_k = min((unsigned long long)klo + ((unsigned long long)b << shift), 0x7F800000ull);
         const unsigned long long ehi_k = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, (unsigned long long)kmax);
-        const double edge_lo = (double)key_val((uint32_t)elo_k);
-        const double edge_hi = fmax((double)key_val((uint32_t)ehi_k), edge_lo);
-        double lo0, hi0, lo1, hi1;
-        if (excl >= 1u) { lo0 = pref * (1.0 - marg); hi0 = pref * (1.0 + marg); }
-        else { lo0 = pref * (1.0 - marg) + edge_lo; hi0 = pref * (1.0 + marg) + edge_hi; }
-        if (excl + c[j] <= n - 1) { lo1 = (pref + s[j]) * (1.0 - marg); hi1 = (pref + s[j]) * (1.0 + marg); }
-        else { lo1 = hi1 = s_tot - vmax; }
-        double nxt_hi;
+        const float edge_lo = key_val((uint32_t)elo_k);
+        const float edge_hi = fmaxf(key_val((uint32_t)ehi_k), edge_lo);
+        // prefix sums at the first (k0) and last (k1) split of the bin, as [lo, hi] intervals
+        const float p0 = (float)pref, p1 = (float)(pref + s[j]), rest0 = (float)(s_tot - pref), rest1 = (float)(s_tot - pref - s[j]);
+        float lo0, hi0, r0lo, r0hi, lo1, hi1, r1lo, r1hi;
+        const float dm0 = marg * p0, dm1 = marg * p1;
+        if (excl >= 1u) { lo0 = p0 - dm0; hi0 = p0 + dm0; r0lo = rest0 - dm0; r0hi = rest0 + dm0; }
+        else { lo0 = p0 - dm0 + edge_lo; hi0 = p0 + dm0 + edge_hi; r0lo = rest0 - dm0 - edge_hi; r0hi = rest0 + dm0 - edge_lo; }
+        if (excl + c[j] <= n - 1) { lo1 = p1 - dm1; hi1 = p1 + dm1; r1lo = rest1 - dm1; r1hi = rest1 + dm1; }
+        else { r1lo = r1hi = key_val(kmax); lo1 = hi1 = (float)(s_tot - (double)key_val(kmax)); }
+        float nxt_hi;
         if (nb != kNoKey) {
           const unsigned long long nh = min((unsigned long long)klo + ((unsigned long long)(nb + 1) << shift) - 1ull, (unsigned long long)kmax);
           const unsigned long long nl = min((unsigned long long)klo + ((unsigned long long)nb << shift), 0x7F800000ull);
-          nxt_hi = fmax((double)key_val((uint32_t)nh), (double)key_val((uint32_t)nl));
+          nxt_hi = fmaxf(key_val((uint32_t)nh), key_val((uint32_t)nl));
         } else {
-          nxt_hi = (double)key_val(min_above);
+          nxt_hi = key_val(min_above);
         }
-        const double h0a = 0.5 * (s_tot - lo0) / (dn - k0), h0b = 0.5 * (s_tot - hi0) / (dn - k0);
-        const double h1a = 0.5 * (s_tot - lo1) / (dn - k1), h1b = 0.5 * (s_tot - hi1) / (dn - k1);
-        const double half_min = fmin(h0a, h0b), half_max = fmax(h1a, h1b);
-        bool hit = (half_max * (1.0 + eps) >= edge_lo) &&
-                   (half_min * (1.0 - eps) <= edge_hi || half_max * (1.0 - eps) <= nxt_hi);
+        const float ih0 = 0.5f / (float)(n - k0), ih1 = 0.5f / (float)(n - k1);
+        const float half_min = r0lo * ih0, half_max = r1hi * ih1;      // hi/2 is monotone in the split
+        bool hit = (half_max * (1.0f + eps) >= edge_lo) &&
+                   (half_min * (1.0f - eps) <= edge_hi || half_max * (1.0f - eps) <= nxt_hi);
         if (!TERN) {
-          const double m0a = h0a + 0.5 * lo0 / k0, m0b = h0b + 0.5 * hi0 / k0;
-          const double m1a = h1a + 0.5 * lo1 / k1, m1b = h1b + 0.5 * hi1 / k1;
-          const double mid_min = fmin(m0a, m0b), mid_max = fmax(m1a, m1b);
-          hit = hit || ((mid_max * (1.0 + eps) >= edge_lo) &&
-                        (mid_min * (1.0 - eps) <= edge_hi || mid_max * (1.0 - eps) <= nxt_hi));
+          const float ik0 = 0.5f / (float)k0, ik1 = 0.5f / (float)k1;
+          const float mid_min = fminf(r0lo * ih0 + lo0 * ik0, r0hi * ih0 + hi0 * ik0) ;
+          const float mid_max = fmaxf(r1lo * ih1 + lo1 * ik1, r1hi * ih1 + hi1 * ik1);
+          // (lo, rest) move in opposite directions: the extremes over the interval are at its ends,
+          // paired as (lo0, r0hi) / (hi0, r0lo); take the enclosing values to stay conservative
+          const float mid_min2 = fminf(mid_min, fminf(r0hi * ih0 + lo0 * ik0, r0lo * ih0 + hi0 * ik0));
+          const float mid_max2 = fmaxf(mid_max, fmaxf(r1hi * ih1 + lo1 * ik1, r1lo * ih1 + hi1 * ik1));
+          hit = hit || ((mid_max2 * (1.0f + eps) >= edge_lo) &&
+                        (mid_min2 * (1.0f - eps) <= edge_hi || mid_max2 * (1.0f - eps) <= nxt_hi));
         }
         if (hit) {
           const int slot = atomicAdd(&sm.nflag, 1);
@@ -432,6 +481,16 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     }
     __syncthreads();
 
+    if (sm.nflag > 1 && sm.nflag <= kMaxFlag && tid < sm.nflag) {
+      const uint32_t mine = sm.fbin[tid];
+      int rank = 0;
+      for (int i = 0; i < sm.nflag; ++i) rank += (sm.fbin[i] < mine) ? 1 : 0;   // bins are distinct
+      sm.ford[rank] = tid;
+    } else if (sm.nflag == 1 && tid == 0) {
+      sm.ford[0] = 0;
+    }
+    __syncthreads();
+    LSQ_TICK(4);   // scan + flag
     // ---- thread 0: flagged bins -> ranges -> collect / refine ---------------------------------------
     if (tid == 0 && sm.nflag > 0) {
       const int nf = min(sm.nflag, kMaxFlag);
@@ -447,12 +506,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
           R[0].blo = sm.fmin; R[0].bhi = sm.fmax; R[0].cnt_below = cbw; R[0].count = cnt;
           nr = 1;
         } else {
-          int* ord = sm.ford;
-          for (int i = 0; i < nf; ++i) {
-            int j = i;
-            while (j > 0 && sm.fbin[ord[j - 1]] > sm.fbin[i]) { ord[j] = ord[j - 1]; --j; }
-            ord[j] = i;
-          }
+          const int* ord = sm.ford;
           // consecutive non-empty flagged bins form one range (kept in place in fexcl/fnext as scratch)
           uint32_t r_end = 0;
           for (int i = 0; i < nf; ++i) {
@@ -484,10 +538,10 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
             const unsigned long long span = r.span.khi - r.span.klo;
             int lg = 0;
             while ((1ull << lg) < span) ++lg;
-            int nshift = lg - 13;
+            int nshift = lg - (from_list ? kListBinsLog2 : 13);
             if (nshift < 0) nshift = 0;
             if (nshift >= shift) nshift = shift - 1;
-            const unsigned long long wspan = (unsigned long long)kBins << nshift;
+            const unsigned long long wspan = (unsigned long long)nbins << nshift;
             for (unsigned long long o = 0; o < span; o += wspan) {
               if (sm.nstack < kStack) {
                 Window ch;
@@ -505,6 +559,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     }
     __syncthreads();
 
+    LSQ_TICK(5);   // thread-0 bookkeeping
     // ---- shift 0: runs of equal values straight from the histogram --------------------------------
     if (sm.direct_eval > 0) {
       const int nf = sm.direct_eval;
@@ -525,20 +580,57 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 #pragma unroll
       for (int g = 0; g < kMaxRanges; ++g) { sb[g] = 0.0; ma[g] = kNoKey; }
       if (tid == 0) { if (from_list) sm.nlist_b = 0u; else sm.nlist_a = 0u; }
+      uint32_t rlo[kMaxRanges], rhi[kMaxRanges];             // [rlo, rhi] inclusive, 32-bit keys
+#pragma unroll
+      for (int g = 0; g < kMaxRanges; ++g) {
+        rlo[g] = (g < nc) ? (uint32_t)sm.rng[g].span.klo : kNoKey;
+        rhi[g] = (g < nc) ? (uint32_t)(sm.rng[g].span.khi - 1ull) : kNoKey;
+      }
       __syncthreads();
       if (!from_list) {
-        for (uint32_t e = tid; e < n; e += blockDim.x) {
-          const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
-          const uint32_t k = __float_as_uint(a);
+        // warp-uniform trip count: the slot allocation below uses full-warp shuffles
+        for (uint32_t eb = (uint32_t)(tid & ~31); eb < n; eb += blockDim.x * kLoadBatch) {
+          const uint32_t e0 = eb + lane;
+          float v[kLoadBatch];
 #pragma unroll
-          for (int g = 0; g < kMaxRanges; ++g) {
-            if (g < nc) {
-              if ((unsigned long long)k < sm.rng[g].span.klo) sb[g] += (double)a;
-              else if ((unsigned long long)k < sm.rng[g].span.khi) {
-                const uint32_t slot = atomicAdd(&sm.nlist_a, 1u);
-                if (slot < (uint32_t)kCap) sm.list_a[slot] = k;
-              } else ma[g] = min(ma[g], k);
+          for (int u = 0; u < kLoadBatch; ++u) {
+            const uint32_t e = e0 + u * blockDim.x;
+            v[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
+          }
+          uint32_t matched = 0u;
+#pragma unroll
+          for (int u = 0; u < kLoadBatch; ++u) {
+            if (e0 + u * blockDim.x >= n) break;
+            const float a = fabsf(clamp_sym(v[u], alpha));
+            const uint32_t k = __float_as_uint(a);
+#pragma unroll
+            for (int g = 0; g < kMaxRanges; ++g) {
+              if (g >= nc) continue;
+              if (k < rlo[g]) sb[g] += (double)a;
+              else if (k <= rhi[g]) matched |= 1u << u;
+              else ma[g] = min(ma[g], k);
             }
+          }
+          // one shared-memory atomic per warp and batch: slots from a warp prefix sum of the match counts
+          const uint32_t cnt = __popc(matched);
+          uint32_t inc = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+          if (total != 0u) {
+            uint32_t base = 0u;
+            if (lane == 31) base = atomicAdd(&sm.nlist_a, total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t pos = base + inc - cnt;
+#pragma unroll
+            for (int u = 0; u < kLoadBatch; ++u)
+              if ((matched >> u) & 1u) {
+                if (pos < (uint32_t)kCap) sm.list_a[pos] = __float_as_uint(fabsf(clamp_sym(v[u], alpha)));
+                ++pos;
+              }
           }
         }
         ++passes;
@@ -546,18 +638,18 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
         const uint32_t la = sm.nlist_a;
         for (uint32_t e = tid; e < la; e += blockDim.x) {
           const uint32_t k = sm.list_a[e];
-          if ((unsigned long long)k < W.base.klo || (unsigned long long)k >= W.base.khi) continue;
+          if (k < base_lo || k > base_hi_incl) continue;
 #pragma unroll
           for (int g = 0; g < kMaxRanges; ++g) {
-            if (g < nc) {
-              if ((unsigned long long)k >= sm.rng[g].span.klo && (unsigned long long)k < sm.rng[g].span.khi) {
-                const uint32_t slot = atomicAdd(&sm.nlist_b, 1u);
-                if (slot < (uint32_t)kFineCap) sm.list_b[slot] = k;
-              } else if ((unsigned long long)k >= sm.rng[g].span.khi) ma[g] = min(ma[g], k);
-            }
+            if (g >= nc) continue;
+            if (k >= rlo[g] && k <= rhi[g]) {
+              const uint32_t slot = atomicAdd(&sm.nlist_b, 1u);
+              if (slot < (uint32_t)kFineCap) sm.list_b[slot] = k;
+            } else if (k > rhi[g]) ma[g] = min(ma[g], k);
           }
         }
       }
+      if (from_list) LSQ_TICK(7); else LSQ_TICK(6);   // collection pass (global / list)
 #pragma unroll
       for (int g = 0; g < kMaxRanges; ++g) {
         if (g < nc) {
@@ -575,6 +667,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
           if (sm.rng[g].span.next_key == kNoKey) sm.rng[g].span.next_key = base_next;
       }
       __syncthreads();
+      LSQ_TICK(8);   // collection reductions
       if (!from_list) {
         // ranges of the global row are now in list A: refine each one in shared memory
         const uint32_t L = min(sm.nlist_a, (uint32_t)kCap);
@@ -585,7 +678,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
             const unsigned long long span = r.span.khi - r.span.klo;
             int lg = 0;
             while ((1ull << lg) < span) ++lg;
-            int nshift = lg - 13;
+            int nshift = lg - kListBinsLog2;
             if (nshift < 0) nshift = 0;
             if (sm.nstack < kStack) {
               Window ch;
@@ -620,6 +713,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
         __syncthreads();
         bitonic_sort(sm.list_b, lp);
         evaluate_list<TERN>(sm, sm.list_b, L, nc, n, s_tot, q_tot, best, ncand);
+        LSQ_TICK(9);   // exact range sums + sort + evaluate
       }
     }
   }
@@ -654,8 +748,10 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     }
     v1_out[row] = (nc_tot > 0) ? key_val(b.key) : 0.0f;
     if (diag) {
-      diag[row * 4 + 0] = passes; diag[row * 4 + 1] = (int)collected; diag[row * 4 + 2] = (int)nc_tot;
-      diag[row * 4 + 3] = sm.flags;
+      diag[row * 16 + 0] = passes; diag[row * 16 + 1] = (int)collected; diag[row * 16 + 2] = (int)nc_tot;
+      diag[row * 16 + 3] = sm.flags;
+      for (int i = 0; i < 10; ++i) diag[row * 16 + 4 + i] = (int)tacc[i];
+      diag[row * 16 + 14] = (int)(clock64() - tprev); diag[row * 16 + 15] = 0;
     }
   }
 }

@@ -109,7 +109,7 @@ def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[fl
     x2d = x2d.contiguous()
     rows, length = x2d.shape
     out = torch.empty(rows, dtype=torch.float32, device=x2d.device)
-    dg = torch.zeros(rows, 4, dtype=torch.int32, device=x2d.device) if diag else None
+    dg = torch.zeros(rows, 16, dtype=torch.int32, device=x2d.device) if diag else None
     with torch.cuda.device(x2d.device), _launch('solve_v1', 4.0 * rows * length):
         _C.check(_C.lib().lsq_solve_v1(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
                                        out.data_ptr(), _ptr(dg), _stream()), 'lsq_solve_v1')

@@ -186,6 +186,8 @@ def stage_solve_timing():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
+            print('INFO phase kcycles mean [pop+zero, hist_g, hist_l, reduce, scan+flag, thread0, collect_g, collect_l, creduce, sort+eval, tail]:',
+                  [round(float(dg[:, 4 + i].float().mean()) / 1e3, 1) for i in range(11)], flush=True)
             print(f'INFO solve 512x{c*hw*hw} tern={int(tern)}: {ms:.3f} ms  ({x.numel()*4/ms/1e6:.0f} GB/s of fp32 input) passes max {int(dg[:,0].max())} '
                   f'collected mean {float(dg[:,1].float().mean()):.0f} cands mean {float(dg[:,2].float().mean()):.1f} flags {int(dg[:,3].max())}', flush=True)
 

@@ -138,6 +138,7 @@ def test_packed_and_generic_routes_agree():
 def test_fp_and_structured_kats():
     # reference tests/binary/test_binary_conv.py:18-67
     from quant.binary.binary_conv import QuantConv2d
+    runtime_strict()
     torch.manual_seed(1234)
     x = torch.randn(8, 3, 40, 40, device=DEV, requires_grad=True)
     ref = nn.Conv2d(3, 30, 5).to(DEV)
@@ -149,6 +150,9 @@ def test_fp_and_structured_kats():
     x[0, :, 4:, :4] = 2
     x[0, :, 4:, 4:] = -3
     conv = QuantConv2d('fp', 'ls-1', 3, 1, (4, 4), stride=4, bias=False).to(DEV)
+    with torch.no_grad():
+        conv.weight[0, 0, 0, :3].abs_()          # unbalanced signs so the sums are not ~0
+        conv.weight[0, 0, 1, :3].abs_()
     y = conv(x.to(DEV)).squeeze()
     assert y.shape == (2, 2) and y[0, 0] == 0
     assert torch.isclose(y[1, 0], -2 * y[0, 1]) and torch.isclose(y[1, 1], 3 * y[0, 1])
