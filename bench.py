@@ -104,6 +104,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=512, help='images per GPU per step')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-fuse', action='store_true', help='keep BatchNorm / ReLU / residual adds as separate torch ops')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -142,6 +143,8 @@ def main():
 
     model = runtime.build_model(CONFIG, dev)
     runtime.calibrate(model, (3, 224, 224))
+    if not args.no_fuse:
+        runtime.optimize_for_inference(model)
     B = args.batch
     g = torch.Generator(device='cpu').manual_seed(1234 + rank)
     host_x = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
@@ -246,7 +249,7 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': B * 3 * 224 * 224 * 4,
                 'd2h_bytes_per_step': B * 1000 * 4},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
-        'roofline': roof, 'cuda_graph': not args.no_graph,
+        'roofline': roof, 'cuda_graph': not args.no_graph, 'fused_blocks': not args.no_fuse,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -49,6 +49,30 @@ enum lsq_status {
 LSQ_API int lsq_abi_version(void);
 LSQ_API const char* lsq_last_error(void);
 
+/* ---- fused neighbours of the path ---------------------------------------------
+ * In XnorBasicBlock (quant/models/resnet.py:180-190) every QuantConv2d is fed by an eval-mode
+ * BatchNorm and followed by bias + ReLU/PReLU + residual add.  The *_ex entry points fold those
+ * elementwise neighbours into the kernels so their tensors never travel through HBM:
+ *   prologue : x' = x * ch_scale[c] + ch_shift[c] before the clamp, c = (index_in_row / inner) % channels
+ *              (eval BatchNorm as a per-channel affine map; NULL pointer = identity)
+ *   epilogue : r = vw*sum(s_j I_j) + bias;  residual_after_act = 1: y = act(r) + residual   (double shortcut,
+ *              resnet.py:182-188)         residual_after_act = 0: y = act(r + residual)    (resnet.py:189-190)
+ *              act: 0 identity, 1 ReLU, 2 PReLU with n_prelu (1 or cout) slopes; d_residual may be NULL. */
+typedef struct lsq_prologue {
+  const float* d_ch_scale;
+  const float* d_ch_shift;
+  int32_t channels;
+  int64_t inner;
+} lsq_prologue;
+
+typedef struct lsq_epilogue {
+  const float* d_residual;   /* [n, cout, ho, wo] like the output, or NULL */
+  const float* d_prelu;      /* PReLU slopes, or NULL */
+  int32_t n_prelu;
+  int32_t act;
+  int32_t residual_after_act;
+} lsq_epilogue;
+
 /* ---- row quantizer primitives ------------------------------------------------------------- */
 
 /* Workspace (bytes) for lsq_row_absmean / lsq_encode_act on `rows` rows of `len` elements.
@@ -64,6 +88,10 @@ LSQ_API int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float a
                     const float* d_scales, int nscales, float* d_out,
                     void* d_ws, size_t ws_bytes, void* stream);
 
+LSQ_API int lsq_row_absmean_ex(const float* d_x, int64_t rows, int64_t len, float alpha,
+                       const float* d_scales, int nscales, float* d_out,
+                       void* d_ws, size_t ws_bytes, const lsq_prologue* pro, void* stream);
+
 /* Least-squares optimal v1 for the 2-bit (ternary = 0) or ternary (= 1) quantizer: replaces
  * opt_v1 / compute_mask / cost_function (quant/binary/optimal.py:16-155).  Only every `skip`-th
  * element of a row enters the solve (optimal.py:134).  d_diag (optional, int32[rows][16]) receives
@@ -71,6 +99,9 @@ LSQ_API int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float a
  * One CTA per row. */
 LSQ_API int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
                  float* d_v1, int32_t* d_diag, void* stream);
+
+LSQ_API int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
+                    float* d_v1, int32_t* d_diag, const lsq_prologue* pro, void* stream);
 
 /* Dense fake-quant tensor  out = sum_j s_j b_j  in the reference's fp32 operation order
  * (quantization.py:56, :89-92, :113-115, :139-146).  ternary = 1: two planes, both scaled by s_1. */
@@ -114,6 +145,11 @@ LSQ_API int lsq_encode_act(const float* d_x, const lsq_act_geom* g, float alpha,
                    uint32_t* d_planes, float* d_last_scale,
                    void* d_ws, size_t ws_bytes, void* stream);
 
+LSQ_API int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alpha,
+                      const float* d_scales, int nscales, int nplanes,
+                      uint32_t* d_planes, float* d_last_scale,
+                      void* d_ws, size_t ws_bytes, const lsq_prologue* pro, void* stream);
+
 /* ---- weights --------------------------------------------------------------------------------- */
 
 /* Packed sign(W) for ls-1 weights [cout, cin, kh, kw] (weight_quantization.py:32-33 without the
@@ -133,6 +169,11 @@ LSQ_API int lsq_pack_weights(const float* d_w, int cout, int cin, int kh, int kw
 LSQ_API int lsq_bconv2d_fwd(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes,
                     const float* d_act_scales, const void* d_wpack, const float* d_w_scale,
                     const float* d_bias, int cout, float* d_y, int impl, void* stream);
+
+LSQ_API int lsq_bconv2d_fwd_ex(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes,
+                       const float* d_act_scales, const void* d_wpack, const float* d_w_scale,
+                       const float* d_bias, int cout, float* d_y, int impl,
+                       const lsq_epilogue* epi, void* stream);
 
 /* 1 if the tensor-core kernel handles this problem */
 LSQ_API int lsq_bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout);

@@ -15,6 +15,7 @@ EXPORTS = [
     'lsq_abi_version', 'lsq_last_error', 'lsq_reduce_workspace_bytes', 'lsq_row_absmean', 'lsq_solve_v1',
     'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry', 'lsq_act_planes_bytes', 'lsq_encode_act',
     'lsq_wpack_bytes', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
+    'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex',
 ]
 
 
@@ -22,6 +23,15 @@ class ActGeom(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ('n', 'c', 'h', 'w', 'kh', 'kw', 'stride', 'pad', 'ho', 'wo', 'cw', 'nphase', 'hv', 'wv', 'ph',
                  'pitch', 'rows_per_sample', 'lead')] + [('vtot', C.c_int64)]
+
+
+class Prologue(C.Structure):
+    _fields_ = [('d_ch_scale', C.c_void_p), ('d_ch_shift', C.c_void_p), ('channels', C.c_int32), ('inner', C.c_int64)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [('d_residual', C.c_void_p), ('d_prelu', C.c_void_p), ('n_prelu', C.c_int32), ('act', C.c_int32),
+                ('residual_after_act', C.c_int32)]
 
 
 class LsqError(RuntimeError):
@@ -58,8 +68,14 @@ def lib():
             L.lsq_pack_weights.argtypes = [vp, i32, i32, i32, i32, vp, vp]
             L.lsq_bconv2d_fwd.argtypes = [vp, gp, i32, vp, vp, vp, vp, i32, vp, i32, vp]
             L.lsq_bconv2d_tc_supported.argtypes = [gp, i32, i32]
+            pp, ep = C.POINTER(Prologue), C.POINTER(Epilogue)
+            L.lsq_row_absmean_ex.argtypes = [vp, i64, i64, f32, vp, i32, vp, vp, sz, pp, vp]
+            L.lsq_solve_v1_ex.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp, pp, vp]
+            L.lsq_encode_act_ex.argtypes = [vp, gp, f32, vp, i32, i32, vp, vp, vp, sz, pp, vp]
+            L.lsq_bconv2d_fwd_ex.argtypes = [vp, gp, i32, vp, vp, vp, vp, i32, vp, i32, ep, vp]
             for name in ('lsq_row_absmean', 'lsq_solve_v1', 'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry',
-                         'lsq_encode_act', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported'):
+                         'lsq_encode_act', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
+                         'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex'):
                 getattr(L, name).restype = i32
             if L.lsq_abi_version() != 1:
                 raise LsqError('liblsq_b200.so ABI version mismatch')

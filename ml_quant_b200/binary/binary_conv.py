@@ -30,6 +30,25 @@ from . import activation_quantization, quantization, weight_quantization
 _PACKED_MAX_PLANES = 4
 
 
+def bn_affine(bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm as y = x * a + b per channel (a = gamma / sqrt(var + eps), b = beta - mean * a),
+    cached on the module until one of its tensors changes."""
+    srcs = [t for t in (bn.running_mean, bn.running_var, bn.weight, bn.bias) if t is not None]
+    key = tuple((t.data_ptr(), t._version) for t in srcs)
+    hit = getattr(bn, '_lsq_affine', None)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            a = torch.rsqrt(bn.running_var + bn.eps)
+            if bn.weight is not None:
+                a = a * bn.weight
+            b = -bn.running_mean * a
+            if bn.bias is not None:
+                b = b + bn.bias
+        hit = (key, a.float().contiguous(), b.float().contiguous())
+        bn._lsq_affine = hit
+    return hit[1], hit[2]
+
+
 class QuantConv2d(nn.Conv2d):
     """Conv2d(w_quant(w), x_quant(clamp(x)))."""
 
@@ -134,9 +153,11 @@ class QuantConv2d(nn.Conv2d):
             wa.v1.copy_(ops.row_absmean(self.weight.detach().reshape(self.out_channels, -1)))
         return wa.v1
 
-    def quantize_input(self, x: torch.Tensor, g) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Packed activation code of x: (bit planes, scale table [planes, batch])."""
+    def quantize_input(self, x: torch.Tensor, g, prologue=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Packed activation code of clamp(x * ch_scale + ch_shift): (bit planes, scale table [planes, batch]).
+        ``prologue`` = (ch_scale, ch_shift, H*W) folds a preceding eval-mode BatchNorm into the kernels."""
         xa, alpha, npl = self.x_approximate, self.clamp_alpha, self._num_planes()
+        pro = prologue
         n = x.shape[0]
         dev = x.device.index or 0
         buf = self._planes_cache.get(dev)
@@ -145,29 +166,52 @@ class QuantConv2d(nn.Conv2d):
         if xa.uses_stored_scales():
             scales = [s.contiguous() for s in xa.stored_scales(n)]
             known = scales[:1] if tern else scales
-            planes, _ = ops.encode_act(x, g, known[:npl], npl, alpha, False, buf)
+            planes, _ = ops.encode_act(x, g, known[:npl], npl, alpha, False, buf, pro)
             table = scales + scales if tern else scales
         elif self.x_quant == 'ls-1':
-            planes, v1 = ops.encode_act(x, g, [], 1, alpha, True, buf)
+            planes, v1 = ops.encode_act(x, g, [], 1, alpha, True, buf, pro)
             table = [v1]
         elif self.x_quant in ('ls-2', 'ls-T'):
-            v1 = ops.solve_v1(rows, tern, 3, alpha)
-            planes, v2 = ops.encode_act(x, g, [v1], 2, alpha, not tern, buf)
+            v1 = ops.solve_v1(rows, tern, 3, alpha, prologue=pro)
+            planes, v2 = ops.encode_act(x, g, [v1], 2, alpha, not tern, buf, pro)
             table = [v1, v1] if tern else [v1, v2]
         else:
             scales: List[torch.Tensor] = []
             for _ in range(npl - 1):
-                scales.append(ops.row_absmean(rows, scales, alpha))
-            planes, last = ops.encode_act(x, g, scales, npl, alpha, True, buf)
+                scales.append(ops.row_absmean(rows, scales, alpha, pro))
+            planes, last = ops.encode_act(x, g, scales, npl, alpha, True, buf, pro)
             table = scales + [last]
         self._planes_cache[dev] = planes
         return planes, torch.stack(table)
 
-    def _forward_packed(self, x: torch.Tensor, g) -> torch.Tensor:
+    def _forward_packed(self, x: torch.Tensor, g, prologue=None, act: int = 0, prelu=None, residual=None,
+                        residual_after_act: bool = True) -> torch.Tensor:
         x = x.contiguous()
-        planes, table = self.quantize_input(x, g)
+        planes, table = self.quantize_input(x, g, prologue)
         return ops.bconv2d(planes, g, self._num_planes(), table, self.packed_weights(), self._weight_scale(),
-                           self.bias, self.out_channels, self.packed_impl)
+                           self.bias, self.out_channels, self.packed_impl, None, residual, act, prelu,
+                           residual_after_act)
+
+    def forward_fused(self, x: torch.Tensor, bn: Optional[nn.BatchNorm2d] = None, nonlin: Optional[nn.Module] = None,
+                      residual: Optional[torch.Tensor] = None, residual_after_act: bool = True) -> torch.Tensor:
+        """nonlin(conv(bn(x))) (+ residual, after or before the non-linearity) with the eval-mode BatchNorm
+        folded into the quantizer kernels and bias / non-linearity / residual into the convolution epilogue.
+        Falls back to the unfused composition whenever the packed route does not apply."""
+        g = self._packed_geometry(x)
+        kind = {nn.ReLU: 1, nn.PReLU: 2, nn.Identity: 0, type(None): 0}.get(type(nonlin))
+        ok = g is not None and kind is not None and (bn is None or (not bn.training and bn.track_running_stats))
+        if not ok:
+            y = self.forward(x if bn is None else bn(x))
+            if residual is not None and not residual_after_act:
+                y = y + residual
+            y = y if nonlin is None else nonlin(y)
+            return y + residual if (residual is not None and residual_after_act) else y
+        pro = None
+        if bn is not None:
+            a, b = bn_affine(bn)
+            pro = (a, b, x.shape[2] * x.shape[3])
+        prelu = nonlin.weight if kind == 2 else None
+        return self._forward_packed(x, g, pro, kind, prelu, residual, residual_after_act)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
         g = self._packed_geometry(x)

@@ -10,7 +10,7 @@ namespace lsq {
 
 int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes, const float* d_act_scales,
                       const void* d_wpack, const float* d_w_scale, const float* d_bias, int cout, float* d_y,
-                      cudaStream_t stream);
+                      const Epilogue& epi, cudaStream_t stream);
 bool bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -58,7 +58,7 @@ template <int NPL>
 __global__ void __launch_bounds__(256)
 bconv_simple_kernel(const uint32_t* __restrict__ planes, ActGeom g, const float* __restrict__ act_scales,
                     const uint32_t* __restrict__ wbits, const float* __restrict__ w_scale,
-                    const float* __restrict__ bias, int cout, float* __restrict__ y) {
+                    const float* __restrict__ bias, int cout, float* __restrict__ y, Epilogue epi) {
   const long long total = (long long)g.n * cout * g.ho * g.wo;
   const int taps = g.kh * g.kw;
   const uint32_t tail_mask = (g.c & 31) ? ((1u << (g.c & 31)) - 1u) : 0xFFFFFFFFu;
@@ -97,7 +97,7 @@ bconv_simple_kernel(const uint32_t* __restrict__ planes, ActGeom g, const float*
     for (int j = 0; j < NPL; ++j) t = fmaf(__ldg(act_scales + (long long)j * g.n + s), (float)acc[j], t);
     float r = __ldg(w_scale + co) * t;
     if (bias) r += __ldg(bias + co);
-    y[idx] = r;
+    y[idx] = apply_epilogue(epi, r, co, idx);
   }
 }
 
@@ -136,27 +136,35 @@ int lsq_bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout) {
 int lsq_bconv2d_fwd(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes, const float* d_act_scales,
                     const void* d_wpack, const float* d_w_scale, const float* d_bias, int cout, float* d_y,
                     int impl, void* stream) {
+  return lsq_bconv2d_fwd_ex(d_planes, g, nplanes, d_act_scales, d_wpack, d_w_scale, d_bias, cout, d_y, impl, nullptr, stream);
+}
+
+int lsq_bconv2d_fwd_ex(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes, const float* d_act_scales,
+                       const void* d_wpack, const float* d_w_scale, const float* d_bias, int cout, float* d_y,
+                       int impl, const lsq_epilogue* epi, void* stream) {
   LSQ_CHECK_ARG(d_planes && g && d_act_scales && d_wpack && d_w_scale && d_y, "lsq_bconv2d_fwd: null pointer");
   LSQ_CHECK_ARG(nplanes >= 1 && nplanes <= 4 && cout > 0, "lsq_bconv2d_fwd: bad nplanes/cout");
   LSQ_CHECK_ARG(impl >= 0 && impl <= 2, "lsq_bconv2d_fwd: bad impl %d", impl);
   cudaStream_t st = (cudaStream_t)stream;
+  const Epilogue de = to_dev(epi);
+  LSQ_CHECK_ARG(de.act >= 0 && de.act <= 2 && (de.act != 2 || (de.prelu && (de.n_prelu == 1 || de.n_prelu == cout))), "lsq_bconv2d_fwd: bad epilogue");
   const bool tc_ok = bconv2d_tc_supported(g, nplanes, cout);
   if (impl == 2 && !tc_ok) {
     set_error("lsq_bconv2d_fwd: shape not supported by the tensor-core kernel (cin=%d cout=%d k=%dx%d)", g->c, cout, g->kh, g->kw);
     return LSQ_ERR_UNSUPPORTED;
   }
   if (impl == 2 || (impl == 0 && tc_ok))
-    return bconv2d_tc_launch(d_planes, g, nplanes, d_act_scales, d_wpack, d_w_scale, d_bias, cout, d_y, st);
+    return bconv2d_tc_launch(d_planes, g, nplanes, d_act_scales, d_wpack, d_w_scale, d_bias, cout, d_y, de, st);
   ActGeom dg = to_dev(*g);
   const long long total = (long long)g->n * cout * g->ho * g->wo;
   unsigned grid = (unsigned)((total + 255) / 256);
   if (grid > 148u * 32u) grid = 148u * 32u;
   const uint32_t* wbits = (const uint32_t*)d_wpack;
   switch (nplanes) {
-    case 1: bconv_simple_kernel<1><<<grid, 256, 0, st>>>(d_planes, dg, d_act_scales, wbits, d_w_scale, d_bias, cout, d_y); break;
-    case 2: bconv_simple_kernel<2><<<grid, 256, 0, st>>>(d_planes, dg, d_act_scales, wbits, d_w_scale, d_bias, cout, d_y); break;
-    case 3: bconv_simple_kernel<3><<<grid, 256, 0, st>>>(d_planes, dg, d_act_scales, wbits, d_w_scale, d_bias, cout, d_y); break;
-    default: bconv_simple_kernel<4><<<grid, 256, 0, st>>>(d_planes, dg, d_act_scales, wbits, d_w_scale, d_bias, cout, d_y); break;
+    case 1: bconv_simple_kernel<1><<<grid, 256, 0, st>>>(d_planes, dg, d_act_scales, wbits, d_w_scale, d_bias, cout, d_y, de); break;
+    case 2: bconv_simple_kernel<2><<<grid, 256, 0, st>>>(d_planes, dg, d_act_scales, wbits, d_w_scale, d_bias, cout, d_y, de); break;
+    case 3: bconv_simple_kernel<3><<<grid, 256, 0, st>>>(d_planes, dg, d_act_scales, wbits, d_w_scale, d_bias, cout, d_y, de); break;
+    default: bconv_simple_kernel<4><<<grid, 256, 0, st>>>(d_planes, dg, d_act_scales, wbits, d_w_scale, d_bias, cout, d_y, de); break;
   }
   LSQ_CUDA_LAUNCH_CHECK("bconv_simple_kernel");
   return LSQ_OK;

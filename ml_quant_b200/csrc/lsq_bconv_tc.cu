@@ -135,7 +135,7 @@ struct Ring {
 __global__ void __launch_bounds__(kTcThreads, 1)
 bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __restrict__ act_scales,
                 const int8_t* __restrict__ wi8, const float* __restrict__ w_scale, const float* __restrict__ bias,
-                float* __restrict__ y, int* __restrict__ err) {
+                float* __restrict__ y, int* __restrict__ err, Epilogue epi) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,7 +184,8 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
         sc[0] = __ldg(act_scales + s);
         if (P.npl > 1) sc[1] = __ldg(act_scales + g.n + s);
       }
-      float* yrow = y + (((long long)s * P.cout + (long long)ntile * P.nt) * g.ho + a) * g.wo + col;
+      const long long yoff = (((long long)s * P.cout + (long long)ntile * P.nt) * g.ho + a) * g.wo + col;
+      float* yrow = y + yoff;
       const long long cstride = (long long)g.ho * g.wo;
       mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
       tc_fence_after();
@@ -202,7 +203,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
             if (P.npl > 1) t = fmaf(sc[1], (float)(int)r1[j], t);
             float o = __ldg(w_scale + c) * t;
             if (bias) o += __ldg(bias + c);
-            yrow[(long long)(c0 + j) * cstride] = o;
+            yrow[(long long)(c0 + j) * cstride] = apply_epilogue(epi, o, c, yoff + (long long)(c0 + j) * cstride);
           }
         }
       }
@@ -348,7 +349,7 @@ bool bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout) {
 
 int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes, const float* d_act_scales,
                       const void* d_wpack, const float* d_w_scale, const float* d_bias, int cout, float* d_y,
-                      cudaStream_t stream) {
+                      const Epilogue& epi, cudaStream_t stream) {
   TcParams P;
   P.g = to_dev(*g);
   P.npl = nplanes; P.cout = cout; P.nt = cout < 128 ? cout : 128; P.n_ntiles = cout / P.nt;
@@ -409,7 +410,7 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n_items < sms ? n_items : sms;
-  bconv_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(d_planes, P, d_act_scales, wi8, d_w_scale, d_bias, d_y, nullptr);
+  bconv_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(d_planes, P, d_act_scales, wi8, d_w_scale, d_bias, d_y, nullptr, epi);
   LSQ_CUDA_LAUNCH_CHECK("bconv_tc_kernel");
   return LSQ_OK;
 }

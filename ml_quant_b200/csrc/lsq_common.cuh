@@ -62,6 +62,44 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
+// Fused per-channel affine prologue (eval BatchNorm) and convolution epilogue, device-side copies.
+struct Prologue {
+  const float* a;
+  const float* b;
+  int channels;
+  long long inner;
+};
+__host__ inline Prologue to_dev(const lsq_prologue* p) {
+  Prologue d{nullptr, nullptr, 1, 1};
+  if (p && p->d_ch_scale && p->d_ch_shift) { d.a = p->d_ch_scale; d.b = p->d_ch_shift; d.channels = p->channels; d.inner = p->inner; }
+  return d;
+}
+__device__ __forceinline__ float apply_prologue(const Prologue& p, float x, long long index_in_row) {
+  if (p.a == nullptr) return x;
+  // rows are < 2^32 elements (checked on the host): 32-bit divisions
+  const unsigned c = ((unsigned)index_in_row / (unsigned)p.inner) % (unsigned)p.channels;
+  return fmaf(x, __ldg(p.a + c), __ldg(p.b + c));
+}
+struct Epilogue {
+  const float* residual;
+  const float* prelu;
+  int n_prelu, act, residual_after_act;
+};
+__host__ inline Epilogue to_dev(const lsq_epilogue* e) {
+  Epilogue d{nullptr, nullptr, 0, 0, 1};
+  if (e) { d.residual = e->d_residual; d.prelu = e->d_prelu; d.n_prelu = e->n_prelu; d.act = e->act; d.residual_after_act = e->residual_after_act; }
+  return d;
+}
+// r = vw * sum(s_j I_j) + bias already formed; apply activation / residual in the requested order
+__device__ __forceinline__ float apply_epilogue(const Epilogue& e, float r, int channel, long long out_index) {
+  const float res = e.residual ? __ldg(e.residual + out_index) : 0.0f;
+  if (!e.residual_after_act) r += res;
+  if (e.act == 1) r = fmaxf(r, 0.0f);
+  else if (e.act == 2) r = r >= 0.0f ? r : r * __ldg(e.prelu + (e.n_prelu > 1 ? channel : 0));
+  if (e.residual_after_act) r += res;
+  return r;
+}
+
 // Geometry helpers shared by the encoder and the convolution kernels (see lsq_b200.h).
 struct ActGeom {
   int n, c, h, w, kh, kw, stride, pad, ho, wo, cw, nphase, hv, wv, ph, pitch, rps, lead;

@@ -42,7 +42,7 @@ __device__ __forceinline__ float fold_residual(float v, const float (&s)[MAXS], 
 __global__ void __launch_bounds__(kRowThreads)
 row_absmean_kernel(const float* __restrict__ x, long long len, float alpha, const float* __restrict__ scales,
                    long long rows, int ns, float* __restrict__ out, double* __restrict__ partial,
-                   unsigned* __restrict__ counter) {
+                   unsigned* __restrict__ counter, Prologue pro) {
   __shared__ double red[32];
   __shared__ bool last;
   const long long r = blockIdx.y;
@@ -54,7 +54,7 @@ row_absmean_kernel(const float* __restrict__ x, long long len, float alpha, cons
   const long long end = min(beg + (long long)kRowChunk, len);
   double acc = 0.0;
   for (long long e = beg + threadIdx.x; e < end; e += kRowThreads) {
-    float v = clamp_sym(__ldg(xr + e), alpha);
+    float v = clamp_sym(apply_prologue(pro, __ldg(xr + e), e), alpha);
     acc += (double)fabsf(fold_residual(v, s, ns));
   }
   double tot = block_sum(acc, red);
@@ -122,7 +122,7 @@ template <int NPL>
 __global__ void __launch_bounds__(kEncThreads)
 encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const float* __restrict__ scales,
                   int ns, uint32_t* __restrict__ planes, double* __restrict__ partial,
-                  unsigned* __restrict__ counter, float* __restrict__ last_scale) {
+                  unsigned* __restrict__ counter, float* __restrict__ last_scale, Prologue pro) {
   __shared__ double red[32];
   __shared__ bool last;
   const int s = blockIdx.y;
@@ -152,7 +152,9 @@ encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const flo
       const int cn = min(32, g.c - cbase);
 #pragma unroll 8
       for (int cc = 0; cc < cn; ++cc) {
-        const float val = clamp_sym(__ldg(xp + (long long)(cbase + cc) * hw), alpha);
+        float raw = __ldg(xp + (long long)(cbase + cc) * hw);
+        if (pro.a) raw = fmaf(raw, __ldg(pro.a + cbase + cc), __ldg(pro.b + cbase + cc));
+        const float val = clamp_sym(raw, alpha);
         float acc = 0.0f, res = val;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
@@ -209,6 +211,11 @@ size_t lsq_reduce_workspace_bytes(int64_t rows, int64_t len) {
 
 int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales,
                     int nscales, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+  return lsq_row_absmean_ex(d_x, rows, len, alpha, d_scales, nscales, d_out, d_ws, ws_bytes, nullptr, stream);
+}
+
+int lsq_row_absmean_ex(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales,
+                       int nscales, float* d_out, void* d_ws, size_t ws_bytes, const lsq_prologue* pro, void* stream) {
   LSQ_CHECK_ARG(d_x && d_out && d_ws, "lsq_row_absmean: null pointer");
   LSQ_CHECK_ARG(rows > 0 && len > 0 && rows <= 65535, "lsq_row_absmean: bad shape rows=%lld len=%lld", (long long)rows, (long long)len);
   LSQ_CHECK_ARG(nscales >= 0 && nscales <= LSQ_MAX_PLANES && (nscales == 0 || d_scales), "lsq_row_absmean: bad nscales %d", nscales);
@@ -220,7 +227,7 @@ int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float alpha, co
   double* partial = (double*)((char*)d_ws + align_up((size_t)rows * 4, 256));
   dim3 grid((unsigned)((len + kRowChunk - 1) / kRowChunk), (unsigned)rows);
   row_absmean_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nscales,
-                                                                     d_out, partial, counter);
+                                                                     d_out, partial, counter, to_dev(pro));
   LSQ_CUDA_LAUNCH_CHECK("row_absmean_kernel");
   return LSQ_OK;
 }
@@ -297,6 +304,12 @@ size_t lsq_act_planes_bytes(const lsq_act_geom* g, int nplanes) {
 int lsq_encode_act(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
                    int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
                    void* stream) {
+  return lsq_encode_act_ex(d_x, g, alpha, d_scales, nscales, nplanes, d_planes, d_last_scale, d_ws, ws_bytes, nullptr, stream);
+}
+
+int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
+                      int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
+                      const lsq_prologue* pro, void* stream) {
   LSQ_CHECK_ARG(d_x && g && d_planes, "lsq_encode_act: null pointer");
   LSQ_CHECK_ARG(nplanes >= 1 && nplanes <= 4, "lsq_encode_act: nplanes %d not in [1,4]", nplanes);
   LSQ_CHECK_ARG(nscales >= 0 && nscales <= nplanes && (nscales == 0 || d_scales), "lsq_encode_act: bad nscales %d", nscales);
@@ -314,13 +327,15 @@ int lsq_encode_act(const float* d_x, const lsq_act_geom* g, float alpha, const f
     partial = (double*)((char*)d_ws + align_up((size_t)g->n * 4, 256));
   }
   ActGeom dg = to_dev(*g);
+  const Prologue dp = to_dev(pro);
+  if (dp.a && dp.channels != g->c) { set_error("lsq_encode_act: prologue has %d channels, tensor has %d", dp.channels, g->c); return LSQ_ERR_ARG; }
   dim3 grid((unsigned)((hw + kEncThreads - 1) / kEncThreads), (unsigned)g->n);
   cudaStream_t st = (cudaStream_t)stream;
   switch (nplanes) {
-    case 1: encode_act_kernel<1><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale); break;
-    case 2: encode_act_kernel<2><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale); break;
-    case 3: encode_act_kernel<3><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale); break;
-    default: encode_act_kernel<4><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale); break;
+    case 1: encode_act_kernel<1><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp); break;
+    case 2: encode_act_kernel<2><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp); break;
+    case 3: encode_act_kernel<3><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp); break;
+    default: encode_act_kernel<4><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp); break;
   }
   LSQ_CUDA_LAUNCH_CHECK("encode_act_kernel");
   return LSQ_OK;

@@ -213,7 +213,7 @@ __device__ void evaluate_list(SolveSmem& sm, const uint32_t* keys, uint32_t L, i
 template <bool TERN>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
-                int* __restrict__ diag) {
+                int* __restrict__ diag, Prologue pro) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
   const long long row = blockIdx.x;
@@ -247,7 +247,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     double ls = 0.0, lq = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u;
     for (uint32_t e = tid; e < n; e += blockDim.x) {
-      const float a = fabsf(clamp_sym(__ldg(xr + (long long)e * skip), alpha));
+      const float a = fabsf(clamp_sym(apply_prologue(pro, __ldg(xr + (long long)e * skip), (long long)e * skip), alpha));
       const uint32_t k = __float_as_uint(a);
       ls += (double)a; lq += (double)a * (double)a;
       kmn = min(kmn, k); kmx = max(kmx, k);
@@ -309,7 +309,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
           const uint32_t e = e0 + u * blockDim.x;
-          v[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
+          v[u] = (e < n) ? apply_prologue(pro, __ldg(xr + (long long)e * skip), (long long)e * skip) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
@@ -595,7 +595,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 #pragma unroll
           for (int u = 0; u < kLoadBatch; ++u) {
             const uint32_t e = e0 + u * blockDim.x;
-            v[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
+            v[u] = (e < n) ? apply_prologue(pro, __ldg(xr + (long long)e * skip), (long long)e * skip) : 0.0f;
           }
           uint32_t matched = 0u;
 #pragma unroll
@@ -762,6 +762,11 @@ using namespace lsq;
 
 extern "C" int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
                             float* d_v1, int32_t* d_diag, void* stream) {
+  return lsq_solve_v1_ex(d_x, rows, len, skip, ternary, alpha, d_v1, d_diag, nullptr, stream);
+}
+
+extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
+                               float* d_v1, int32_t* d_diag, const lsq_prologue* pro, void* stream) {
   LSQ_CHECK_ARG(d_x && d_v1, "lsq_solve_v1: null pointer");
   LSQ_CHECK_ARG(rows > 0 && len > 0 && skip >= 1, "lsq_solve_v1: bad shape rows=%lld len=%lld skip=%d", (long long)rows, (long long)len, skip);
   LSQ_CHECK_ARG((len + skip - 1) / skip < (1ll << 31), "lsq_solve_v1: row too long");
@@ -773,9 +778,10 @@ extern "C" int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int ski
     set_error("lsq_solve_v1: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return LSQ_ERR_CUDA;
   }
+  const Prologue dp = to_dev(pro);
   dim3 grid((unsigned)rows);
-  if (ternary) solve_v1_kernel<true><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag);
-  else solve_v1_kernel<false><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag);
+  if (ternary) solve_v1_kernel<true><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp);
+  else solve_v1_kernel<false><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp);
   LSQ_CUDA_LAUNCH_CHECK("solve_v1_kernel");
   return LSQ_OK;
 }

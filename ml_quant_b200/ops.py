@@ -86,7 +86,18 @@ def _alpha(alpha: Optional[float]) -> float:
     return float(alpha) if alpha is not None and alpha > 0 else 0.0
 
 
-def row_absmean(x2d: torch.Tensor, scales: Sequence[torch.Tensor] = (), alpha: Optional[float] = None) -> torch.Tensor:
+def _prologue(pro, keep):
+    """pro = (ch_scale, ch_shift, inner) or None -> ctypes pointer (tensors kept alive in ``keep``)."""
+    if pro is None:
+        return None
+    a, b, inner = pro
+    a, b = a.contiguous(), b.contiguous()
+    keep.extend([a, b])
+    return C.byref(_C.Prologue(a.data_ptr(), b.data_ptr(), a.numel(), int(inner)))
+
+
+def row_absmean(x2d: torch.Tensor, scales: Sequence[torch.Tensor] = (), alpha: Optional[float] = None,
+                prologue=None) -> torch.Tensor:
     """mean |residual| per row after folding ``scales`` (include/lsq_b200.h: lsq_row_absmean)."""
     require_cuda(x2d)
     x2d = x2d.contiguous()
@@ -97,13 +108,15 @@ def row_absmean(x2d: torch.Tensor, scales: Sequence[torch.Tensor] = (), alpha: O
     need = L.lsq_reduce_workspace_bytes(rows, length)
     ws = workspace(x2d.device, need)
     with torch.cuda.device(x2d.device), _launch('row_absmean', 4.0 * rows * length):
-        _C.check(L.lsq_row_absmean(x2d.data_ptr(), rows, length, _alpha(alpha), _ptr(tab), len(scales),
-                                   out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), 'lsq_row_absmean')
+        keep = []
+        _C.check(L.lsq_row_absmean_ex(x2d.data_ptr(), rows, length, _alpha(alpha), _ptr(tab), len(scales),
+                                      out.data_ptr(), ws.data_ptr(), ws.numel(), _prologue(prologue, keep), _stream()),
+                 'lsq_row_absmean')
     return out
 
 
 def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[float] = None,
-             diag: bool = False):
+             diag: bool = False, prologue=None):
     """Optimal v1 per row (lsq_solve_v1); returns [rows] (and the int32 [rows,4] diagnostics)."""
     require_cuda(x2d)
     x2d = x2d.contiguous()
@@ -111,8 +124,9 @@ def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[fl
     out = torch.empty(rows, dtype=torch.float32, device=x2d.device)
     dg = torch.zeros(rows, 16, dtype=torch.int32, device=x2d.device) if diag else None
     with torch.cuda.device(x2d.device), _launch('solve_v1', 4.0 * rows * length):
-        _C.check(_C.lib().lsq_solve_v1(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
-                                       out.data_ptr(), _ptr(dg), _stream()), 'lsq_solve_v1')
+        keep = []
+        _C.check(_C.lib().lsq_solve_v1_ex(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
+                                          out.data_ptr(), _ptr(dg), _prologue(prologue, keep), _stream()), 'lsq_solve_v1')
     return (out, dg) if diag else out
 
 
@@ -154,7 +168,7 @@ def act_geometry(n: int, c: int, h: int, w: int, kh: int, kw: int, stride: int, 
 
 def encode_act(x: torch.Tensor, g: _C.ActGeom, scales: Sequence[torch.Tensor], nplanes: int,
                alpha: Optional[float] = None, want_next_scale: bool = False,
-               planes: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               planes: Optional[torch.Tensor] = None, prologue=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """x [n,c,h,w] -> bit planes (int32 buffer) and optionally the next per-sample scale (lsq_encode_act)."""
     require_cuda(x)
     x = x.contiguous()
@@ -167,8 +181,10 @@ def encode_act(x: torch.Tensor, g: _C.ActGeom, scales: Sequence[torch.Tensor], n
     need = L.lsq_reduce_workspace_bytes(g.n, g.c * g.h * g.w)
     ws = workspace(x.device, need)
     with torch.cuda.device(x.device), _launch('encode_act', x.numel() * (4.0 + nplanes / 8.0)):
-        _C.check(L.lsq_encode_act(x.data_ptr(), C.byref(g), _alpha(alpha), _ptr(tab), len(scales), nplanes,
-                                  planes.data_ptr(), _ptr(nxt), ws.data_ptr(), ws.numel(), _stream()), 'lsq_encode_act')
+        keep = []
+        _C.check(L.lsq_encode_act_ex(x.data_ptr(), C.byref(g), _alpha(alpha), _ptr(tab), len(scales), nplanes,
+                                     planes.data_ptr(), _ptr(nxt), ws.data_ptr(), ws.numel(),
+                                     _prologue(prologue, keep), _stream()), 'lsq_encode_act')
     return planes, nxt
 
 
@@ -189,8 +205,10 @@ def pack_weights(w: torch.Tensor) -> torch.Tensor:
 
 def bconv2d(planes: torch.Tensor, g: _C.ActGeom, nplanes: int, act_scales: torch.Tensor, wpack: torch.Tensor,
             w_scale: torch.Tensor, bias: Optional[torch.Tensor], cout: int, impl: int = 0,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Binary convolution forward (lsq_bconv2d_fwd): act_scales is the [nplanes, n] table."""
+            out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = 0,
+            prelu: Optional[torch.Tensor] = None, residual_after_act: bool = True) -> torch.Tensor:
+    """Binary convolution forward (lsq_bconv2d_fwd_ex): act_scales is the [nplanes, n] table; the optional
+    epilogue applies act (0 none, 1 ReLU, 2 PReLU) and adds ``residual`` after or before it."""
     if out is None:
         out = torch.empty(g.n, cout, g.ho, g.wo, dtype=torch.float32, device=planes.device)
     act_scales = act_scales.contiguous()
@@ -199,10 +217,17 @@ def bconv2d(planes: torch.Tensor, g: _C.ActGeom, nplanes: int, act_scales: torch
     n_out = g.n * cout * g.ho * g.wo
     macs = float(n_out) * g.c * g.kh * g.kw * nplanes
     name = 'bconv_tc' if (impl == 2 or (impl == 0 and tc_supported(g, nplanes, cout))) else 'bconv_simple'
-    with torch.cuda.device(planes.device), _launch(name, 4.0 * n_out + nplanes * g.n * g.c * g.h * g.w / 8.0, 2.0 * macs):
-        _C.check(_C.lib().lsq_bconv2d_fwd(planes.data_ptr(), C.byref(g), nplanes, act_scales.data_ptr(),
-                                          wpack.data_ptr(), w_scale.data_ptr(), _ptr(b), cout, out.data_ptr(),
-                                          int(impl), _stream()), 'lsq_bconv2d_fwd')
+    nres = 4.0 * n_out if residual is not None else 0.0
+    with torch.cuda.device(planes.device), _launch(name, 4.0 * n_out + nres + nplanes * g.n * g.c * g.h * g.w / 8.0, 2.0 * macs):
+        if residual is not None:
+            residual = residual.contiguous()
+            if tuple(residual.shape) != tuple(out.shape):
+                raise ValueError(f'residual shape {tuple(residual.shape)} != output shape {tuple(out.shape)}')
+        pr = None if prelu is None else prelu.detach().contiguous()
+        epi = _C.Epilogue(_ptr(residual), _ptr(pr), 0 if pr is None else pr.numel(), int(act), int(bool(residual_after_act)))
+        _C.check(_C.lib().lsq_bconv2d_fwd_ex(planes.data_ptr(), C.byref(g), nplanes, act_scales.data_ptr(),
+                                             wpack.data_ptr(), w_scale.data_ptr(), _ptr(b), cout, out.data_ptr(),
+                                             int(impl), C.byref(epi), _stream()), 'lsq_bconv2d_fwd')
     return out
 
 

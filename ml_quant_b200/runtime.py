@@ -58,6 +58,73 @@ def calibrate(model: nn.Module, input_shape, batches: int = 2, batch: int = 32, 
     return model.eval()
 
 
+def _xnor_block_fused(blk, x: torch.Tensor) -> torch.Tensor:
+    """XnorBasicBlock.forward (quant/models/resnet.py:180-190) with bn1/bn2 folded into the quantizer
+    kernels and nonlin / residual adds into the convolution epilogues."""
+    sc = blk.shortcut(x) if len(blk.shortcut) else x
+    if blk.double_shortcut:
+        first = blk.conv1.forward_fused(x, blk.bn1, blk.nonlin1, sc, True)
+        return blk.conv2.forward_fused(first, blk.bn2, blk.nonlin2, first, True)
+    first = blk.conv1.forward_fused(x, blk.bn1, blk.nonlin1)
+    return blk.conv2.forward_fused(first, blk.bn2, blk.nonlin2, sc, False)
+
+
+class _FusedStem(nn.Module):
+    """conv1 -> bn1 -> relu -> maxpool of QResNet with the eval BatchNorm folded into the convolution
+    weights and the max-pool taken before the ReLU (they commute), so the largest tensor of the network is
+    written once and read once."""
+
+    def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, pool: nn.Module):
+        super().__init__()
+        self.conv, self.bn, self.pool = conv, bn, pool
+        self._key = None
+
+    def _folded(self):
+        from .binary.binary_conv import bn_affine
+        a, b = bn_affine(self.bn)
+        key = (self.conv.weight.data_ptr(), self.conv.weight._version, a.data_ptr())
+        if self._key != key:
+            with torch.no_grad():
+                self._w = (self.conv.weight * a.view(-1, 1, 1, 1)).contiguous()
+                self._b = b if self.conv.bias is None else (b + a * self.conv.bias)
+            self._key = key
+        return self._w, self._b
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
+        if self.bn.training or torch.is_grad_enabled():
+            return self.pool(F.relu(self.bn(self.conv(x))))
+        w, b = self._folded()
+        y = F.conv2d(x, w, b, self.conv.stride, self.conv.padding, self.conv.dilation, self.conv.groups)
+        return F.relu_(self.pool(y))
+
+
+def optimize_for_inference(model: nn.Module) -> nn.Module:
+    """Rewrite the callers of the hot path for eval-mode inference: every XnorBasicBlock
+    runs its two QuantConv2d through ``forward_fused`` and the stem uses a BatchNorm-folded convolution.
+    Parameters, buffers and state_dict keys are untouched; training mode falls back to the original graph."""
+    import types
+    from .nets import QResNet, XnorBasicBlock
+    for m in model.modules():
+        if isinstance(m, XnorBasicBlock) and not hasattr(m, '_lsq_orig_forward'):
+            m._lsq_orig_forward = m.forward
+            m.forward = types.MethodType(
+                lambda self, x: _xnor_block_fused(self, x) if not self.training else self._lsq_orig_forward(x), m)
+    if isinstance(model, QResNet) and not isinstance(model.blocks[0], _FusedStem):
+        stem = _FusedStem(model.conv1, model.bn1, model.maxpool)
+        object.__setattr__(model, '_lsq_stem', stem)      # not registered: state_dict stays the reference's
+        orig_forward = model.forward
+
+        def fwd(self, x):
+            if self.training or torch.is_grad_enabled():
+                return orig_forward(x)
+            x = self._lsq_stem(x)
+            for blk in list(self.blocks)[1:]:
+                x = blk(x)
+            return self.linear_classifier(x)
+        model.forward = types.MethodType(fwd, model)
+    return model
+
+
 class GraphedForward:
     """model(x) for a fixed input shape as one CUDA graph: no per-layer launch gaps, no host work."""
 

@@ -226,3 +226,55 @@ def test_cuda_graph_and_host_pipeline_match_eager():
     pipe = runtime.HostPipeline(model, (8, 3, 32, 32), torch.device(DEV))
     hx = x.pin_memory()
     assert torch.equal(pipe.run([hx, hx, hx]).clone(), eager)
+
+
+def test_fused_prologue_epilogue_matches_composition():
+    """forward_fused(x, bn, nonlin, residual) equals nonlin(conv(bn(x))) (+) residual built from the same
+    kernels, bit for bit, when bn(x) is formed with one rounding (the kernels use fmaf)."""
+    import torch.nn as nn
+    from quant.binary.binary_conv import QuantConv2d, bn_affine
+    torch.manual_seed(4)
+    for xs, stride, nonlin, after in [('ls-2', 1, nn.ReLU(), True), ('ls-1', 2, nn.PReLU(), True),
+                                      ('ls-T', 1, nn.ReLU(), False), ('gf-2', 1, nn.PReLU(64), True)]:
+        m = QuantConv2d(xs, 'ls-1', 64, 64, 3, {'kind': 'symmetric', 'alpha': 3.0}, stride=stride, padding=1).to(DEV)
+        bn = nn.BatchNorm2d(64).to(DEV)
+        with torch.no_grad():
+            bn.running_mean.normal_(0, 0.5)
+            bn.running_var.uniform_(0.5, 2.0)
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.normal_(0, 0.3)
+            if isinstance(nonlin, nn.PReLU):
+                nonlin.weight.uniform_(0.1, 0.4)
+        nonlin = nonlin.to(DEV)
+        x = torch.randn(5, 64, 18, 18, device=DEV) * 2
+        with torch.no_grad():
+            m.train()
+            m(x)
+            m.eval()
+            bn.eval()
+            a, b = bn_affine(bn)
+            xb = (x.double() * a.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1)).float()
+            conv = m(xb)
+            res = torch.randn_like(conv)
+            want = nonlin(conv) + res if after else nonlin(conv + res)
+            got = m.forward_fused(x, bn, nonlin, res, after)
+            # the plain (non-packed) route composes the same thing from torch ops
+            m.allow_packed = False
+            slow = m.forward_fused(x, bn, nonlin, res, after)
+        assert torch.equal(got, want), (xs, float((got - want).abs().max()))
+        assert float((slow - want).abs().max() / want.abs().max()) < 2e-2
+
+
+def test_optimized_network_matches_plain_network():
+    from ml_quant_b200 import runtime
+    runtime_strict()
+    for cfg, shape in [('cifar100_resnet18_ls1w_ls2a', (3, 32, 32)), ('imagenet_resnet18_ls1w_ls1a', (3, 64, 64))]:
+        model = runtime.build_model(cfg, torch.device(DEV))
+        runtime.calibrate(model, shape, batches=1, batch=16)
+        x = torch.randn(8, *shape, device=DEV)
+        with torch.no_grad():
+            plain = model(x)
+            fused = runtime.optimize_for_inference(model)(x)
+        assert list(model.state_dict()) == list(runtime.build_model(cfg).state_dict())
+        err = float((plain - fused).abs().max() / plain.abs().max())
+        assert err < 5e-2 and torch.equal(plain.argmax(1), fused.argmax(1)), (cfg, err)
