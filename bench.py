@@ -220,6 +220,16 @@ def main():
         d['bytes'] += nbytes
         d['ops'] += nops
     ops.PROFILE = None
+    stem_ms = None
+    if hasattr(model, '_lsq_stem'):
+        se0, se1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.no_grad():
+            model._lsq_stem(x)
+            se0.record()
+            model._lsq_stem(x)
+            se1.record()
+        torch.cuda.synchronize()
+        stem_ms = se0.elapsed_time(se1)
     ours_ms = sum(d['ms'] for d in agg.values())
     top = max(agg, key=lambda k: agg[k]['ms'])
     td = agg[top]
@@ -237,7 +247,7 @@ def main():
     roof.update({'traffic': traffic, 'kernel': top, 'launches': td['launches'], 'avg_ms': td['ms'] / td['launches'],
                  'share_of_step': td['ms'] / eager_ms, 'peak_source': peak_src,
                  'kernels_ms': {k: round(v['ms'], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])},
-                 'eager_step_ms': eager_ms, 'our_kernels_share': ours_ms / eager_ms})
+                 'eager_step_ms': eager_ms, 'our_kernels_share': ours_ms / eager_ms, 'fp32_stem_ms': stem_ms})
     # whole-forward HBM roofline (29.5 MB/image with ideal fusion)
     roof['forward_hbm_frac'] = (value / world) * 29.5e6 / (hbm_peak * 1e9)
 

@@ -187,23 +187,35 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       const long long yoff = (((long long)s * P.cout + (long long)ntile * P.nt) * g.ho + a) * g.wo + col;
       float* yrow = y + yoff;
       const long long cstride = (long long)g.ho * g.wo;
-      mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
-      tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc.stage * acc_cols;
-      for (int c0 = 0; c0 < P.nt; c0 += 16) {
-        uint32_t r0[16], r1[16];
-        tmem_ld16(tbase + (uint32_t)c0, r0);
-        if (P.npl > 1) tmem_ld16(tbase + (uint32_t)(P.nt + c0), r1);
-        tmem_ld_wait();
-        if (valid) {
+      const bool has_res = epi.residual != nullptr;
+      for (int c0 = 0; c0 < P.nt; c0 += 32) {
+        // residual values of 32 channels in flight before the accumulators are needed (first group: before
+        // the MMAs of this item have even finished)
+        float res[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = ntile * P.nt + c0 + j;
-            float t = sc[0] * (float)(int)r0[j];
-            if (P.npl > 1) t = fmaf(sc[1], (float)(int)r1[j], t);
-            float o = __ldg(w_scale + c) * t;
-            if (bias) o += __ldg(bias + c);
-            yrow[(long long)(c0 + j) * cstride] = apply_epilogue(epi, o, c, yoff + (long long)(c0 + j) * cstride);
+        for (int j = 0; j < 32; ++j)
+          res[j] = (has_res && valid) ? __ldg(epi.residual + yoff + (long long)(c0 + j) * cstride) : 0.0f;
+        if (c0 == 0) {
+          mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(tbase + (uint32_t)(c0 + 16 * h), r0);
+          if (P.npl > 1) tmem_ld16(tbase + (uint32_t)(P.nt + c0 + 16 * h), r1);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = ntile * P.nt + c0 + 16 * h + j;
+              float t = sc[0] * (float)(int)r0[j];
+              if (P.npl > 1) t = fmaf(sc[1], (float)(int)r1[j], t);
+              float o = __ldg(w_scale + c) * t;
+              if (bias) o += __ldg(bias + c);
+              yrow[(long long)(c0 + 16 * h + j) * cstride] = apply_epilogue_res(epi, o, c, res[16 * h + j]);
+            }
           }
         }
       }

@@ -68,16 +68,20 @@ struct Prologue {
   const float* b;
   int channels;
   long long inner;
+  unsigned long long magic;   // ceil(2^40 / inner): index / inner == (index * magic) >> 40 for index < 2^40 / inner
 };
 __host__ inline Prologue to_dev(const lsq_prologue* p) {
-  Prologue d{nullptr, nullptr, 1, 1};
-  if (p && p->d_ch_scale && p->d_ch_shift) { d.a = p->d_ch_scale; d.b = p->d_ch_shift; d.channels = p->channels; d.inner = p->inner; }
+  Prologue d{nullptr, nullptr, 1, 1, 1ull << 40};
+  if (p && p->d_ch_scale && p->d_ch_shift && p->inner > 0) {
+    d.a = p->d_ch_scale; d.b = p->d_ch_shift; d.channels = p->channels; d.inner = p->inner;
+    d.magic = ((1ull << 40) + (unsigned long long)p->inner - 1ull) / (unsigned long long)p->inner;
+  }
   return d;
 }
+// the caller guarantees row length == channels * inner (one row = one sample), so index / inner < channels
 __device__ __forceinline__ float apply_prologue(const Prologue& p, float x, long long index_in_row) {
   if (p.a == nullptr) return x;
-  // rows are < 2^32 elements (checked on the host): 32-bit divisions
-  const unsigned c = ((unsigned)index_in_row / (unsigned)p.inner) % (unsigned)p.channels;
+  const unsigned c = (unsigned)(((unsigned long long)index_in_row * p.magic) >> 40);
   return fmaf(x, __ldg(p.a + c), __ldg(p.b + c));
 }
 struct Epilogue {
@@ -91,6 +95,13 @@ __host__ inline Epilogue to_dev(const lsq_epilogue* e) {
   return d;
 }
 // r = vw * sum(s_j I_j) + bias already formed; apply activation / residual in the requested order
+__device__ __forceinline__ float apply_epilogue_res(const Epilogue& e, float r, int channel, float res) {
+  if (!e.residual_after_act) r += res;
+  if (e.act == 1) r = fmaxf(r, 0.0f);
+  else if (e.act == 2) r = r >= 0.0f ? r : r * __ldg(e.prelu + (e.n_prelu > 1 ? channel : 0));
+  if (e.residual_after_act) r += res;
+  return r;
+}
 __device__ __forceinline__ float apply_epilogue(const Epilogue& e, float r, int channel, long long out_index) {
   const float res = e.residual ? __ldg(e.residual + out_index) : 0.0f;
   if (!e.residual_after_act) r += res;

@@ -223,6 +223,10 @@ int lsq_row_absmean_ex(const float* d_x, int64_t rows, int64_t len, float alpha,
     set_error("lsq_row_absmean: workspace %zu < %zu", ws_bytes, lsq_reduce_workspace_bytes(rows, len));
     return LSQ_ERR_WORKSPACE;
   }
+  if (pro && pro->d_ch_scale && ((int64_t)pro->channels * pro->inner != len || len >= (1ll << 26))) {
+    set_error("lsq_row_absmean: prologue needs len == channels * inner (< 2^26)");
+    return LSQ_ERR_ARG;
+  }
   unsigned* counter = (unsigned*)d_ws;
   double* partial = (double*)((char*)d_ws + align_up((size_t)rows * 4, 256));
   dim3 grid((unsigned)((len + kRowChunk - 1) / kRowChunk), (unsigned)rows);

@@ -25,10 +25,11 @@
 
 namespace lsq {
 
-constexpr int kSolveThreads = 1024;
+constexpr int kSolveThreads = 512;    // two CTAs per SM: one row's serial phases overlap the other's passes
 constexpr int kBins = 8192;
 constexpr int kBinsPerThread = kBins / kSolveThreads;
-constexpr int kListBins = 1024;   // bins of a shared-memory refinement window (one per thread)
+constexpr int kListBins = 1024;   // bins of a shared-memory refinement window
+constexpr int kListBinsPerThread = kListBins / kSolveThreads;
 constexpr int kListBinsLog2 = 10;
 constexpr int kCap = 8192;      // list A: elements of the flagged ranges of a global window
 constexpr int kFineCap = 2048;  // list B: elements that are sorted and evaluated one by one
@@ -211,7 +212,7 @@ __device__ void evaluate_list(SolveSmem& sm, const uint32_t* keys, uint32_t L, i
 }
 
 template <bool TERN>
-__global__ void __launch_bounds__(kSolveThreads, 1)
+__global__ void __launch_bounds__(kSolveThreads, 2)
 solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
                 int* __restrict__ diag, Prologue pro) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -284,7 +285,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       sm.nrange = 0; sm.direct_eval = 0; sm.action = 0;
     }
     for (int b = tid; b < kBins; b += blockDim.x) { sm.hist[b] = 0u; sm.bsum.lo[b] = 0u; }
-    if (tid < kListBins) sm.bhi[tid] = 0u;
+    for (int b = tid; b < kListBins; b += blockDim.x) sm.bhi[b] = 0u;
     __syncthreads();
     LSQ_TICK(0);   // pop + zero
     const Window W = sm.cur;
@@ -369,7 +370,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     uint32_t c[kBinsPerThread];
     double s[kBinsPerThread];
     uint32_t ct = 0; double stt = 0.0; uint32_t fn = kNoKey;
-    const int bpt = from_list ? 1 : kBinsPerThread;
+    const int bpt = from_list ? kListBinsPerThread : kBinsPerThread;
 #pragma unroll
     for (int j = 0; j < kBinsPerThread; ++j) {
       const uint32_t b = tid * bpt + j;
@@ -408,7 +409,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     uint32_t coff = 0; double soff = 0.0;
     for (int w = 0; w < wid; ++w) { coff += sm.wcnt[w]; soff += sm.wsum[w]; }
     uint32_t nxt_after = nxt_in_warp;
-    for (int w = wid + 1; w < 32 && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
+    for (int w = wid + 1; w < (int)(blockDim.x >> 5) && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
     uint32_t excl = cnt_below_w + coff + ci - ct;
     double pref = sum_below_w + soff + si - stt;
 
@@ -777,6 +778,10 @@ extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int 
   if (e != cudaSuccess) {
     set_error("lsq_solve_v1: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return LSQ_ERR_CUDA;
+  }
+  if (pro && pro->d_ch_scale && ((int64_t)pro->channels * pro->inner != len || len >= (1ll << 26))) {
+    set_error("lsq_solve_v1: prologue needs len == channels * inner (< 2^26)");
+    return LSQ_ERR_ARG;
   }
   const Prologue dp = to_dev(pro);
   dim3 grid((unsigned)rows);

@@ -51,10 +51,17 @@ def calibrate(model: nn.Module, input_shape, batches: int = 2, batch: int = 32, 
     statistics, by ``batches`` train-mode forwards on seeded N(0,1) inputs.
     A freshly constructed model in eval() has v1 = 0 and outputs only biases."""
     dev = next(model.parameters()).device
+    bns = [m for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)]
+    saved = [m.momentum for m in bns]
+    for m in bns:                     # cumulative average: running stats = mean of the batch statistics
+        m.reset_running_stats()
+        m.momentum = None
     model.train()
     for i in range(batches):
         g = torch.Generator(device='cpu').manual_seed(seed + i)
         model(torch.randn(batch, *input_shape, generator=g).to(dev))
+    for m, mom in zip(bns, saved):
+        m.momentum = mom
     return model.eval()
 
 
