@@ -175,6 +175,14 @@ LSQ_API int lsq_bconv2d_fwd_ex(const uint32_t* d_planes, const lsq_act_geom* g, 
                        const float* d_bias, int cout, float* d_y, int impl,
                        const lsq_epilogue* epi, void* stream);
 
+/* ---- fp32 stem of QResNet (not part of the quantized path) ----------------------
+ * out = relu(maxpool3x3/s2/p1(conv7x7/s2/p3(x, w) + bias)) for x [n,3,h,w] -> out [n,64,hp,wp]
+ * (quant/models/resnet.py:283-308 with the eval BatchNorm folded into w / bias by the caller).
+ * d_w: float[64][152], k = c*49 + ky*7 + kx, columns 147..151 zero.  3xTF32 tensor-core arithmetic
+ * (fp32-level accuracy); the conv output never reaches HBM. */
+LSQ_API int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_w, const float* d_bias,
+                 float* d_out, void* stream);
+
 /* 1 if the tensor-core kernel handles this problem */
 LSQ_API int lsq_bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout);
 

@@ -15,7 +15,7 @@ EXPORTS = [
     'lsq_abi_version', 'lsq_last_error', 'lsq_reduce_workspace_bytes', 'lsq_row_absmean', 'lsq_solve_v1',
     'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry', 'lsq_act_planes_bytes', 'lsq_encode_act',
     'lsq_wpack_bytes', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
-    'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex',
+    'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex', 'lsq_stem_fwd',
 ]
 
 
@@ -73,6 +73,8 @@ def lib():
             L.lsq_solve_v1_ex.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp, pp, vp]
             L.lsq_encode_act_ex.argtypes = [vp, gp, f32, vp, i32, i32, vp, vp, vp, sz, pp, vp]
             L.lsq_bconv2d_fwd_ex.argtypes = [vp, gp, i32, vp, vp, vp, vp, i32, vp, i32, ep, vp]
+            L.lsq_stem_fwd.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+            L.lsq_stem_fwd.restype = i32
             for name in ('lsq_row_absmean', 'lsq_solve_v1', 'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry',
                          'lsq_encode_act', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
                          'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex'):

@@ -22,7 +22,7 @@
 
 namespace lsq {
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 448;   // 4 epilogue + MMA + loader + 4 producer + 4 more epilogue warps
 constexpr int kTileM = 128;
 constexpr int kMaxTaps = 9;
 constexpr int kBStages = 4;
@@ -42,6 +42,7 @@ struct TcParams {
   int tap_off[kMaxTaps];         // tap offset relative to dmin of its phase (>= 0)
   uint32_t a_stage_bytes, b_stage_bytes;
   uint32_t smem_a, smem_b, smem_bar;  // offsets in dynamic smem
+  unsigned long long pitch_magic, rps_magic;   // ceil(2^40 / d): x / d == (x * magic) >> 40 for x * d < 2^40
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -123,6 +124,20 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib) {
   return 0xFFFFFFFFu - y * 0xFEu;
 }
 
+// (n, row, col) of a virtual position, by multiplication (positions < 2^31, divisors <= 2^8..2^15)
+struct PosInfo { int s, a, col; bool in_range; };
+__device__ __forceinline__ PosInfo decode_pos(const TcParams& P, long long q) {
+  PosInfo r;
+  const long long rel = q - P.g.lead;
+  r.in_range = rel >= 0;
+  const unsigned long long urel = r.in_range ? (unsigned long long)rel : 0ull;
+  const unsigned R = (unsigned)((urel * P.pitch_magic) >> 40);
+  r.col = (int)(urel - (unsigned long long)R * (unsigned)P.g.pitch);
+  r.s = (int)(((unsigned long long)R * P.rps_magic) >> 40);
+  r.a = (int)R - r.s * P.g.rps - P.g.ph;
+  return r;
+}
+
 struct Ring {
   int stage, n;
   uint32_t phase;
@@ -155,7 +170,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < kAccStages; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
@@ -167,62 +182,86 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
   const int n_items = P.m_tiles * P.n_ntiles;
   const uint32_t acc_cols = (uint32_t)(P.npl * P.nt);
 
-  if (warp < 4) {
-    // ===================== epilogue =====================
-    Ring acc(kAccStages);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int mt = item / P.n_ntiles, ntile = item - mt * P.n_ntiles;
-      const long long q = P.q_begin + (long long)mt * kTileM + warp * 32 + lane;
-      const long long rel = q - g.lead;
-      const int R = (int)(rel / g.pitch);
-      const int col = (int)(rel - (long long)R * g.pitch);
-      const int s = R / g.rps;
-      const int a = R - s * g.rps - g.ph;
-      const bool valid = (rel >= 0) && (s < g.n) && (a >= 0) && (a < g.ho) && (col < g.wo);
-      float sc[2] = {0.0f, 0.0f};
-      if (valid) {
-        sc[0] = __ldg(act_scales + s);
-        if (P.npl > 1) sc[1] = __ldg(act_scales + g.n + s);
+  if (warp < 4 || warp >= 10) {
+    // ===================== epilogue (8 warps: two per TMEM lane quarter) =====================
+    // Warp w reads TMEM lanes 32*(w%4)..+31 (= tile rows); the two warps of a quarter split the channels
+    // in interleaved groups of 32.  Residual values are prefetched one group ahead, across tiles, so the
+    // loads of the next group are in flight while this one is scaled and stored.
+    const int quarter = warp & 3;
+    const int egrp = warp < 4 ? 0 : 1;
+    const int ngroups = P.nt / 64;                     // groups of 32 channels handled by this warp per item
+    const bool has_res = epi.residual != nullptr;
+    const long long cstride = (long long)g.ho * g.wo;
+    struct Row { bool valid; long long yoff; float sc0, sc1; int ntile; };
+    auto decode_row = [&](int item) {
+      Row r;
+      const int mt = item / P.n_ntiles;
+      r.ntile = item - mt * P.n_ntiles;
+      const PosInfo pi = decode_pos(P, P.q_begin + (long long)mt * kTileM + quarter * 32 + lane);
+      r.valid = pi.in_range && (pi.s < g.n) && (pi.a >= 0) && (pi.a < g.ho) && (pi.col < g.wo);
+      r.sc0 = 0.0f; r.sc1 = 0.0f;
+      if (r.valid) {
+        r.sc0 = __ldg(act_scales + pi.s);
+        if (P.npl > 1) r.sc1 = __ldg(act_scales + g.n + pi.s);
       }
-      const long long yoff = (((long long)s * P.cout + (long long)ntile * P.nt) * g.ho + a) * g.wo + col;
-      float* yrow = y + yoff;
-      const long long cstride = (long long)g.ho * g.wo;
-      const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc.stage * acc_cols;
-      const bool has_res = epi.residual != nullptr;
-      for (int c0 = 0; c0 < P.nt; c0 += 32) {
-        // residual values of 32 channels in flight before the accumulators are needed (first group: before
-        // the MMAs of this item have even finished)
-        float res[32];
+      r.yoff = (((long long)pi.s * P.cout + (long long)r.ntile * P.nt) * g.ho + pi.a) * g.wo + pi.col;
+      return r;
+    };
+    auto load_res = [&](float (&dst)[32], const Row& r, int c0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          res[j] = (has_res && valid) ? __ldg(epi.residual + yoff + (long long)(c0 + j) * cstride) : 0.0f;
-        if (c0 == 0) {
-          mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
-          tc_fence_after();
-        }
+      for (int j = 0; j < 32; ++j)
+        dst[j] = (has_res && r.valid) ? __ldg(epi.residual + r.yoff + (long long)(c0 + j) * cstride) : 0.0f;
+    };
+    Ring acc(kAccStages);
+    int item = blockIdx.x;
+    if (item < n_items) {
+      Row cur = decode_row(item);
+      float res[32];
+      load_res(res, cur, egrp * 32);
+      for (; item < n_items; item += gridDim.x) {
+        Row nxt = cur;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc.stage * acc_cols;
+        for (int gi = 0; gi < ngroups; ++gi) {
+          const int c0 = egrp * 32 + gi * 64;
+          float nres[32];
+          if (gi + 1 < ngroups) {
+            load_res(nres, cur, c0 + 64);
+          } else if (item + (int)gridDim.x < n_items) {
+            nxt = decode_row(item + (int)gridDim.x);
+            load_res(nres, nxt, egrp * 32);
+          }
+          if (gi == 0) {
+            mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
+            tc_fence_after();
+          }
+          float* yrow = y + cur.yoff;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r0[16], r1[16];
-          tmem_ld16(tbase + (uint32_t)(c0 + 16 * h), r0);
-          if (P.npl > 1) tmem_ld16(tbase + (uint32_t)(P.nt + c0 + 16 * h), r1);
-          tmem_ld_wait();
-          if (valid) {
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(tbase + (uint32_t)(c0 + 16 * h), r0);
+            if (P.npl > 1) tmem_ld16(tbase + (uint32_t)(P.nt + c0 + 16 * h), r1);
+            tmem_ld_wait();
+            if (cur.valid) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = ntile * P.nt + c0 + 16 * h + j;
-              float t = sc[0] * (float)(int)r0[j];
-              if (P.npl > 1) t = fmaf(sc[1], (float)(int)r1[j], t);
-              float o = __ldg(w_scale + c) * t;
-              if (bias) o += __ldg(bias + c);
-              yrow[(long long)(c0 + 16 * h + j) * cstride] = apply_epilogue_res(epi, o, c, res[16 * h + j]);
+              for (int j = 0; j < 16; ++j) {
+                const int c = cur.ntile * P.nt + c0 + 16 * h + j;
+                float t = cur.sc0 * (float)(int)r0[j];
+                if (P.npl > 1) t = fmaf(cur.sc1, (float)(int)r1[j], t);
+                float o = __ldg(w_scale + c) * t;
+                if (bias) o += __ldg(bias + c);
+                yrow[(long long)(c0 + 16 * h + j) * cstride] = apply_epilogue_res(epi, o, c, res[16 * h + j]);
+              }
             }
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) res[j] = nres[j];
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(acc.stage));
+        acc.advance();
+        cur = nxt;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(acc.stage));
-      acc.advance();
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
@@ -292,40 +331,47 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       for (int cb = 0; cb < P.ncb; ++cb) {
         mbar_wait(a_empty(ra.stage), ra.phase ^ 1u, err, 6);
         unsigned char* a_stage = smem + P.smem_a + (size_t)ra.stage * P.a_stage_bytes;
-        for (int task = pt; task < ntask; task += 128) {
-          const int pos = task % P.pp;
-          const int pp_idx = task / P.pp;          // pl * nphase + phase
-          const int phase = pp_idx % g.nphase;
-          const long long q = q0 + P.dmin[phase] + pos;
-          // validity of this position in this phase (zero padding / beyond the image)
-          const long long rel = q - g.lead;
-          bool valid = rel >= 0;
-          int R = 0, col = 0, s = 0, a = 0;
-          if (valid) {
-            R = (int)(rel / g.pitch); col = (int)(rel - (long long)R * g.pitch);
-            s = R / g.rps; a = R - s * g.rps - g.ph;
-            int hv_p = g.hv, wv_p = g.wv;
-            if (g.nphase == 4) { hv_p = (g.h - (phase >> 1) + 1) >> 1; wv_p = (g.w - (phase & 1) + 1) >> 1; }
-            else { hv_p = g.h; wv_p = g.w; }
-            valid = (s < g.n) && (a >= 0) && (a < hv_p) && (col < wv_p);
-          }
-          uint2 bits = make_uint2(0u, 0u);
-          if (valid) {
-            const uint32_t* src = planes + ((long long)pp_idx * g.vtot + q) * g.cw + cb * 2;
-            bits = __ldg(reinterpret_cast<const uint2*>(src));
-          }
-          const uint32_t vm = valid ? 0xFFFFFFFFu : 0u;
-          unsigned char* dst = a_stage + (size_t)pp_idx * ((size_t)P.pp * 64) + (size_t)pos * 16;
+        constexpr int kPB = 4;   // tasks whose plane-bit loads are in flight together
+        for (int task0 = pt; task0 < ntask; task0 += 128 * kPB) {
+          uint2 bits[kPB];
+          uint32_t vm[kPB];
+          unsigned char* dst[kPB];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t w = (j < 2) ? bits.x : bits.y;
-            const uint32_t h16 = (w >> ((j & 1) * 16)) & 0xFFFFu;
-            uint4 v;
-            v.x = expand4(h16 & 0xFu) & vm;
-            v.y = expand4((h16 >> 4) & 0xFu) & vm;
-            v.z = expand4((h16 >> 8) & 0xFu) & vm;
-            v.w = expand4((h16 >> 12) & 0xFu) & vm;
-            *reinterpret_cast<uint4*>(dst + (size_t)j * ((size_t)P.pp * 16)) = v;
+          for (int u = 0; u < kPB; ++u) {
+            const int task = task0 + u * 128;
+            bits[u] = make_uint2(0u, 0u);
+            vm[u] = 0u;
+            dst[u] = nullptr;
+            if (task < ntask) {
+              const int pp_idx = task / P.pp;          // pl * nphase + phase
+              const int pos = task - pp_idx * P.pp;
+              const int phase = pp_idx % g.nphase;
+              const long long q = q0 + P.dmin[phase] + pos;
+              const PosInfo pi = decode_pos(P, q);
+              int hv_p = g.h, wv_p = g.w;
+              if (g.nphase == 4) { hv_p = (g.h - (phase >> 1) + 1) >> 1; wv_p = (g.w - (phase & 1) + 1) >> 1; }
+              const bool valid = pi.in_range && (pi.s < g.n) && (pi.a >= 0) && (pi.a < hv_p) && (pi.col < wv_p);
+              if (valid) {
+                bits[u] = __ldg(reinterpret_cast<const uint2*>(planes + ((long long)pp_idx * g.vtot + q) * g.cw + cb * 2));
+                vm[u] = 0xFFFFFFFFu;
+              }
+              dst[u] = a_stage + (size_t)pp_idx * ((size_t)P.pp * 64) + (size_t)pos * 16;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kPB; ++u) {
+            if (dst[u] == nullptr) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w = (j < 2) ? bits[u].x : bits[u].y;
+              const uint32_t h16 = (w >> ((j & 1) * 16)) & 0xFFFFu;
+              uint4 v;
+              v.x = expand4(h16 & 0xFu) & vm[u];
+              v.y = expand4((h16 >> 4) & 0xFu) & vm[u];
+              v.z = expand4((h16 >> 8) & 0xFu) & vm[u];
+              v.w = expand4((h16 >> 12) & 0xFu) & vm[u];
+              *reinterpret_cast<uint4*>(dst[u] + (size_t)j * ((size_t)P.pp * 16)) = v;
+            }
           }
         }
         fence_proxy_async();
@@ -407,6 +453,8 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   P.smem_b = (P.smem_b + 127u) / 128u * 128u;
   P.smem_bar = P.smem_b + (uint32_t)kBStages * P.b_stage_bytes;
   const size_t smem_bytes = (size_t)P.smem_bar + 256;
+  P.pitch_magic = ((1ull << 40) + (unsigned long long)g->pitch - 1ull) / (unsigned long long)g->pitch;
+  P.rps_magic = ((1ull << 40) + (unsigned long long)g->rows_per_sample - 1ull) / (unsigned long long)g->rows_per_sample;
   P.q_begin = (long long)g->lead + (long long)g->ph * g->pitch;
   const long long qspan = (long long)g->n * g->rows_per_sample * g->pitch;
   P.m_tiles = (int)((qspan + kTileM - 1) / kTileM);

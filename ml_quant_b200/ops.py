@@ -233,3 +233,20 @@ def bconv2d(planes: torch.Tensor, g: _C.ActGeom, nplanes: int, act_scales: torch
 
 def tc_supported(g: _C.ActGeom, nplanes: int, cout: int) -> bool:
     return bool(_C.lib().lsq_bconv2d_tc_supported(C.byref(g), nplanes, cout))
+
+
+def stem_fwd(x: torch.Tensor, w152: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """relu(maxpool3x3s2p1(conv7x7s2p3(x, w) + bias)) in one kernel (lsq_stem_fwd); w152 is [64, 152]."""
+    require_cuda(x, 'x')
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    if c != 3 or tuple(w152.shape) != (64, 152):
+        raise ValueError('stem_fwd handles 3 -> 64 channel 7x7 stems only')
+    hc, wc = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    hp, wp = (hc - 1) // 2 + 1, (wc - 1) // 2 + 1
+    out = torch.empty(n, 64, hp, wp, dtype=torch.float32, device=x.device)
+    macs = float(n) * 64 * hc * wc * 147
+    with torch.cuda.device(x.device), _launch('stem', 4.0 * (x.numel() + out.numel()), 2.0 * macs):
+        _C.check(_C.lib().lsq_stem_fwd(x.data_ptr(), n, h, w, w152.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                       _stream()), 'lsq_stem_fwd')
+    return out

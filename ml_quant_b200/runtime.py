@@ -85,6 +85,8 @@ class _FusedStem(nn.Module):
         super().__init__()
         self.conv, self.bn, self.pool = conv, bn, pool
         self._key = None
+        self._w152, self._w152_key = None, None
+        self.use_kernel = True
 
     def _folded(self):
         from .binary.binary_conv import bn_affine
@@ -97,12 +99,26 @@ class _FusedStem(nn.Module):
             self._key = key
         return self._w, self._b
 
+    def _kernel_ok(self, x: torch.Tensor) -> bool:
+        c, p = self.conv, self.pool
+        return (x.is_cuda and x.dtype == torch.float32 and c.in_channels == 3 and c.out_channels == 64
+                and tuple(c.kernel_size) == (7, 7) and tuple(c.stride) == (2, 2) and tuple(c.padding) == (3, 3)
+                and tuple(c.dilation) == (1, 1) and c.groups == 1 and isinstance(p, nn.MaxPool2d)
+                and p.kernel_size == 3 and p.stride == 2 and p.padding == 1 and p.dilation == 1 and not p.ceil_mode)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
         if self.bn.training or torch.is_grad_enabled():
             return self.pool(F.relu(self.bn(self.conv(x))))
         w, b = self._folded()
-        y = F.conv2d(x, w, b, self.conv.stride, self.conv.padding, self.conv.dilation, self.conv.groups)
-        return F.relu_(self.pool(y))
+        if self.use_kernel and self._kernel_ok(x):
+            from . import ops
+            if self._w152 is None or self._w152_key != self._key:
+                self._w152 = F.pad(w.reshape(64, 147), (0, 5)).contiguous()
+                self._w152_key = self._key
+            return ops.stem_fwd(x, self._w152, b.contiguous())
+        # bias and ReLU commute with the max-pool: apply them on the 4x smaller pooled tensor
+        y = F.conv2d(x, w, None, self.conv.stride, self.conv.padding, self.conv.dilation, self.conv.groups)
+        return F.relu_(self.pool(y).add_(b.view(1, -1, 1, 1)))
 
 
 def optimize_for_inference(model: nn.Module) -> nn.Module:
