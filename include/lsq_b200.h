@@ -76,7 +76,9 @@ typedef struct lsq_epilogue {
 /* ---- row quantizer primitives ------------------------------------------------------------- */
 
 /* Workspace (bytes) for lsq_row_absmean / lsq_encode_act on `rows` rows of `len` elements.
- * Must be zero-filled once before first use; the kernels leave it zeroed. */
+ * Layout: 256 KiB of arrival counters (fixed size, independent of `rows`) followed by per-block fp64
+ * partial sums.  The counter area must be zero-filled once before first use; the kernels leave it zeroed
+ * (the partials are scratch and may hold anything). */
 LSQ_API size_t lsq_reduce_workspace_bytes(int64_t rows, int64_t len);
 
 /* out[r] = mean_j |res(x[r][j])|, res = x after clamping and after folding `nscales` planes:

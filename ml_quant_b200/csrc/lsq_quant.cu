@@ -25,6 +25,10 @@ void set_error(const char* fmt, ...) {
 constexpr int kRowThreads = 256;
 constexpr int kRowChunk = 4096;   // elements per block in row kernels
 constexpr int kEncThreads = 128;  // pixels per block in the encoder
+// Reduce workspace = [arrival counters: fixed 65536 x u32][per-block fp64 partials].  The counter area has a
+// fixed size so that the partials of one call can never land on the (zero at rest) counters of a later call
+// with more rows.
+constexpr size_t kCounterBytes = 65536 * sizeof(unsigned);
 
 struct ScaleTab {  // up to LSQ_MAX_PLANES per-row scales, passed by value
   const float* p[LSQ_MAX_PLANES];
@@ -192,7 +196,6 @@ encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const flo
   }
 }
 
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace lsq
 
@@ -206,7 +209,7 @@ const char* lsq_last_error(void) { return lsq::g_err; }
 size_t lsq_reduce_workspace_bytes(int64_t rows, int64_t len) {
   if (rows <= 0 || len <= 0) return 256;
   size_t nblk = (size_t)((len + kEncThreads - 1) / kEncThreads) + 1;
-  return align_up((size_t)rows * 4, 256) + (size_t)rows * nblk * 8 + 256;
+  return kCounterBytes + (size_t)rows * nblk * 8 + 256;
 }
 
 int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales,
@@ -228,7 +231,7 @@ int lsq_row_absmean_ex(const float* d_x, int64_t rows, int64_t len, float alpha,
     return LSQ_ERR_ARG;
   }
   unsigned* counter = (unsigned*)d_ws;
-  double* partial = (double*)((char*)d_ws + align_up((size_t)rows * 4, 256));
+  double* partial = (double*)((char*)d_ws + kCounterBytes);
   dim3 grid((unsigned)((len + kRowChunk - 1) / kRowChunk), (unsigned)rows);
   row_absmean_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nscales,
                                                                      d_out, partial, counter, to_dev(pro));
@@ -328,7 +331,7 @@ int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alpha, cons
       return LSQ_ERR_WORKSPACE;
     }
     counter = (unsigned*)d_ws;
-    partial = (double*)((char*)d_ws + align_up((size_t)g->n * 4, 256));
+    partial = (double*)((char*)d_ws + kCounterBytes);
   }
   ActGeom dg = to_dev(*g);
   const Prologue dp = to_dev(pro);

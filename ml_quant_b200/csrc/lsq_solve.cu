@@ -278,7 +278,9 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 
   while (true) {
     __syncthreads();
-    if (sm.nstack == 0) break;
+    const int pending = sm.nstack;
+    __syncthreads();              // every thread has read the depth before thread 0 pops
+    if (pending == 0) break;
     if (tid == 0) {
       sm.cur = sm.stack[--sm.nstack];
       sm.cnt_below = 0u; sm.min_above = kNoKey; sm.nflag = 0; sm.fmin = kNoKey; sm.fmax = 0u;
