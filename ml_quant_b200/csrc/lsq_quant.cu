@@ -119,63 +119,119 @@ __global__ void ste_backward_kernel(const float* __restrict__ x, const float* __
   }
 }
 
-// One thread per pixel, looping over channels: loads are coalesced along W (NCHW input), the
-// channel bits of a pixel accumulate in a register word and leave as one 32-bit store per 32 channels
-// into the position-major plane layout (adjacent stores of a thread fill the same sector, L2 merges).
-template <int NPL>
+// Activation encoder.  One work item = VEC consecutive pixels x one 32-channel group: the thread loads the
+// 32 channels (VEC = 4: one 16-byte load per channel, coalesced along W of the NCHW input, 8 loads in
+// flight), folds the per-channel affine prologue and the clamp, and shifts one sign bit per element and plane
+// into a register word with a funnel shift (channels are walked from 31 down to 0, so channel c lands on bit
+// c).  The sign bit IS the reference's sign(x) = [x >= 0] because no value tested here can be -0.0: the
+// prologue is always applied as fma(x, a, b) with b = -0.0 replaced by +0.0 (identity: a = 1, b = +0.0, which
+// maps -0.0 to +0.0 and every other float to itself), and u - v is never -0.0 for u != -0.0.
+// s * sign(d) is formed exactly by xor-ing d's sign bit into s.
+template <int NPL, int VEC, bool FULL>
+__device__ __forceinline__ void encode_group(const float* __restrict__ xp, long long cstride, int cn,
+                                             const float2* __restrict__ ab, float alpha, const float (&sc)[NPL], int ns,
+                                             uint32_t (&word)[VEC][NPL], float (&gsum)[VEC]) {
+#pragma unroll
+  for (int p = 0; p < VEC; ++p) {
+    gsum[p] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) word[p][j] = 0u;
+  }
+  constexpr int kBatch = 8;
+#pragma unroll 1
+  for (int c0 = 32 - kBatch; c0 >= 0; c0 -= kBatch) {
+    float raw[kBatch][VEC];
+#pragma unroll
+    for (int u = kBatch - 1; u >= 0; --u) {
+      const int cc = c0 + u;
+      if (FULL || cc < cn) {
+        if (VEC == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(xp + (long long)cc * cstride));
+          raw[u][0] = t.x; raw[u][1 % VEC] = t.y; raw[u][2 % VEC] = t.z; raw[u][3 % VEC] = t.w;
+        } else {
+          raw[u][0] = __ldg(xp + (long long)cc * cstride);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = kBatch - 1; u >= 0; --u) {
+      const int cc = c0 + u;
+      const bool have = FULL || cc < cn;
+      const float2 k = have ? ab[cc] : make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int p = 0; p < VEC; ++p) {
+        if (!have) {   // channel beyond C: bit 0 in every plane, nothing added to the residual sum
+#pragma unroll
+          for (int j = 0; j < NPL; ++j) word[p][j] = __funnelshift_l(0x80000000u, word[p][j], 1);
+          continue;
+        }
+        const float val = clamp_sym(fmaf(raw[u][p], k.x, k.y), alpha);
+        float acc = 0.0f, res = val;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const float d = (j == 0) ? val : __fsub_rn(val, acc);
+          word[p][j] = __funnelshift_l(__float_as_uint(d), word[p][j], 1);
+          if (j < ns) {
+            const float t = __uint_as_float(__float_as_uint(sc[j]) ^ (__float_as_uint(d) & 0x80000000u));
+            acc = (j == 0) ? t : __fadd_rn(acc, t);
+            res = __fsub_rn(res, __uint_as_float(__float_as_uint(sc[j]) ^ (__float_as_uint(res) & 0x80000000u)));
+          }
+        }
+        gsum[p] += fabsf(res);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < VEC; ++p)
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) word[p][j] = ~word[p][j];
+}
+
+template <int NPL, int VEC>
 __global__ void __launch_bounds__(kEncThreads)
 encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const float* __restrict__ scales,
                   int ns, uint32_t* __restrict__ planes, double* __restrict__ partial,
                   unsigned* __restrict__ counter, float* __restrict__ last_scale, Prologue pro) {
   __shared__ double red[32];
   __shared__ bool last;
+  extern __shared__ float2 ab[];            // per-channel (scale, shift), padded to a multiple of 32 channels
   const int s = blockIdx.y;
   const int hw = g.h * g.w;
-  const int p = blockIdx.x * kEncThreads + threadIdx.x;
-  const bool valid = p < hw;
+  for (int c = threadIdx.x; c < g.cw * 32; c += kEncThreads) {
+    float2 k = make_float2(1.0f, 0.0f);
+    if (pro.a && c < g.c) k = make_float2(__ldg(pro.a + c), __ldg(pro.b + c) + 0.0f);
+    ab[c] = k;
+  }
   float sc[NPL];
 #pragma unroll
   for (int i = 0; i < NPL; ++i) sc[i] = (i < ns) ? scales[(long long)i * g.n + s] : 0.0f;
+  __syncthreads();
+  const int nq = (hw + VEC - 1) / VEC;                      // pixel groups per channel plane
+  const int item = blockIdx.x * kEncThreads + threadIdx.x;  // (channel group, pixel group)
   double acc_sum = 0.0;
-  if (valid) {
-    const int yi = p / g.w, xi = p - yi * g.w;
-    int phase = 0, a = yi, b = xi;
-    if (g.nphase == 4) {
-      phase = ((yi & 1) << 1) | (xi & 1);
-      a = yi >> 1;
-      b = xi >> 1;
-    }
-    const long long v = vpos(g, s, a, b);
-    const float* xp = x + (long long)s * g.c * hw + p;
-    for (int cg = 0; cg < g.cw; ++cg) {
-      uint32_t word[NPL];
+  if (item < nq * g.cw) {
+    const int cg = item / nq, q = item - cg * nq;
+    const int p0 = q * VEC;
+    const int cbase = cg * 32;
+    const int cn = min(32, g.c - cbase);
+    const float* xp = x + ((long long)s * g.c + cbase) * hw + p0;
+    uint32_t word[VEC][NPL];
+    float gsum[VEC];
+    if (cn == 32) encode_group<NPL, VEC, true>(xp, hw, cn, ab + cbase, alpha, sc, ns, word, gsum);
+    else encode_group<NPL, VEC, false>(xp, hw, cn, ab + cbase, alpha, sc, ns, word, gsum);
+    int yi = p0 / g.w, xi = p0 - yi * g.w;
 #pragma unroll
-      for (int j = 0; j < NPL; ++j) word[j] = 0u;
-      float gsum = 0.0f;
-      const int cbase = cg * 32;
-      const int cn = min(32, g.c - cbase);
-#pragma unroll 8
-      for (int cc = 0; cc < cn; ++cc) {
-        float raw = __ldg(xp + (long long)(cbase + cc) * hw);
-        if (pro.a) raw = fmaf(raw, __ldg(pro.a + cbase + cc), __ldg(pro.b + cbase + cc));
-        const float val = clamp_sym(raw, alpha);
-        float acc = 0.0f, res = val;
+    for (int p = 0; p < VEC; ++p) {
+      if (p0 + p < hw) {
+        int phase = 0, a = yi, b = xi;
+        if (g.nphase == 4) { phase = ((yi & 1) << 1) | (xi & 1); a = yi >> 1; b = xi >> 1; }
+        const long long v = vpos(g, s, a, b);
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-          const float bj = sign_pm1(j == 0 ? val : __fsub_rn(val, acc));
-          word[j] |= (bj > 0.0f ? 1u : 0u) << cc;
-          if (j < ns) {
-            const float t = __fmul_rn(sc[j], bj);
-            acc = (j == 0) ? t : __fadd_rn(acc, t);
-            res = __fsub_rn(res, __fmul_rn(sc[j], sign_pm1(res)));
-          }
-        }
-        gsum += fabsf(res);
+        for (int j = 0; j < NPL; ++j)
+          planes[(((long long)j * g.nphase + phase) * g.vtot + v) * g.cw + cg] = word[p][j];
+        acc_sum += (double)gsum[p];
       }
-      acc_sum += (double)gsum;
-#pragma unroll
-      for (int j = 0; j < NPL; ++j)
-        planes[(((long long)j * g.nphase + phase) * g.vtot + v) * g.cw + cg] = word[j];
+      if (++xi == g.w) { xi = 0; ++yi; }
     }
   }
   if (last_scale == nullptr) return;
@@ -195,7 +251,6 @@ encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const flo
     counter[s] = 0u;
   }
 }
-
 
 }  // namespace lsq
 
@@ -336,14 +391,25 @@ int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alpha, cons
   ActGeom dg = to_dev(*g);
   const Prologue dp = to_dev(pro);
   if (dp.a && dp.channels != g->c) { set_error("lsq_encode_act: prologue has %d channels, tensor has %d", dp.channels, g->c); return LSQ_ERR_ARG; }
-  dim3 grid((unsigned)((hw + kEncThreads - 1) / kEncThreads), (unsigned)g->n);
+  // 16-byte loads need every channel plane of every sample to start 16-byte aligned
+  const bool vec4 = (hw % 4 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0);
+  const int nq = vec4 ? hw / 4 : hw;
+  dim3 grid((unsigned)(((long long)nq * g->cw + kEncThreads - 1) / kEncThreads), (unsigned)g->n);
+  const size_t smem = (size_t)g->cw * 32 * sizeof(float2);
+  LSQ_CHECK_ARG(smem <= 40 * 1024, "lsq_encode_act: too many channels (%d)", g->c);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (nplanes) {
-    case 1: encode_act_kernel<1><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp); break;
-    case 2: encode_act_kernel<2><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp); break;
-    case 3: encode_act_kernel<3><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp); break;
-    default: encode_act_kernel<4><<<grid, kEncThreads, 0, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp); break;
+#define LSQ_ENC(NPL, VEC) encode_act_kernel<NPL, VEC><<<grid, kEncThreads, smem, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp)
+  switch (nplanes * 2 + (vec4 ? 1 : 0)) {
+    case 2: LSQ_ENC(1, 1); break;
+    case 3: LSQ_ENC(1, 4); break;
+    case 4: LSQ_ENC(2, 1); break;
+    case 5: LSQ_ENC(2, 4); break;
+    case 6: LSQ_ENC(3, 1); break;
+    case 7: LSQ_ENC(3, 4); break;
+    case 8: LSQ_ENC(4, 1); break;
+    default: LSQ_ENC(4, 4); break;
   }
+#undef LSQ_ENC
   LSQ_CUDA_LAUNCH_CHECK("encode_act_kernel");
   return LSQ_OK;
 }
