@@ -32,6 +32,7 @@ constexpr int kListBins = 1024;   // bins of a shared-memory refinement window
 constexpr int kListBinsPerThread = kListBins / kSolveThreads;
 constexpr int kListBinsLog2 = 10;
 constexpr int kCap = 8192;      // list A: elements of the flagged ranges of a global window
+constexpr int kSmallCap = 21504;  // list A when it holds a whole (sampled) row: it then extends over Bins::l.ext
 constexpr int kFineCap = 2048;  // list B: elements that are sorted and evaluated one by one
 constexpr int kMaxRanges = 4;
 constexpr int kMaxFlag = 64;
@@ -39,8 +40,10 @@ constexpr int kStack = 24;
 constexpr int kTopShift = 18;
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 constexpr int kLoadBatch = 8;
+constexpr int kMaxGroups = 128;        // flagged 16-bin groups whose bins get the fine test in parallel
+constexpr int kMaxProChannels = 512;   // prologue tables up to this many channels are staged in shared memory
+constexpr int kFineShift = 14, kFineListShift = 16;   // bin width of a top window anchored at the clamp bound
 constexpr uint32_t kMaxExactN = 262144;  // sum(m >> 9) of a bin fits 32 bits up to this many elements
-
 // A contiguous run of the sorted row: keys in [klo, khi), preceded by cnt_below elements whose
 // exact sum is sum_below, followed by next_key (smallest key >= khi, or the row maximum).
 struct Span {
@@ -60,17 +63,28 @@ struct Range {        // flagged bins [blo, bhi] of the current window
   uint32_t list_start;
 };
 
+// Shared memory (112 KB, two CTAs per SM).  Lifetimes overlap as little as possible so regions are reused:
+//   list_a                     : per-thread bin-group prefixes while a global window is scanned
+//   bins.l.ext                 : tail of list A when the whole sampled row lives in shared memory
+union Bins {
+  struct { uint32_t hist[kBins]; uint32_t bsum[kBins]; } g;     // global windows: counts, sum(m >> 9)
+  struct {
+    uint32_t ext[2 * kBins - 3 * kListBins];
+    uint32_t hist[kListBins], lo[kListBins], hi[kListBins];     // list windows: counts, sum(m & 0xFFF), sum(m >> 12)
+  } l;
+};
 struct SolveSmem {
-  uint32_t hist[kBins];
-  union { float f[kBins]; uint32_t lo[kBins]; } bsum;   // global windows: sum(m >> 9); list windows: sum(m & 0xFFF)
-  uint32_t bhi[kListBins];                               // list windows: sum(m >> 12)
-  uint32_t list_a[kCap];
   uint32_t list_b[kFineCap];
+  uint32_t list_a[kCap];
+  Bins bins;
+  float2 ab[kMaxProChannels];            // per-channel (scale, shift) of the fused prologue
   double red[32];
   double wsum[32];
   uint32_t wcnt[32];
   uint32_t wfirst[32];
-  int nflag;
+  uint32_t wnz[32];
+  int nflag, ngroup;
+  uint16_t glist[kMaxGroups];
   uint32_t fmin, fmax;
   uint16_t fbin[kMaxFlag];
   uint32_t fexcl[kMaxFlag];
@@ -83,20 +97,47 @@ struct SolveSmem {
   int nstack;
   Window stack[kStack];
   Window cur;
-  uint32_t cnt_below, min_above, kmin, kmax, nlist_a, nlist_b;
+  uint32_t cnt_below, min_above, win_min, kmin, kmax, nlist_a, nlist_b;
   int direct_eval, flags, action;   // action: 0 none, 1 collect ranges into a list
   double best_cost[32];
   uint32_t best_pos[32], best_key[32], ncand;
 };
+static_assert(sizeof(SolveSmem) <= 113 * 1024, "two CTAs per SM need <= 113 KB each (228 KB - 2 x 1 KB reserved)");
+static_assert(sizeof(Bins) == 2 * kBins * 4, "Bins views must have the same size");
+static_assert(offsetof(SolveSmem, bins) == (kFineCap + kCap) * 4, "list_a must run into bins.l.ext");
+static_assert(kSolveThreads * 16 <= kCap * 4, "group prefix records must fit list A");
+static_assert(kSmallCap <= kCap + 2 * kBins - 3 * kListBins, "small-row list does not fit");
+
+// Calls body(v, e0, e_end) on batches of sampled elements: this thread's elements are e = e0 + u * blockDim.x
+// (u < kLoadBatch, valid while e < e_end), v[u] = x[e * skip]; kLoadBatch independent loads are in flight per
+// thread.  Trip counts are warp uniform.  (A cp.async.bulk ring feeding the same loop was measured slower:
+// scripts/mb/mb_hist.cu, 3.4 vs 4.7 TB/s.)
+template <class Body>
+__device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip, uint32_t n, Body&& body) {
+  const int tid = threadIdx.x;
+  for (uint32_t eb = 0; eb < n; eb += kSolveThreads * kLoadBatch) {
+    float v[kLoadBatch];
+    const uint32_t e0 = eb + tid;
+#pragma unroll
+    for (int u = 0; u < kLoadBatch; ++u) {
+      const uint32_t e = e0 + u * kSolveThreads;
+      v[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
+    }
+    body(v, e0, min(n, eb + (uint32_t)(kSolveThreads * kLoadBatch)));
+  }
+}
 
 __device__ __forceinline__ float key_val(uint32_t k) { return __uint_as_float(k); }
+
+// 2^e as a double (-1022 <= e <= 1023): scaling by it is exact, like ldexp
+__device__ __forceinline__ double pow2d(int e) { return __hiloint2double((e + 1023) << 20, 0); }
 
 // exact value sum of `cnt` keys sharing one exponent: lo = sum(m & 0xFFF), hi = sum(m >> 12)
 __device__ __forceinline__ double exact_bin_sum(uint32_t any_key, uint32_t cnt, uint32_t lo, uint32_t hi) {
   const int e = (int)(any_key >> 23);
   const double msum = (double)hi * 4096.0 + (double)lo;
-  if (e == 0) return ldexp(msum, -149);
-  return ldexp((double)cnt * 8388608.0 + msum, e - 150);
+  if (e == 0) return msum * pow2d(-149);
+  return ((double)cnt * 8388608.0 + msum) * pow2d(e - 150);
 }
 
 // value sum of `cnt` keys sharing one exponent from s9 = sum(m >> 9): midpoint of the possible range,
@@ -104,8 +145,8 @@ __device__ __forceinline__ double exact_bin_sum(uint32_t any_key, uint32_t cnt, 
 __device__ __forceinline__ double approx_bin_sum(uint32_t any_key, uint32_t cnt, uint32_t s9) {
   const int e = (int)(any_key >> 23);
   const double msum = (double)s9 * 512.0 + 256.0 * (double)cnt;
-  if (e == 0) return ldexp(msum, -149);
-  return ldexp((double)cnt * 8388608.0 + msum, e - 150);
+  if (e == 0) return msum * pow2d(-149);
+  return ((double)cnt * 8388608.0 + msum) * pow2d(e - 150);
 }
 
 struct Best {
@@ -138,6 +179,47 @@ __device__ __forceinline__ double closed_cost2(double c, double k, double s_i, d
   const double sq = q_tot - 2.0 * c * s_tot + n * c * c;
   if (TERN) return sq - 2.0 * c * sabs + n * c * c;
   return sq - sabs * sabs / n;
+}
+
+// Can the bin of keys [elo_k, ehi_k] -- cnt elements summing to s, preceded in sorted order by excl elements
+// summing to pref (both known to a relative `marg`) and followed by a key of value <= nxt_hi -- contain a
+// position the reference accepts as a candidate (optimal.py:73-80)?  Conservative: intervals of the two
+// threshold functions over the bin are compared with the bin's value range.
+template <bool TERN>
+__device__ __forceinline__ bool may_hold(uint32_t elo_k, uint32_t ehi_k, uint32_t cnt, double s, uint32_t excl, double pref,
+                                         float nxt_hi, uint32_t n, double s_tot, uint32_t kmax, float marg) {
+  const uint32_t k0 = max(excl, 1u), k1 = min(excl + cnt, n - 1);
+  if (k0 > k1) return false;
+  const float eps = 4e-6f;
+  const float edge_lo = key_val(elo_k);
+  const float edge_hi = fmaxf(key_val(ehi_k), edge_lo);
+  // prefix sums at the first (k0) and last (k1) split of the bin, as [lo, hi] intervals
+  const float p0 = (float)pref, p1 = (float)(pref + s), rest0 = (float)(s_tot - pref), rest1 = (float)(s_tot - pref - s);
+  float lo0, hi0, r0lo, r0hi, lo1, hi1, r1lo, r1hi;
+  const float dm0 = marg * p0, dm1 = marg * p1;
+  if (excl >= 1u) { lo0 = p0 - dm0; hi0 = p0 + dm0; r0lo = rest0 - dm0; r0hi = rest0 + dm0; }
+  else { lo0 = p0 - dm0 + edge_lo; hi0 = p0 + dm0 + edge_hi; r0lo = rest0 - dm0 - edge_hi; r0hi = rest0 + dm0 - edge_lo; }
+  if (excl + cnt <= n - 1) { lo1 = p1 - dm1; hi1 = p1 + dm1; r1lo = rest1 - dm1; r1hi = rest1 + dm1; }
+  else { r1lo = r1hi = key_val(kmax); lo1 = hi1 = (float)(s_tot - (double)key_val(kmax)); }
+  // fast division: its 2 ulp are far inside eps
+  const float ih0 = __fdividef(0.5f, (float)(n - k0)), ih1 = __fdividef(0.5f, (float)(n - k1));
+  const float half_min = r0lo * ih0, half_max = r1hi * ih1;      // hi/2 is monotone in the split
+  // some threshold must reach the bin from above, and either pass below a later element of the bin or -- for
+  // the last element, whose threshold is at least r1lo * ih1 -- below the next key after the bin
+  bool hit = (half_max * (1.0f + eps) >= edge_lo) &&
+             (half_min * (1.0f - eps) <= edge_hi || r1lo * ih1 * (1.0f - eps) <= nxt_hi);
+  if (!TERN) {
+    const float ik0 = __fdividef(0.5f, (float)k0), ik1 = __fdividef(0.5f, (float)k1);
+    const float mid_min = fminf(r0lo * ih0 + lo0 * ik0, r0hi * ih0 + hi0 * ik0);
+    const float mid_max = fmaxf(r1lo * ih1 + lo1 * ik1, r1hi * ih1 + hi1 * ik1);
+    // (lo, rest) move in opposite directions: the extremes over the interval are at its ends,
+    // paired as (lo0, r0hi) / (hi0, r0lo); take the enclosing values to stay conservative
+    const float mid_min2 = fminf(mid_min, fminf(r0hi * ih0 + lo0 * ik0, r0lo * ih0 + hi0 * ik0));
+    const float mid_max2 = fmaxf(mid_max, fmaxf(r1hi * ih1 + lo1 * ik1, r1lo * ih1 + hi1 * ik1));
+    hit = hit || ((mid_max2 * (1.0f + eps) >= edge_lo) &&
+                  (mid_min2 * (1.0f - eps) <= edge_hi || (r1lo * ih1 + lo1 * ik1) * (1.0f - eps) <= nxt_hi));
+  }
+  return hit;
 }
 
 template <bool TERN>
@@ -221,6 +303,18 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
   const float* xr = x + row * len;
   const uint32_t n = (uint32_t)((len + skip - 1) / skip);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // fused per-channel affine prologue: the table is staged in shared memory (global loads of it miss L1
+  // behind the streamed row and stalled the passes)
+  const bool pro_on = pro.a != nullptr, pro_smem = pro_on && pro.channels <= kMaxProChannels;
+  if (pro_smem)
+    for (int c = tid; c < pro.channels; c += blockDim.x) sm.ab[c] = make_float2(__ldg(pro.a + c), __ldg(pro.b + c));
+  auto prologue = [&](float v, long long index_in_row) -> float {
+    if (!pro_on) return v;
+    const unsigned c = (unsigned)(((unsigned long long)index_in_row * pro.magic) >> 40);
+    if (pro_smem) { const float2 k = sm.ab[c]; return fmaf(v, k.x, k.y); }
+    return fmaf(v, __ldg(pro.a + c), __ldg(pro.b + c));
+  };
+  uint32_t* const list_a = sm.list_a;      // runs on into sm.bins.l.ext for rows held entirely in shared memory
   Best best{1e300, 0xFFFFFFFFu, 0u};
   uint32_t ncand = 0;
   int passes = 0;
@@ -243,16 +337,16 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 
   double s_tot = 0.0, q_tot = 0.0;
   bool first = true;          // row totals not yet known
-  if (n <= (uint32_t)kCap) {
+  if (n <= (uint32_t)kSmallCap) {
     // ---- small row: list A is the whole row --------------------------------------------------
     double ls = 0.0, lq = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u;
     for (uint32_t e = tid; e < n; e += blockDim.x) {
-      const float a = fabsf(clamp_sym(apply_prologue(pro, __ldg(xr + (long long)e * skip), (long long)e * skip), alpha));
+      const float a = fabsf(clamp_sym(prologue(__ldg(xr + (long long)e * skip), (long long)e * skip), alpha));
       const uint32_t k = __float_as_uint(a);
       ls += (double)a; lq += (double)a * (double)a;
       kmn = min(kmn, k); kmx = max(kmx, k);
-      sm.list_a[e] = k;
+      list_a[e] = k;
     }
     s_tot = block_sum(ls, sm.red);
     q_tot = block_sum(lq, sm.red);
@@ -266,12 +360,16 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       Window w;
       w.base.klo = 0ull; w.base.khi = 1ull << 32; w.base.sum_below = 0.0; w.base.cnt_below = 0u; w.base.next_key = sm.kmax;
       w.klo = 0u; w.shift = 31 - kListBinsLog2; w.from_list = 1;
+      const uint32_t ka = __float_as_uint(alpha) >> kFineListShift;     // clamped rows: all keys <= key(alpha)
+      if (alpha > 0.0f && ka + 1u >= (uint32_t)kListBins) { w.klo = (ka + 1u - kListBins) << kFineListShift; w.shift = kFineListShift; }
       sm.stack[0] = w; sm.nstack = 1;
     }
   } else if (tid == 0) {
     Window w;
     w.base.klo = 0ull; w.base.khi = 1ull << 32; w.base.sum_below = 0.0; w.base.cnt_below = 0u; w.base.next_key = 0u;
     w.klo = 0u; w.shift = kTopShift; w.from_list = 0;
+    const uint32_t ka = __float_as_uint(alpha) >> kFineShift;
+    if (alpha > 0.0f && ka + 1u >= (uint32_t)kBins) { w.klo = (ka + 1u - kBins) << kFineShift; w.shift = kFineShift; }
     sm.stack[0] = w; sm.nstack = 1;
   }
   __syncthreads();
@@ -283,17 +381,25 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     if (pending == 0) break;
     if (tid == 0) {
       sm.cur = sm.stack[--sm.nstack];
-      sm.cnt_below = 0u; sm.min_above = kNoKey; sm.nflag = 0; sm.fmin = kNoKey; sm.fmax = 0u;
+      sm.cnt_below = 0u; sm.min_above = kNoKey; sm.win_min = kNoKey; sm.nflag = 0; sm.fmin = kNoKey; sm.fmax = 0u;
       sm.nrange = 0; sm.direct_eval = 0; sm.action = 0;
     }
-    for (int b = tid; b < kBins; b += blockDim.x) { sm.hist[b] = 0u; sm.bsum.lo[b] = 0u; }
-    for (int b = tid; b < kListBins; b += blockDim.x) sm.bhi[b] = 0u;
-    __syncthreads();
-    LSQ_TICK(0);   // pop + zero
+    __syncthreads();              // sm.cur is published
     const Window W = sm.cur;
     const uint32_t klo = W.klo;
     const int shift = W.shift;
     const bool from_list = W.from_list != 0;
+    // bin arrays of this window: counts, low sums, (list windows) high sums
+    uint32_t* const hist = from_list ? sm.bins.l.hist : sm.bins.g.hist;
+    uint32_t* const blo_sum = from_list ? sm.bins.l.lo : sm.bins.g.bsum;
+    uint32_t* const bhi_sum = sm.bins.l.hi;
+    if (from_list) {
+      for (int b = tid; b < kListBins; b += blockDim.x) { hist[b] = 0u; blo_sum[b] = 0u; bhi_sum[b] = 0u; }
+    } else {
+      for (int b = tid; b < kBins; b += blockDim.x) { hist[b] = 0u; blo_sum[b] = 0u; }
+    }
+    __syncthreads();
+    LSQ_TICK(0);   // pop + zero
     const int nbins = from_list ? kListBins : kBins;
     const unsigned long long khi = min((unsigned long long)klo + ((unsigned long long)nbins << shift), W.base.khi);
     // how bin sums are known: 2 = exact integers (list windows), 1 = mantissa sums truncated to 14 bits
@@ -304,45 +410,42 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 
     // ---- histogram pass over the window's source ---------------------------------------------
     double ls = 0.0, lq = 0.0, lb = 0.0;
-    uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey;
+    uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey, kwin = kNoKey;
     if (!from_list) {
-      // kLoadBatch independent loads in flight per thread (the pass is latency bound otherwise)
-      for (uint32_t e0 = tid; e0 < n; e0 += blockDim.x * kLoadBatch) {
-        float v[kLoadBatch];
+      sweep_row(xr, skip, n,
+                [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
-          const uint32_t e = e0 + u * blockDim.x;
-          v[u] = (e < n) ? apply_prologue(pro, __ldg(xr + (long long)e * skip), (long long)e * skip) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < kLoadBatch; ++u) {
-          if (e0 + u * blockDim.x >= n) break;
-          const float a = fabsf(clamp_sym(v[u], alpha));
+          const uint32_t e = e0 + u * kSolveThreads;
+          if (e >= e_end) break;
+          const float a = fabsf(clamp_sym(prologue(v[u], (long long)e * skip), alpha));
           const uint32_t k = __float_as_uint(a);
           if (first) { ls += (double)a; lq += (double)a * (double)a; kmn = min(kmn, k); kmx = max(kmx, k); }
           if (k < klo) { ++cb; lb += (double)a; }
           else if (k > khi_incl) { mab = min(mab, k); }
           else {
             const uint32_t b = (k - klo) >> shift;
-            atomicAdd(&sm.hist[b], 1u);
-            if (sum_mode == 1) atomicAdd(&sm.bsum.lo[b], (k & 0x7FFFFFu) >> 9);
+            kwin = min(kwin, k);
+            atomicAdd(&hist[b], 1u);
+            if (sum_mode == 1) atomicAdd(&blo_sum[b], (k & 0x7FFFFFu) >> 9);
           }
         }
-      }
+      });
       ++passes;
     } else {
       const uint32_t la = sm.nlist_a;
       for (uint32_t e = tid; e < la; e += blockDim.x) {
-        const uint32_t k = sm.list_a[e];
+        const uint32_t k = list_a[e];
         if (k < base_lo || k > base_hi_incl) continue;
         if (k < klo) { ++cb; lb += (double)key_val(k); }
         else if (k > khi_incl) { mab = min(mab, k); }
         else {
           const uint32_t b = (k - klo) >> shift;
           const uint32_t m = k & 0x7FFFFFu;
-          atomicAdd(&sm.hist[b], 1u);
-          atomicAdd(&sm.bsum.lo[b], m & 0xFFFu);
-          atomicAdd(&sm.bhi[b], m >> 12);
+          kwin = min(kwin, k);
+          atomicAdd(&hist[b], 1u);
+          atomicAdd(&blo_sum[b], m & 0xFFFu);
+          atomicAdd(&bhi_sum[b], m >> 12);
         }
       }
     }
@@ -360,7 +463,8 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     const double sum_below_w = W.base.sum_below + block_sum(lb, sm.red);
     cb = (uint32_t)__reduce_add_sync(0xffffffffu, cb);
     mab = warp_min_u32(mab);
-    if (lane == 0) { atomicAdd(&sm.cnt_below, cb); atomicMin(&sm.min_above, mab); }
+    kwin = warp_min_u32(kwin);
+    if (lane == 0) { atomicAdd(&sm.cnt_below, cb); atomicMin(&sm.min_above, mab); atomicMin(&sm.win_min, kwin); }
     __syncthreads();
     const uint32_t kmax = sm.kmax;
     const uint32_t base_next = (W.base.next_key != 0u) ? W.base.next_key : kmax;   // top window: maximum not known at push time
@@ -368,119 +472,170 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     const uint32_t cnt_below_w = W.base.cnt_below + sm.cnt_below;
 
     LSQ_TICK(3);   // reductions
-    // ---- scan bins: thread owns bins [8*tid, 8*tid+8) ---------------------------------------------
-    uint32_t c[kBinsPerThread];
-    double s[kBinsPerThread];
-    uint32_t ct = 0; double stt = 0.0; uint32_t fn = kNoKey;
+    // ---- S1: prefix counts / sums over the bins (thread owns bpt consecutive bins) ------------------
     const int bpt = from_list ? kListBinsPerThread : kBinsPerThread;
-#pragma unroll
-    for (int j = 0; j < kBinsPerThread; ++j) {
-      const uint32_t b = tid * bpt + j;
-      if (j >= bpt) { c[j] = 0u; s[j] = 0.0; continue; }
-      c[j] = sm.hist[b];
-      if (c[j] == 0u) s[j] = 0.0;
-      else if (shift == 0) s[j] = (double)c[j] * (double)key_val(klo + b);
-      else if (sum_mode == 2) s[j] = exact_bin_sum(klo + (b << shift), c[j], sm.bsum.lo[b], sm.bhi[b]);
-      else if (sum_mode == 1) s[j] = approx_bin_sum(klo + (b << shift), c[j], sm.bsum.lo[b]);
-      else {
-        const unsigned long long e1 = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, 0x7F800000ull);
-        s[j] = 0.5 * (double)c[j] * ((double)key_val(klo + (b << shift)) + (double)key_val((uint32_t)e1));
+    auto bin_sum = [&](uint32_t b, uint32_t cnt) -> double {
+      if (shift == 0) return (double)cnt * (double)key_val(klo + b);
+      if (sum_mode == 2) return exact_bin_sum(klo + (b << shift), cnt, blo_sum[b], bhi_sum[b]);
+      if (sum_mode == 1) return approx_bin_sum(klo + (b << shift), cnt, blo_sum[b]);
+      const unsigned long long e1 = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, 0x7F800000ull);
+      return 0.5 * (double)cnt * ((double)key_val(klo + (b << shift)) + (double)key_val((uint32_t)e1));
+    };
+    uint32_t ct = 0, nz = 0, fn = kNoKey;
+    double stt = 0.0;
+    for (int j = 0; j < bpt; ++j) {
+      const uint32_t b = tid * bpt + j, cnt = hist[b];
+      if (cnt != 0u) {
+        ct += cnt; stt += bin_sum(b, cnt); ++nz;
+        if (fn == kNoKey) fn = b;
       }
-      ct += c[j]; stt += s[j];
-      if (c[j] != 0u && fn == kNoKey) fn = b;
     }
-    uint32_t ci = ct; double si = stt;
+    uint32_t ci = ct, zi = nz;
+    double si = stt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t tc = __shfl_up_sync(0xffffffffu, ci, o);
-      double ts = __shfl_up_sync(0xffffffffu, si, o);
-      if (lane >= o) { ci += tc; si += ts; }
+      const uint32_t tc = __shfl_up_sync(0xffffffffu, ci, o);
+      const uint32_t tz = __shfl_up_sync(0xffffffffu, zi, o);
+      const double ts = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) { ci += tc; zi += tz; si += ts; }
     }
     uint32_t sfx = fn;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_down_sync(0xffffffffu, sfx, o);
+      const uint32_t t = __shfl_down_sync(0xffffffffu, sfx, o);
       if (lane + o < 32) sfx = min(sfx, t);
     }
     uint32_t nxt_in_warp = __shfl_down_sync(0xffffffffu, sfx, 1);
     if (lane == 31) nxt_in_warp = kNoKey;
     __syncthreads();
-    if (lane == 31) { sm.wcnt[wid] = ci; sm.wsum[wid] = si; }
+    if (lane == 31) { sm.wcnt[wid] = ci; sm.wsum[wid] = si; sm.wnz[wid] = zi; }
     if (lane == 0) sm.wfirst[wid] = sfx;
     __syncthreads();
-    uint32_t coff = 0; double soff = 0.0;
-    for (int w = 0; w < wid; ++w) { coff += sm.wcnt[w]; soff += sm.wsum[w]; }
+    uint32_t coff = 0, zoff = 0, nz_total = 0;
+    double soff = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      if (w < wid) { coff += sm.wcnt[w]; soff += sm.wsum[w]; zoff += sm.wnz[w]; }
+      nz_total += sm.wnz[w];
+    }
     uint32_t nxt_after = nxt_in_warp;
     for (int w = wid + 1; w < (int)(blockDim.x >> 5) && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
-    uint32_t excl = cnt_below_w + coff + ci - ct;
-    double pref = sum_below_w + soff + si - stt;
+    const uint32_t excl0 = cnt_below_w + coff + ci - ct;
+    const double pref0 = sum_below_w + soff + si - stt;
+    const uint32_t zidx0 = zoff + zi - nz;
 
-    // ---- flag bins that can hold a candidate ------------------------------------------------------
-    // relative uncertainty of the prefix sums (see sum_mode) and of the fp32 threshold arithmetic below
+    // ---- S2: flag the bins that can hold a candidate ------------------------------------------------
+    // relative uncertainty of the prefix sums (see sum_mode); the fp32 threshold arithmetic adds eps (may_hold)
     const float marg = (shift == 0 || sum_mode == 2) ? 0.0f : (sum_mode == 1 ? 1e-4f : 0.02f);
-    const float eps = 4e-6f;
-#pragma unroll
-    for (int j = 0; j < kBinsPerThread; ++j) {
-      if (c[j] == 0u) continue;
-      const uint32_t b = tid * bpt + j;
-      uint32_t nb = kNoKey;
-#pragma unroll
-      for (int j2 = kBinsPerThread - 1; j2 > j; --j2)
-        if (c[j2] != 0u) nb = tid * bpt + j2;
-      if (nb == kNoKey) nb = nxt_after;
-      const uint32_t k0 = max(excl, 1u), k1 = min(excl + c[j], n - 1);
-      if (k0 <= k1) {
-        const unsigned long long elo_k = min((unsigned long long)klo + ((unsigned long long)b << shift), 0x7F800000ull);
-        const unsigned long long ehi_k = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, (unsigned long long)kmax);
-        const float edge_lo = key_val((uint32_t)elo_k);
-        const float edge_hi = fmaxf(key_val((uint32_t)ehi_k), edge_lo);
-        // prefix sums at the first (k0) and last (k1) split of the bin, as [lo, hi] intervals
-        const float p0 = (float)pref, p1 = (float)(pref + s[j]), rest0 = (float)(s_tot - pref), rest1 = (float)(s_tot - pref - s[j]);
-        float lo0, hi0, r0lo, r0hi, lo1, hi1, r1lo, r1hi;
-        const float dm0 = marg * p0, dm1 = marg * p1;
-        if (excl >= 1u) { lo0 = p0 - dm0; hi0 = p0 + dm0; r0lo = rest0 - dm0; r0hi = rest0 + dm0; }
-        else { lo0 = p0 - dm0 + edge_lo; hi0 = p0 + dm0 + edge_hi; r0lo = rest0 - dm0 - edge_hi; r0hi = rest0 + dm0 - edge_lo; }
-        if (excl + c[j] <= n - 1) { lo1 = p1 - dm1; hi1 = p1 + dm1; r1lo = rest1 - dm1; r1hi = rest1 + dm1; }
-        else { r1lo = r1hi = key_val(kmax); lo1 = hi1 = (float)(s_tot - (double)key_val(kmax)); }
-        float nxt_hi;
-        if (nb != kNoKey) {
-          const unsigned long long nh = min((unsigned long long)klo + ((unsigned long long)(nb + 1) << shift) - 1ull, (unsigned long long)kmax);
-          const unsigned long long nl = min((unsigned long long)klo + ((unsigned long long)nb << shift), 0x7F800000ull);
-          nxt_hi = fmaxf(key_val((uint32_t)nh), key_val((uint32_t)nl));
-        } else {
-          nxt_hi = key_val(min_above);
-        }
-        const float ih0 = 0.5f / (float)(n - k0), ih1 = 0.5f / (float)(n - k1);
-        const float half_min = r0lo * ih0, half_max = r1hi * ih1;      // hi/2 is monotone in the split
-        bool hit = (half_max * (1.0f + eps) >= edge_lo) &&
-                   (half_min * (1.0f - eps) <= edge_hi || half_max * (1.0f - eps) <= nxt_hi);
-        if (!TERN) {
-          const float ik0 = 0.5f / (float)k0, ik1 = 0.5f / (float)k1;
-          const float mid_min = fminf(r0lo * ih0 + lo0 * ik0, r0hi * ih0 + hi0 * ik0) ;
-          const float mid_max = fmaxf(r1lo * ih1 + lo1 * ik1, r1hi * ih1 + hi1 * ik1);
-          // (lo, rest) move in opposite directions: the extremes over the interval are at its ends,
-          // paired as (lo0, r0hi) / (hi0, r0lo); take the enclosing values to stay conservative
-          const float mid_min2 = fminf(mid_min, fminf(r0hi * ih0 + lo0 * ik0, r0lo * ih0 + hi0 * ik0));
-          const float mid_max2 = fmaxf(mid_max, fmaxf(r1hi * ih1 + lo1 * ik1, r1lo * ih1 + hi1 * ik1));
-          hit = hit || ((mid_max2 * (1.0f + eps) >= edge_lo) &&
-                        (mid_min2 * (1.0f - eps) <= edge_hi || mid_max2 * (1.0f - eps) <= nxt_hi));
-        }
-        if (hit) {
-          const int slot = atomicAdd(&sm.nflag, 1);
-          atomicMin(&sm.fmin, b); atomicMax(&sm.fmax, b);
-          if (slot < kMaxFlag) {
-            sm.fbin[slot] = (uint16_t)b; sm.fexcl[slot] = excl; sm.fsumb[slot] = pref;
-            sm.fnext[slot] = (nb != kNoKey) ? (uint32_t)min((unsigned long long)klo + ((unsigned long long)nb << shift), 0xFFFFFFFEull) : min_above;
-          } else if (shift == 0) {
-            const uint32_t kv = klo + b;
-            const uint32_t knx = (nb != kNoKey) ? klo + nb : min_above;
-            for (uint32_t jj = 0; jj < c[j]; ++jj)
-              try_position<TERN>(best, ncand, kv, (jj + 1 < c[j]) ? kv : knx, excl + jj,
-                                 pref + (double)(jj + 1) * (double)key_val(kv), n, s_tot, q_tot);
+    auto bin_upper = [&](uint32_t b) -> float {      // largest value a key of bin b can have
+      const unsigned long long nh = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, (unsigned long long)kmax);
+      const unsigned long long nl = min((unsigned long long)klo + ((unsigned long long)b << shift), 0x7F800000ull);
+      return fmaxf(key_val((uint32_t)nh), key_val((uint32_t)nl));
+    };
+    auto test_bin = [&](uint32_t b, uint32_t cnt, double s, uint32_t excl, double pref, uint32_t nb) {
+      const unsigned long long elo_k = min((unsigned long long)klo + ((unsigned long long)b << shift), 0x7F800000ull);
+      const unsigned long long ehi_k = min((unsigned long long)klo + ((unsigned long long)(b + 1) << shift) - 1ull, (unsigned long long)kmax);
+      const float nxt_hi = (nb != kNoKey) ? bin_upper(nb) : key_val(min_above);
+      if (!may_hold<TERN>((uint32_t)elo_k, (uint32_t)ehi_k, cnt, s, excl, pref, nxt_hi, n, s_tot, kmax, marg)) return;
+      const int slot = atomicAdd(&sm.nflag, 1);
+      atomicMin(&sm.fmin, b); atomicMax(&sm.fmax, b);
+      if (slot < kMaxFlag) {
+        sm.fbin[slot] = (uint16_t)b; sm.fexcl[slot] = excl; sm.fsumb[slot] = pref;
+        sm.fnext[slot] = (nb != kNoKey) ? (uint32_t)min((unsigned long long)klo + ((unsigned long long)nb << shift), 0xFFFFFFFEull) : min_above;
+      } else if (shift == 0) {
+        const uint32_t kv = klo + b;
+        const uint32_t knx = (nb != kNoKey) ? klo + nb : min_above;
+        for (uint32_t jj = 0; jj < cnt; ++jj)
+          try_position<TERN>(best, ncand, kv, (jj + 1 < cnt) ? kv : knx, excl + jj,
+                             pref + (double)(jj + 1) * (double)key_val(kv), n, s_tot, q_tot);
+      }
+    };
+    if (from_list) {
+      // two bins per thread: tested in place (list A is the source of this window and stays intact)
+      uint32_t excl = excl0;
+      double pref = pref0;
+      for (int j = 0; j < bpt; ++j) {
+        const uint32_t b = tid * bpt + j, cnt = hist[b];
+        if (cnt == 0u) continue;
+        uint32_t nb = kNoKey;
+        for (int j2 = bpt - 1; j2 > j; --j2)
+          if (hist[tid * bpt + j2] != 0u) nb = tid * bpt + j2;
+        if (nb == kNoKey) nb = nxt_after;
+        const double s = bin_sum(b, cnt);
+        test_bin(b, cnt, s, excl, pref, nb);
+        excl += cnt; pref += s;
+      }
+    } else {
+      // Two levels: every thread tests the union of its own bins as one coarse bin (one balanced test per
+      // thread; may_hold is conservative for any bin width); only the bins of the few flagged groups get the
+      // fine test, spread over the block.  Group prefixes are parked in the idle list A.
+      uint32_t* const gexcl = list_a;
+      uint32_t* const gnext = list_a + kSolveThreads;
+      double* const gpref = reinterpret_cast<double*>(list_a + 2 * kSolveThreads);
+      if (tid == 0) sm.ngroup = 0;
+      __syncthreads();
+      gexcl[tid] = excl0; gnext[tid] = nxt_after; gpref[tid] = pref0;
+      if (nz != 0u) {
+        const unsigned long long elo_k = min((unsigned long long)klo + ((unsigned long long)(tid * bpt) << shift), 0x7F800000ull);
+        const unsigned long long ehi_k = min((unsigned long long)klo + ((unsigned long long)(tid * bpt + bpt) << shift) - 1ull, (unsigned long long)kmax);
+        const float nxt_hi = (nxt_after != kNoKey) ? bin_upper(nxt_after) : key_val(min_above);
+        if (may_hold<TERN>((uint32_t)elo_k, (uint32_t)ehi_k, ct, stt, excl0, pref0, nxt_hi, n, s_tot, kmax, marg)) {
+          const int slot = atomicAdd(&sm.ngroup, 1);
+          if (slot < kMaxGroups) sm.glist[slot] = (uint16_t)tid;
+          else {
+            // more flagged groups than the list holds (not seen in practice): the owner tests its bins itself
+            uint32_t excl = excl0;
+            double pref = pref0;
+            for (int j = 0; j < bpt; ++j) {
+              const uint32_t b = tid * bpt + j, cnt = hist[b];
+              if (cnt == 0u) continue;
+              uint32_t nb = kNoKey;
+              for (int j2 = bpt - 1; j2 > j; --j2)
+                if (hist[tid * bpt + j2] != 0u) nb = tid * bpt + j2;
+              if (nb == kNoKey) nb = nxt_after;
+              const double s = bin_sum(b, cnt);
+              test_bin(b, cnt, s, excl, pref, nb);
+              excl += cnt; pref += s;
+            }
           }
         }
       }
-      excl += c[j]; pref += s[j];
+      __syncthreads();
+      const uint32_t nfine = (uint32_t)min(sm.ngroup, kMaxGroups) * (uint32_t)bpt;
+      for (uint32_t idx = tid; idx < nfine; idx += blockDim.x) {
+        const uint32_t gid = sm.glist[idx / bpt], j = idx % bpt;
+        const uint32_t b = gid * bpt + j, cnt = hist[b];
+        if (cnt == 0u) continue;
+        uint32_t excl = gexcl[gid];
+        double pref = gpref[gid];
+        for (uint32_t j1 = 0; j1 < j; ++j1) {
+          const uint32_t c1 = hist[gid * bpt + j1];
+          if (c1 != 0u) { excl += c1; pref += bin_sum(gid * bpt + j1, c1); }
+        }
+        uint32_t nb = kNoKey;
+        for (uint32_t j2 = bpt - 1; j2 > j; --j2)
+          if (hist[gid * bpt + j2] != 0u) nb = gid * bpt + j2;
+        if (nb == kNoKey) nb = gnext[gid];
+        test_bin(b, cnt, bin_sum(b, cnt), excl, pref, nb);
+      }
+      __syncthreads();
+    }
+    // the part of the base span below the window (anchored top windows) is one pseudo bin: if it could hold
+    // a candidate it gets its own window (never seen on clamped activations; kept for exactness)
+    if (tid == 0 && sm.cnt_below != 0u && (unsigned long long)klo > W.base.klo && shift != 0) {
+      uint32_t fb = kNoKey;
+      for (int w = 0; w < (int)(blockDim.x >> 5) && fb == kNoKey; ++w) fb = sm.wfirst[w];
+      const float nxt_hi = (fb != kNoKey) ? bin_upper(fb) : key_val(min_above);
+      if (may_hold<TERN>((uint32_t)W.base.klo, klo - 1u, sm.cnt_below, sum_below_w - W.base.sum_below, W.base.cnt_below,
+                         W.base.sum_below, nxt_hi, n, s_tot, kmax, 0.0f)) {
+        if (sm.nstack < kStack) {
+          Window ch;
+          ch.base = W.base; ch.base.khi = klo; ch.base.next_key = (sm.win_min != kNoKey) ? sm.win_min : min_above;
+          ch.klo = (uint32_t)W.base.klo; ch.shift = from_list ? 31 - kListBinsLog2 : kTopShift; ch.from_list = W.from_list;
+          sm.stack[sm.nstack++] = ch;
+        } else {
+          sm.flags |= 1;
+        }
+      }
     }
     __syncthreads();
 
@@ -504,8 +659,8 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
         Range* R = sm.rng;
         if (sm.nflag > kMaxFlag) {
           uint32_t cbw = cnt_below_w, cnt = 0;
-          for (uint32_t b = 0; b < sm.fmin; ++b) cbw += sm.hist[b];
-          for (uint32_t b = sm.fmin; b <= sm.fmax; ++b) cnt += sm.hist[b];
+          for (uint32_t b = 0; b < sm.fmin; ++b) cbw += hist[b];
+          for (uint32_t b = sm.fmin; b <= sm.fmax; ++b) cnt += hist[b];
           R[0].blo = sm.fmin; R[0].bhi = sm.fmax; R[0].cnt_below = cbw; R[0].count = cnt;
           nr = 1;
         } else {
@@ -514,7 +669,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
           uint32_t r_end = 0;
           for (int i = 0; i < nf; ++i) {
             const int sl = ord[i];
-            const uint32_t b = sm.fbin[sl], ex = sm.fexcl[sl], en = ex + sm.hist[b];
+            const uint32_t b = sm.fbin[sl], ex = sm.fexcl[sl], en = ex + hist[b];
             if (nr > 0 && r_end == ex && nr <= kMaxRanges) { R[nr - 1].bhi = b; R[nr - 1].count = en - R[nr - 1].cnt_below; }
             else if (nr < kMaxRanges) { R[nr].blo = b; R[nr].bhi = b; R[nr].cnt_below = ex; R[nr].count = en - ex; ++nr; }
             else {
@@ -567,7 +722,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     if (sm.direct_eval > 0) {
       const int nf = sm.direct_eval;
       for (int sl = 0; sl < nf; ++sl) {
-        const uint32_t b = sm.fbin[sl], cnt = sm.hist[b], kv = klo + b;
+        const uint32_t b = sm.fbin[sl], cnt = hist[b], kv = klo + b;
         const double base = sm.fsumb[sl], v = (double)key_val(kv);
         for (uint32_t jj = tid; jj < cnt; jj += blockDim.x)
           try_position<TERN>(best, ncand, kv, (jj + 1 < cnt) ? kv : sm.fnext[sl], sm.fexcl[sl] + jj,
@@ -591,21 +746,16 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       }
       __syncthreads();
       if (!from_list) {
-        // warp-uniform trip count: the slot allocation below uses full-warp shuffles
-        for (uint32_t eb = (uint32_t)(tid & ~31); eb < n; eb += blockDim.x * kLoadBatch) {
-          const uint32_t e0 = eb + lane;
-          float v[kLoadBatch];
-#pragma unroll
-          for (int u = 0; u < kLoadBatch; ++u) {
-            const uint32_t e = e0 + u * blockDim.x;
-            v[u] = (e < n) ? apply_prologue(pro, __ldg(xr + (long long)e * skip), (long long)e * skip) : 0.0f;
-          }
+        sweep_row(xr, skip, n,
+                  [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
           uint32_t matched = 0u;
+          uint32_t keys[kLoadBatch];
 #pragma unroll
           for (int u = 0; u < kLoadBatch; ++u) {
-            if (e0 + u * blockDim.x >= n) break;
-            const float a = fabsf(clamp_sym(v[u], alpha));
+            if (e0 + u * kSolveThreads >= e_end) break;
+            const float a = fabsf(clamp_sym(prologue(v[u], (long long)(e0 + u * kSolveThreads) * skip), alpha));
             const uint32_t k = __float_as_uint(a);
+            keys[u] = k;
 #pragma unroll
             for (int g = 0; g < kMaxRanges; ++g) {
               if (g >= nc) continue;
@@ -631,16 +781,16 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 #pragma unroll
             for (int u = 0; u < kLoadBatch; ++u)
               if ((matched >> u) & 1u) {
-                if (pos < (uint32_t)kCap) sm.list_a[pos] = __float_as_uint(fabsf(clamp_sym(v[u], alpha)));
+                if (pos < (uint32_t)kCap) list_a[pos] = keys[u];
                 ++pos;
               }
           }
-        }
+        });
         ++passes;
       } else {
         const uint32_t la = sm.nlist_a;
         for (uint32_t e = tid; e < la; e += blockDim.x) {
-          const uint32_t k = sm.list_a[e];
+          const uint32_t k = list_a[e];
           if (k < base_lo || k > base_hi_incl) continue;
 #pragma unroll
           for (int g = 0; g < kMaxRanges; ++g) {
@@ -672,9 +822,20 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       __syncthreads();
       LSQ_TICK(8);   // collection reductions
       if (!from_list) {
-        // ranges of the global row are now in list A: refine each one in shared memory
+        // ranges of the global row are now in list A
         const uint32_t L = min(sm.nlist_a, (uint32_t)kCap);
-        if (tid == 0) {
+        if (sm.nlist_a <= (uint32_t)kFineCap) {
+          // few elements (the usual case with a fine top window): sort them -- every range becomes one
+          // ascending segment -- and give each element the reference's own candidate test
+          uint32_t lp = 2;
+          while (lp < L) lp <<= 1;
+          for (uint32_t e = L + tid; e < lp; e += blockDim.x) list_a[e] = kNoKey;
+          __syncthreads();
+          bitonic_sort(list_a, lp);
+          evaluate_list<TERN>(sm, list_a, L, nc, n, s_tot, q_tot, best, ncand);
+          LSQ_TICK(9);   // sort + evaluate
+        } else if (tid == 0) {
+          // too many: refine each range in shared memory with exact integer bin sums
           if (sm.nlist_a > (uint32_t)kCap) { sm.flags |= 2; sm.nlist_a = kCap; }
           for (int g = nc - 1; g >= 0; --g) {
             const Range& r = sm.rng[g];
@@ -703,8 +864,8 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
           double part = 0.0;
           const uint32_t blo = sm.rng[g].blo;
           for (uint32_t b = tid; b < blo; b += blockDim.x) {
-            const uint32_t cc = sm.hist[b];
-            if (cc) part += exact_bin_sum(klo + (b << shift), cc, sm.bsum.lo[b], sm.bhi[b]);
+            const uint32_t cc = hist[b];
+            if (cc) part += exact_bin_sum(klo + (b << shift), cc, blo_sum[b], bhi_sum[b]);
           }
           const double t = block_sum(part, sm.red);
           __syncthreads();
