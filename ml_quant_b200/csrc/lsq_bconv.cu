@@ -17,18 +17,20 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 // --- weight image layout ---------------------------------------------------------------------
 // bits : uint32[cout][kh*kw][cw]
-// i8   : int8 [cout/NT][cin/64][kh*kw][4][NT][16]   (only when cout % 64 == 0 and cin % 64 == 0)
-//        NT = min(cout, 128): one (n-tile, 64-channel block, tap) slab is the K-major, non-swizzled
-//        tcgen05 shared-memory operand (8-row x 16-byte core matrices, LBO = NT*16, SBO = 128), so
-//        the tensor-core kernel fetches it with a single bulk copy.
-__host__ __device__ inline int wpack_nt(int cout) { return cout < 128 ? cout : 128; }
+// i8   : int8 [ceil(cout/128)][cin/64][kh*kw][4][128][16]   (only when cout % 64 == 0 and cin % 64 == 0)
+//        one (channel tile, 64-channel block, tap) slab is the K-major, non-swizzled tcgen05 shared-memory
+//        operand (8-row x 16-byte core matrices, LBO = 128*16, SBO = 128) with M = 128 rows, so the
+//        tensor-core kernel fetches it with a single bulk copy.  A 64-channel layer stores channel r in rows
+//        r and r + 64: both halves of the accumulator then hold the same channels and all eight epilogue
+//        warps share the work.
+__host__ __device__ inline int wpack_rows(int cout) { return cout < 128 ? 128 : cout; }
 __host__ __device__ inline bool wpack_has_i8(int cout, int cin) { return (cout % 64 == 0) && (cin % 64 == 0) && (cout <= 128 || cout % 128 == 0); }
 static inline size_t wpack_bits_bytes(int cout, int cin, int kh, int kw) {
   return align_up((size_t)cout * kh * kw * ((cin + 31) / 32) * 4, 1024);
 }
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int taps, int cw,
-                                    uint32_t* __restrict__ bits, int8_t* __restrict__ i8, int nt) {
+                                    uint32_t* __restrict__ bits, int8_t* __restrict__ i8) {
   // one thread per (co, tap, word)
   const long long total = (long long)cout * taps * cw;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -43,9 +45,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
       const bool pos = v >= 0.0f;
       word |= (pos ? 1u : 0u) << cc;
       if (i8) {
-        const int ntile = co / nt, r = co % nt, cb = c >> 6, j = (c & 63) >> 4, byte = c & 15;
-        const long long off = ((((long long)ntile * (cin >> 6) + cb) * taps + tap) * 4 + j) * ((long long)nt * 16) + (long long)r * 16 + byte;
+        const int ctile = co >> 7, r = co & 127, cb = c >> 6, j = (c & 63) >> 4, byte = c & 15;
+        const long long off = ((((long long)ctile * (cin >> 6) + cb) * taps + tap) * 4 + j) * (128ll * 16) + (long long)r * 16 + byte;
         i8[off] = pos ? (int8_t)1 : (int8_t)-1;
+        if (cout < 128) i8[off + (long long)cout * 16] = pos ? (int8_t)1 : (int8_t)-1;
       }
     }
     bits[idx] = word;
@@ -110,7 +113,7 @@ extern "C" {
 size_t lsq_wpack_bytes(int cout, int cin, int kh, int kw) {
   if (cout <= 0 || cin <= 0 || kh <= 0 || kw <= 0) return 0;
   size_t b = wpack_bits_bytes(cout, cin, kh, kw);
-  if (wpack_has_i8(cout, cin)) b += align_up((size_t)cout * cin * kh * kw, 1024);
+  if (wpack_has_i8(cout, cin)) b += align_up((size_t)wpack_rows(cout) * cin * kh * kw, 1024);
   return b;
 }
 
@@ -124,7 +127,7 @@ int lsq_pack_weights(const float* d_w, int cout, int cin, int kh, int kw, void* 
   const long long total = (long long)cout * taps * cw;
   unsigned grid = (unsigned)((total + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_w, cout, cin, taps, cw, bits, i8, wpack_nt(cout));
+  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_w, cout, cin, taps, cw, bits, i8);
   LSQ_CUDA_LAUNCH_CHECK("pack_weights_kernel");
   return LSQ_OK;
 }

@@ -3,45 +3,56 @@
 // sm_100a has no 1-bit MMA; the +-1 planes are expanded to int8 on
 // the fly and contracted with int8 +-1 weights, int32 accumulators in TMEM -- exact integers.
 //
-// Implicit GEMM without im2col:  D[128 positions, NT out-channels] += A_tap[128, 64] * B_tap[64, NT]
-// summed over 64-channel blocks and taps.  The activation planes live in HBM as bits in a "virtual
-// raster" (lsq_b200.h) in which a tap is a uniform shift of the position index, so ONE expanded
-// int8 patch per channel block in shared memory (tile + halo, zero at padding positions) serves all
-// kh*kw taps: the A operand of tap t is the same patch read through a shared-memory matrix
-// descriptor whose start address is shifted by d(t) rows (K-major, no swizzle: a row is 16 bytes per
-// 16-channel chunk, 8-row core matrices are contiguous, so any row shift is a 16-byte offset).
+// Operand roles.  One tcgen05.mma with 8-bit operands (K = 32) takes ~135 clocks whatever M <= 128 and
+// N <= 256 are (measured, scripts/mb/mb_umma.cu: 4.3 POP/s at M = 128, N = 256, half of that at N = 128), so
+// the instruction must be as large as it can be for EVERY layer, also those with 64 or 128 output channels:
+//     D[128 out-channels, N = positions x planes] += W_tap[128, 64] * P_tap[64, N]
+//   A = weights  : M = 128 rows (a 64-channel layer stores its rows twice, lsq_bconv.cu: lanes 64..127 of the
+//                  accumulator repeat lanes 0..63 and the epilogue warps of those lanes take other positions),
+//   B = patch    : N = 256 columns = 128 consecutive positions x 2 planes interleaved (1 plane: 256 positions),
+// summed over 64-channel blocks and taps.  The activation planes live in HBM as bits in a "virtual raster"
+// (lsq_b200.h) in which a tap is a uniform shift of the position index, so ONE expanded int8 patch per channel
+// block in shared memory (tile + halo, zero at padding positions) serves all kh*kw taps: the B operand of tap t
+// is the same patch read through a shared-memory matrix descriptor whose start address is shifted by d(t)
+// positions (K-major, no swizzle: a row is 16 bytes per 16-channel chunk, 8-row core matrices are contiguous,
+// so any row shift is a 16-byte multiple).
 //
-// Warp roles (320 threads, one CTA per SM, persistent over (m-tile, n-tile) items):
-//   warps 0-3  epilogue : tcgen05.ld accumulators -> vw[c]*(s1[n]*I1 + s2[n]*I2) + bias[c] -> NCHW fp32
-//   warp  4    MMA      : one elected thread issues tcgen05.mma / tcgen05.commit; owns TMEM alloc
-//   warp  5    weights  : cp.async.bulk (TMA engine, 1-D) of pre-packed operand slabs, mbarrier tx
-//   warps 6-9  patches  : plane bits (L2) -> int8 patch in shared memory, fence.proxy.async
-// Pipelines: patch ring (per channel block), weight ring (per channel block x tap), 2 accumulator
+// Warp roles (448 threads, one CTA per SM, persistent over (position tile, channel tile) items):
+//   warps 0-3, 10-13  epilogue : thread = output channel (TMEM lane).  tcgen05.ld 16 positions x planes ->
+//                     vw[c] * (s1[n] I1 + s2[n] I2) + bias[c] -> transposed through shared memory so that
+//                     global accesses run along positions (NCHW rows); activation and residual (prefetched
+//                     with cp.async several steps ahead) are applied on the way out
+//   warp  4           MMA      : one thread issues tcgen05.mma / tcgen05.commit; owns the TMEM allocation
+//   warp  5           weights  : cp.async.bulk (TMA engine, 1-D) of pre-packed operand slabs, mbarrier tx
+//   warps 6-9         patches  : plane bits (L2) -> int8 patch in shared memory, fence.proxy.async
+// Pipelines: patch ring (per channel block), weight ring (per channel block x tap group), 2 accumulator
 // stages in TMEM so the epilogue of item i overlaps the MMAs of item i+1.
+#include <stdlib.h>
 #include "lsq_common.cuh"
 
 namespace lsq {
 
 constexpr int kTcThreads = 448;   // 4 epilogue + MMA + loader + 4 producer + 4 more epilogue warps
-constexpr int kTileM = 128;
 constexpr int kMaxTaps = 9;
-constexpr int kBStages = 4;
+constexpr int kMaxWStages = 6;
 constexpr int kAccStages = 2;
-constexpr int kMaxAStages = 3;
+constexpr int kMaxPStages = 3;
+constexpr int kResStages = 6;     // residual staging: 16-position steps in flight per epilogue warp (2 KB each)
+constexpr int kOutPitch = 20;     // transposition tile: 32 channels x 16 positions; 20 words: 16-byte rows, conflict-free both ways
 constexpr unsigned long long kWatchdogCycles = 4000000000ull;  // ~2 s: trap instead of hanging
 
 struct TcParams {
   ActGeom g;
-  int npl, cout, nt, n_ntiles, ncb, taps;
-  int m_tiles;
+  int npl, cout, creal, n_ctiles, ncb, taps, tps;   // creal: distinct channels per 128-row tile (64 or 128)
+  int tp, p_tiles;               // positions per tile (N = tp * npl), number of position tiles
   long long q_begin;             // first output position
-  int pp;                        // patch positions per (plane, phase)
-  int a_stages;
+  int pp;                        // patch positions per phase
+  int p_stages, w_stages, r_stages;
   int dmin[4];                   // per phase: smallest tap offset (positions)
   int tap_phase[kMaxTaps];
   int tap_off[kMaxTaps];         // tap offset relative to dmin of its phase (>= 0)
-  uint32_t a_stage_bytes, b_stage_bytes;
-  uint32_t smem_a, smem_b, smem_bar;  // offsets in dynamic smem
+  uint32_t lbo_p, phase_bytes, p_stage_bytes, w_slab_bytes, w_stage_bytes;
+  uint32_t smem_p, smem_w, smem_bar, smem_tab, smem_scl, smem_out, smem_res;  // offsets in dynamic smem
   unsigned long long pitch_magic, rps_magic;   // ceil(2^40 / d): x / d == (x * magic) >> 40 for x * d < 2^40
 };
 
@@ -76,6 +87,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
       asm volatile("trap;");
     }
   }
+}
+// mbar_wait that also accumulates the cycles spent waiting (role diagnostics, LSQ_TC_DIAG=1)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int* err, int code, long long& acc) {
+  const long long t0 = clock64();      // try_wait itself may suspend the thread: time the first probe too
+  mbar_wait(bar, parity, err, code);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -150,187 +167,290 @@ struct Ring {
 __global__ void __launch_bounds__(kTcThreads, 1)
 bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __restrict__ act_scales,
                 const int8_t* __restrict__ wi8, const float* __restrict__ w_scale, const float* __restrict__ bias,
-                float* __restrict__ y, int* __restrict__ err, Epilogue epi) {
+                float* __restrict__ y, int* __restrict__ err, Epilogue epi, long long* __restrict__ diag) {
+  long long w0 = 0, w1 = 0, w2 = 0;
+  const long long t_start = clock64();
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ActGeom& g = P.g;
 
-  // barrier block: a_full[kMaxAStages] a_empty[kMaxAStages] b_full[kBStages] b_empty[kBStages]
+  // barrier block: p_full[kMaxPStages] p_empty[kMaxPStages] w_full[kMaxWStages] w_empty[kMaxWStages]
   //                acc_full[2] acc_empty[2] | tmem base
   const uint32_t bar0 = sbase + P.smem_bar;
-  auto a_full = [&](int s) { return bar0 + 8u * s; };
-  auto a_empty = [&](int s) { return bar0 + 8u * (kMaxAStages + s); };
-  auto b_full = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + s); };
-  auto b_empty = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + kBStages + s); };
-  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kBStages + s); };
-  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kBStages + kAccStages + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * (2 * kMaxAStages + 2 * kBStages + 2 * kAccStages));
+  auto p_full = [&](int s) { return bar0 + 8u * s; };
+  auto p_empty = [&](int s) { return bar0 + 8u * (kMaxPStages + s); };
+  auto w_full = [&](int s) { return bar0 + 8u * (2 * kMaxPStages + s); };
+  auto w_empty = [&](int s) { return bar0 + 8u * (2 * kMaxPStages + kMaxWStages + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kMaxPStages + 2 * kMaxWStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kMaxPStages + 2 * kMaxWStages + kAccStages + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * (2 * kMaxPStages + 2 * kMaxWStages + 2 * kAccStages));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < kMaxPStages; ++s) { mbar_init(p_full(s), 4); mbar_init(p_empty(s), 1); }
+    for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int s = 0; s < kAccStages; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // per-output-channel epilogue constants (weight scale, bias, PReLU slope)
+  float4* const ctab = reinterpret_cast<float4*>(smem + P.smem_tab);
+  for (int c = threadIdx.x; c < P.cout; c += kTcThreads)
+    ctab[c] = make_float4(__ldg(w_scale + c), bias ? __ldg(bias + c) : 0.0f,
+                          epi.act == 2 ? __ldg(epi.prelu + (epi.n_prelu > 1 ? c : 0)) : 0.0f, 0.0f);
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_items = P.m_tiles * P.n_ntiles;
-  const uint32_t acc_cols = (uint32_t)(P.npl * P.nt);
+  const int n_items = P.p_tiles * P.n_ctiles;
+  const uint32_t acc_cols = (uint32_t)(P.tp * P.npl);
 
   if (warp < 4 || warp >= 10) {
-    // ===================== epilogue (8 warps: two per TMEM lane quarter) =====================
-    // Warp w reads TMEM lanes 32*(w%4)..+31 (= tile rows); the two warps of a quarter split the channels
-    // in interleaved groups of 32.  Residual values are prefetched one group ahead, across tiles, so the
-    // loads of the next group are in flight while this one is scaled and stored.
+    // ===================== epilogue (8 warps) =====================
+    // quarter = TMEM lane quarter = 32 output channels of the channel tile; the two warps of a quarter take
+    // one half of the tile's positions each and walk it in steps of 16 positions.
+    // quarter = TMEM lane quarter; 128-channel tiles: quarter = channel group, the two warps of a quarter split
+    // the positions in 2; 64-channel tiles: lanes 64..127 repeat lanes 0..63, positions are split in 4.
     const int quarter = warp & 3;
-    const int egrp = warp < 4 ? 0 : 1;
-    const int ngroups = P.nt / 64;                     // groups of 32 channels handled by this warp per item
+    const int half = warp < 4 ? 0 : 1;
+    const int ewarp = quarter + 4 * half;
+    const int cq = P.creal >> 5;                        // quarters holding distinct channels (2 or 4)
+    const int chb = 32 * (quarter % cq);                // first channel (within the tile) of this warp
+    const int nparts = 8 / cq;                          // position parts per tile (2 or 4)
+    const int part = half * (nparts >> 1) + quarter / cq;
+    const int tph = P.tp / nparts;                      // positions of this warp per item
+    const int pbase = part * tph;
+    const int spi = tph >> 4;                           // steps per item
+    const int nch = 32;
     const bool has_res = epi.residual != nullptr;
+    const int R = P.r_stages;
     const long long cstride = (long long)g.ho * g.wo;
-    struct Row { bool valid; long long yoff; float sc0, sc1; int ntile; };
-    auto decode_row = [&](int item) {
-      Row r;
-      const int mt = item / P.n_ntiles;
-      r.ntile = item - mt * P.n_ntiles;
-      const PosInfo pi = decode_pos(P, P.q_begin + (long long)mt * kTileM + quarter * 32 + lane);
-      r.valid = pi.in_range && (pi.s < g.n) && (pi.a >= 0) && (pi.a < g.ho) && (pi.col < g.wo);
-      r.sc0 = 0.0f; r.sc1 = 0.0f;
-      if (r.valid) {
-        r.sc0 = __ldg(act_scales + pi.s);
-        if (P.npl > 1) r.sc1 = __ldg(act_scales + g.n + pi.s);
-      }
-      r.yoff = (((long long)pi.s * P.cout + (long long)r.ntile * P.nt) * g.ho + pi.a) * g.wo + pi.col;
-      return r;
+    float* const res0 = reinterpret_cast<float*>(smem + P.smem_res) + (size_t)ewarp * R * 512;
+    float* const outt = reinterpret_cast<float*>(smem + P.smem_out) + (size_t)ewarp * 32 * kOutPitch;
+    float2* const scl = reinterpret_cast<float2*>(smem + P.smem_scl) + (size_t)ewarp * 128;
+    const int ch_sub = lane >> 4, pl16 = lane & 15;     // write-out role: two channels x 16 positions per instruction
+
+    // where does position `p` of tile `ptile` land in the output?  (offset of channel 0 of the channel tile, or -1)
+    auto out_offset = [&](int ptile, int ctile, int p, int& sample) -> long long {
+      const PosInfo pi = decode_pos(P, P.q_begin + (long long)ptile * P.tp + p);
+      sample = pi.s;
+      const bool valid = pi.in_range && (pi.s < g.n) && (pi.a >= 0) && (pi.a < g.ho) && (pi.col < g.wo);
+      if (!valid) return -1;
+      return (((long long)pi.s * P.cout + (long long)ctile * 128) * g.ho + pi.a) * g.wo + pi.col;
     };
-    auto load_res = [&](float (&dst)[32], const Row& r, int c0) {
+    struct Cursor { int item, step; };
+    auto advance = [&](Cursor& c) {
+      if (++c.step == spi) { c.step = 0; c.item += (int)gridDim.x; }
+    };
+    auto issue = [&](const Cursor& c, int slot) {      // always commits a group so the group count stays uniform
+      if (has_res && nch > 0 && c.item < n_items) {
+        const int ptile = c.item / P.n_ctiles, ctile = c.item - ptile * P.n_ctiles;
+        int sample;
+        const long long off = out_offset(ptile, ctile, pbase + 16 * c.step + pl16, sample);
+        const uint32_t dst = smem_u32(res0 + slot * 512 + lane);
+        const int sz = off >= 0 ? 4 : 0;
+        // instruction i covers channels c_i and c_i + 4 (c_i = 8 * (i / 4) + i % 4) x 16 positions
+        const float* src = epi.residual + (off >= 0 ? off + (long long)(chb + 4 * ch_sub) * cstride : 0);
+        const long long s1 = off >= 0 ? cstride : 0, s5 = off >= 0 ? 5 * cstride : 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        dst[j] = (has_res && r.valid) ? __ldg(epi.residual + r.yoff + (long long)(c0 + j) * cstride) : 0.0f;
+        for (int i = 0; i < 16; ++i) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)i * 128u), "l"(src), "r"(sz) : "memory");
+          src += ((i & 3) == 3) ? s5 : s1;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     Ring acc(kAccStages);
-    int item = blockIdx.x;
-    if (item < n_items) {
-      Row cur = decode_row(item);
-      float res[32];
-      load_res(res, cur, egrp * 32);
-      for (; item < n_items; item += gridDim.x) {
-        Row nxt = cur;
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc.stage * acc_cols;
-        for (int gi = 0; gi < ngroups; ++gi) {
-          const int c0 = egrp * 32 + gi * 64;
-          float nres[32];
-          if (gi + 1 < ngroups) {
-            load_res(nres, cur, c0 + 64);
-          } else if (item + (int)gridDim.x < n_items) {
-            nxt = decode_row(item + (int)gridDim.x);
-            load_res(nres, nxt, egrp * 32);
-          }
-          if (gi == 0) {
-            mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
-            tc_fence_after();
-          }
-          float* yrow = y + cur.yoff;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t r0[16], r1[16];
-            tmem_ld16(tbase + (uint32_t)(c0 + 16 * h), r0);
-            if (P.npl > 1) tmem_ld16(tbase + (uint32_t)(P.nt + c0 + 16 * h), r1);
-            tmem_ld_wait();
-            if (cur.valid) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c = cur.ntile * P.nt + c0 + 16 * h + j;
-                float t = cur.sc0 * (float)(int)r0[j];
-                if (P.npl > 1) t = fmaf(cur.sc1, (float)(int)r1[j], t);
-                float o = __ldg(w_scale + c) * t;
-                if (bias) o += __ldg(bias + c);
-                yrow[(long long)(c0 + 16 * h + j) * cstride] = apply_epilogue_res(epi, o, c, res[16 * h + j]);
-              }
+    Cursor is{(int)blockIdx.x, 0}, co{(int)blockIdx.x, 0};
+    int islot = 0, cslot = 0;
+    for (int r = 0; r + 1 < R; ++r) {
+      issue(is, islot);
+      advance(is);
+      if (++islot == R) islot = 0;
+    }
+    float ws = 0.0f, bs = 0.0f;
+    while (co.item < n_items) {
+      issue(is, islot);
+      advance(is);
+      if (++islot == R) islot = 0;
+      // all but the R-1 most recent groups are complete -> the step being consumed has landed
+      if (R >= 6) asm volatile("cp.async.wait_group 5;" ::: "memory");
+      else if (R == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+      else if (R == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const int ptile = co.item / P.n_ctiles, ctile = co.item - ptile * P.n_ctiles;
+      if (co.step == 0) {
+        // per-position activation scales of this warp's positions, per-thread channel constants
+        if (nch > 0) {
+          for (int p = lane; p < tph; p += 32) {
+            int sample;
+            const long long off = out_offset(ptile, ctile, pbase + p, sample);
+            float2 s2 = make_float2(0.0f, 0.0f);
+            if (off >= 0) {
+              s2.x = __ldg(act_scales + sample);
+              if (P.npl > 1) s2.y = __ldg(act_scales + g.n + sample);
             }
+            scl[p] = s2;
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) res[j] = nres[j];
+          const float4 k = ctab[ctile * 128 + chb + lane];
+          ws = k.x; bs = k.y;
         }
+        __syncwarp();
+        mbar_wait_t(acc_full(acc.stage), acc.phase, err, 1, w0);
+        tc_fence_after();
+      }
+      if (nch > 0) {
+        // ---- thread = channel: 16 positions x planes from TMEM, scale, bias -> transposition tile ----
+        const uint32_t col0 = (uint32_t)acc.stage * acc_cols + (uint32_t)((pbase + 16 * co.step) * P.npl);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
+        uint32_t rr[32];                                   // columns col0 .. col0 + 16 * planes - 1
+        tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&rr[0]));
+        if (P.npl > 1) tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(&rr[16]));
+        const float4* sp = reinterpret_cast<const float4*>(scl + 16 * co.step);     // (s1, s2) of two positions
+        float4 s4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s4[j] = sp[j];
+        tmem_ld_wait();
+        float o[16];
+        if (P.npl > 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float sx = (j & 1) ? s4[j >> 1].z : s4[j >> 1].x, sy = (j & 1) ? s4[j >> 1].w : s4[j >> 1].y;
+            const float t = fmaf(sy, (float)(int)rr[2 * j + 1], sx * (float)(int)rr[2 * j]);   // planes interleave
+            o[j] = __fadd_rn(__fmul_rn(ws, t), bs);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float sx = (j & 1) ? s4[j >> 1].z : s4[j >> 1].x;
+            o[j] = __fadd_rn(__fmul_rn(ws, sx * (float)(int)rr[j]), bs);
+          }
+        }
+        float4* orow = reinterpret_cast<float4*>(outt + lane * kOutPitch);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) orow[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        __syncwarp();
+        // ---- lanes along positions: activation, residual, coalesced stores ----
+        int sample;
+        const long long off = out_offset(ptile, ctile, pbase + 16 * co.step + pl16, sample);
+        if (off >= 0) {
+          const float* rs_base = res0 + cslot * 512 + lane;
+          const float* ot = outt + (4 * ch_sub) * kOutPitch + pl16;
+          // all shared-memory reads first, then the arithmetic, then the stores (16 independent chains);
+          // instruction i covers channels c_i and c_i + 4 with c_i = 8 * (i / 4) + i % 4: conflict-free reads
+          float v[16], rs[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = ot[(8 * (i >> 2) + (i & 3)) * kOutPitch];
+            rs[i] = has_res ? rs_base[i * 32] : 0.0f;
+          }
+          if (!epi.residual_after_act) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += rs[i];
+          }
+          if (epi.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+          } else if (epi.act == 2) {
+            const float4* tab = ctab + ctile * 128 + chb + 4 * ch_sub;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.0f ? v[i] : v[i] * tab[8 * (i >> 2) + (i & 3)].z;
+          }
+          if (epi.residual_after_act) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += rs[i];
+          }
+          float* yp = y + off + (long long)(chb + 4 * ch_sub) * cstride;
+          const long long s5 = 5 * cstride;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            *yp = v[i];
+            yp += ((i & 3) == 3) ? s5 : cstride;
+          }
+        }
+        __syncwarp();
+      }
+      if (co.step == spi - 1) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(acc.stage));
         acc.advance();
-        cur = nxt;
       }
+      advance(co);
+      if (++cslot == R) cslot = 0;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    Ring acc(kAccStages), ra(P.a_stages), rb(kBStages);
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    const uint32_t lbo_a = (uint32_t)P.pp * 16u, lbo_b = (uint32_t)P.nt * 16u;
-    const uint32_t plane_phase_bytes = (uint32_t)P.pp * 64u;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      mbar_wait(acc_empty(acc.stage), acc.phase ^ 1u, err, 2);
-      tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)acc.stage * acc_cols;
-      for (int cb = 0; cb < P.ncb; ++cb) {
-        mbar_wait(a_full(ra.stage), ra.phase, err, 3);
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      Ring acc(kAccStages), rp(P.p_stages), rw(P.w_stages);
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((P.tp * P.npl) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lbo_w = 128u * 16u, lbo_p = P.lbo_p;
+      const int ngroups = P.taps / P.tps;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait_t(acc_empty(acc.stage), acc.phase ^ 1u, err, 2, w0);
         tc_fence_after();
-        const uint32_t a_stage = sbase + P.smem_a + (uint32_t)ra.stage * P.a_stage_bytes;
-        for (int tap = 0; tap < P.taps; ++tap) {
-          mbar_wait(b_full(rb.stage), rb.phase, err, 4);
+        const uint32_t d0 = tmem_base + (uint32_t)acc.stage * acc_cols;
+        for (int cb = 0; cb < P.ncb; ++cb) {
+          mbar_wait_t(p_full(rp.stage), rp.phase, err, 3, w1);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t b_stage = sbase + P.smem_b + (uint32_t)rb.stage * P.b_stage_bytes;
-            for (int pl = 0; pl < P.npl; ++pl) {
-              const uint32_t a_addr = a_stage + (uint32_t)(pl * g.nphase + P.tap_phase[tap]) * plane_phase_bytes +
-                                      (uint32_t)P.tap_off[tap] * 16u;
+          const uint32_t patch = sbase + P.smem_p + (uint32_t)rp.stage * P.p_stage_bytes;
+          for (int tg = 0; tg < ngroups; ++tg) {
+            mbar_wait_t(w_full(rw.stage), rw.phase, err, 4, w2);
+            tc_fence_after();
+            const uint32_t wst = sbase + P.smem_w + (uint32_t)rw.stage * P.w_stage_bytes;
+            for (int tt = 0; tt < P.tps; ++tt) {
+              const int tap = tg * P.tps + tt;
+              const uint32_t b_addr = patch + (uint32_t)P.tap_phase[tap] * P.phase_bytes + (uint32_t)(P.tap_off[tap] * P.npl) * 16u;
+              const uint32_t a_addr = wst + (uint32_t)tt * P.w_slab_bytes;
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const uint64_t ad = make_desc(a_addr + (uint32_t)(2 * h) * lbo_a, lbo_a, 128u);
-                const uint64_t bd = make_desc(b_stage + (uint32_t)(2 * h) * lbo_b, lbo_b, 128u);
-                umma_i8(d0 + (uint32_t)(pl * P.nt), ad, bd, idesc, (cb | tap | h) != 0 ? 1u : 0u);
+                const uint64_t ad = make_desc(a_addr + (uint32_t)(2 * h) * lbo_w, lbo_w, 128u);
+                const uint64_t bd = make_desc(b_addr + (uint32_t)(2 * h) * lbo_p, lbo_p, 128u);
+                umma_i8(d0, ad, bd, idesc, (cb | tap | h) != 0 ? 1u : 0u);
               }
             }
-            umma_commit(b_empty(rb.stage));
-            if (tap == P.taps - 1) umma_commit(a_empty(ra.stage));
-            if (tap == P.taps - 1 && cb == P.ncb - 1) umma_commit(acc_full(acc.stage));
+            umma_commit(w_empty(rw.stage));
+            rw.advance();
           }
-          __syncwarp();
-          rb.advance();
+          umma_commit(p_empty(rp.stage));
+          rp.advance();
         }
-        ra.advance();
+        umma_commit(acc_full(acc.stage));
+        acc.advance();
       }
-      acc.advance();
     }
+    __syncwarp();
   } else if (warp == 5) {
     // ===================== weight loader =====================
-    Ring rb(kBStages);
+    Ring rw(P.w_stages);
     if (lane == 0) {
+      const int ngroups = P.taps / P.tps;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ntile = item % P.n_ntiles;
-        const int8_t* wsrc = wi8 + (long long)ntile * P.ncb * P.taps * P.b_stage_bytes;
+        const int ctile = item % P.n_ctiles;
+        const int8_t* wsrc = wi8 + (long long)ctile * P.ncb * P.taps * P.w_slab_bytes;
         for (int cb = 0; cb < P.ncb; ++cb)
-          for (int tap = 0; tap < P.taps; ++tap) {
-            mbar_wait(b_empty(rb.stage), rb.phase ^ 1u, err, 5);
-            mbar_expect_tx(b_full(rb.stage), P.b_stage_bytes);
-            bulk_g2s(sbase + P.smem_b + (uint32_t)rb.stage * P.b_stage_bytes,
-                     wsrc + ((long long)cb * P.taps + tap) * P.b_stage_bytes, P.b_stage_bytes, b_full(rb.stage));
-            rb.advance();
+          for (int tg = 0; tg < ngroups; ++tg) {
+            mbar_wait_t(w_empty(rw.stage), rw.phase ^ 1u, err, 5, w0);
+            mbar_expect_tx(w_full(rw.stage), P.w_stage_bytes);
+            bulk_g2s(sbase + P.smem_w + (uint32_t)rw.stage * P.w_stage_bytes,
+                     wsrc + ((long long)cb * P.taps + tg * P.tps) * P.w_slab_bytes, P.w_stage_bytes, w_full(rw.stage));
+            rw.advance();
           }
       }
     }
   } else {
     // ===================== patch producers (128 threads) =====================
-    Ring ra(P.a_stages);
+    Ring rp(P.p_stages);
     const int pt = threadIdx.x - 6 * 32;
     const int ntask = P.npl * g.nphase * P.pp;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int mt = item / P.n_ntiles;
-      const long long q0 = P.q_begin + (long long)mt * kTileM;
+      const int ptile = item / P.n_ctiles;
+      const long long q0 = P.q_begin + (long long)ptile * P.tp;
       for (int cb = 0; cb < P.ncb; ++cb) {
-        mbar_wait(a_empty(ra.stage), ra.phase ^ 1u, err, 6);
-        unsigned char* a_stage = smem + P.smem_a + (size_t)ra.stage * P.a_stage_bytes;
+        mbar_wait_t(p_empty(rp.stage), rp.phase ^ 1u, err, 6, w0);
+        unsigned char* p_stage = smem + P.smem_p + (size_t)rp.stage * P.p_stage_bytes;
         constexpr int kPB = 4;   // tasks whose plane-bit loads are in flight together
         for (int task0 = pt; task0 < ntask; task0 += 128 * kPB) {
           uint2 bits[kPB];
@@ -345,7 +465,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
             if (task < ntask) {
               const int pp_idx = task / P.pp;          // pl * nphase + phase
               const int pos = task - pp_idx * P.pp;
-              const int phase = pp_idx % g.nphase;
+              const int pl = pp_idx / g.nphase, phase = pp_idx - pl * g.nphase;
               const long long q = q0 + P.dmin[phase] + pos;
               const PosInfo pi = decode_pos(P, q);
               int hv_p = g.h, wv_p = g.w;
@@ -355,7 +475,8 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
                 bits[u] = __ldg(reinterpret_cast<const uint2*>(planes + ((long long)pp_idx * g.vtot + q) * g.cw + cb * 2));
                 vm[u] = 0xFFFFFFFFu;
               }
-              dst[u] = a_stage + (size_t)pp_idx * ((size_t)P.pp * 64) + (size_t)pos * 16;
+              // row = position * planes + plane inside the phase's [16-channel chunk][row][16 B] block
+              dst[u] = p_stage + (size_t)phase * P.phase_bytes + ((size_t)pos * P.npl + pl) * 16;
             }
           }
 #pragma unroll
@@ -370,48 +491,33 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
               v.y = expand4((h16 >> 4) & 0xFu) & vm[u];
               v.z = expand4((h16 >> 8) & 0xFu) & vm[u];
               v.w = expand4((h16 >> 12) & 0xFu) & vm[u];
-              *reinterpret_cast<uint4*>(dst[u] + (size_t)j * ((size_t)P.pp * 16)) = v;
+              *reinterpret_cast<uint4*>(dst[u] + (size_t)j * P.lbo_p) = v;
             }
           }
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(ra.stage));
-        ra.advance();
+        if (lane == 0) mbar_arrive(p_full(rp.stage));
+        rp.advance();
       }
     }
   }
 
+  if (diag && lane == 0 && blockIdx.x == 0) {
+    long long* d = diag + warp * 4;
+    d[0] = clock64() - t_start; d[1] = w0; d[2] = w1; d[3] = w2;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
-bool bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout) {
-  if (nplanes < 1 || nplanes > 2) return false;
-  if (g->c % 64 != 0 || cout % 64 != 0) return false;
-  if (cout > 128 && cout % 128 != 0) return false;
-  if (g->kh * g->kw > kMaxTaps) return false;
-  if (g->stride != 1 && g->stride != 2) return false;
-  // patch + weight ring must fit shared memory
-  const int span = g->ph * g->pitch + g->ph;  // |tap offset| bound in one phase
-  const int pp = kTileM + 2 * span + 2;
-  const size_t a_stage = (size_t)nplanes * g->nphase * pp * 64;
-  const int nt = cout < 128 ? cout : 128;
-  const size_t b = (size_t)kBStages * nt * 64;
-  if (a_stage + b + 1024 > 220 * 1024) return false;
-  if ((size_t)pp * 16 > 0x3FFF * 16) return false;
-  if ((long long)g->n * g->rows_per_sample * g->pitch > (1ll << 31) - 4096) return false;
-  return true;
-}
-
-int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes, const float* d_act_scales,
-                      const void* d_wpack, const float* d_w_scale, const float* d_bias, int cout, float* d_y,
-                      const Epilogue& epi, cudaStream_t stream) {
-  TcParams P;
+// Shared-memory plan for a tile of `tp` positions; returns false when it does not fit.
+static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, int tp, TcParams& P) {
   P.g = to_dev(*g);
-  P.npl = nplanes; P.cout = cout; P.nt = cout < 128 ? cout : 128; P.n_ntiles = cout / P.nt;
+  P.npl = nplanes; P.cout = cout; P.creal = cout < 128 ? cout : 128; P.n_ctiles = (cout + 127) / 128;
   P.ncb = g->c / 64; P.taps = g->kh * g->kw;
+  P.tp = tp;
   // per-tap phase and position offset: input coordinate = stride*out + d - pad
   auto fdiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
   for (int ph = 0; ph < 4; ++ph) P.dmin[ph] = 0;
@@ -436,29 +542,82 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
     if (seen[ph] && dmax[ph] - P.dmin[ph] > span) span = dmax[ph] - P.dmin[ph];
   for (int t = 0; t < P.taps; ++t) P.tap_off[t] = off[t] - P.dmin[P.tap_phase[t]];
   for (int t = P.taps; t < kMaxTaps; ++t) { P.tap_phase[t] = 0; P.tap_off[t] = 0; }
-  P.pp = (kTileM + span + 7) / 8 * 8;
-  P.a_stage_bytes = (uint32_t)((size_t)nplanes * g->nphase * P.pp * 64);
-  P.b_stage_bytes = (uint32_t)(P.nt * 64);
-  const size_t budget = 220 * 1024;
-  const size_t fixed = (size_t)kBStages * P.b_stage_bytes + 1024;
-  int a_st = (int)((budget - fixed) / P.a_stage_bytes);
-  if (a_st < 1) { set_error("bconv2d_tc: patch does not fit shared memory"); return LSQ_ERR_UNSUPPORTED; }
-  if (a_st > kMaxAStages) a_st = kMaxAStages;
-  if (a_st > P.ncb && P.ncb >= 1) a_st = P.ncb < 2 ? 2 : P.ncb;  // more stages than blocks buys nothing
-  if (a_st > kMaxAStages) a_st = kMaxAStages;
-  if ((size_t)a_st * P.a_stage_bytes + fixed > budget) a_st = (int)((budget - fixed) / P.a_stage_bytes);
-  P.a_stages = a_st;
-  P.smem_a = 0;
-  P.smem_b = (uint32_t)((size_t)a_st * P.a_stage_bytes);
-  P.smem_b = (P.smem_b + 127u) / 128u * 128u;
-  P.smem_bar = P.smem_b + (uint32_t)kBStages * P.b_stage_bytes;
-  const size_t smem_bytes = (size_t)P.smem_bar + 256;
+  P.pp = (tp + span + 7) / 8 * 8;
+  P.lbo_p = (uint32_t)P.pp * nplanes * 16u;
+  if (P.lbo_p > 0x3FFFu * 16u) return false;
+  P.phase_bytes = 4u * P.lbo_p;
+  P.p_stage_bytes = (uint32_t)g->nphase * P.phase_bytes;
+  P.w_slab_bytes = 128u * 64u;
+  const size_t total = 225 * 1024;
+  const size_t bar_bytes = 512, tab_bytes = (size_t)cout * 16;
+  const size_t scl_bytes = 8 * 128 * sizeof(float2), out_bytes = 8 * 32 * kOutPitch * sizeof(float);
+  const size_t slack = 0;
+  const size_t fixed = bar_bytes + tab_bytes + scl_bytes + out_bytes + slack;
+  // minimum: 2 patch stages (1 when there is a single channel block and nothing to overlap with is no option:
+  // the next item's patch is built while this one is multiplied), 2 weight stages of one tap, 2 residual steps
+  const size_t res_min = has_res ? (size_t)8 * 2 * 2048 : 0;
+  if (fixed + 2 * (size_t)P.p_stage_bytes + 2 * (size_t)P.w_slab_bytes + res_min > total) return false;
+  size_t left = total - fixed - res_min - 2 * (size_t)P.p_stage_bytes;
+  // weights: whole tap rows per stage when they fit twice (fewer commits), else single taps
+  P.tps = (P.taps % g->kw == 0 && 2 * (size_t)g->kw * P.w_slab_bytes <= left) ? g->kw : 1;
+  P.w_stage_bytes = (uint32_t)P.tps * P.w_slab_bytes;
+  P.w_stages = 2;
+  left -= 2 * (size_t)P.w_stage_bytes;
+  // then: deeper residual staging, a third patch stage, more weight stages
+  P.r_stages = has_res ? 2 : 1;
+  if (has_res) {
+    const int want[2] = {kResStages, 4};
+    for (int k = 0; k < 2; ++k) {
+      const size_t extra = (size_t)8 * (want[k] - 2) * 2048;
+      if (extra <= left) { P.r_stages = want[k]; left -= extra; break; }
+    }
+  }
+  P.p_stages = 2;
+  if (P.ncb >= 3 && P.p_stage_bytes <= left) { P.p_stages = 3; left -= P.p_stage_bytes; }
+  while (P.w_stages < kMaxWStages && P.w_stages * P.tps < 2 * P.taps && P.w_stage_bytes <= left) { ++P.w_stages; left -= P.w_stage_bytes; }
+  uint32_t o = 0;
+  P.smem_p = o; o += (uint32_t)P.p_stages * P.p_stage_bytes; o = (o + 127u) / 128u * 128u;
+  P.smem_w = o; o += (uint32_t)P.w_stages * P.w_stage_bytes + (uint32_t)slack;
+  P.smem_bar = o; o += (uint32_t)bar_bytes;
+  P.smem_tab = o; o += (uint32_t)tab_bytes;
+  P.smem_scl = o; o += (uint32_t)scl_bytes;
+  P.smem_out = o; o += (uint32_t)out_bytes;
+  P.smem_res = o; o += has_res ? (uint32_t)(8 * P.r_stages * 2048) : 0u;
+  return o <= 227 * 1024;
+}
+
+static int tc_pick_tile(const lsq_act_geom* g, int nplanes, int cout, bool has_res, TcParams& P) {
+  for (int tp = 256 / nplanes; tp >= 64; tp >>= 1)
+    if (tc_plan(g, nplanes, cout, has_res, tp, P)) return tp;
+  return 0;
+}
+
+bool bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout) {
+  if (nplanes < 1 || nplanes > 2) return false;
+  if (g->c % 64 != 0 || cout % 64 != 0) return false;
+  if (cout > 128 && cout % 128 != 0) return false;
+  if (g->kh * g->kw > kMaxTaps) return false;
+  if (g->stride != 1 && g->stride != 2) return false;
+  if ((long long)g->n * g->rows_per_sample * g->pitch > (1ll << 31) - 4096) return false;
+  TcParams P;
+  return tc_pick_tile(g, nplanes, cout, true, P) != 0;
+}
+
+int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes, const float* d_act_scales,
+                      const void* d_wpack, const float* d_w_scale, const float* d_bias, int cout, float* d_y,
+                      const Epilogue& epi, cudaStream_t stream) {
+  TcParams P;
+  if (tc_pick_tile(g, nplanes, cout, epi.residual != nullptr, P) == 0) {
+    set_error("bconv2d_tc: patch does not fit shared memory");
+    return LSQ_ERR_UNSUPPORTED;
+  }
   P.pitch_magic = ((1ull << 40) + (unsigned long long)g->pitch - 1ull) / (unsigned long long)g->pitch;
   P.rps_magic = ((1ull << 40) + (unsigned long long)g->rows_per_sample - 1ull) / (unsigned long long)g->rows_per_sample;
   P.q_begin = (long long)g->lead + (long long)g->ph * g->pitch;
   const long long qspan = (long long)g->n * g->rows_per_sample * g->pitch;
-  P.m_tiles = (int)((qspan + kTileM - 1) / kTileM);
-  const int n_items = P.m_tiles * P.n_ntiles;
+  P.p_tiles = (int)((qspan + P.tp - 1) / P.tp);
+  const int n_items = P.p_tiles * P.n_ctiles;
+  const size_t smem_bytes = (size_t)P.smem_res + (epi.residual ? (size_t)8 * P.r_stages * 2048 : 0);
 
   // the weight image follows the bit image inside d_wpack (lsq_bconv.cu)
   const size_t bits_bytes = ((size_t)cout * g->kh * g->kw * g->cw * 4 + 1023) / 1024 * 1024;
@@ -470,8 +629,22 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n_items < sms ? n_items : sms;
-  bconv_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(d_planes, P, d_act_scales, wi8, d_w_scale, d_bias, d_y, nullptr, epi);
+  static const bool want_diag = getenv("LSQ_TC_DIAG") != nullptr;     // development aid: per-role wait cycles of CTA 0
+  long long* d_diag = nullptr;
+  if (want_diag) { cudaMalloc(&d_diag, 14 * 4 * sizeof(long long)); cudaMemsetAsync(d_diag, 0, 14 * 4 * sizeof(long long), stream); }
+  bconv_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(d_planes, P, d_act_scales, wi8, d_w_scale, d_bias, d_y, nullptr, epi, d_diag);
   LSQ_CUDA_LAUNCH_CHECK("bconv_tc_kernel");
+  if (want_diag) {
+    long long h[14 * 4];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, d_diag, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_diag);
+    const char* role[14] = {"epi0", "epi1", "epi2", "epi3", "mma", "wload", "prod0", "prod1", "prod2", "prod3", "epi4", "epi5", "epi6", "epi7"};
+    fprintf(stderr, "[bconv_tc diag] cin %d cout %d %dx%d stride %d items %d grid %d tp %d pp %d p_stages %d w_stages %d x %d taps r_stages %d smem %zu\n",
+            g->c, cout, g->h, g->w, g->stride, n_items, grid, P.tp, P.pp, P.p_stages, P.w_stages, P.tps, P.r_stages, smem_bytes);
+    for (int w = 0; w < 14; ++w)
+      fprintf(stderr, "   %-6s total %9lld  wait0 %9lld  wait1(p_full) %9lld  wait2(w_full) %9lld\n", role[w], h[w * 4], h[w * 4 + 1], h[w * 4 + 2], h[w * 4 + 3]);
+  }
   return LSQ_OK;
 }
 

@@ -511,17 +511,15 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     if (lane == 31) { sm.wcnt[wid] = ci; sm.wsum[wid] = si; sm.wnz[wid] = zi; }
     if (lane == 0) sm.wfirst[wid] = sfx;
     __syncthreads();
-    uint32_t coff = 0, zoff = 0, nz_total = 0;
+    uint32_t coff = 0;
     double soff = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-      if (w < wid) { coff += sm.wcnt[w]; soff += sm.wsum[w]; zoff += sm.wnz[w]; }
-      nz_total += sm.wnz[w];
+      if (w < wid) { coff += sm.wcnt[w]; soff += sm.wsum[w]; }
     }
     uint32_t nxt_after = nxt_in_warp;
     for (int w = wid + 1; w < (int)(blockDim.x >> 5) && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
     const uint32_t excl0 = cnt_below_w + coff + ci - ct;
     const double pref0 = sum_below_w + soff + si - stt;
-    const uint32_t zidx0 = zoff + zi - nz;
 
     // ---- S2: flag the bins that can hold a candidate ------------------------------------------------
     // relative uncertainty of the prefix sums (see sum_mode); the fp32 threshold arithmetic adds eps (may_hold)
