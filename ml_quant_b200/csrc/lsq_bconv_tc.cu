@@ -72,9 +72,9 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // suspend (no issue slots) up to the hint
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
