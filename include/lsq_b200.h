@@ -178,12 +178,19 @@ LSQ_API int lsq_bconv2d_fwd_ex(const uint32_t* d_planes, const lsq_act_geom* g, 
                        const lsq_epilogue* epi, void* stream);
 
 /* ---- fp32 stem of QResNet (not part of the quantized path) ----------------------
- * out = relu(maxpool3x3/s2/p1(conv7x7/s2/p3(x, w) + bias)) for x [n,3,h,w] -> out [n,64,hp,wp]
+ * out = maxpool3x3/s2/p1(relu(conv7x7/s2/p3(x, w) + bias)) for x [n,3,h,w] -> out [n,64,hp,wp]
  * (quant/models/resnet.py:283-308 with the eval BatchNorm folded into w / bias by the caller).
- * d_w: float[64][152], k = c*49 + ky*7 + kx, columns 147..151 zero.  3xTF32 tensor-core arithmetic
- * (fp32-level accuracy); the conv output never reaches HBM. */
-LSQ_API int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_w, const float* d_bias,
-                 float* d_out, void* stream);
+ * The convolution runs on the tcgen05 tensor cores (kind::tf32, 3xTF32 split: fp32-level accuracy).
+ *   lsq_stem_pack_weights: d_w float[64][147] (k = c*49 + ky*7 + kx) -> operand image of
+ *                          lsq_stem_image_bytes() bytes (16-byte aligned), once per weight version
+ *   lsq_stem_fwd:          d_conv_ws = scratch of lsq_stem_workspace_bytes(n, h, w) bytes (the rectified
+ *                          convolution output [n,64,hc,wc]) */
+LSQ_API size_t lsq_stem_image_bytes(void);
+LSQ_API size_t lsq_stem_workspace_bytes(int n, int h, int w);
+LSQ_API int lsq_stem_supported(int n, int h, int w);
+LSQ_API int lsq_stem_pack_weights(const float* d_w, float* d_image, void* stream);
+LSQ_API int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_image, const float* d_bias,
+                 float* d_conv_ws, float* d_out, void* stream);
 
 /* 1 if the tensor-core kernel handles this problem */
 LSQ_API int lsq_bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout);

@@ -16,6 +16,7 @@ EXPORTS = [
     'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry', 'lsq_act_planes_bytes', 'lsq_encode_act',
     'lsq_wpack_bytes', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
     'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex', 'lsq_stem_fwd',
+    'lsq_stem_image_bytes', 'lsq_stem_workspace_bytes', 'lsq_stem_supported', 'lsq_stem_pack_weights',
 ]
 
 
@@ -73,8 +74,16 @@ def lib():
             L.lsq_solve_v1_ex.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp, pp, vp]
             L.lsq_encode_act_ex.argtypes = [vp, gp, f32, vp, i32, i32, vp, vp, vp, sz, pp, vp]
             L.lsq_bconv2d_fwd_ex.argtypes = [vp, gp, i32, vp, vp, vp, vp, i32, vp, i32, ep, vp]
-            L.lsq_stem_fwd.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+            L.lsq_stem_fwd.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
             L.lsq_stem_fwd.restype = i32
+            L.lsq_stem_image_bytes.restype = sz
+            L.lsq_stem_image_bytes.argtypes = []
+            L.lsq_stem_workspace_bytes.restype = sz
+            L.lsq_stem_workspace_bytes.argtypes = [i32, i32, i32]
+            L.lsq_stem_supported.restype = i32
+            L.lsq_stem_supported.argtypes = [i32, i32, i32]
+            L.lsq_stem_pack_weights.restype = i32
+            L.lsq_stem_pack_weights.argtypes = [vp, vp, vp]
             for name in ('lsq_row_absmean', 'lsq_solve_v1', 'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry',
                          'lsq_encode_act', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
                          'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex'):

@@ -1,216 +1,390 @@
-// Fused ImageNet stem of QResNet: conv 7x7 / stride 2 / pad 3 (3 -> 64 channels, eval BatchNorm folded
-// into weights and bias) -> max-pool 3x3 / stride 2 / pad 1 -> ReLU, fp32 in, fp32 out.
-// (quant/models/resnet.py:283-308: blocks[0] = Sequential(conv1, bn1, ReLU, maxpool); ReLU and max-pool
-//  commute.)  The 1.6 GB conv output of a 512-image batch never reaches HBM: a CTA computes the conv
-// outputs feeding a 2 x 14 tile of pooled pixels in shared memory and writes only the pooled tile.
+// ImageNet stem of QResNet on the 5th-generation tensor cores: conv 7x7 / stride 2 / pad 3 (3 -> 64 channels,
+// eval BatchNorm folded into weights and bias) + ReLU as an implicit GEMM with tcgen05.mma kind::tf32 and the
+// 3xTF32 split (x = hi + lo, x*w ~ lo*hi + hi*lo + hi*hi: fp32-level accuracy, ~1e-6 relative), followed by a
+// small max-pool kernel.  (quant/models/resnet.py:283-308: blocks[0] = Sequential(conv1, bn1, ReLU, maxpool).)
+// This layer is outside the quantized path proper; it is here because after the quantized
+// layers were fused it was the largest item of the forward step (legacy mma.sync TF32 runs at CUDA-core rate
+// on sm_100a: the previous mma.sync kernel took 4.2 ms of a 13 ms step).
 //
-// Arithmetic: implicit GEMM (M = conv pixels, N = 64, K = 147 padded to 152) on the tensor cores with
-// mma.sync m16n8k8 TF32 and the 3xTF32 split (x = hi + lo, x*w ~ hi*hi + hi*lo + lo*hi), which restores
-// fp32-level accuracy (~1e-6 relative) while the reference's own GPU path (cuDNN, TF32 allowed by
-// default) is at ~1e-3.  This layer is outside the quantized path proper; it is fused
-// because after the quantized layers were fused it was the largest item of the forward step.
+// Same construction as the binary convolution (lsq_bconv_tc.cu): the input is viewed as 4 stride phases in the
+// "virtual raster" of lsq_act_geometry, in which a tap is a uniform shift of the position index, so a tile of
+// 256 consecutive output positions needs ONE patch per phase in shared memory: [position][c0 c1 c2 0] fp32
+// (16 bytes = one K chunk of 4), once as TF32 "hi" and once as the fp32 remainder "lo".
+//     D[64 channels (M = 128, upper half don't-care), N = 256 positions] += W[., K = 8] * P[K = 8, N]
+// One MMA contracts TWO taps: its two K chunks are the same patch at two shifts -- the descriptor's start
+// address selects the first tap, its leading-dimension byte offset (LBO) the distance to the second.
+// 49 taps -> 25 tap pairs x 3 split terms = 75 MMAs per tile; all weights (100 KB) stay in shared memory.
 #include "lsq_common.cuh"
+#include "lsq_tc.cuh"
 
 namespace lsq {
 
-constexpr int kStemThreads = 160;   // 5 warps x 2 m16 tiles = 160 conv-pixel rows (145 used)
-constexpr int kPH = 2, kPW = 14;    // pooled tile
-constexpr int kCR = 2 * kPH + 1;    // conv rows per tile (5)
-constexpr int kCC = 2 * kPW + 1;    // conv cols per tile (29)
-constexpr int kPR = 4 * kPH + 7;    // input rows (15)
-constexpr int kPC = 4 * kPW + 7;    // input cols (63)
-constexpr int kPPitch = 64;         // patch row pitch (floats)
-constexpr int kK = 152;             // 3*7*7 = 147 padded to a multiple of 8
-constexpr int kWPitch = 156;        // weight row pitch (floats): conflict-free B fragments
-constexpr int kCPitch = 66;         // conv staging pitch (floats per pixel)
+constexpr int kStThreads = 448;
+constexpr int kStTile = 256;        // output positions per tile = N
+constexpr int kStPairs = 25;
+constexpr int kStPStages = 4;       // ring of per-phase patches
+constexpr int kStOutPitch = 20;
+constexpr int kStProducerWarps = 5;
+constexpr uint32_t kStWeightBytes = kStPairs * 2 * 2048;   // [pair][hi, lo][chunk 2][64 rows][4 floats]
 
-constexpr int kPatchElems = 3 * kPR * kPPitch;
-struct StemSmem {                       // 102 KB: two CTAs per SM, their load / GEMM / pool phases interleave
-  float w[64 * kWPitch];                // folded weights, resident: 39.9 KB
-  float patch[2][kPatchElems];          // double-buffered input patch: 2 x 11.5 KB
-  float conv[kCR * kCC * kCPitch];      // 38.3 KB
-  int koff[kK];
-  float bias[64];
+struct StemTaps {                   // static description of the 7x7 / stride 2 / pad 3 taps
+  int tap[kStPairs][2];             // ky*7+kx of the two chunks of a pair, -1 = none (zero weights)
+  int phase[kStPairs];
+  int qy[kStPairs][2], qx[kStPairs][2];
+  int first[4], count[4];           // pairs of a phase
 };
 
-// 4-byte async copy global -> shared, zero-filled when !valid (cp.async with src-size 0)
-__device__ __forceinline__ void cp_async_f32(float* dst, const float* src, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-  const int sz = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// x = hi + lo with hi the TF32 truncation of x (the tensor core ignores the low 13 mantissa bits)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xFFFFE000u;
-  lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi)));
-}
-
-// Persistent: two CTAs per SM keep the weights in shared memory and walk over the tiles; the input patch
-// of the next tile is fetched with cp.async while the tensor cores work on the current one.
-__global__ void __launch_bounds__(kStemThreads, 2)
-stem_kernel(const float* __restrict__ x, const float* __restrict__ wg, const float* __restrict__ bias,
-            float* __restrict__ out, int n, int h, int w, int hc, int wc, int hp, int wp, int tiles_x, int tiles_y,
-            int n_tiles) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  StemSmem& sm = *reinterpret_cast<StemSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (int i = tid; i < 64 * kK; i += kStemThreads) sm.w[(i / kK) * kWPitch + (i % kK)] = __ldg(wg + i);
-  for (int i = tid; i < 64; i += kStemThreads) sm.bias[i] = __ldg(bias + i);
-  for (int k = tid; k < kK; k += kStemThreads) {
-    const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
-    sm.koff[k] = (k < 147) ? (c * kPR * kPPitch + ky * kPPitch + kx) : 0;
+static StemTaps stem_taps() {
+  StemTaps T;
+  auto fdiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+  int np = 0;
+  for (int phase = 0; phase < 4; ++phase) {
+    T.first[phase] = np;
+    int list[16][3], nl = 0;        // (tap, qy, qx) in ascending (qy, qx) = ascending offset
+    for (int ky = 0; ky < 7; ++ky)
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ey = ky - 3, ex = kx - 3;
+        const int qy = fdiv(ey, 2), qx = fdiv(ex, 2);
+        if ((ey - 2 * qy) * 2 + (ex - 2 * qx) != phase) continue;
+        list[nl][0] = ky * 7 + kx; list[nl][1] = qy; list[nl][2] = qx; ++nl;
+      }
+    for (int i = 0; i < nl; i += 2, ++np) {
+      T.phase[np] = phase;
+      T.tap[np][0] = list[i][0]; T.qy[np][0] = list[i][1]; T.qx[np][0] = list[i][2];
+      if (i + 1 < nl) { T.tap[np][1] = list[i + 1][0]; T.qy[np][1] = list[i + 1][1]; T.qx[np][1] = list[i + 1][2]; }
+      else { T.tap[np][1] = -1; T.qy[np][1] = list[i][1]; T.qx[np][1] = list[i][2] + 1; }   // zero weights x the next position
+    }
+    T.count[phase] = np - T.first[phase];
   }
+  return T;   // np == 25
+}
 
-  const int gid = lane >> 2, tig = lane & 3;
-  int base[2][2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t)
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      int m = (warp * 2 + t) * 16 + gid + hh * 8;
-      if (m >= kCR * kCC) m = 0;                      // padding rows compute garbage that is never stored
-      const int r = m / kCC, cx = m - r * kCC;
-      base[t][hh] = 2 * r * kPPitch + 2 * cx;
-    }
+struct StemParams {
+  ActGeom g;
+  int hc, wc, p_tiles, pp;
+  long long q_begin;
+  int dmin[4], first[4], count[4];
+  int pair_off[kStPairs], pair_lbo[kStPairs];   // first-tap offset (relative to dmin of the phase) and distance to the second, in positions
+  uint32_t phase_bytes, stage_bytes, smem_w, smem_p, smem_bar, smem_out;
+  unsigned long long pitch_magic, rps_magic;
+};
 
-  auto prefetch_patch = [&](int tile, int buf) {
-    const int tx = tile % tiles_x;
-    const int ty = (tile / tiles_x) % tiles_y;
-    const int s = tile / (tiles_x * tiles_y);
-    const int iy0 = 4 * (ty * kPH) - 5, ix0 = 4 * (tx * kPW) - 5;    // first input row / col of the patch
-    const float* xs = x + (long long)s * 3 * h * w;
-    for (int i = tid; i < kPatchElems; i += kStemThreads) {
-      const int col = i % kPPitch, row = (i / kPPitch) % kPR, c = i / (kPPitch * kPR);
-      const int iy = iy0 + row, ix = ix0 + col;
-      const bool ok = col < kPC && iy >= 0 && iy < h && ix >= 0 && ix < w;
-      cp_async_f32(&sm.patch[buf][i], ok ? xs + ((long long)c * h + iy) * w + ix : xs, ok);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 
-  int buf = 0;
-  if ((int)blockIdx.x < n_tiles) prefetch_patch(blockIdx.x, 0);
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    const int tx = tile % tiles_x;
-    const int ty = (tile / tiles_x) % tiles_y;
-    const int s = tile / (tiles_x * tiles_y);
-    const int py0 = ty * kPH, px0 = tx * kPW;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();          // patch[buf] visible; the previous tile's pooling is done with sm.conv
-    if (tile + (int)gridDim.x < n_tiles) prefetch_patch(tile + gridDim.x, buf ^ 1);
-    const float* patch = sm.patch[buf];
+struct StPos { int s, a, col; bool in_range; };
+__device__ __forceinline__ StPos st_decode(const StemParams& P, long long q) {
+  StPos r;
+  const long long rel = q - P.g.lead;
+  r.in_range = rel >= 0;
+  const unsigned long long urel = r.in_range ? (unsigned long long)rel : 0ull;
+  const unsigned R = (unsigned)((urel * P.pitch_magic) >> 40);
+  r.col = (int)(urel - (unsigned long long)R * (unsigned)P.g.pitch);
+  r.s = (int)(((unsigned long long)R * P.rps_magic) >> 40);
+  r.a = (int)R - r.s * P.g.rps - P.g.ph;
+  return r;
+}
 
-    // ---- implicit GEMM: each warp owns two m16 tiles (32 conv pixels), all 64 output channels --------
-    float acc[2][8][4];
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[t][nt][e] = 0.0f;
+// image[pair][hl][chunk][row][k]: weights of tap(pair, chunk), input channel k (k = 3: zero), as TF32 hi / fp32 lo
+__global__ void stem_pack_kernel(const float* __restrict__ w, float* __restrict__ image, StemTaps T) {
+  const int total = kStPairs * 2 * 2 * 64 * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 3, row = (i >> 2) & 63, chunk = (i >> 8) & 1, hl = (i >> 9) & 1, pair = i >> 10;
+    const int tap = T.tap[pair][chunk];
+    const float v = (k < 3 && tap >= 0) ? w[row * 147 + k * 49 + tap] : 0.0f;
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    image[i] = hl == 0 ? hi : __fsub_rn(v, hi);
+  }
+}
 
-#pragma unroll 1
-    for (int ks = 0; ks < kK / 8; ++ks) {
-      const int k0 = ks * 8;
-      const int o0 = sm.koff[k0 + tig], o1 = sm.koff[k0 + tig + 4];
-      uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        split_tf32(patch[base[t][0] + o0], ahi[t][0], alo[t][0]);
-        split_tf32(patch[base[t][1] + o0], ahi[t][1], alo[t][1]);
-        split_tf32(patch[base[t][0] + o1], ahi[t][2], alo[t][2]);
-        split_tf32(patch[base[t][1] + o1], ahi[t][3], alo[t][3]);
-      }
-      uint2 b0[8], b1[8];   // (hi, lo)
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        split_tf32(sm.w[(nt * 8 + gid) * kWPitch + k0 + tig], b0[nt].x, b0[nt].y);
-        split_tf32(sm.w[(nt * 8 + gid) * kWPitch + k0 + tig + 4], b1[nt].x, b1[nt].y);
-      }
-      // three passes, small terms first; consecutive MMAs touch different accumulators
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int t = 0; t < 2; ++t) mma_tf32(acc[t][nt], alo[t], b0[nt].x, b1[nt].x);
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int t = 0; t < 2; ++t) mma_tf32(acc[t][nt], ahi[t], b0[nt].y, b1[nt].y);
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int t = 0; t < 2; ++t) mma_tf32(acc[t][nt], ahi[t], b0[nt].x, b1[nt].x);
-    }
+__global__ void __launch_bounds__(kStThreads, 1)
+stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restrict__ wimage, const float* __restrict__ bias,
+                 float* __restrict__ conv) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ActGeom& g = P.g;
+  // barriers: p_full[4] p_empty[4] acc_full[2] acc_empty[2] | tmem base
+  const uint32_t bar0 = sbase + P.smem_bar;
+  auto p_full = [&](int s) { return bar0 + 8u * s; };
+  auto p_empty = [&](int s) { return bar0 + 8u * (kStPStages + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kStPStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kStPStages + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * (2 * kStPStages + 4));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStPStages; ++s) { mbar_init(p_full(s), kStProducerWarps); mbar_init(p_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // resident weights
+  {
+    const float4* src = reinterpret_cast<const float4*>(wimage);
+    float4* dst = reinterpret_cast<float4*>(smem + P.smem_w);
+    for (int i = threadIdx.x; i < (int)(kStWeightBytes / 16); i += kStThreads) dst[i] = __ldg(src + i);
+  }
+  fence_proxy_async();
+  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  int* const err = nullptr;
 
-    // ---- conv + bias -> shared staging -------------------------------------------------------------
+  const bool is_epi = (warp & 3) < 2;            // TMEM lane quarters 0, 1 hold the 64 channels
+  if (is_epi) {
+    // ===================== epilogue (8 warps): bias + ReLU, transposed, stored along positions ==========
+    const int chg = warp & 3, part = warp >> 2;  // 32 channels x 64 positions per warp and tile
+    const int ewarp = chg + 2 * part;
+    float* const outt = reinterpret_cast<float*>(smem + P.smem_out) + (size_t)ewarp * 32 * kStOutPitch;
+    const float bs = __ldg(bias + 32 * chg + lane);
+    const int ch_sub = lane >> 4, pl16 = lane & 15;
+    const long long cstride = (long long)P.hc * P.wc;
+    Ring acc(2);
+    for (int tile = blockIdx.x; tile < P.p_tiles; tile += gridDim.x) {
+      mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
+      tc_fence_after();
+      for (int st = 0; st < 4; ++st) {
+        const int p0 = part * 64 + 16 * st;
+        uint32_t rr[16];
+        tmem_ld16(tmem_base + ((uint32_t)(chg * 32) << 16) + (uint32_t)(acc.stage * kStTile + p0), rr);
+        tmem_ld_wait();
+        float4* orow = reinterpret_cast<float4*>(outt + lane * kStOutPitch);
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
+        for (int j = 0; j < 4; ++j)
+          orow[j] = make_float4(fmaxf(__uint_as_float(rr[4 * j]) + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 1]) + bs, 0.0f),
+                                fmaxf(__uint_as_float(rr[4 * j + 2]) + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 3]) + bs, 0.0f));
+        __syncwarp();
+        const StPos pi = st_decode(P, P.q_begin + (long long)tile * kStTile + p0 + pl16);
+        if (pi.in_range && pi.s < g.n && pi.a >= 0 && pi.a < P.hc && pi.col < P.wc) {
+          const float* ot = outt + (4 * ch_sub) * kStOutPitch + pl16;
+          float v[16];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int m = (warp * 2 + t) * 16 + gid + hh * 8;
-        if (m < kCR * kCC) {
+          for (int i = 0; i < 16; ++i) v[i] = ot[(8 * (i >> 2) + (i & 3)) * kStOutPitch];
+          float* yp = conv + (((long long)pi.s * 64 + 32 * chg + 4 * ch_sub) * P.hc + pi.a) * P.wc + pi.col;
+          const long long s5 = 5 * cstride;
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
-            const int ch = nt * 8 + 2 * tig;
-            *reinterpret_cast<float2*>(&sm.conv[m * kCPitch + ch]) =
-                make_float2(acc[t][nt][hh * 2 + 0] + sm.bias[ch], acc[t][nt][hh * 2 + 1] + sm.bias[ch + 1]);
+          for (int i = 0; i < 16; ++i) {
+            *yp = v[i];
+            yp += ((i & 3) == 3) ? s5 : cstride;
           }
         }
+        __syncwarp();
       }
-    __syncthreads();
-
-    // ---- 3x3 / stride 2 / pad 1 max-pool + ReLU, pooled tile -> NCHW ----------------------------------
-    float* os = out + (long long)s * 64 * hp * wp;
-    for (int i = tid; i < 64 * kPH * kPW; i += kStemThreads) {
-      const int pxl = i % kPW, pyl = (i / kPW) % kPH, ch = i / (kPW * kPH);
-      const int py = py0 + pyl, px = px0 + pxl;
-      if (py >= hp || px >= wp) continue;
-      float m = -INFINITY;
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int cy = 2 * py - 1 + dy;
-        if (cy < 0 || cy >= hc) continue;
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int cxg = 2 * px - 1 + dx;
-          if (cxg < 0 || cxg >= wc) continue;
-          m = fmaxf(m, sm.conv[((2 * pyl + dy) * kCC + (2 * pxl + dx)) * kCPitch + ch]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(acc.stage));
+      acc.advance();
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      Ring acc(2), rp(kStPStages);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kStTile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t wbase = sbase + P.smem_w;
+      for (int tile = blockIdx.x; tile < P.p_tiles; tile += gridDim.x) {
+        mbar_wait(acc_empty(acc.stage), acc.phase ^ 1u, err, 2);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc.stage * kStTile);
+        for (int phase = 0; phase < 4; ++phase) {
+          mbar_wait(p_full(rp.stage), rp.phase, err, 3);
+          tc_fence_after();
+          const uint32_t p_hi = sbase + P.smem_p + (uint32_t)rp.stage * P.stage_bytes, p_lo = p_hi + P.phase_bytes;
+#pragma unroll 1
+          for (int term = 0; term < 3; ++term) {        // small terms first: W_lo P_hi, W_hi P_lo, W_hi P_hi
+            const uint32_t wsel = term == 0 ? 2048u : 0u;
+            const uint32_t pb = term == 1 ? p_lo : p_hi;
+            for (int k = 0; k < P.count[phase]; ++k) {
+              const int pair = P.first[phase] + k;
+              const uint64_t ad = make_desc(wbase + (uint32_t)pair * 4096u + wsel, 1024u, 128u);
+              const uint64_t bd = make_desc(pb + (uint32_t)P.pair_off[pair] * 16u, (uint32_t)P.pair_lbo[pair] * 16u, 128u);
+              umma_tf32(d0, ad, bd, idesc, (phase | term | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(p_empty(rp.stage));
+          rp.advance();
         }
+        umma_commit(acc_full(acc.stage));
+        acc.advance();
       }
-      os[((long long)ch * hp + py) * wp + px] = fmaxf(m, 0.0f);
+    }
+    __syncwarp();
+  } else {
+    // ===================== patch producers (5 warps) =====================
+    // warps 3, 6, 7, 10, 11 -> producer thread index 0..159
+    const int pw = warp == 3 ? 0 : (warp == 6 ? 1 : (warp == 7 ? 2 : (warp == 10 ? 3 : 4)));
+    const int pt = pw * 32 + lane;
+    const long long plane = (long long)g.h * g.w;
+    Ring rp(kStPStages);
+    for (int tile = blockIdx.x; tile < P.p_tiles; tile += gridDim.x) {
+      const long long q0 = P.q_begin + (long long)tile * kStTile;
+      for (int phase = 0; phase < 4; ++phase) {
+        mbar_wait(p_empty(rp.stage), rp.phase ^ 1u, err, 6);
+        float4* hi = reinterpret_cast<float4*>(smem + P.smem_p + (size_t)rp.stage * P.stage_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem + P.smem_p + (size_t)rp.stage * P.stage_bytes + P.phase_bytes);
+        const int py = phase >> 1, px = phase & 1;
+        constexpr int kB = 4;
+        for (int pos0 = pt; pos0 < P.pp; pos0 += kB * kStProducerWarps * 32) {
+          float v[kB][3];
+#pragma unroll
+          for (int u = 0; u < kB; ++u) {
+            const int pos = pos0 + u * kStProducerWarps * 32;
+            v[u][0] = v[u][1] = v[u][2] = 0.0f;
+            if (pos < P.pp) {
+              const StPos pi = st_decode(P, q0 + P.dmin[phase] + pos);
+              const int iy = 2 * pi.a + py, ix = 2 * pi.col + px;
+              if (pi.in_range && pi.s < g.n && pi.a >= 0 && iy < g.h && ix < g.w) {
+                const float* xp = x + ((long long)pi.s * 3 * g.h + iy) * g.w + ix;
+                v[u][0] = __ldg(xp); v[u][1] = __ldg(xp + plane); v[u][2] = __ldg(xp + 2 * plane);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kB; ++u) {
+            const int pos = pos0 + u * kStProducerWarps * 32;
+            if (pos < P.pp) {
+              float h3[3], l3[3];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                h3[c] = __uint_as_float(__float_as_uint(v[u][c]) & 0xFFFFE000u);
+                l3[c] = __fsub_rn(v[u][c], h3[c]);
+              }
+              hi[pos] = make_float4(h3[0], h3[1], h3[2], 0.0f);
+              lo[pos] = make_float4(l3[0], l3[1], l3[2], 0.0f);
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(rp.stage));
+        rp.advance();
+      }
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// max-pool 3x3 / stride 2 / pad 1 of the (already rectified, >= 0) convolution output
+__global__ void __launch_bounds__(256)
+stem_pool_kernel(const float* __restrict__ conv, float* __restrict__ out, int planes, int hc, int wc, int hp, int wp) {
+  const long long total = (long long)planes * hp * wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % wp), py = (int)((i / wp) % hp);
+    const long long pl = i / ((long long)wp * hp);
+    const float* c = conv + pl * hc * wc;
+    float m = 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int cy = 2 * py - 1 + dy;
+      if (cy < 0 || cy >= hc) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int cx = 2 * px - 1 + dx;
+        if (cx < 0 || cx >= wc) continue;
+        m = fmaxf(m, __ldg(c + (long long)cy * wc + cx));
+      }
+    }
+    out[i] = m;
+  }
+}
+
+static bool stem_plan(int n, int h, int w, StemParams& P, size_t& smem_bytes) {
+  lsq_act_geom g;
+  if (lsq_act_geometry(n, 3, h, w, 7, 7, 2, 3, &g) != LSQ_OK) return false;
+  if ((long long)g.n * g.rows_per_sample * g.pitch > (1ll << 31) - 4096) return false;
+  P.g = to_dev(g);
+  P.hc = g.ho; P.wc = g.wo;
+  const StemTaps T = stem_taps();
+  int dmax[4];
+  for (int ph = 0; ph < 4; ++ph) { P.dmin[ph] = 1 << 30; dmax[ph] = -(1 << 30); P.first[ph] = T.first[ph]; P.count[ph] = T.count[ph]; }
+  int off[kStPairs][2];
+  for (int p = 0; p < kStPairs; ++p)
+    for (int c = 0; c < 2; ++c) {
+      off[p][c] = T.qy[p][c] * g.pitch + T.qx[p][c];
+      const int ph = T.phase[p];
+      if (off[p][c] < P.dmin[ph]) P.dmin[ph] = off[p][c];
+      if (off[p][c] > dmax[ph]) dmax[ph] = off[p][c];
+    }
+  int span = 0;
+  for (int ph = 0; ph < 4; ++ph) if (dmax[ph] - P.dmin[ph] > span) span = dmax[ph] - P.dmin[ph];
+  for (int p = 0; p < kStPairs; ++p) {
+    P.pair_off[p] = off[p][0] - P.dmin[T.phase[p]];
+    P.pair_lbo[p] = off[p][1] - off[p][0];
+    if (P.pair_lbo[p] <= 0 || P.pair_lbo[p] >= 0x3FFF) return false;
+  }
+  P.pp = (kStTile + span + 7) / 8 * 8;
+  P.phase_bytes = (uint32_t)P.pp * 16u;
+  P.stage_bytes = 2u * P.phase_bytes;
+  uint32_t o = 0;
+  P.smem_w = o; o += kStWeightBytes;
+  P.smem_p = o; o += kStPStages * P.stage_bytes;     // also absorbs the 1 KB over-read of the last weight slab (M = 128 rows)
+  P.smem_bar = o; o += 256;
+  P.smem_out = o; o += 8 * 32 * kStOutPitch * 4;
+  smem_bytes = o;
+  if (smem_bytes > 227 * 1024) return false;
+  P.pitch_magic = ((1ull << 40) + (unsigned long long)g.pitch - 1ull) / (unsigned long long)g.pitch;
+  P.rps_magic = ((1ull << 40) + (unsigned long long)g.rows_per_sample - 1ull) / (unsigned long long)g.rows_per_sample;
+  P.q_begin = (long long)g.lead + (long long)g.ph * g.pitch;
+  const long long qspan = (long long)g.n * g.rows_per_sample * g.pitch;
+  P.p_tiles = (int)((qspan + kStTile - 1) / kStTile);
+  return true;
 }
 
 }  // namespace lsq
 
 using namespace lsq;
 
-extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_w, const float* d_bias,
-                            float* d_out, void* stream) {
-  LSQ_CHECK_ARG(d_x && d_w && d_bias && d_out, "lsq_stem_fwd: null pointer");
+extern "C" size_t lsq_stem_image_bytes(void) { return kStWeightBytes; }
+
+extern "C" size_t lsq_stem_workspace_bytes(int n, int h, int w) {
+  if (n <= 0 || h < 7 || w < 7) return 0;
+  const size_t hc = (size_t)(h - 1) / 2 + 1, wc = (size_t)(w - 1) / 2 + 1;
+  return (size_t)n * 64 * hc * wc * sizeof(float);
+}
+
+extern "C" int lsq_stem_supported(int n, int h, int w) {
+  StemParams P;
+  size_t smem = 0;
+  return (n > 0 && h >= 7 && w >= 7 && stem_plan(n, h, w, P, smem)) ? 1 : 0;
+}
+
+extern "C" int lsq_stem_pack_weights(const float* d_w, float* d_image, void* stream) {
+  LSQ_CHECK_ARG(d_w && d_image, "lsq_stem_pack_weights: null pointer");
+  stem_pack_kernel<<<50, 256, 0, (cudaStream_t)stream>>>(d_w, d_image, stem_taps());
+  LSQ_CUDA_LAUNCH_CHECK("stem_pack_kernel");
+  return LSQ_OK;
+}
+
+extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_image, const float* d_bias,
+                            float* d_conv_ws, float* d_out, void* stream) {
+  LSQ_CHECK_ARG(d_x && d_image && d_bias && d_conv_ws && d_out, "lsq_stem_fwd: null pointer");
   LSQ_CHECK_ARG(n > 0 && h >= 7 && w >= 7, "lsq_stem_fwd: bad shape");
-  const int hc = (h + 6 - 7) / 2 + 1, wc = (w + 6 - 7) / 2 + 1;
-  const int hp = (hc + 2 - 3) / 2 + 1, wp = (wc + 2 - 3) / 2 + 1;
-  const int tiles_x = (wp + kPW - 1) / kPW, tiles_y = (hp + kPH - 1) / kPH;
-  const long long tiles = (long long)n * tiles_x * tiles_y;
-  LSQ_CHECK_ARG(tiles < (1ll << 31), "lsq_stem_fwd: too many tiles");
-  const size_t smem = sizeof(StemSmem);
-  cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  LSQ_CHECK_ARG(((uintptr_t)d_image & 15) == 0, "lsq_stem_fwd: weight image must be 16-byte aligned");
+  StemParams P;
+  size_t smem = 0;
+  if (!stem_plan(n, h, w, P, smem)) {
+    set_error("lsq_stem_fwd: image %dx%d not supported (patch does not fit shared memory)", h, w);
+    return LSQ_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("lsq_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return LSQ_ERR_CUDA; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)(tiles < 2 * sms ? tiles : 2 * sms);
-  stem_kernel<<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(d_x, d_w, d_bias, d_out, n, h, w, hc, wc, hp, wp,
-                                                                  tiles_x, tiles_y, (int)tiles);
-  LSQ_CUDA_LAUNCH_CHECK("stem_kernel");
+  const int grid = P.p_tiles < sms ? P.p_tiles : sms;
+  stem_conv_kernel<<<grid, kStThreads, smem, (cudaStream_t)stream>>>(d_x, P, d_image, d_bias, d_conv_ws);
+  LSQ_CUDA_LAUNCH_CHECK("stem_conv_kernel");
+  const int hp = (P.hc - 1) / 2 + 1, wp = (P.wc - 1) / 2 + 1;
+  const long long total = (long long)n * 64 * hp * wp;
+  unsigned pgrid = (unsigned)((total + 255) / 256);
+  if (pgrid > 148u * 32u) pgrid = 148u * 32u;
+  stem_pool_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(d_conv_ws, d_out, n * 64, P.hc, P.wc, hp, wp);
+  LSQ_CUDA_LAUNCH_CHECK("stem_pool_kernel");
   return LSQ_OK;
 }

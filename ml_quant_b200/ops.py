@@ -235,18 +235,44 @@ def tc_supported(g: _C.ActGeom, nplanes: int, cout: int) -> bool:
     return bool(_C.lib().lsq_bconv2d_tc_supported(C.byref(g), nplanes, cout))
 
 
-def stem_fwd(x: torch.Tensor, w152: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """relu(maxpool3x3s2p1(conv7x7s2p3(x, w) + bias)) in one kernel (lsq_stem_fwd); w152 is [64, 152]."""
+def stem_supported(n: int, h: int, w: int) -> bool:
+    return bool(_C.lib().lsq_stem_supported(int(n), int(h), int(w)))
+
+
+def stem_pack(w: torch.Tensor) -> torch.Tensor:
+    """Tensor-core operand image of folded stem weights [64, 3, 7, 7] (lsq_stem_pack_weights)."""
+    require_cuda(w, 'weight')
+    if tuple(w.shape) != (64, 3, 7, 7):
+        raise ValueError('stem_pack handles 3 -> 64 channel 7x7 stems only')
+    w = w.detach().contiguous()
+    L = _C.lib()
+    image = torch.empty(L.lsq_stem_image_bytes() // 4, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device), _launch('stem_pack', 4.0 * w.numel()):
+        _C.check(L.lsq_stem_pack_weights(w.data_ptr(), image.data_ptr(), _stream()), 'lsq_stem_pack_weights')
+    return image
+
+
+_stem_ws = {}
+
+
+def stem_fwd(x: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """maxpool3x3s2p1(relu(conv7x7s2p3(x, w) + bias)) (lsq_stem_fwd); image comes from stem_pack."""
     require_cuda(x, 'x')
     x = x.contiguous()
     n, c, h, w = x.shape
-    if c != 3 or tuple(w152.shape) != (64, 152):
+    if c != 3:
         raise ValueError('stem_fwd handles 3 -> 64 channel 7x7 stems only')
+    L = _C.lib()
     hc, wc = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     hp, wp = (hc - 1) // 2 + 1, (wc - 1) // 2 + 1
+    key = (x.device.index, _stream())
+    ws = _stem_ws.get(key)
+    need = L.lsq_stem_workspace_bytes(n, h, w) // 4
+    if ws is None or ws.numel() < need:
+        ws = _stem_ws[key] = torch.empty(need, dtype=torch.float32, device=x.device)
     out = torch.empty(n, 64, hp, wp, dtype=torch.float32, device=x.device)
     macs = float(n) * 64 * hc * wc * 147
     with torch.cuda.device(x.device), _launch('stem', 4.0 * (x.numel() + out.numel()), 2.0 * macs):
-        _C.check(_C.lib().lsq_stem_fwd(x.data_ptr(), n, h, w, w152.data_ptr(), bias.data_ptr(), out.data_ptr(),
-                                       _stream()), 'lsq_stem_fwd')
+        _C.check(L.lsq_stem_fwd(x.data_ptr(), n, h, w, image.data_ptr(), bias.contiguous().data_ptr(), ws.data_ptr(),
+                                out.data_ptr(), _stream()), 'lsq_stem_fwd')
     return out

@@ -85,7 +85,7 @@ class _FusedStem(nn.Module):
         super().__init__()
         self.conv, self.bn, self.pool = conv, bn, pool
         self._key = None
-        self._w152, self._w152_key = None, None
+        self._image, self._image_key = None, None
         self.use_kernel = True
 
     def _folded(self):
@@ -112,10 +112,11 @@ class _FusedStem(nn.Module):
         w, b = self._folded()
         if self.use_kernel and self._kernel_ok(x):
             from . import ops
-            if self._w152 is None or self._w152_key != self._key:
-                self._w152 = F.pad(w.reshape(64, 147), (0, 5)).contiguous()
-                self._w152_key = self._key
-            return ops.stem_fwd(x, self._w152, b.contiguous())
+            if ops.stem_supported(x.shape[0], x.shape[2], x.shape[3]):
+                if self._image is None or self._image_key != self._key:
+                    self._image = ops.stem_pack(w)
+                    self._image_key = self._key
+                return ops.stem_fwd(x, self._image, b.contiguous())
         # bias and ReLU commute with the max-pool: apply them on the 4x smaller pooled tensor
         y = F.conv2d(x, w, None, self.conv.stride, self.conv.padding, self.conv.dilation, self.conv.groups)
         return F.relu_(self.pool(y).add_(b.view(1, -1, 1, 1)))

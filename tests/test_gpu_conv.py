@@ -295,7 +295,7 @@ def test_optimized_network_matches_plain_network():
 
 
 def test_fused_stem_kernel_matches_torch():
-    """lsq_stem_fwd (3xTF32 tensor cores) vs conv + bias + max-pool + ReLU in fp32 ATen (cuDNN off)."""
+    """lsq_stem_fwd (tcgen05 kind::tf32, 3xTF32 split) vs conv + bias + max-pool + ReLU in fp32 ATen (cuDNN off)."""
     import torch.nn.functional as F
     from ml_quant_b200 import ops
     runtime_strict()
@@ -305,7 +305,8 @@ def test_fused_stem_kernel_matches_torch():
         wt = torch.randn(64, 3, 7, 7, device=DEV) * 0.1
         b = torch.randn(64, device=DEV)
         want = F.relu(F.max_pool2d(F.conv2d(x, wt, b, 2, 3), 3, 2, 1))
-        got = ops.stem_fwd(x, F.pad(wt.reshape(64, 147), (0, 5)).contiguous(), b)
+        assert ops.stem_supported(n, h, w)
+        got = ops.stem_fwd(x, ops.stem_pack(wt), b)
         assert got.shape == want.shape
         err = float((got - want).abs().max() / want.abs().max())
         assert err < 2e-5, (n, h, w, err)
