@@ -294,6 +294,40 @@ stem_pool_kernel(const float* __restrict__ conv, float* __restrict__ out, int pl
   }
 }
 
+// same, one CTA per (sample, channel) plane staged in shared memory: one coalesced read of the plane, one
+// coalesced write of the pooled plane (HBM bound)
+__global__ void __launch_bounds__(256)
+stem_pool_plane_kernel(const float* __restrict__ conv, float* __restrict__ out, int hc, int wc, int hp, int wp) {
+  extern __shared__ __align__(16) float plane[];
+  const int np = hc * wc;
+  const float* c = conv + (long long)blockIdx.x * np;
+  if ((np & 3) == 0) {
+    const float4* c4 = reinterpret_cast<const float4*>(c);
+    float4* p4 = reinterpret_cast<float4*>(plane);
+    for (int i = threadIdx.x; i < (np >> 2); i += 256) p4[i] = __ldg(c4 + i);
+  } else {
+    for (int i = threadIdx.x; i < np; i += 256) plane[i] = __ldg(c + i);
+  }
+  __syncthreads();
+  float* o = out + (long long)blockIdx.x * hp * wp;
+  for (int i = threadIdx.x; i < hp * wp; i += 256) {
+    const int py = i / wp, px = i - py * wp;
+    float m = 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int cy = 2 * py - 1 + dy;
+      if (cy < 0 || cy >= hc) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int cx = 2 * px - 1 + dx;
+        if (cx < 0 || cx >= wc) continue;
+        m = fmaxf(m, plane[cy * wc + cx]);
+      }
+    }
+    o[i] = m;
+  }
+}
+
 static bool stem_plan(int n, int h, int w, StemParams& P, size_t& smem_bytes) {
   lsq_act_geom g;
   if (lsq_act_geometry(n, 3, h, w, 7, 7, 2, 3, &g) != LSQ_OK) return false;
@@ -381,10 +415,17 @@ extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* 
   stem_conv_kernel<<<grid, kStThreads, smem, (cudaStream_t)stream>>>(d_x, P, d_image, d_bias, d_conv_ws);
   LSQ_CUDA_LAUNCH_CHECK("stem_conv_kernel");
   const int hp = (P.hc - 1) / 2 + 1, wp = (P.wc - 1) / 2 + 1;
-  const long long total = (long long)n * 64 * hp * wp;
-  unsigned pgrid = (unsigned)((total + 255) / 256);
-  if (pgrid > 148u * 32u) pgrid = 148u * 32u;
-  stem_pool_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(d_conv_ws, d_out, n * 64, P.hc, P.wc, hp, wp);
+  const size_t plane_bytes = (size_t)P.hc * P.wc * sizeof(float);
+  if (plane_bytes <= 56 * 1024 && ((uintptr_t)d_conv_ws & 15) == 0) {
+    e = cudaFuncSetAttribute(stem_pool_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
+    if (e != cudaSuccess) { set_error("lsq_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return LSQ_ERR_CUDA; }
+    stem_pool_plane_kernel<<<(unsigned)(n * 64), 256, plane_bytes, (cudaStream_t)stream>>>(d_conv_ws, d_out, P.hc, P.wc, hp, wp);
+  } else {
+    const long long total = (long long)n * 64 * hp * wp;
+    unsigned pgrid = (unsigned)((total + 255) / 256);
+    if (pgrid > 148u * 32u) pgrid = 148u * 32u;
+    stem_pool_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(d_conv_ws, d_out, n * 64, P.hc, P.wc, hp, wp);
+  }
   LSQ_CUDA_LAUNCH_CHECK("stem_pool_kernel");
   return LSQ_OK;
 }
