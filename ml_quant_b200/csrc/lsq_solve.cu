@@ -26,18 +26,13 @@
 namespace lsq {
 
 constexpr int kSolveThreads = 512;    // two CTAs per SM: one row's serial phases overlap the other's passes
-constexpr int kBins = 8192;
-constexpr int kBinsPerThread = kBins / kSolveThreads;
 constexpr int kListBins = 1024;   // bins of a shared-memory refinement window
 constexpr int kListBinsPerThread = kListBins / kSolveThreads;
 constexpr int kListBinsLog2 = 10;
-constexpr int kCap = 8192;      // list A: elements of the flagged ranges of a global window
-constexpr int kSmallCap = 21504;  // list A when it holds a whole (sampled) row: it then extends over Bins::l.ext
 constexpr int kFineCap = 2048;  // list B: elements that are sorted and evaluated one by one
 constexpr int kMaxRanges = 4;
 constexpr int kMaxFlag = 64;
 constexpr int kStack = 24;
-constexpr int kTopShift = 18;
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 constexpr int kLoadBatch = 8;
 constexpr int kMaxGroups = 128;        // flagged 16-bin groups whose bins get the fine test in parallel
@@ -63,68 +58,123 @@ struct Range {        // flagged bins [blo, bhi] of the current window
   uint32_t list_start;
 };
 
-// Shared memory (112 KB, two CTAs per SM).  Lifetimes overlap as little as possible so regions are reused:
-//   list_a                     : per-thread bin-group prefixes while a global window is scanned
-//   bins.l.ext                 : tail of list A when the whole sampled row lives in shared memory
-union Bins {
-  struct { uint32_t hist[kBins]; uint32_t bsum[kBins]; } g;     // global windows: counts, sum(m >> 9)
-  struct {
-    uint32_t ext[2 * kBins - 3 * kListBins];
-    uint32_t hist[kListBins], lo[kListBins], hi[kListBins];     // list windows: counts, sum(m & 0xFFF), sum(m >> 12)
-  } l;
+// Shared memory.  Two layouts (template parameter of the kernel):
+//   L = SolveLayout<13, 8192>  115 KB, two CTAs per SM: rows of up to 21504 sampled elements stay entirely in
+//                              shared memory (one pass over HBM), 8192 bins, list A of 8192 elements;
+//   L = SolveLayout<12, 2048, 3> 103 KB, two CTAs per SM (the register file allows no more): long rows (two
+//                              streaming passes).  4096 bins still cover 16 octaves below the clamp bound at 256
+//                              bins per octave; the memory saved holds a 3-stage cp.async staging ring, which
+//                              triples the bytes each thread keeps in flight at no register cost.
+// Lifetimes overlap as little as possible so regions are reused:
+//   list_a       : per-thread bin-group prefixes while a global window is scanned
+//   bins.l.ext   : tail of list A when the whole sampled row lives in shared memory
+template <int LOG2_BINS, int CAP, int NSTAGE>
+struct SolveLayout {
+  static constexpr int kStages = NSTAGE;
+  static constexpr int kBinsLog2 = LOG2_BINS;
+  static constexpr int kBins = 1 << LOG2_BINS;
+  static constexpr int kBinsPerThread = kBins / kSolveThreads;
+  static constexpr int kCap = CAP;                               // list A: elements of the flagged ranges of a global window
+  static constexpr int kSmallCap = CAP + 2 * kBins - 3 * kListBins;   // list A when it holds a whole sampled row
+  static constexpr int kTopShift = 31 - LOG2_BINS;
+  union Bins {
+    struct { uint32_t hist[kBins]; uint32_t bsum[kBins]; } g;     // global windows: counts, sum(m >> 9)
+    struct {
+      uint32_t ext[2 * kBins - 3 * kListBins];
+      uint32_t hist[kListBins], lo[kListBins], hi[kListBins];     // list windows: counts, sum(m & 0xFFF), sum(m >> 12)
+    } l;
+  };
+  struct Smem {
+    uint32_t list_b[kFineCap];
+    uint32_t list_a[kCap];
+    Bins bins;
+    float2 ab[kMaxProChannels];            // per-channel (scale, shift) of the fused prologue
+    double red[32];
+    double wsum[32];
+    uint32_t wcnt[32];
+    uint32_t wfirst[32];
+    uint32_t wnz[32];
+    int nflag, ngroup;
+    uint16_t glist[kMaxGroups];
+    uint32_t fmin, fmax;
+    uint16_t fbin[kMaxFlag];
+    uint32_t fexcl[kMaxFlag];
+    uint32_t fnext[kMaxFlag];
+    double fsumb[kMaxFlag];
+    int ford[kMaxFlag];
+    int nrange;
+    Range rng[kMaxRanges];
+    double seg_base[kMaxRanges];
+    int nstack;
+    Window stack[kStack];
+    Window cur;
+    uint32_t cnt_below, min_above, win_min, kmin, kmax, nlist_a, nlist_b;
+    int direct_eval, flags, action;   // action: 0 none, 1 collect ranges into a list
+    double best_cost[32];
+    uint32_t best_pos[32], best_key[32], ncand;
+    float stage[NSTAGE > 0 ? NSTAGE * kSolveThreads * kLoadBatch : 1];   // cp.async staging ring of the row passes
+  };
+  static_assert(sizeof(Bins) == 2 * kBins * 4, "Bins views must have the same size");
+  static_assert(offsetof(Smem, bins) == (kFineCap + kCap) * 4, "list_a must run into bins.l.ext");
+  static_assert(kSolveThreads * 16 <= kCap * 4, "group prefix records must fit list A");
 };
-struct SolveSmem {
-  uint32_t list_b[kFineCap];
-  uint32_t list_a[kCap];
-  Bins bins;
-  float2 ab[kMaxProChannels];            // per-channel (scale, shift) of the fused prologue
-  double red[32];
-  double wsum[32];
-  uint32_t wcnt[32];
-  uint32_t wfirst[32];
-  uint32_t wnz[32];
-  int nflag, ngroup;
-  uint16_t glist[kMaxGroups];
-  uint32_t fmin, fmax;
-  uint16_t fbin[kMaxFlag];
-  uint32_t fexcl[kMaxFlag];
-  uint32_t fnext[kMaxFlag];
-  double fsumb[kMaxFlag];
-  int ford[kMaxFlag];
-  int nrange;
-  Range rng[kMaxRanges];
-  double seg_base[kMaxRanges];
-  int nstack;
-  Window stack[kStack];
-  Window cur;
-  uint32_t cnt_below, min_above, win_min, kmin, kmax, nlist_a, nlist_b;
-  int direct_eval, flags, action;   // action: 0 none, 1 collect ranges into a list
-  double best_cost[32];
-  uint32_t best_pos[32], best_key[32], ncand;
-};
-static_assert(sizeof(SolveSmem) <= 113 * 1024, "two CTAs per SM need <= 113 KB each (228 KB - 2 x 1 KB reserved)");
-static_assert(sizeof(Bins) == 2 * kBins * 4, "Bins views must have the same size");
-static_assert(offsetof(SolveSmem, bins) == (kFineCap + kCap) * 4, "list_a must run into bins.l.ext");
-static_assert(kSolveThreads * 16 <= kCap * 4, "group prefix records must fit list A");
-static_assert(kSmallCap <= kCap + 2 * kBins - 3 * kListBins, "small-row list does not fit");
+using LayoutBig = SolveLayout<13, 8192, 0>;
+using LayoutSmall = SolveLayout<12, 2048, 3>;
+static_assert(sizeof(LayoutBig::Smem) <= 113 * 1024, "two CTAs per SM need <= 113 KB each (228 KB - 2 x 1 KB reserved)");
+static_assert(sizeof(LayoutSmall::Smem) <= 113 * 1024, "two CTAs per SM need <= 113 KB each");
 
 // Calls body(v, e0, e_end) on batches of sampled elements: this thread's elements are e = e0 + u * blockDim.x
 // (u < kLoadBatch, valid while e < e_end), v[u] = x[e * skip]; kLoadBatch independent loads are in flight per
 // thread.  Trip counts are warp uniform.  (A cp.async.bulk ring feeding the same loop was measured slower:
 // scripts/mb/mb_hist.cu, 3.4 vs 4.7 TB/s.)
-template <class Body>
-__device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip, uint32_t n, Body&& body) {
+template <int NSTAGE, class Body>
+__device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip, uint32_t n, float* stage, Body&& body) {
   const int tid = threadIdx.x;
-  for (uint32_t eb = 0; eb < n; eb += kSolveThreads * kLoadBatch) {
-    float v[kLoadBatch];
-    const uint32_t e0 = eb + tid;
+  constexpr uint32_t kBatch = kSolveThreads * kLoadBatch;
+  if (NSTAGE == 0) {
+    for (uint32_t eb = 0; eb < n; eb += kBatch) {
+      float v[kLoadBatch];
+      const uint32_t e0 = eb + tid;
 #pragma unroll
-    for (int u = 0; u < kLoadBatch; ++u) {
-      const uint32_t e = e0 + u * kSolveThreads;
-      v[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
+      for (int u = 0; u < kLoadBatch; ++u) {
+        const uint32_t e = e0 + u * kSolveThreads;
+        v[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
+      }
+      body(v, e0, min(n, eb + kBatch));
     }
-    body(v, e0, min(n, eb + (uint32_t)(kSolveThreads * kLoadBatch)));
+    return;
   }
+  // staged: every thread copies its own elements of the next NSTAGE-1 batches into shared memory with cp.async
+  // and reads back only what it copied itself, so cp.async.wait_group is the only synchronisation needed
+  auto issue = [&](uint32_t eb, int slot) {
+    if (eb < n) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + slot * kBatch + tid);
+#pragma unroll
+      for (int u = 0; u < kLoadBatch; ++u) {
+        const uint32_t e = eb + tid + u * kSolveThreads;
+        const bool ok = e < n;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)u * kSolveThreads * 4u),
+                     "l"(xr + (ok ? (long long)e * skip : 0ll)), "r"(ok ? 4 : 0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int islot = 0, cslot = 0;
+  uint32_t ieb = 0;
+  for (int k = 0; k + 1 < NSTAGE; ++k) { issue(ieb, islot); ieb += kBatch; if (++islot == NSTAGE) islot = 0; }
+  for (uint32_t eb = 0; eb < n; eb += kBatch) {
+    issue(ieb, islot); ieb += kBatch; if (++islot == NSTAGE) islot = 0;
+    if (NSTAGE == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else if (NSTAGE == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    float v[kLoadBatch];
+    const float* sp = stage + cslot * kBatch + tid;
+#pragma unroll
+    for (int u = 0; u < kLoadBatch; ++u) v[u] = sp[u * kSolveThreads];
+    body(v, eb + tid, min(n, eb + kBatch));
+    if (++cslot == NSTAGE) cslot = 0;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ float key_val(uint32_t k) { return __uint_as_float(k); }
@@ -249,8 +299,8 @@ __device__ __forceinline__ void bitonic_sort(uint32_t* keys, uint32_t lp) {
 }
 
 // Evaluate the sorted list keys[0..L) made of the `nseg` ranges sm.rng[] (ascending key order).
-template <bool TERN>
-__device__ void evaluate_list(SolveSmem& sm, const uint32_t* keys, uint32_t L, int nseg, uint32_t n, double s_tot,
+template <bool TERN, class SM>
+__device__ void evaluate_list(SM& sm, const uint32_t* keys, uint32_t L, int nseg, uint32_t n, double s_tot,
                               double q_tot, Best& best, uint32_t& ncand) {
   const uint32_t per = (L + blockDim.x - 1) / blockDim.x;
   const uint32_t j0 = min(threadIdx.x * per, L), j1 = min(j0 + per, L);
@@ -293,11 +343,13 @@ __device__ void evaluate_list(SolveSmem& sm, const uint32_t* keys, uint32_t L, i
   __syncthreads();
 }
 
-template <bool TERN>
+template <bool TERN, class L>
 __global__ void __launch_bounds__(kSolveThreads, 2)
 solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
                 int* __restrict__ diag, Prologue pro) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  using SolveSmem = typename L::Smem;
+  constexpr int kBins = L::kBins, kBinsPerThread = L::kBinsPerThread, kCap = L::kCap, kSmallCap = L::kSmallCap, kTopShift = L::kTopShift;
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
   const long long row = blockIdx.x;
   const float* xr = x + row * len;
@@ -412,7 +464,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     double ls = 0.0, lq = 0.0, lb = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey, kwin = kNoKey;
     if (!from_list) {
-      sweep_row(xr, skip, n,
+      sweep_row<L::kStages>(xr, skip, n, sm.stage,
                 [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
@@ -694,7 +746,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
             const unsigned long long span = r.span.khi - r.span.klo;
             int lg = 0;
             while ((1ull << lg) < span) ++lg;
-            int nshift = lg - (from_list ? kListBinsLog2 : 13);
+            int nshift = lg - (from_list ? kListBinsLog2 : L::kBinsLog2);
             if (nshift < 0) nshift = 0;
             if (nshift >= shift) nshift = shift - 1;
             const unsigned long long wspan = (unsigned long long)nbins << nshift;
@@ -744,7 +796,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       }
       __syncthreads();
       if (!from_list) {
-        sweep_row(xr, skip, n,
+        sweep_row<L::kStages>(xr, skip, n, sm.stage,
                   [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
           uint32_t matched = 0u;
           uint32_t keys[kLoadBatch];
@@ -932,22 +984,30 @@ extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int 
   LSQ_CHECK_ARG(d_x && d_v1, "lsq_solve_v1: null pointer");
   LSQ_CHECK_ARG(rows > 0 && len > 0 && skip >= 1, "lsq_solve_v1: bad shape rows=%lld len=%lld skip=%d", (long long)rows, (long long)len, skip);
   LSQ_CHECK_ARG((len + skip - 1) / skip < (1ll << 31), "lsq_solve_v1: row too long");
-  const size_t smem = sizeof(SolveSmem);
-  cudaError_t e;
-  if (ternary) e = cudaFuncSetAttribute(solve_v1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  else e = cudaFuncSetAttribute(solve_v1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_error("lsq_solve_v1: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    return LSQ_ERR_CUDA;
-  }
   if (pro && pro->d_ch_scale && ((int64_t)pro->channels * pro->inner != len || len >= (1ll << 26))) {
     set_error("lsq_solve_v1: prologue needs len == channels * inner (< 2^26)");
     return LSQ_ERR_ARG;
   }
   const Prologue dp = to_dev(pro);
   dim3 grid((unsigned)rows);
-  if (ternary) solve_v1_kernel<true><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp);
-  else solve_v1_kernel<false><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp);
+  // rows whose sampled elements fit shared memory take the layout that keeps them there (one pass over HBM)
+  // (unclamped long rows keep the 8192-bin layout: their top window cannot be anchored and stays coarse)
+  const bool big = (len + skip - 1) / skip <= (int64_t)LayoutBig::kSmallCap || !(alpha > 0.0f);
+  const size_t smem = big ? sizeof(LayoutBig::Smem) : sizeof(LayoutSmall::Smem);
+  cudaError_t e;
+#define LSQ_SOLVE(T, LAY)                                                                                          \
+  do {                                                                                                             \
+    e = cudaFuncSetAttribute(solve_v1_kernel<T, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    if (e == cudaSuccess)                                                                                          \
+      solve_v1_kernel<T, LAY><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp); \
+  } while (0)
+  if (ternary) { if (big) LSQ_SOLVE(true, LayoutBig); else LSQ_SOLVE(true, LayoutSmall); }
+  else { if (big) LSQ_SOLVE(false, LayoutBig); else LSQ_SOLVE(false, LayoutSmall); }
+#undef LSQ_SOLVE
+  if (e != cudaSuccess) {
+    set_error("lsq_solve_v1: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return LSQ_ERR_CUDA;
+  }
   LSQ_CUDA_LAUNCH_CHECK("solve_v1_kernel");
   return LSQ_OK;
 }
