@@ -233,10 +233,11 @@ def main():
     ours_ms = sum(d['ms'] for d in agg.values())
     top = max(agg, key=lambda k: agg[k]['ms'])
     td = agg[top]
-    traffic = None
+    traffic, traffic_instance = None, None
     tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top)
+        tj = json.load(open(tpath))
+        traffic, traffic_instance = tj.get(top), tj.get(top + '_instance')
     if top.startswith('bconv_tc'):
         # kind::i8 issues at twice the bf16 rate: denominator = 2 x measured bf16 (sustained, MEASURED_PEAKS.json).
         # (scripts/mb/mb_umma.cu measures 4.3 POP/s for back-to-back M128 N256 K32 tcgen05.mma on this part.)
@@ -246,7 +247,7 @@ def main():
     else:
         ach = td['bytes'] / (td['ms'] / 1e3) / 1e9
         roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak}
-    roof.update({'traffic': traffic, 'kernel': top, 'launches': td['launches'], 'avg_ms': td['ms'] / td['launches'],
+    roof.update({'traffic': traffic, 'traffic_instance': traffic_instance, 'kernel': top, 'launches': td['launches'], 'avg_ms': td['ms'] / td['launches'],
                  'share_of_step': td['ms'] / (ms / args.steps), 'peak_source': peak_src,
                  'kernels_ms': {k: round(v['ms'], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])},
                  'graph_step_ms': ms / args.steps, 'our_kernels_share': ours_ms / (ms / args.steps), 'fp32_stem_ms': stem_ms})

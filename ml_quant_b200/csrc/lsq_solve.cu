@@ -873,7 +873,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       LSQ_TICK(8);   // collection reductions
       if (!from_list) {
         // ranges of the global row are now in list A
-        const uint32_t L = min(sm.nlist_a, (uint32_t)kCap);
+        const uint32_t L = min(sm.nlist_a, (uint32_t)kCap);   // shadows the layout parameter in this scope
         if (sm.nlist_a <= (uint32_t)kFineCap) {
           // few elements (the usual case with a fine top window): sort them -- every range becomes one
           // ascending segment -- and give each element the reference's own candidate test
