@@ -198,3 +198,28 @@ def test_weight_quantizer_modules():
         b = q(w2)
         q.eval()
         assert torch.equal(b, q(w2))
+
+
+# BASELINE.json configs[4]: the 20 distinct conv-weight shapes of torchvision resnet50
+RESNET50_WEIGHT_SHAPES = [(64, 3, 7, 7), (64, 64, 1, 1), (64, 64, 3, 3), (64, 256, 1, 1), (128, 128, 3, 3), (128, 256, 1, 1),
+                          (128, 512, 1, 1), (256, 64, 1, 1), (256, 256, 3, 3), (256, 512, 1, 1), (256, 1024, 1, 1),
+                          (512, 128, 1, 1), (512, 256, 1, 1), (512, 512, 3, 3), (512, 1024, 1, 1), (512, 2048, 1, 1),
+                          (1024, 256, 1, 1), (1024, 512, 1, 1), (2048, 512, 1, 1), (2048, 1024, 1, 1)]
+
+
+@pytest.mark.parametrize('tern', [False, True])
+def test_solver_resnet50_weight_sweep(tern):
+    """ls-2 / ls-T scale solve on ResNet-50-sized weight tensors (rows = output channels, 64..4608 elements,
+    skip 3 and 1, no clamp): every row meets the solver contract against the oracle; ls-1 scales to 1e-6."""
+    from ml_quant_b200 import ops
+    g = torch.Generator().manual_seed(50)
+    for shape in RESNET50_WEIGHT_SHAPES:
+        w = torch.randn(*shape, generator=g) * (2.0 / (shape[1] * shape[2] * shape[3])) ** 0.5     # kaiming-like
+        rows = w.reshape(shape[0], -1)[:96]                      # the oracle is O(n log n) per row on the CPU
+        for skip in (3, 1):
+            if (rows.shape[1] + skip - 1) // skip < 3:
+                continue
+            v = ops.solve_v1(rows.to(DEV), tern, skip).cpu()
+            v_ref = O.solve_v1(rows, tern, skip, chunk=32).view(-1)
+            _solver_contract(rows, v, v_ref, tern, skip)
+        assert _close(ops.row_absmean(rows.to(DEV)), rows.abs().mean(1))
