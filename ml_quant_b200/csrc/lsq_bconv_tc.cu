@@ -38,8 +38,8 @@ constexpr int kMaxTaps = 9;
 constexpr int kMaxWStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kMaxPStages = 3;
-constexpr int kResStages = 6;     // residual staging: 16-position steps in flight per epilogue warp (2 KB each)
-constexpr int kOutPitch = 20;     // transposition tile: 32 channels x 16 positions; 20 words: 16-byte rows, conflict-free both ways
+constexpr int kResStages = 4;     // residual staging: 32-position steps in flight per epilogue warp (4 KB each)
+constexpr int kOutPitch = 36;     // transposition tile: 32 channels x 32 positions; 36 words: 16-byte rows, conflict-free both ways
 
 struct TcParams {
   ActGeom g;
@@ -121,10 +121,11 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
 
   if (warp < 4 || warp >= 10) {
     // ===================== epilogue (8 warps) =====================
-    // quarter = TMEM lane quarter = 32 output channels of the channel tile; the two warps of a quarter take
-    // one half of the tile's positions each and walk it in steps of 16 positions.
     // quarter = TMEM lane quarter; 128-channel tiles: quarter = channel group, the two warps of a quarter split
     // the positions in 2; 64-channel tiles: lanes 64..127 repeat lanes 0..63, positions are split in 4.
+    // A warp walks its positions in steps of 32: thread = channel converts and scales two 16-position halves into
+    // a 32 x 32 transposition tile, then lane = position applies activation / residual and stores one 128-byte
+    // row segment per channel.
     const int quarter = warp & 3;
     const int half = warp < 4 ? 0 : 1;
     const int ewarp = quarter + 4 * half;
@@ -132,17 +133,15 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
     const int chb = 32 * (quarter % cq);                // first channel (within the tile) of this warp
     const int nparts = 8 / cq;                          // position parts per tile (2 or 4)
     const int part = half * (nparts >> 1) + quarter / cq;
-    const int tph = P.tp / nparts;                      // positions of this warp per item
+    const int tph = P.tp / nparts;                      // positions of this warp per item (multiple of 32)
     const int pbase = part * tph;
-    const int spi = tph >> 4;                           // steps per item
-    const int nch = 32;
+    const int spi = tph >> 5;                           // steps per item
     const bool has_res = epi.residual != nullptr;
     const int R = P.r_stages;
     const long long cstride = (long long)g.ho * g.wo;
-    float* const res0 = reinterpret_cast<float*>(smem + P.smem_res) + (size_t)ewarp * R * 512;
+    float* const res0 = reinterpret_cast<float*>(smem + P.smem_res) + (size_t)ewarp * R * 1024;
     float* const outt = reinterpret_cast<float*>(smem + P.smem_out) + (size_t)ewarp * 32 * kOutPitch;
     float2* const scl = reinterpret_cast<float2*>(smem + P.smem_scl) + (size_t)ewarp * 128;
-    const int ch_sub = lane >> 4, pl16 = lane & 15;     // write-out role: two channels x 16 positions per instruction
 
     // where does position `p` of tile `ptile` land in the output?  (offset of channel 0 of the channel tile, or -1)
     auto out_offset = [&](int ptile, int ctile, int p, int& sample) -> long long {
@@ -157,19 +156,18 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       if (++c.step == spi) { c.step = 0; c.item += (int)gridDim.x; }
     };
     auto issue = [&](const Cursor& c, int slot) {      // always commits a group so the group count stays uniform
-      if (has_res && nch > 0 && c.item < n_items) {
+      if (has_res && c.item < n_items) {
         const int ptile = c.item / P.n_ctiles, ctile = c.item - ptile * P.n_ctiles;
         int sample;
-        const long long off = out_offset(ptile, ctile, pbase + 16 * c.step + pl16, sample);
-        const uint32_t dst = smem_u32(res0 + slot * 512 + lane);
+        const long long off = out_offset(ptile, ctile, pbase + 32 * c.step + lane, sample);
+        const uint32_t dst = smem_u32(res0 + slot * 1024 + lane);
         const int sz = off >= 0 ? 4 : 0;
-        // instruction i covers channels c_i and c_i + 4 (c_i = 8 * (i / 4) + i % 4) x 16 positions
-        const float* src = epi.residual + (off >= 0 ? off + (long long)(chb + 4 * ch_sub) * cstride : 0);
-        const long long s1 = off >= 0 ? cstride : 0, s5 = off >= 0 ? 5 * cstride : 0;
+        const float* src = epi.residual + (off >= 0 ? off + (long long)chb * cstride : 0);
+        const long long s1 = off >= 0 ? cstride : 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)i * 128u), "l"(src), "r"(sz) : "memory");
-          src += ((i & 3) == 3) ? s5 : s1;
+        for (int ch = 0; ch < 32; ++ch) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)ch * 128u), "l"(src), "r"(sz) : "memory");
+          src += s1;
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -188,39 +186,39 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       advance(is);
       if (++islot == R) islot = 0;
       // all but the R-1 most recent groups are complete -> the step being consumed has landed
-      if (R >= 6) asm volatile("cp.async.wait_group 5;" ::: "memory");
-      else if (R == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+      if (R >= 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+      else if (R == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else if (R == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
       const int ptile = co.item / P.n_ctiles, ctile = co.item - ptile * P.n_ctiles;
       if (co.step == 0) {
         // per-position activation scales of this warp's positions, per-thread channel constants
-        if (nch > 0) {
-          for (int p = lane; p < tph; p += 32) {
-            int sample;
-            const long long off = out_offset(ptile, ctile, pbase + p, sample);
-            float2 s2 = make_float2(0.0f, 0.0f);
-            if (off >= 0) {
-              s2.x = __ldg(act_scales + sample);
-              if (P.npl > 1) s2.y = __ldg(act_scales + g.n + sample);
-            }
-            scl[p] = s2;
+        for (int p = lane; p < tph; p += 32) {
+          int sample;
+          const long long off = out_offset(ptile, ctile, pbase + p, sample);
+          float2 s2 = make_float2(0.0f, 0.0f);
+          if (off >= 0) {
+            s2.x = __ldg(act_scales + sample);
+            if (P.npl > 1) s2.y = __ldg(act_scales + g.n + sample);
           }
-          const float4 k = ctab[ctile * 128 + chb + lane];
-          ws = k.x; bs = k.y;
+          scl[p] = s2;
         }
+        const float4 k = ctab[ctile * 128 + chb + lane];
+        ws = k.x; bs = k.y;
         __syncwarp();
         mbar_wait_t(acc_full(acc.stage), acc.phase, err, 1, w0);
         tc_fence_after();
       }
-      if (nch > 0) {
-        // ---- thread = channel: 16 positions x planes from TMEM, scale, bias -> transposition tile ----
-        const uint32_t col0 = (uint32_t)acc.stage * acc_cols + (uint32_t)((pbase + 16 * co.step) * P.npl);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
-        uint32_t rr[32];                                   // columns col0 .. col0 + 16 * planes - 1
+      // ---- thread = channel: two halves of 16 positions x planes from TMEM, scale, bias -> transposition tile ----
+      float4* orow = reinterpret_cast<float4*>(outt + lane * kOutPitch);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int p0 = pbase + 32 * co.step + 16 * sub;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc.stage * acc_cols + (uint32_t)(p0 * P.npl);
+        uint32_t rr[32];                                   // 16 positions x planes (interleaved)
         tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&rr[0]));
         if (P.npl > 1) tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(&rr[16]));
-        const float4* sp = reinterpret_cast<const float4*>(scl + 16 * co.step);     // (s1, s2) of two positions
+        const float4* sp = reinterpret_cast<const float4*>(scl + 32 * co.step + 16 * sub);     // (s1, s2) of two positions
         float4 s4[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) s4[j] = sp[j];
@@ -230,7 +228,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float sx = (j & 1) ? s4[j >> 1].z : s4[j >> 1].x, sy = (j & 1) ? s4[j >> 1].w : s4[j >> 1].y;
-            const float t = fmaf(sy, (float)(int)rr[2 * j + 1], sx * (float)(int)rr[2 * j]);   // planes interleave
+            const float t = fmaf(sy, (float)(int)rr[2 * j + 1], sx * (float)(int)rr[2 * j]);
             o[j] = __fadd_rn(__fmul_rn(ws, t), bs);
           }
         } else {
@@ -240,50 +238,52 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
             o[j] = __fadd_rn(__fmul_rn(ws, sx * (float)(int)rr[j]), bs);
           }
         }
-        float4* orow = reinterpret_cast<float4*>(outt + lane * kOutPitch);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) orow[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        __syncwarp();
-        // ---- lanes along positions: activation, residual, coalesced stores ----
+        for (int j = 0; j < 4; ++j) orow[4 * sub + j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+      __syncwarp();
+      // ---- lane = position: activation, residual, one 128-byte row segment per channel ----
+      {
         int sample;
-        const long long off = out_offset(ptile, ctile, pbase + 16 * co.step + pl16, sample);
+        const long long off = out_offset(ptile, ctile, pbase + 32 * co.step + lane, sample);
         if (off >= 0) {
-          const float* rs_base = res0 + cslot * 512 + lane;
-          const float* ot = outt + (4 * ch_sub) * kOutPitch + pl16;
-          // all shared-memory reads first, then the arithmetic, then the stores (16 independent chains);
-          // instruction i covers channels c_i and c_i + 4 with c_i = 8 * (i / 4) + i % 4: conflict-free reads
-          float v[16], rs[16];
+          const float* rs_base = res0 + cslot * 1024 + lane;
+          const float* ot = outt + lane;
+          const float4* tab = ctab + ctile * 128 + chb;
+          float* yp = y + off + (long long)chb * cstride;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = ot[(8 * (i >> 2) + (i & 3)) * kOutPitch];
-            rs[i] = has_res ? rs_base[i * 32] : 0.0f;
-          }
-          if (!epi.residual_after_act) {
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            // all shared-memory reads first, then the arithmetic, then the stores (16 independent chains)
+            float v[16], rs[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += rs[i];
-          }
-          if (epi.act == 1) {
+            for (int i = 0; i < 16; ++i) {
+              v[i] = ot[(c0 + i) * kOutPitch];
+              rs[i] = has_res ? rs_base[(c0 + i) * 32] : 0.0f;
+            }
+            if (!epi.residual_after_act) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-          } else if (epi.act == 2) {
-            const float4* tab = ctab + ctile * 128 + chb + 4 * ch_sub;
+              for (int i = 0; i < 16; ++i) v[i] += rs[i];
+            }
+            if (epi.act == 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.0f ? v[i] : v[i] * tab[8 * (i >> 2) + (i & 3)].z;
-          }
-          if (epi.residual_after_act) {
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+            } else if (epi.act == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += rs[i];
-          }
-          float* yp = y + off + (long long)(chb + 4 * ch_sub) * cstride;
-          const long long s5 = 5 * cstride;
+              for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.0f ? v[i] : v[i] * tab[c0 + i].z;
+            }
+            if (epi.residual_after_act) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            *yp = v[i];
-            yp += ((i & 3) == 3) ? s5 : cstride;
+              for (int i = 0; i < 16; ++i) v[i] += rs[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              *yp = v[i];
+              yp += cstride;
+            }
           }
         }
-        __syncwarp();
       }
+      __syncwarp();
       if (co.step == spi - 1) {
         tc_fence_before();
         __syncwarp();
@@ -431,6 +431,7 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   P.npl = nplanes; P.cout = cout; P.creal = cout < 128 ? cout : 128; P.n_ctiles = (cout + 127) / 128;
   P.ncb = g->c / 64; P.taps = g->kh * g->kw;
   P.tp = tp;
+  if (tp / (8 / (P.creal >> 5)) < 32) return false;       // every epilogue warp takes whole 32-position steps
   // per-tap phase and position offset: input coordinate = stride*out + d - pad
   auto fdiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
   for (int ph = 0; ph < 4; ++ph) P.dmin[ph] = 0;
@@ -468,7 +469,7 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   const size_t fixed = bar_bytes + tab_bytes + scl_bytes + out_bytes + slack;
   // minimum: 2 patch stages (1 when there is a single channel block and nothing to overlap with is no option:
   // the next item's patch is built while this one is multiplied), 2 weight stages of one tap, 2 residual steps
-  const size_t res_min = has_res ? (size_t)8 * 2 * 2048 : 0;
+  const size_t res_min = has_res ? (size_t)8 * 2 * 4096 : 0;
   if (fixed + 2 * (size_t)P.p_stage_bytes + 2 * (size_t)P.w_slab_bytes + res_min > total) return false;
   size_t left = total - fixed - res_min - 2 * (size_t)P.p_stage_bytes;
   // weights: whole tap rows per stage when they fit twice (fewer commits), else single taps
@@ -479,9 +480,9 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   // then: deeper residual staging, a third patch stage, more weight stages
   P.r_stages = has_res ? 2 : 1;
   if (has_res) {
-    const int want[2] = {kResStages, 4};
+    const int want[2] = {kResStages, 3};
     for (int k = 0; k < 2; ++k) {
-      const size_t extra = (size_t)8 * (want[k] - 2) * 2048;
+      const size_t extra = (size_t)8 * (want[k] - 2) * 4096;
       if (extra <= left) { P.r_stages = want[k]; left -= extra; break; }
     }
   }
@@ -495,7 +496,7 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   P.smem_tab = o; o += (uint32_t)tab_bytes;
   P.smem_scl = o; o += (uint32_t)scl_bytes;
   P.smem_out = o; o += (uint32_t)out_bytes;
-  P.smem_res = o; o += has_res ? (uint32_t)(8 * P.r_stages * 2048) : 0u;
+  P.smem_res = o; o += has_res ? (uint32_t)(8 * P.r_stages * 4096) : 0u;
   return o <= 227 * 1024;
 }
 
@@ -530,7 +531,7 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   const long long qspan = (long long)g->n * g->rows_per_sample * g->pitch;
   P.p_tiles = (int)((qspan + P.tp - 1) / P.tp);
   const int n_items = P.p_tiles * P.n_ctiles;
-  const size_t smem_bytes = (size_t)P.smem_res + (epi.residual ? (size_t)8 * P.r_stages * 2048 : 0);
+  const size_t smem_bytes = (size_t)P.smem_res + (epi.residual ? (size_t)8 * P.r_stages * 4096 : 0);
 
   // the weight image follows the bit image inside d_wpack (lsq_bconv.cu)
   const size_t bits_bytes = ((size_t)cout * g->kh * g->kw * g->cw * 4 + 1023) / 1024 * 1024;
