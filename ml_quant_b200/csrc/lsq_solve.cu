@@ -970,6 +970,102 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
   }
 }
 
+// ---- short rows (<= 2048 sampled elements: every conv / linear weight row with skip 3) ---------------------
+// The whole sampled row is sorted in shared memory by a 128-thread CTA and every position gets the reference's
+// own candidate test -- the reference algorithm itself (optimal.py:41-83), without the histogram machinery whose
+// per-row latency dominated such rows (16 CTAs per SM instead of 2).
+constexpr int kSmallThreads = 128;
+constexpr int kSmallRow = 2048;
+struct SmallSmem {
+  uint32_t keys[kSmallRow];
+  double red[32];
+  double wsum[32];
+  Range rng[kMaxRanges];
+  double seg_base[kMaxRanges];
+  double best_cost[32];
+  uint32_t best_pos[32], best_key[32], kmin, kmax, ncand;
+};
+
+template <bool TERN>
+__global__ void __launch_bounds__(kSmallThreads)
+solve_v1_small_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
+                      int* __restrict__ diag, Prologue pro) {
+  __shared__ SmallSmem sm;
+  const long long row = blockIdx.x;
+  const float* xr = x + row * len;
+  const uint32_t n = (uint32_t)((len + skip - 1) / skip);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { sm.kmin = kNoKey; sm.kmax = 0u; sm.ncand = 0u; }
+  __syncthreads();
+  if (n < 3) {
+    if (tid == 0) {
+      v1_out[row] = 0.0f;
+      if (diag) for (int i = 0; i < 16; ++i) diag[row * 16 + i] = 0;
+    }
+    return;
+  }
+  double ls = 0.0, lq = 0.0;
+  uint32_t kmn = kNoKey, kmx = 0u;
+  for (uint32_t e = tid; e < n; e += kSmallThreads) {
+    const long long idx = (long long)e * skip;
+    const float a = fabsf(clamp_sym(apply_prologue(pro, __ldg(xr + idx), idx), alpha));
+    const uint32_t k = __float_as_uint(a);
+    ls += (double)a; lq += (double)a * (double)a;
+    kmn = min(kmn, k); kmx = max(kmx, k);
+    sm.keys[e] = k;
+  }
+  uint32_t lp = 2;
+  while (lp < n) lp <<= 1;
+  for (uint32_t e = n + tid; e < lp; e += kSmallThreads) sm.keys[e] = kNoKey;
+  const double s_tot = block_sum(ls, sm.red);
+  const double q_tot = block_sum(lq, sm.red);
+  kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
+  if (lane == 0) { atomicMin(&sm.kmin, kmn); atomicMax(&sm.kmax, kmx); }
+  __syncthreads();
+  if (tid == 0) {
+    Range r;
+    r.blo = 0u; r.bhi = 0u; r.cnt_below = 0u; r.count = n; r.list_start = 0u;
+    r.span.klo = 0ull; r.span.khi = 1ull << 32; r.span.sum_below = 0.0; r.span.cnt_below = 0u; r.span.next_key = sm.kmax;
+    sm.rng[0] = r;
+  }
+  bitonic_sort(sm.keys, lp);          // ends with a block barrier
+  Best best{1e300, 0xFFFFFFFFu, 0u};
+  uint32_t ncand = 0;
+  evaluate_list<TERN>(sm, sm.keys, n, 1, n, s_tot, q_tot, best, ncand);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, best.cost, o);
+    const uint32_t op = __shfl_xor_sync(0xffffffffu, best.pos, o);
+    const uint32_t ok = __shfl_xor_sync(0xffffffffu, best.key, o);
+    best.offer(oc, op, ok);
+  }
+  ncand = (uint32_t)__reduce_add_sync(0xffffffffu, ncand);
+  if (lane == 0) {
+    sm.best_cost[wid] = best.cost; sm.best_pos[wid] = best.pos; sm.best_key[wid] = best.key;
+    atomicAdd(&sm.ncand, ncand);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    Best b{1e300, 0xFFFFFFFFu, 0u};
+    for (int w = 0; w < kSmallThreads / 32; ++w) b.offer(sm.best_cost[w], sm.best_pos[w], sm.best_key[w]);
+    uint32_t nc_tot = sm.ncand;
+    if (TERN) {
+      // optimal.py:86-118: when min > mean/2 the value mean/2 (not a data element) is appended last
+      const float mean = (float)(s_tot / (double)n);
+      const float half_mean = __fmul_rn(0.5f, mean);
+      if (key_val(sm.kmin) > half_mean) {
+        ++nc_tot;
+        b.offer(closed_cost2<true>((double)half_mean, 0.0, 0.0, (double)n, s_tot, q_tot), n, __float_as_uint(half_mean));
+      }
+    }
+    v1_out[row] = (nc_tot > 0) ? key_val(b.key) : 0.0f;
+    if (diag) {
+      for (int i = 0; i < 16; ++i) diag[row * 16 + i] = 0;
+      diag[row * 16 + 0] = 1; diag[row * 16 + 2] = (int)nc_tot;
+    }
+  }
+}
+
 }  // namespace lsq
 
 using namespace lsq;
@@ -990,6 +1086,12 @@ extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int 
   }
   const Prologue dp = to_dev(pro);
   dim3 grid((unsigned)rows);
+  if ((len + skip - 1) / skip <= (int64_t)kSmallRow) {
+    if (ternary) solve_v1_small_kernel<true><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp);
+    else solve_v1_small_kernel<false><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp);
+    LSQ_CUDA_LAUNCH_CHECK("solve_v1_small_kernel");
+    return LSQ_OK;
+  }
   // rows whose sampled elements fit shared memory take the layout that keeps them there (one pass over HBM)
   // (unclamped long rows keep the 8192-bin layout: their top window cannot be anchored and stays coarse)
   const bool big = (len + skip - 1) / skip <= (int64_t)LayoutBig::kSmallCap || !(alpha > 0.0f);
