@@ -192,6 +192,17 @@ LSQ_API int lsq_stem_pack_weights(const float* d_w, float* d_image, void* stream
 LSQ_API int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_image, const float* d_bias,
                  float* d_conv_ws, float* d_out, void* stream);
 
+/* ---- fp32 pointwise strided convolution (downsampling shortcuts) ----------------
+ * y[n,co,oy,ox] = sum_ci w[co,ci] * x[n,ci,stride*oy,stride*ox] + bias[co]  (quant/models/resnet.py:24-39,
+ * Conv2d(kernel_size=1, stride) + eval BatchNorm2d folded into w / bias by the caller), tcgen05 kind::tf32
+ * with the 3xTF32 split.  Needs cin % 16 == 0 and cout % 128 == 0 (lsq_pwconv_supported).
+ *   lsq_pwconv_pack_weights: d_w float[cout][cin] -> operand image of lsq_pwconv_image_bytes(cout, cin) bytes */
+LSQ_API int lsq_pwconv_supported(int cin, int cout);
+LSQ_API size_t lsq_pwconv_image_bytes(int cout, int cin);
+LSQ_API int lsq_pwconv_pack_weights(const float* d_w, int cout, int cin, float* d_image, void* stream);
+LSQ_API int lsq_pwconv_fwd(const float* d_x, int n, int cin, int h, int w, int stride, const float* d_image,
+                   const float* d_bias, int cout, float* d_y, void* stream);
+
 /* 1 if the tensor-core kernel handles this problem */
 LSQ_API int lsq_bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout);
 

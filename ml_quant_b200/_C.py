@@ -17,6 +17,7 @@ EXPORTS = [
     'lsq_wpack_bytes', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
     'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex', 'lsq_stem_fwd',
     'lsq_stem_image_bytes', 'lsq_stem_workspace_bytes', 'lsq_stem_supported', 'lsq_stem_pack_weights',
+    'lsq_pwconv_supported', 'lsq_pwconv_image_bytes', 'lsq_pwconv_pack_weights', 'lsq_pwconv_fwd',
 ]
 
 
@@ -84,6 +85,14 @@ def lib():
             L.lsq_stem_supported.argtypes = [i32, i32, i32]
             L.lsq_stem_pack_weights.restype = i32
             L.lsq_stem_pack_weights.argtypes = [vp, vp, vp]
+            L.lsq_pwconv_supported.restype = i32
+            L.lsq_pwconv_supported.argtypes = [i32, i32]
+            L.lsq_pwconv_image_bytes.restype = sz
+            L.lsq_pwconv_image_bytes.argtypes = [i32, i32]
+            L.lsq_pwconv_pack_weights.restype = i32
+            L.lsq_pwconv_pack_weights.argtypes = [vp, i32, i32, vp, vp]
+            L.lsq_pwconv_fwd.restype = i32
+            L.lsq_pwconv_fwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]
             for name in ('lsq_row_absmean', 'lsq_solve_v1', 'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry',
                          'lsq_encode_act', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
                          'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex'):

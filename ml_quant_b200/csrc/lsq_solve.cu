@@ -343,13 +343,13 @@ __device__ void evaluate_list(SM& sm, const uint32_t* keys, uint32_t L, int nseg
   __syncthreads();
 }
 
-template <bool TERN, class L>
+template <bool TERN, class LAY>
 __global__ void __launch_bounds__(kSolveThreads, 2)
 solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
                 int* __restrict__ diag, Prologue pro) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using SolveSmem = typename L::Smem;
-  constexpr int kBins = L::kBins, kBinsPerThread = L::kBinsPerThread, kCap = L::kCap, kSmallCap = L::kSmallCap, kTopShift = L::kTopShift;
+  using SolveSmem = typename LAY::Smem;
+  constexpr int kBins = LAY::kBins, kBinsPerThread = LAY::kBinsPerThread, kCap = LAY::kCap, kSmallCap = LAY::kSmallCap, kTopShift = LAY::kTopShift;
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
   const long long row = blockIdx.x;
   const float* xr = x + row * len;
@@ -464,7 +464,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     double ls = 0.0, lq = 0.0, lb = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey, kwin = kNoKey;
     if (!from_list) {
-      sweep_row<L::kStages>(xr, skip, n, sm.stage,
+      sweep_row<LAY::kStages>(xr, skip, n, sm.stage,
                 [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
@@ -746,7 +746,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
             const unsigned long long span = r.span.khi - r.span.klo;
             int lg = 0;
             while ((1ull << lg) < span) ++lg;
-            int nshift = lg - (from_list ? kListBinsLog2 : L::kBinsLog2);
+            int nshift = lg - (from_list ? kListBinsLog2 : LAY::kBinsLog2);
             if (nshift < 0) nshift = 0;
             if (nshift >= shift) nshift = shift - 1;
             const unsigned long long wspan = (unsigned long long)nbins << nshift;
@@ -796,7 +796,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       }
       __syncthreads();
       if (!from_list) {
-        sweep_row<L::kStages>(xr, skip, n, sm.stage,
+        sweep_row<LAY::kStages>(xr, skip, n, sm.stage,
                   [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
           uint32_t matched = 0u;
           uint32_t keys[kLoadBatch];

@@ -69,14 +69,6 @@ struct StemParams {
   unsigned long long pitch_magic, rps_magic;
 };
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
 struct StPos { int s, a, col; bool in_range; };
 __device__ __forceinline__ StPos st_decode(const StemParams& P, long long q) {
   StPos r;

@@ -276,3 +276,33 @@ def stem_fwd(x: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.
         _C.check(L.lsq_stem_fwd(x.data_ptr(), n, h, w, image.data_ptr(), bias.contiguous().data_ptr(), ws.data_ptr(),
                                 out.data_ptr(), _stream()), 'lsq_stem_fwd')
     return out
+
+
+def pwconv_supported(cin: int, cout: int) -> bool:
+    return bool(_C.lib().lsq_pwconv_supported(int(cin), int(cout)))
+
+
+def pwconv_pack(w2d: torch.Tensor) -> torch.Tensor:
+    """Tensor-core operand image of pointwise-convolution weights [cout, cin] (lsq_pwconv_pack_weights)."""
+    require_cuda(w2d, 'weight')
+    w2d = w2d.detach().contiguous()
+    cout, cin = w2d.shape
+    L = _C.lib()
+    image = torch.empty(L.lsq_pwconv_image_bytes(cout, cin) // 4, dtype=torch.float32, device=w2d.device)
+    with torch.cuda.device(w2d.device), _launch('pwconv_pack', 12.0 * w2d.numel()):
+        _C.check(L.lsq_pwconv_pack_weights(w2d.data_ptr(), cout, cin, image.data_ptr(), _stream()), 'lsq_pwconv_pack_weights')
+    return image
+
+
+def pwconv_fwd(x: torch.Tensor, image: torch.Tensor, bias: torch.Tensor, cout: int, stride: int) -> torch.Tensor:
+    """y = conv1x1(x, w, stride) + bias in fp32 (3xTF32 on the tensor cores; lsq_pwconv_fwd)."""
+    require_cuda(x, 'x')
+    x = x.contiguous()
+    n, cin, h, w = x.shape
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    out = torch.empty(n, cout, ho, wo, dtype=torch.float32, device=x.device)
+    macs = float(n) * cout * ho * wo * cin
+    with torch.cuda.device(x.device), _launch('pwconv', 4.0 * (n * cin * ho * wo + out.numel()), 2.0 * macs):
+        _C.check(_C.lib().lsq_pwconv_fwd(x.data_ptr(), n, cin, h, w, int(stride), image.data_ptr(), bias.contiguous().data_ptr(),
+                                         int(cout), out.data_ptr(), _stream()), 'lsq_pwconv_fwd')
+    return out

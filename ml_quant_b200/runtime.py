@@ -67,9 +67,10 @@ def calibrate(model: nn.Module, input_shape, batches: int = 2, batch: int = 32, 
 
 def _shortcut_fused(blk, x: torch.Tensor) -> torch.Tensor:
     """The full-precision downsampling shortcut (1x1 strided convolution + eval BatchNorm,
-    quant/models/resnet.py:24-39) as ONE batched fp32 GEMM on the NCHW tensor: BatchNorm folded into the
-    weights, the stride taken by slicing.  cuDNN ran it as layout transposes of the whole input + TF32
-    convolution + bias add + BatchNorm kernel (1.2 ms of a 10.5 ms step for the three shortcuts)."""
+    quant/models/resnet.py:24-39) with the BatchNorm folded into the weights: one tcgen05 3xTF32 kernel
+    (lsq_pwconv_fwd) when the channel counts allow it, else one batched fp32 GEMM on the strided slice.
+    cuDNN ran it as layout transposes of the whole input + TF32 convolution + bias add + BatchNorm kernel
+    (1.2 ms of a 10.5 ms step for the three shortcuts)."""
     sc = blk.shortcut
     if len(sc) == 0:
         return x
@@ -88,10 +89,15 @@ def _shortcut_fused(blk, x: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():
             w = (conv.weight.reshape(conv.out_channels, conv.in_channels) * a.view(-1, 1)).contiguous()
             bias = (b if conv.bias is None else b + a * conv.bias).reshape(1, -1, 1).contiguous()
-        hit = (key, w, bias)
+        from . import ops
+        image = ops.pwconv_pack(w) if ops.pwconv_supported(conv.in_channels, conv.out_channels) else None
+        hit = (key, w, bias, image)
         blk._lsq_shortcut = hit
-    _, w, bias = hit
+    _, w, bias, image = hit
     st = conv.stride[0]
+    if image is not None and x.dtype == torch.float32:
+        from . import ops
+        return ops.pwconv_fwd(x, image, bias.reshape(-1), conv.out_channels, st)
     xs = x[:, :, ::st, ::st] if st > 1 else x
     n, c, h, wd = xs.shape
     xs = xs.reshape(n, c, h * wd)                      # copies the strided slice once

@@ -310,3 +310,21 @@ def test_fused_stem_kernel_matches_torch():
         assert got.shape == want.shape
         err = float((got - want).abs().max() / want.abs().max())
         assert err < 2e-5, (n, h, w, err)
+
+
+def test_pointwise_strided_conv_matches_torch():
+    """lsq_pwconv_fwd (tcgen05 kind::tf32, 3xTF32 split) vs F.conv2d(kernel 1x1, stride) in fp32 ATen."""
+    from ml_quant_b200 import ops
+    runtime_strict()
+    torch.manual_seed(10)
+    for n, cin, cout, h, w, st in [(5, 64, 128, 56, 56, 2), (3, 128, 256, 28, 28, 2), (9, 256, 512, 14, 14, 2),
+                                   (2, 32, 128, 17, 23, 2), (2, 16, 256, 9, 7, 1), (70, 64, 128, 8, 8, 2)]:
+        assert ops.pwconv_supported(cin, cout)
+        x = torch.randn(n, cin, h, w, device=DEV)
+        wt = torch.randn(cout, cin, device=DEV) * (1.0 / cin) ** 0.5
+        b = torch.randn(cout, device=DEV)
+        want = F.conv2d(x, wt.view(cout, cin, 1, 1), b, st)
+        got = ops.pwconv_fwd(x, ops.pwconv_pack(wt), b, cout, st)
+        assert got.shape == want.shape
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err < 2e-5, (n, cin, cout, h, w, st, err)
