@@ -393,13 +393,18 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     // ---- small row: list A is the whole row --------------------------------------------------
     double ls = 0.0, lq = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u;
-    for (uint32_t e = tid; e < n; e += blockDim.x) {
-      const float a = fabsf(clamp_sym(prologue(__ldg(xr + (long long)e * skip), (long long)e * skip), alpha));
-      const uint32_t k = __float_as_uint(a);
-      ls += (double)a; lq += (double)a * (double)a;
-      kmn = min(kmn, k); kmx = max(kmx, k);
-      list_a[e] = k;
-    }
+    sweep_row<0>(xr, skip, n, nullptr, [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
+#pragma unroll
+      for (int u = 0; u < kLoadBatch; ++u) {       // kLoadBatch loads in flight (one at a time left this phase latency bound)
+        const uint32_t e = e0 + u * kSolveThreads;
+        if (e >= e_end) break;
+        const float a = fabsf(clamp_sym(prologue(v[u], (long long)e * skip), alpha));
+        const uint32_t k = __float_as_uint(a);
+        ls += (double)a; lq += (double)a * (double)a;
+        kmn = min(kmn, k); kmx = max(kmx, k);
+        list_a[e] = k;
+      }
+    });
     s_tot = block_sum(ls, sm.red);
     q_tot = block_sum(lq, sm.red);
     kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
