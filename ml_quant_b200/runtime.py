@@ -191,9 +191,11 @@ def optimize_for_inference(model: nn.Module) -> nn.Module:
 class GraphedForward:
     """model(x) for a fixed input shape as one CUDA graph: no per-layer launch gaps, no host work."""
 
-    def __init__(self, model: nn.Module, example: torch.Tensor, warmup: int = 2):
+    def __init__(self, model: nn.Module, example: torch.Tensor, warmup: int = 2, clone: bool = True):
         self.model = model
-        self.static_in = example.clone()
+        # clone=False: the graph reads ``example`` itself (a caller-owned device buffer that is refilled
+        # between replays, e.g. the upload buffers of HostPipeline)
+        self.static_in = example.clone() if clone else example
         side = torch.cuda.Stream(device=example.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -223,7 +225,9 @@ class HostPipeline:
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.freed = [torch.cuda.Event() for _ in range(2)]
         self.model = model
-        self.fwd = [GraphedForward(model, b) if use_graph else None for b in self.bufs]
+        for b in self.bufs:
+            b.zero_()                     # defined contents for the capture warm-up runs
+        self.fwd = [GraphedForward(model, b, clone=False) if use_graph else None for b in self.bufs]
         n_out = self._run(0).shape
         self.host_out = torch.empty(n_out, pin_memory=True)
         for e in self.freed:

@@ -223,9 +223,17 @@ def test_cuda_graph_and_host_pipeline_match_eager():
         eager = model(x.to(DEV)).cpu()
     fwd = runtime.GraphedForward(model, x.to(DEV))
     assert torch.equal(fwd().cpu(), eager)
-    pipe = runtime.HostPipeline(model, (8, 3, 32, 32), torch.device(DEV))
+    # the pipeline must classify what is uploaded: different batches per step, last one checked, for both
+    # buffer parities, with and without graphs
+    other = [torch.randn(8, 3, 32, 32).pin_memory() for _ in range(3)]
     hx = x.pin_memory()
-    assert torch.equal(pipe.run([hx, hx, hx]).clone(), eager)
+    for use_graph in (True, False):
+        pipe = runtime.HostPipeline(model, (8, 3, 32, 32), torch.device(DEV), use_graph=use_graph)
+        assert torch.equal(pipe.run([other[0], other[1], hx]).clone(), eager)
+        assert torch.equal(pipe.run([other[2], hx]).clone(), eager)
+        with torch.no_grad():
+            want = model(other[1].to(DEV)).cpu()
+        assert torch.equal(pipe.run([hx, other[1]]).clone(), want)
 
 
 def test_fused_prologue_epilogue_matches_composition():
