@@ -220,3 +220,52 @@ class QuantConv2d(nn.Conv2d):
         x_q = self.x_approximate(self.clamping_fn(x))
         w_q = self.w_approximate(self.weight)
         return F.conv2d(x_q, w_q, self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+
+class QuantLinear(nn.Module):
+    """Linear layer on scaled-binary weights and activations: ``y = w_quant(W) @ x_quant(clamp(x)) + b``.
+
+    The reference has no quantized linear layer (its classifiers are ``nn.Linear``, quant/models/resnet.py:339,
+    lenet.py:75-76); BASELINE.json's north star names one, so it is provided as the 1x1 / no-spatial case of
+    ``QuantConv2d``: a row of ``x`` is one sample [in_features, 1, 1], hence per-row activation
+    scales and per-output-feature weight scales, the same schemes, clamp and moving-average options, and the same
+    kernels (packed route: solve + encode + tcgen05 binary GEMM when in/out features are multiples of 64).
+    Inputs of shape [..., in_features] are flattened over the leading dimensions.
+    """
+
+    def __init__(self, x_quant: str, w_quant: str, in_features: int, out_features: int, clamp: Optional[Dict] = None,
+                 moving_average_mode: str = 'off', moving_average_momentum: float = 0.99, bias: bool = True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.conv = QuantConv2d(x_quant, w_quant, in_features, out_features, 1, clamp, moving_average_mode,
+                                moving_average_momentum, bias=bias)
+
+    @property
+    def weight(self) -> torch.Tensor:
+        return self.conv.weight.view(self.out_features, self.in_features)
+
+    @property
+    def bias(self) -> Optional[torch.Tensor]:
+        return self.conv.bias
+
+    @property
+    def x_approximate(self) -> nn.Module:
+        return self.conv.x_approximate
+
+    @property
+    def w_approximate(self) -> nn.Module:
+        return self.conv.w_approximate
+
+    @property
+    def quantized_parameters(self) -> Dict[str, List[torch.Tensor]]:
+        return self.conv.quantized_parameters
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
+        if x.shape[-1] != self.in_features:
+            raise ValueError(f'QuantLinear: expected last dimension {self.in_features}, got {tuple(x.shape)}')
+        lead = x.shape[:-1]
+        y = self.conv(x.reshape(-1, self.in_features, 1, 1))
+        return y.reshape(*lead, self.out_features)
+
+    def extra_repr(self) -> str:
+        return f'in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}'

