@@ -13,19 +13,23 @@
 //     D[64 channels (M = 128, upper half don't-care), N = 256 positions] += W[., K = 8] * P[K = 8, N]
 // One MMA contracts TWO taps: its two K chunks are the same patch at two shifts -- the descriptor's start
 // address selects the first tap, its leading-dimension byte offset (LBO) the distance to the second.
-// 49 taps -> 25 tap pairs x 3 split terms = 75 MMAs per tile; all weights (100 KB) stay in shared memory.
+// The 64 channels use only half of the M = 128 rows, so the other half carries the second weight term:
+// rows 0..63 = W_hi, rows 64..127 = W_lo; with B = P_hi and then B = P_lo the accumulator holds
+// W_hi (P_hi + P_lo) in lanes 0..63 and W_lo (P_hi + P_lo) in lanes 64..127 -- all four product terms in TWO MMAs
+// per tap pair instead of three.  49 taps -> 25 pairs x 2 = 50 MMAs per tile; the epilogue adds the two lane
+// halves (warp pairs exchange through shared memory).  All weights (100 KB) stay in shared memory.
 #include "lsq_common.cuh"
 #include "lsq_tc.cuh"
 
 namespace lsq {
 
-constexpr int kStThreads = 448;
+constexpr int kStThreads = 704;      // 8 + 8 epilogue warps (lane halves), MMA warp 16, producer warps 17-21
 constexpr int kStTile = 256;        // output positions per tile = N
 constexpr int kStPairs = 25;
 constexpr int kStPStages = 4;       // ring of per-phase patches
 constexpr int kStOutPitch = 20;
 constexpr int kStProducerWarps = 5;
-constexpr uint32_t kStWeightBytes = kStPairs * 2 * 2048;   // [pair][hi, lo][chunk 2][64 rows][4 floats]
+constexpr uint32_t kStWeightBytes = kStPairs * 4096;       // [pair][chunk 2][128 rows: 64 hi, 64 lo][4 floats]
 
 struct StemTaps {                   // static description of the 7x7 / stride 2 / pad 3 taps
   int tap[kStPairs][2];             // ky*7+kx of the two chunks of a pair, -1 = none (zero weights)
@@ -82,11 +86,12 @@ __device__ __forceinline__ StPos st_decode(const StemParams& P, long long q) {
   return r;
 }
 
-// image[pair][hl][chunk][row][k]: weights of tap(pair, chunk), input channel k (k = 3: zero), as TF32 hi / fp32 lo
+// image[pair][chunk][row][k]: weights of tap(pair, chunk), channel row & 63, input channel k (k = 3: zero);
+// rows 0..63 TF32 hi, rows 64..127 fp32 remainder lo
 __global__ void stem_pack_kernel(const float* __restrict__ w, float* __restrict__ image, StemTaps T) {
   const int total = kStPairs * 2 * 2 * 64 * 4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int k = i & 3, row = (i >> 2) & 63, chunk = (i >> 8) & 1, hl = (i >> 9) & 1, pair = i >> 10;
+    const int k = i & 3, row = (i >> 2) & 63, hl = (i >> 8) & 1, chunk = (i >> 9) & 1, pair = i >> 10;
     const int tap = T.tap[pair][chunk];
     const float v = (k < 3 && tap >= 0) ? w[row * 147 + k * 49 + tap] : 0.0f;
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -110,7 +115,7 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * (2 * kStPStages + 4));
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStPStages; ++s) { mbar_init(p_full(s), kStProducerWarps); mbar_init(p_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // resident weights
@@ -120,18 +125,22 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
     for (int i = threadIdx.x; i < (int)(kStWeightBytes / 16); i += kStThreads) dst[i] = __ldg(src + i);
   }
   fence_proxy_async();
-  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  if (warp == 16) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   int* const err = nullptr;
 
-  const bool is_epi = (warp & 3) < 2;            // TMEM lane quarters 0, 1 hold the 64 channels
-  if (is_epi) {
-    // ===================== epilogue (8 warps): bias + ReLU, transposed, stored along positions ==========
-    const int chg = warp & 3, part = warp >> 2;  // 32 channels x 64 positions per warp and tile
-    const int ewarp = chg + 2 * part;
+  if (warp < 16) {
+    // ===================== epilogue (16 warps) =====================
+    // Warps with (warp & 3) < 2 read accumulator lanes 0..63 (the W_hi half), their partners warp + 2 lanes
+    // 64..127 (the W_lo half) of the same 32 channels x 64 positions; the partner parks its half in the pair's
+    // transposition tile, the main warp adds it, applies bias + ReLU, transposes and stores along positions.
+    const bool upper = (warp & 3) >= 2;
+    const int chg = warp & 1, part = warp >> 2;
+    const int ewarp = chg + 2 * part;                  // pair index 0..7
+    const int bar_id = 1 + ewarp;                      // named barrier of the pair (64 threads)
     float* const outt = reinterpret_cast<float*>(smem + P.smem_out) + (size_t)ewarp * 32 * kStOutPitch;
     const float bs = __ldg(bias + 32 * chg + lane);
     const int ch_sub = lane >> 4, pl16 = lane & 15;
@@ -143,13 +152,24 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
       for (int st = 0; st < 4; ++st) {
         const int p0 = part * 64 + 16 * st;
         uint32_t rr[16];
-        tmem_ld16(tmem_base + ((uint32_t)(chg * 32) << 16) + (uint32_t)(acc.stage * kStTile + p0), rr);
+        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc.stage * kStTile + p0), rr);
         tmem_ld_wait();
         float4* orow = reinterpret_cast<float4*>(outt + lane * kStOutPitch);
+        if (upper) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          orow[j] = make_float4(fmaxf(__uint_as_float(rr[4 * j]) + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 1]) + bs, 0.0f),
-                                fmaxf(__uint_as_float(rr[4 * j + 2]) + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 3]) + bs, 0.0f));
+          for (int j = 0; j < 4; ++j)
+            orow[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // half parked
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // tile consumed: may be overwritten
+          continue;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 u = orow[j];
+          orow[j] = make_float4(fmaxf(__uint_as_float(rr[4 * j]) + u.x + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 1]) + u.y + bs, 0.0f),
+                                fmaxf(__uint_as_float(rr[4 * j + 2]) + u.z + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 3]) + u.w + bs, 0.0f));
+        }
         __syncwarp();
         const StPos pi = st_decode(P, P.q_begin + (long long)tile * kStTile + p0 + pl16);
         if (pi.in_range && pi.s < g.n && pi.a >= 0 && pi.a < P.hc && pi.col < P.wc) {
@@ -165,14 +185,14 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
             yp += ((i & 3) == 3) ? s5 : cstride;
           }
         }
-        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(acc.stage));
       acc.advance();
     }
-  } else if (warp == 2) {
+  } else if (warp == 16) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       Ring acc(2), rp(kStPStages);
@@ -187,12 +207,11 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
           tc_fence_after();
           const uint32_t p_hi = sbase + P.smem_p + (uint32_t)rp.stage * P.stage_bytes, p_lo = p_hi + P.phase_bytes;
 #pragma unroll 1
-          for (int term = 0; term < 3; ++term) {        // small terms first: W_lo P_hi, W_hi P_lo, W_hi P_hi
-            const uint32_t wsel = term == 0 ? 2048u : 0u;
-            const uint32_t pb = term == 1 ? p_lo : p_hi;
+          for (int term = 0; term < 2; ++term) {        // small operand first: [W_hi; W_lo] P_lo, then [W_hi; W_lo] P_hi
+            const uint32_t pb = term == 0 ? p_lo : p_hi;
             for (int k = 0; k < P.count[phase]; ++k) {
               const int pair = P.first[phase] + k;
-              const uint64_t ad = make_desc(wbase + (uint32_t)pair * 4096u + wsel, 1024u, 128u);
+              const uint64_t ad = make_desc(wbase + (uint32_t)pair * 4096u, 2048u, 128u);
               const uint64_t bd = make_desc(pb + (uint32_t)P.pair_off[pair] * 16u, (uint32_t)P.pair_lbo[pair] * 16u, 128u);
               umma_tf32(d0, ad, bd, idesc, (phase | term | k) != 0 ? 1u : 0u);
             }
@@ -206,9 +225,8 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
     }
     __syncwarp();
   } else {
-    // ===================== patch producers (5 warps) =====================
-    // warps 3, 6, 7, 10, 11 -> producer thread index 0..159
-    const int pw = warp == 3 ? 0 : (warp == 6 ? 1 : (warp == 7 ? 2 : (warp == 10 ? 3 : 4)));
+    // ===================== patch producers (warps 17-21) =====================
+    const int pw = warp - 17;
     const int pt = pw * 32 + lane;
     const long long plane = (long long)g.h * g.w;
     Ring rp(kStPStages);
@@ -259,7 +277,7 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // max-pool 3x3 / stride 2 / pad 1 of the (already rectified, >= 0) convolution output
@@ -349,7 +367,7 @@ static bool stem_plan(int n, int h, int w, StemParams& P, size_t& smem_bytes) {
   P.stage_bytes = 2u * P.phase_bytes;
   uint32_t o = 0;
   P.smem_w = o; o += kStWeightBytes;
-  P.smem_p = o; o += kStPStages * P.stage_bytes;     // also absorbs the 1 KB over-read of the last weight slab (M = 128 rows)
+  P.smem_p = o; o += kStPStages * P.stage_bytes;
   P.smem_bar = o; o += 256;
   P.smem_out = o; o += 8 * 32 * kStOutPitch * 4;
   smem_bytes = o;
