@@ -17,7 +17,7 @@ from .nets import QLeNet5, QResNet
 def strict_fp32(disable_cudnn: bool = True) -> None:
     """IEEE fp32 for the full-precision layers around the hot path (stem, shortcuts, classifier) in
     parity tests.  torch defaults cuDNN convolutions to TF32, and on B200 cuDNN's fp32 convolutions stay
-    ~1e-3 off an fp32 reference even with TF32 disabled (measured, tests/gpu_diag_tf32.py); only the
+    ~1e-3 off an fp32 reference even with TF32 disabled (measured, scripts/dev/gpu_diag_tf32.py); only the
     native ATen convolution (cudnn.enabled = False) reproduces the CPU result to ~6e-7."""
     if disable_cudnn:
         torch.backends.cudnn.enabled = False

@@ -1,6 +1,6 @@
 """Debug helper: find the first QuantConv2d producing NaN in the plain (unfused) CIFAR network and dump why."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from ml_quant_b200 import runtime, ops
 from ml_quant_b200.binary.binary_conv import QuantConv2d

@@ -1,6 +1,6 @@
 """Development aid: replay time of CUDA graphs captured one after the other (are later captures slower?)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from ml_quant_b200 import runtime
 dev = torch.device('cuda:0')
