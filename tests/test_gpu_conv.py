@@ -361,3 +361,36 @@ def test_quantlinear_matches_oracle():
         assert err < (1e-5 if xs == 'ls-1' else 5e-2), (xs, fin, fout, err)
         assert y.shape == (33, fout)
     assert m(torch.randn(2, 3, 100, device=DEV)).shape == (2, 3, 10)
+
+
+def test_tensor_core_kernel_random_shapes():
+    """bconv_tc against the CUDA-core kernel (same exact integer accumulators) over random shapes: batch sizes and
+    image sizes that straddle tiles, both strides, 1 and 2 planes, every epilogue variant."""
+    import random
+    from ml_quant_b200 import ops
+    rng = random.Random(1234)
+    torch.manual_seed(13)
+    tried = 0
+    while tried < 24:
+        cin, cout = rng.choice([64, 128, 192, 256, 512]), rng.choice([64, 128, 256, 384, 512])
+        n, h, w = rng.randint(1, 9), rng.randint(5, 40), rng.randint(5, 40)
+        st, npl = rng.choice([1, 1, 2]), rng.choice([1, 2])
+        g = ops.act_geometry(n, cin, h, w, 3, 3, st, 1)
+        if g is None or not ops.tc_supported(g, npl, cout):
+            continue
+        tried += 1
+        x = torch.randn(n, cin, h, w, device=DEV)
+        wt = torch.randn(cout, cin, 3, 3, device=DEV)
+        v1 = torch.rand(n, device=DEV) + 0.5
+        planes, v2 = ops.encode_act(x, g, [v1] if npl == 2 else [], npl, None, True)
+        table = torch.stack([v1, v2]) if npl == 2 else v2[None]
+        wp = ops.pack_weights(wt)
+        ws, b = torch.rand(cout, device=DEV), torch.randn(cout, device=DEV)
+        act = rng.choice([0, 1, 2])
+        prelu = (torch.rand(rng.choice([1, cout]), device=DEV) * 0.5) if act == 2 else None
+        res = torch.randn(n, cout, g.ho, g.wo, device=DEV) if rng.random() < 0.7 else None
+        after = rng.random() < 0.5
+        y1 = ops.bconv2d(planes, g, npl, table, wp, ws, b, cout, 1, None, res, act, prelu, after)
+        y2 = ops.bconv2d(planes, g, npl, table, wp, ws, b, cout, 2, None, res, act, prelu, after)
+        err = float((y1 - y2).abs().max() / y1.abs().max())
+        assert err < 1e-6, (n, cin, cout, h, w, st, npl, act, res is not None, after, err)
