@@ -27,7 +27,6 @@ namespace lsq {
 
 constexpr int kSolveThreads = 512;    // two CTAs per SM: one row's serial phases overlap the other's passes
 constexpr int kListBins = 1024;   // bins of a shared-memory refinement window
-constexpr int kListBinsPerThread = kListBins / kSolveThreads;
 constexpr int kListBinsLog2 = 10;
 constexpr int kFineCap = 2048;  // list B: elements that are sorted and evaluated one by one
 constexpr int kMaxRanges = 4;
@@ -59,21 +58,23 @@ struct Range {        // flagged bins [blo, bhi] of the current window
 };
 
 // Shared memory.  Two layouts (template parameter of the kernel):
-//   L = SolveLayout<13, 8192>  115 KB, two CTAs per SM: rows of up to 21504 sampled elements stay entirely in
+//   L = SolveLayout<13, 8192, 0, 512 threads, 2 CTAs/SM>  115 KB: rows of up to 21504 sampled elements stay entirely in
 //                              shared memory (one pass over HBM), 8192 bins, list A of 8192 elements;
-//   L = SolveLayout<12, 2048, 3> 103 KB, two CTAs per SM (the register file allows no more): long rows (two
-//                              streaming passes).  4096 bins still cover 16 octaves below the clamp bound at 256
-//                              bins per octave; the memory saved holds a 3-stage cp.async staging ring, which
-//                              triples the bytes each thread keeps in flight at no register cost.
+//   L = SolveLayout<12, 2048, 0, 256 threads, 4 CTAs/SM>  55 KB: long rows (two streaming passes).  512 rows over
+//                              592 slots run as ONE wave (296 slots of 512 threads needed two, the second 73 %
+//                              full), and four rows per SM overlap their serial phases; 4096 bins still cover 16
+//                              octaves below the clamp bound at 256 bins per octave.  (A cp.async staging ring in
+//                              the spare memory of a 2-CTA variant brought 3 %: the passes are instruction bound.)
 // Lifetimes overlap as little as possible so regions are reused:
 //   list_a       : per-thread bin-group prefixes while a global window is scanned
 //   bins.l.ext   : tail of list A when the whole sampled row lives in shared memory
-template <int LOG2_BINS, int CAP, int NSTAGE>
+template <int LOG2_BINS, int CAP, int NSTAGE, int THREADS, int MINBLOCKS, int PROCH>
 struct SolveLayout {
   static constexpr int kStages = NSTAGE;
+  static constexpr int kThreads = THREADS, kMinBlocks = MINBLOCKS, kProChannels = PROCH;
   static constexpr int kBinsLog2 = LOG2_BINS;
   static constexpr int kBins = 1 << LOG2_BINS;
-  static constexpr int kBinsPerThread = kBins / kSolveThreads;
+  static constexpr int kBinsPerThread = kBins / THREADS;
   static constexpr int kCap = CAP;                               // list A: elements of the flagged ranges of a global window
   static constexpr int kSmallCap = CAP + 2 * kBins - 3 * kListBins;   // list A when it holds a whole sampled row
   static constexpr int kTopShift = 31 - LOG2_BINS;
@@ -88,7 +89,7 @@ struct SolveLayout {
     uint32_t list_b[kFineCap];
     uint32_t list_a[kCap];
     Bins bins;
-    float2 ab[kMaxProChannels];            // per-channel (scale, shift) of the fused prologue
+    float2 ab[PROCH];                      // per-channel (scale, shift) of the fused prologue
     double red[32];
     double wsum[32];
     uint32_t wcnt[32];
@@ -112,32 +113,32 @@ struct SolveLayout {
     int direct_eval, flags, action;   // action: 0 none, 1 collect ranges into a list
     double best_cost[32];
     uint32_t best_pos[32], best_key[32], ncand;
-    float stage[NSTAGE > 0 ? NSTAGE * kSolveThreads * kLoadBatch : 1];   // cp.async staging ring of the row passes
+    float stage[NSTAGE > 0 ? NSTAGE * THREADS * kLoadBatch : 1];   // cp.async staging ring of the row passes
   };
   static_assert(sizeof(Bins) == 2 * kBins * 4, "Bins views must have the same size");
   static_assert(offsetof(Smem, bins) == (kFineCap + kCap) * 4, "list_a must run into bins.l.ext");
-  static_assert(kSolveThreads * 16 <= kCap * 4, "group prefix records must fit list A");
+  static_assert(THREADS * 16 <= kCap * 4, "group prefix records must fit list A");
 };
-using LayoutBig = SolveLayout<13, 8192, 0>;
-using LayoutSmall = SolveLayout<12, 2048, 3>;
+using LayoutBig = SolveLayout<13, 8192, 0, 512, 2, kMaxProChannels>;
+using LayoutSmall = SolveLayout<12, 2048, 0, 256, 4, 256>;
 static_assert(sizeof(LayoutBig::Smem) <= 113 * 1024, "two CTAs per SM need <= 113 KB each (228 KB - 2 x 1 KB reserved)");
-static_assert(sizeof(LayoutSmall::Smem) <= 113 * 1024, "two CTAs per SM need <= 113 KB each");
+static_assert(sizeof(LayoutSmall::Smem) <= 55 * 1024 + 768, "four CTAs per SM need <= 55.75 KB each");
 
 // Calls body(v, e0, e_end) on batches of sampled elements: this thread's elements are e = e0 + u * blockDim.x
 // (u < kLoadBatch, valid while e < e_end), v[u] = x[e * skip]; kLoadBatch independent loads are in flight per
 // thread.  Trip counts are warp uniform.  (A cp.async.bulk ring feeding the same loop was measured slower:
 // scripts/mb/mb_hist.cu, 3.4 vs 4.7 TB/s.)
-template <int NSTAGE, class Body>
+template <int NSTAGE, int THREADS, class Body>
 __device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip, uint32_t n, float* stage, Body&& body) {
   const int tid = threadIdx.x;
-  constexpr uint32_t kBatch = kSolveThreads * kLoadBatch;
+  constexpr uint32_t kBatch = THREADS * kLoadBatch;
   if (NSTAGE == 0) {
     for (uint32_t eb = 0; eb < n; eb += kBatch) {
       float v[kLoadBatch];
       const uint32_t e0 = eb + tid;
 #pragma unroll
       for (int u = 0; u < kLoadBatch; ++u) {
-        const uint32_t e = e0 + u * kSolveThreads;
+        const uint32_t e = e0 + u * THREADS;
         v[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
       }
       body(v, e0, min(n, eb + kBatch));
@@ -151,9 +152,9 @@ __device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + slot * kBatch + tid);
 #pragma unroll
       for (int u = 0; u < kLoadBatch; ++u) {
-        const uint32_t e = eb + tid + u * kSolveThreads;
+        const uint32_t e = eb + tid + u * THREADS;
         const bool ok = e < n;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)u * kSolveThreads * 4u),
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)u * THREADS * 4u),
                      "l"(xr + (ok ? (long long)e * skip : 0ll)), "r"(ok ? 4 : 0) : "memory");
       }
     }
@@ -170,7 +171,7 @@ __device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip
     float v[kLoadBatch];
     const float* sp = stage + cslot * kBatch + tid;
 #pragma unroll
-    for (int u = 0; u < kLoadBatch; ++u) v[u] = sp[u * kSolveThreads];
+    for (int u = 0; u < kLoadBatch; ++u) v[u] = sp[u * THREADS];
     body(v, eb + tid, min(n, eb + kBatch));
     if (++cslot == NSTAGE) cslot = 0;
   }
@@ -344,11 +345,12 @@ __device__ void evaluate_list(SM& sm, const uint32_t* keys, uint32_t L, int nseg
 }
 
 template <bool TERN, class LAY>
-__global__ void __launch_bounds__(kSolveThreads, 2)
+__global__ void __launch_bounds__(LAY::kThreads, LAY::kMinBlocks)
 solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
                 int* __restrict__ diag, Prologue pro) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SolveSmem = typename LAY::Smem;
+  constexpr int kT = LAY::kThreads;
   constexpr int kBins = LAY::kBins, kBinsPerThread = LAY::kBinsPerThread, kCap = LAY::kCap, kSmallCap = LAY::kSmallCap, kTopShift = LAY::kTopShift;
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
   const long long row = blockIdx.x;
@@ -357,7 +359,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // fused per-channel affine prologue: the table is staged in shared memory (global loads of it miss L1
   // behind the streamed row and stalled the passes)
-  const bool pro_on = pro.a != nullptr, pro_smem = pro_on && pro.channels <= kMaxProChannels;
+  const bool pro_on = pro.a != nullptr, pro_smem = pro_on && pro.channels <= LAY::kProChannels;
   if (pro_smem)
     for (int c = tid; c < pro.channels; c += blockDim.x) sm.ab[c] = make_float2(__ldg(pro.a + c), __ldg(pro.b + c));
   auto prologue = [&](float v, long long index_in_row) -> float {
@@ -393,10 +395,10 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     // ---- small row: list A is the whole row --------------------------------------------------
     double ls = 0.0, lq = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u;
-    sweep_row<0>(xr, skip, n, nullptr, [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
+    sweep_row<0, kT>(xr, skip, n, nullptr, [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
 #pragma unroll
       for (int u = 0; u < kLoadBatch; ++u) {       // kLoadBatch loads in flight (one at a time left this phase latency bound)
-        const uint32_t e = e0 + u * kSolveThreads;
+        const uint32_t e = e0 + u * kT;
         if (e >= e_end) break;
         const float a = fabsf(clamp_sym(prologue(v[u], (long long)e * skip), alpha));
         const uint32_t k = __float_as_uint(a);
@@ -469,11 +471,11 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     double ls = 0.0, lq = 0.0, lb = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey, kwin = kNoKey;
     if (!from_list) {
-      sweep_row<LAY::kStages>(xr, skip, n, sm.stage,
+      sweep_row<LAY::kStages, kT>(xr, skip, n, sm.stage,
                 [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
-          const uint32_t e = e0 + u * kSolveThreads;
+          const uint32_t e = e0 + u * kT;
           if (e >= e_end) break;
           const float a = fabsf(clamp_sym(prologue(v[u], (long long)e * skip), alpha));
           const uint32_t k = __float_as_uint(a);
@@ -530,7 +532,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 
     LSQ_TICK(3);   // reductions
     // ---- S1: prefix counts / sums over the bins (thread owns bpt consecutive bins) ------------------
-    const int bpt = from_list ? kListBinsPerThread : kBinsPerThread;
+    const int bpt = from_list ? (kListBins / kT) : kBinsPerThread;
     auto bin_sum = [&](uint32_t b, uint32_t cnt) -> double {
       if (shift == 0) return (double)cnt * (double)key_val(klo + b);
       if (sum_mode == 2) return exact_bin_sum(klo + (b << shift), cnt, blo_sum[b], bhi_sum[b]);
@@ -624,8 +626,8 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       // thread; may_hold is conservative for any bin width); only the bins of the few flagged groups get the
       // fine test, spread over the block.  Group prefixes are parked in the idle list A.
       uint32_t* const gexcl = list_a;
-      uint32_t* const gnext = list_a + kSolveThreads;
-      double* const gpref = reinterpret_cast<double*>(list_a + 2 * kSolveThreads);
+      uint32_t* const gnext = list_a + kT;
+      double* const gpref = reinterpret_cast<double*>(list_a + 2 * kT);
       if (tid == 0) sm.ngroup = 0;
       __syncthreads();
       gexcl[tid] = excl0; gnext[tid] = nxt_after; gpref[tid] = pref0;
@@ -801,14 +803,14 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       }
       __syncthreads();
       if (!from_list) {
-        sweep_row<LAY::kStages>(xr, skip, n, sm.stage,
+        sweep_row<LAY::kStages, kT>(xr, skip, n, sm.stage,
                   [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
           uint32_t matched = 0u;
           uint32_t keys[kLoadBatch];
 #pragma unroll
           for (int u = 0; u < kLoadBatch; ++u) {
-            if (e0 + u * kSolveThreads >= e_end) break;
-            const float a = fabsf(clamp_sym(prologue(v[u], (long long)(e0 + u * kSolveThreads) * skip), alpha));
+            if (e0 + u * kT >= e_end) break;
+            const float a = fabsf(clamp_sym(prologue(v[u], (long long)(e0 + u * kT) * skip), alpha));
             const uint32_t k = __float_as_uint(a);
             keys[u] = k;
 #pragma unroll
@@ -1106,7 +1108,7 @@ extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int 
   do {                                                                                                             \
     e = cudaFuncSetAttribute(solve_v1_kernel<T, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     if (e == cudaSuccess)                                                                                          \
-      solve_v1_kernel<T, LAY><<<grid, kSolveThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp); \
+      solve_v1_kernel<T, LAY><<<grid, LAY::kThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp); \
   } while (0)
   if (ternary) { if (big) LSQ_SOLVE(true, LayoutBig); else LSQ_SOLVE(true, LayoutSmall); }
   else { if (big) LSQ_SOLVE(false, LayoutBig); else LSQ_SOLVE(false, LayoutSmall); }
