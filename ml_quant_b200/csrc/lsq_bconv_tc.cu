@@ -33,7 +33,8 @@
 
 namespace lsq {
 
-constexpr int kTcThreads = 448;   // 4 epilogue + MMA + loader + 4 producer + 4 more epilogue warps
+constexpr int kTcThreads = 576;   // 4 epilogue + MMA + loader + 4 producer + 4 more epilogue + 4 more producer warps
+constexpr int kProdThreads = 256; // (issue slots are less than half used: more warps hide the producers' L2 latency)
 constexpr int kMaxTaps = 9;
 constexpr int kMaxWStages = 6;
 constexpr int kAccStages = 2;
@@ -100,7 +101,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * (2 * kMaxPStages + 2 * kMaxWStages + 2 * kAccStages));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxPStages; ++s) { mbar_init(p_full(s), 4); mbar_init(p_empty(s), 1); }
+    for (int s = 0; s < kMaxPStages; ++s) { mbar_init(p_full(s), kProdThreads / 32); mbar_init(p_empty(s), 1); }
     for (int s = 0; s < kMaxWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int s = 0; s < kAccStages; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,7 +120,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
   const int n_items = P.p_tiles * P.n_ctiles;
   const uint32_t acc_cols = (uint32_t)(P.tp * P.npl);
 
-  if (warp < 4 || warp >= 10) {
+  if (warp < 4 || (warp >= 10 && warp < 14)) {
     // ===================== epilogue (8 warps) =====================
     // quarter = TMEM lane quarter; 128-channel tiles: quarter = channel group, the two warps of a quarter split
     // the positions in 2; 64-channel tiles: lanes 64..127 repeat lanes 0..63, positions are split in 4.
@@ -356,7 +357,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
   } else {
     // ===================== patch producers (128 threads) =====================
     Ring rp(P.p_stages);
-    const int pt = threadIdx.x - 6 * 32;
+    const int pt = (warp < 10 ? threadIdx.x - 6 * 32 : threadIdx.x - 14 * 32 + 128);     // warps 6-9 and 14-17
     const int ntask = P.npl * g.nphase * P.pp;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int ptile = item / P.n_ctiles;
@@ -365,13 +366,13 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
         mbar_wait_t(p_empty(rp.stage), rp.phase ^ 1u, err, 6, w0);
         unsigned char* p_stage = smem + P.smem_p + (size_t)rp.stage * P.p_stage_bytes;
         constexpr int kPB = 4;   // tasks whose plane-bit loads are in flight together
-        for (int task0 = pt; task0 < ntask; task0 += 128 * kPB) {
+        for (int task0 = pt; task0 < ntask; task0 += kProdThreads * kPB) {
           uint2 bits[kPB];
           uint32_t vm[kPB];
           unsigned char* dst[kPB];
 #pragma unroll
           for (int u = 0; u < kPB; ++u) {
-            const int task = task0 + u * 128;
+            const int task = task0 + u * kProdThreads;
             bits[u] = make_uint2(0u, 0u);
             vm[u] = 0u;
             dst[u] = nullptr;
@@ -545,18 +546,19 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   const int grid = n_items < sms ? n_items : sms;
   static const bool want_diag = getenv("LSQ_TC_DIAG") != nullptr;     // development aid: per-role wait cycles of CTA 0
   long long* d_diag = nullptr;
-  if (want_diag) { cudaMalloc(&d_diag, 14 * 4 * sizeof(long long)); cudaMemsetAsync(d_diag, 0, 14 * 4 * sizeof(long long), stream); }
+  if (want_diag) { cudaMalloc(&d_diag, 18 * 4 * sizeof(long long)); cudaMemsetAsync(d_diag, 0, 18 * 4 * sizeof(long long), stream); }
   bconv_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(d_planes, P, d_act_scales, wi8, d_w_scale, d_bias, d_y, nullptr, epi, d_diag);
   LSQ_CUDA_LAUNCH_CHECK("bconv_tc_kernel");
   if (want_diag) {
-    long long h[14 * 4];
+    long long h[18 * 4];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, d_diag, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d_diag);
-    const char* role[14] = {"epi0", "epi1", "epi2", "epi3", "mma", "wload", "prod0", "prod1", "prod2", "prod3", "epi4", "epi5", "epi6", "epi7"};
+    const char* role[18] = {"epi0", "epi1", "epi2", "epi3", "mma", "wload", "prod0", "prod1", "prod2", "prod3", "epi4", "epi5", "epi6", "epi7",
+                            "prod4", "prod5", "prod6", "prod7"};
     fprintf(stderr, "[bconv_tc diag] cin %d cout %d %dx%d stride %d items %d grid %d tp %d pp %d p_stages %d w_stages %d x %d taps r_stages %d smem %zu\n",
             g->c, cout, g->h, g->w, g->stride, n_items, grid, P.tp, P.pp, P.p_stages, P.w_stages, P.tps, P.r_stages, smem_bytes);
-    for (int w = 0; w < 14; ++w)
+    for (int w = 0; w < 18; ++w)
       fprintf(stderr, "   %-6s total %9lld  wait0 %9lld  wait1(p_full) %9lld  wait2(w_full) %9lld\n", role[w], h[w * 4], h[w * 4 + 1], h[w * 4 + 2], h[w * 4 + 3]);
   }
   return LSQ_OK;
