@@ -546,19 +546,19 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   const int grid = n_items < sms ? n_items : sms;
   static const bool want_diag = getenv("LSQ_TC_DIAG") != nullptr;     // development aid: per-role wait cycles of CTA 0
   long long* d_diag = nullptr;
-  if (want_diag) { cudaMalloc(&d_diag, 18 * 4 * sizeof(long long)); cudaMemsetAsync(d_diag, 0, 18 * 4 * sizeof(long long), stream); }
+  if (want_diag) { cudaMalloc(&d_diag, 22 * 4 * sizeof(long long)); cudaMemsetAsync(d_diag, 0, 22 * 4 * sizeof(long long), stream); }
   bconv_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(d_planes, P, d_act_scales, wi8, d_w_scale, d_bias, d_y, nullptr, epi, d_diag);
   LSQ_CUDA_LAUNCH_CHECK("bconv_tc_kernel");
   if (want_diag) {
-    long long h[18 * 4];
+    long long h[22 * 4];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, d_diag, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d_diag);
-    const char* role[18] = {"epi0", "epi1", "epi2", "epi3", "mma", "wload", "prod0", "prod1", "prod2", "prod3", "epi4", "epi5", "epi6", "epi7",
-                            "prod4", "prod5", "prod6", "prod7"};
+    const char* role[22] = {"epi0", "epi1", "epi2", "epi3", "mma", "wload", "prod0", "prod1", "prod2", "prod3", "epi4", "epi5", "epi6", "epi7",
+                            "prod4", "prod5", "prod6", "prod7", "prod8", "prod9", "prod10", "prod11"};
     fprintf(stderr, "[bconv_tc diag] cin %d cout %d %dx%d stride %d items %d grid %d tp %d pp %d p_stages %d w_stages %d x %d taps r_stages %d smem %zu\n",
             g->c, cout, g->h, g->w, g->stride, n_items, grid, P.tp, P.pp, P.p_stages, P.w_stages, P.tps, P.r_stages, smem_bytes);
-    for (int w = 0; w < 18; ++w)
+    for (int w = 0; w < kTcThreads / 32; ++w)
       fprintf(stderr, "   %-6s total %9lld  wait0 %9lld  wait1(p_full) %9lld  wait2(w_full) %9lld\n", role[w], h[w * 4], h[w * 4 + 1], h[w * 4 + 2], h[w * 4 + 3]);
   }
   return LSQ_OK;
