@@ -23,12 +23,12 @@
 
 namespace lsq {
 
-constexpr int kStThreads = 704;      // 8 + 8 epilogue warps (lane halves), MMA warp 16, producer warps 17-21
+constexpr int kStThreads = 800;      // 8 + 8 epilogue warps (lane halves), MMA warp 16, producer warps 17-24
 constexpr int kStTile = 256;        // output positions per tile = N
 constexpr int kStPairs = 25;
 constexpr int kStPStages = 4;       // ring of per-phase patches
 constexpr int kStOutPitch = 20;
-constexpr int kStProducerWarps = 5;
+constexpr int kStProducerWarps = 8;
 constexpr uint32_t kStWeightBytes = kStPairs * 4096;       // [pair][chunk 2][128 rows: 64 hi, 64 lo][4 floats]
 
 struct StemTaps {                   // static description of the 7x7 / stride 2 / pad 3 taps
@@ -225,7 +225,7 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
     }
     __syncwarp();
   } else {
-    // ===================== patch producers (warps 17-21) =====================
+    // ===================== patch producers (warps 17-24) =====================
     const int pw = warp - 17;
     const int pt = pw * 32 + lane;
     const long long plane = (long long)g.h * g.w;
