@@ -188,7 +188,7 @@ __device__ __forceinline__ void encode_group(const float* __restrict__ xp, long 
 }
 
 template <int NPL, int VEC>
-__global__ void __launch_bounds__(kEncThreads)
+__global__ void __launch_bounds__(kEncThreads, 8)
 encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const float* __restrict__ scales,
                   int ns, uint32_t* __restrict__ planes, double* __restrict__ partial,
                   unsigned* __restrict__ counter, float* __restrict__ last_scale, Prologue pro) {
