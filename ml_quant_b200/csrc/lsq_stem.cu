@@ -18,6 +18,7 @@
 // W_hi (P_hi + P_lo) in lanes 0..63 and W_lo (P_hi + P_lo) in lanes 64..127 -- all four product terms in TWO MMAs
 // per tap pair instead of three.  49 taps -> 25 pairs x 2 = 50 MMAs per tile; the epilogue adds the two lane
 // halves (warp pairs exchange through shared memory).  All weights (100 KB) stay in shared memory.
+#include <stdlib.h>
 #include "lsq_common.cuh"
 #include "lsq_tc.cuh"
 
@@ -101,11 +102,13 @@ __global__ void stem_pack_kernel(const float* __restrict__ w, float* __restrict_
 
 __global__ void __launch_bounds__(kStThreads, 1)
 stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restrict__ wimage, const float* __restrict__ bias,
-                 float* __restrict__ conv) {
+                 float* __restrict__ conv, long long* __restrict__ diag) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ActGeom& g = P.g;
+  long long w0 = 0, w1 = 0;
+  const long long t_start = clock64();
   // barriers: p_full[4] p_empty[4] acc_full[2] acc_empty[2] | tmem base
   const uint32_t bar0 = sbase + P.smem_bar;
   auto p_full = [&](int s) { return bar0 + 8u * s; };
@@ -147,7 +150,7 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
     const long long cstride = (long long)P.hc * P.wc;
     Ring acc(2);
     for (int tile = blockIdx.x; tile < P.p_tiles; tile += gridDim.x) {
-      mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
+      mbar_wait_t(acc_full(acc.stage), acc.phase, err, 1, w0);
       tc_fence_after();
       for (int st = 0; st < 4; ++st) {
         const int p0 = part * 64 + 16 * st;
@@ -199,11 +202,11 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kStTile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t wbase = sbase + P.smem_w;
       for (int tile = blockIdx.x; tile < P.p_tiles; tile += gridDim.x) {
-        mbar_wait(acc_empty(acc.stage), acc.phase ^ 1u, err, 2);
+        mbar_wait_t(acc_empty(acc.stage), acc.phase ^ 1u, err, 2, w0);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc.stage * kStTile);
         for (int phase = 0; phase < 4; ++phase) {
-          mbar_wait(p_full(rp.stage), rp.phase, err, 3);
+          mbar_wait_t(p_full(rp.stage), rp.phase, err, 3, w1);
           tc_fence_after();
           const uint32_t p_hi = sbase + P.smem_p + (uint32_t)rp.stage * P.stage_bytes, p_lo = p_hi + P.phase_bytes;
 #pragma unroll 1
@@ -233,7 +236,7 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
     for (int tile = blockIdx.x; tile < P.p_tiles; tile += gridDim.x) {
       const long long q0 = P.q_begin + (long long)tile * kStTile;
       for (int phase = 0; phase < 4; ++phase) {
-        mbar_wait(p_empty(rp.stage), rp.phase ^ 1u, err, 6);
+        mbar_wait_t(p_empty(rp.stage), rp.phase ^ 1u, err, 6, w0);
         float4* hi = reinterpret_cast<float4*>(smem + P.smem_p + (size_t)rp.stage * P.stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + P.smem_p + (size_t)rp.stage * P.stage_bytes + P.phase_bytes);
         const int py = phase >> 1, px = phase & 1;
@@ -275,6 +278,7 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
       }
     }
   }
+  if (diag && lane == 0 && blockIdx.x == 0) { diag[warp * 3] = clock64() - t_start; diag[warp * 3 + 1] = w0; diag[warp * 3 + 2] = w1; }
   tc_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem_base, 512);
@@ -422,8 +426,21 @@ extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = P.p_tiles < sms ? P.p_tiles : sms;
-  stem_conv_kernel<<<grid, kStThreads, smem, (cudaStream_t)stream>>>(d_x, P, d_image, d_bias, d_conv_ws);
+  static const bool want_diag = getenv("LSQ_TC_DIAG") != nullptr;     // development aid: wait cycles per warp of CTA 0
+  long long* d_diag = nullptr;
+  if (want_diag) { cudaMalloc(&d_diag, 32 * 3 * sizeof(long long)); cudaMemsetAsync(d_diag, 0, 32 * 3 * sizeof(long long), (cudaStream_t)stream); }
+  stem_conv_kernel<<<grid, kStThreads, smem, (cudaStream_t)stream>>>(d_x, P, d_image, d_bias, d_conv_ws, d_diag);
   LSQ_CUDA_LAUNCH_CHECK("stem_conv_kernel");
+  if (want_diag) {
+    long long h[32 * 3];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(h, d_diag, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_diag);
+    fprintf(stderr, "[stem diag] tiles %d grid %d pp %d\n", P.p_tiles, grid, P.pp);
+    for (int w = 0; w < kStThreads / 32; ++w)
+      fprintf(stderr, "   warp %2d (%s) total %9lld  wait0 %9lld  wait1(p_full) %9lld\n", w,
+              w < 16 ? ((w & 3) < 2 ? "epi-main" : "epi-upper") : (w == 16 ? "mma" : "producer"), h[w * 3], h[w * 3 + 1], h[w * 3 + 2]);
+  }
   const int hp = (P.hc - 1) / 2 + 1, wp = (P.wc - 1) / 2 + 1;
   const size_t plane_bytes = (size_t)P.hc * P.wc * sizeof(float);
   if (plane_bytes <= 56 * 1024 && ((uintptr_t)d_conv_ws & 15) == 0) {
