@@ -25,7 +25,7 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 template <int KIND>
-__global__ void __launch_bounds__(128, 1) k(int N, int layout, int iters, int kchunks, long long* cycles, int a_shift, int M, int commit_each) {
+__global__ void __launch_bounds__(128, 1) k(int N, int layout, int iters, int kchunks, long long* cycles, int a_shift, int M, int commit_each, int b_shift) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ unsigned long long bar;
   __shared__ unsigned long long bar2[8];
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128, 1) k(int N, int layout, int iters, int kc
     t0 = clock64();
     if (lane == 0) {
       for (int it = 0; it < iters; ++it) {
-        const uint32_t a0 = sb + (uint32_t)(it & 1) * 32768u + (uint32_t)a_shift * ((it >> 1) & 7), b0 = sb + 65536u + (uint32_t)(it & 3) * 32768u;
+        const uint32_t a0 = sb + (uint32_t)(it & 1) * 32768u + (uint32_t)a_shift * ((it >> 1) & 7), b0 = sb + 65536u + (uint32_t)(it & 3) * 32768u + (uint32_t)b_shift * ((it >> 1) & 3);
         for (int kc = 0; kc < kchunks; ++kc) {
           uint64_t ad, bd;
           if (layout == 0) {   // K-major, core matrices 8 x 16 B contiguous, LBO between K-adjacent (2 KB / N*16), SBO 128 B
@@ -82,14 +82,14 @@ __global__ void __launch_bounds__(128, 1) k(int N, int layout, int iters, int kc
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512) : "memory");
 }
 template <int KIND>
-void run(const char* name, int N, int layout, long long* dcyc, int a_shift = 0, int M = 128, int commit_each = 0) {
+void run(const char* name, int N, int layout, long long* dcyc, int a_shift = 0, int M = 128, int commit_each = 0, int b_shift = 0) {
   const int iters = 2000, kch = 4;
   CK(cudaFuncSetAttribute(k<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  k<KIND><<<148, 128, 200 * 1024>>>(N, layout, 200, kch, dcyc, a_shift, M, commit_each);
+  k<KIND><<<148, 128, 200 * 1024>>>(N, layout, 200, kch, dcyc, a_shift, M, commit_each, b_shift);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  k<KIND><<<148, 128, 200 * 1024>>>(N, layout, iters, kch, dcyc, a_shift, M, commit_each);
+  k<KIND><<<148, 128, 200 * 1024>>>(N, layout, iters, kch, dcyc, a_shift, M, commit_each, b_shift);
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -100,10 +100,11 @@ void run(const char* name, int N, int layout, long long* dcyc, int a_shift = 0, 
 }
 int main() {
   long long* dcyc; CK(cudaMalloc(&dcyc, 8));
-  run<0>("i8 M128", 256, 0, dcyc);
-  run<0>("i8 M128 commit every 4 MMAs", 256, 0, dcyc, 0, 128, 1);
-  run<0>("i8 M64", 256, 0, dcyc, 0, 64);
-  run<0>("i8 M64", 128, 0, dcyc, 0, 64);
-  run<0>("i8 M128 N=192", 192, 0, dcyc);
+  run<0>("i8 M128 N256 aligned", 256, 0, dcyc);
+  run<0>("i8 M128 N256 B start + k*32 B", 256, 0, dcyc, 0, 128, 0, 32);
+  run<0>("i8 M128 N256 B start + k*16 B", 256, 0, dcyc, 0, 128, 0, 16);
+  run<0>("i8 M128 N256 A and B shifted", 256, 0, dcyc, 48, 128, 0, 32);
+  run<0>("i8 M128 N256 64B swizzle aligned", 256, 4, dcyc);
+  run<0>("i8 M128 N256 64B swizzle B + k*64 B", 256, 4, dcyc, 0, 128, 0, 64);
   return 0;
 }
