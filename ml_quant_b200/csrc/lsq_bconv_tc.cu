@@ -377,9 +377,12 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
             vm[u] = 0u;
             dst[u] = nullptr;
             if (task < ntask) {
-              const int pp_idx = task / P.pp;          // pl * nphase + phase
-              const int pos = task - pp_idx * P.pp;
-              const int pl = pp_idx / g.nphase, phase = pp_idx - pl * g.nphase;
+              // task -> (phase, position, plane) with the plane fastest: consecutive lanes write consecutive
+              // 16-byte rows of the patch (position-fastest lanes stored at a 32-byte stride: 2-way bank conflicts)
+              const int phase = task / (P.pp * P.npl);
+              const int rem = task - phase * (P.pp * P.npl);
+              const int pos = (P.npl == 2) ? (rem >> 1) : rem, pl = (P.npl == 2) ? (rem & 1) : 0;
+              const int pp_idx = pl * g.nphase + phase;
               const long long q = q0 + P.dmin[phase] + pos;
               const PosInfo pi = decode_pos(P, q);
               int hv_p = g.h, wv_p = g.w;
