@@ -275,6 +275,7 @@ def stem_fwd(x: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.
     with torch.cuda.device(x.device), _launch('stem', 4.0 * (x.numel() + out.numel()), 2.0 * macs):
         _C.check(L.lsq_stem_fwd(x.data_ptr(), n, h, w, image.data_ptr(), bias.contiguous().data_ptr(), ws.data_ptr(),
                                 out.data_ptr(), _stream()), 'lsq_stem_fwd')
+    LAUNCHES['stem_pool'] = LAUNCHES.get('stem_pool', 0) + 1      # lsq_stem_fwd launches two kernels (conv, pool)
     return out
 
 
