@@ -16,6 +16,12 @@ Algorithm (per row; a = |clamp(x)|[::skip], n elements, key = float bits of a, m
   evaluate(i): the reference's fp32 arithmetic on (float)prefix sums (optimal.py:56-80), so the
       candidate set equals the reference's; the cost of a candidate is the closed form of
       optimal.py:31-38 in fp64, first minimum in ascending order wins.
+
+The kernel adds performance-only refinements on top of this logic (none changes which positions are evaluated
+exactly): for clamped rows the top window is anchored at the clamp bound with 256 bins per octave and everything
+below it is one pseudo bin; the bins of a window are first tested in groups (a conservative coarse test), only
+flagged groups get the per-bin test; few collected elements are sorted directly instead of being refined again;
+rows of up to 21.5 K elements are held in shared memory, rows of up to 2 K are simply sorted.
 """
 import numpy as np
 

@@ -143,3 +143,26 @@ torch.save(out, sys.argv[1])
         assert torch.equal(a, b)
     assert torch.equal(O.quant_gf(x, 3)[1], ref['gf3'][1])
     assert torch.equal(O.quant_ls1(x)[1], ref['ls1'][1])
+
+
+def test_sort_free_solver_model_matches_oracle():
+    """tests/solver_model.py (the serial numpy specification of the CUDA solver's window / flag / collect /
+    evaluate logic) picks a candidate of the oracle's own candidate set with no worse exact cost -- on rows long
+    enough to take the windowed path, for both quantizers.  CPU only: the algorithm is validated before any GPU time."""
+    import numpy as np
+    from tests import solver_model as M
+    torch.manual_seed(21)
+    x = torch.randn(3, 24000).clamp(-3, 3)
+    x[2] = x[2].abs() + 0.5                     # a row whose minimum exceeds half its mean (ternary edge case)
+    for tern in (False, True):
+        v, infos = M.solve(x.numpy(), tern, skip=1)
+        v_ref = O.solve_v1(x, tern, 1, chunk=1).view(-1)
+        a = x.abs()
+        srt, mask = O.candidate_mask(a, tern)
+        for r in range(3):
+            cands = torch.masked_select(srt[r, 1:-1], mask[r])
+            edge = tern and bool(a[r].min() > 0.5 * a[r].mean())
+            assert bool((cands == float(v[r])).any()) or edge or cands.numel() == 0, (tern, r, float(v[r]))
+        c_my = O.exact_cost(x, torch.from_numpy(np.asarray(v, dtype=np.float32)), tern, 1)
+        c_or = O.exact_cost(x, v_ref, tern, 1)
+        assert bool((c_my <= c_or * (1 + 1e-5) + 1e-12).all())
