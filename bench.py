@@ -120,7 +120,7 @@ def main():
             return
         cores = os.cpu_count() or 1
         steps = max(1, min(args.steps, 3))
-        sample = 32
+        sample = 64
         ips, sec = cpu_reference_arm(sample, steps, min(args.warmup, 1))
         print(json.dumps({
             'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
@@ -266,9 +266,9 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ips, sec = cpu_reference_arm(16, 2, 1)
+        ips, sec = cpu_reference_arm(64, 4, 1)      # ~5-10 s of CPU work on the box's host cores
         out['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                               'sample': f'2 forwards of 16 images (oracle/lsq_oracle.py, torch CPU, {cores} threads)'}
+                               'sample': f'4 forwards of 64 images (oracle/lsq_oracle.py, torch CPU, {cores} threads)'}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
