@@ -394,3 +394,35 @@ def test_tensor_core_kernel_random_shapes():
         y2 = ops.bconv2d(planes, g, npl, table, wp, ws, b, cout, 2, None, res, act, prelu, after)
         err = float((y1 - y2).abs().max() / y1.abs().max())
         assert err < 1e-6, (n, cin, cout, h, w, st, npl, act, res is not None, after, err)
+
+
+def test_full_size_resnet18_ls2_headline_config():
+    """The benchmark's own network (ImageNet ResNet-18, ls-1 weights / ls-2 activations, 224 x 224, random init)
+    against the oracle on the CPU, plain and after optimize_for_inference.  This network is chaotic: the oracle's
+    OWN logits move by 2-3 % of max|logit| when its input is perturbed by 1e-7 relative
+    (scripts/dev/oracle_sensitivity.py), because ls-2 picks v1 among candidates whose costs tie to 7 digits
+     and 16 random-init sign layers amplify every flipped pick.  Two correct implementations with
+    different fp32 summation orders therefore agree only coarsely end to end (measured 4-8 %); the strict parity
+    checks are the per-layer tests.  Here: logits within 15 % of max|logit|, top-1 equal on at least 3 of 4
+    samples, and -- exactly -- identical results for a sharded batch and for the CUDA-graph replay."""
+    runtime_strict()
+    from ml_quant_b200 import configs, runtime
+    cfg = 'imagenet_resnet18_ls1w_ls2a'
+    model = runtime.build_model(cfg, torch.device(DEV))
+    runtime.calibrate(model, (3, 224, 224), batches=1, batch=8)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(4, 3, 224, 224, generator=g)
+    y_ref = O.resnet_forward(sd, configs.arch(cfg), x)
+    with torch.no_grad():
+        y = model(x.to(DEV)).cpu()
+        fused_model = runtime.optimize_for_inference(model)
+        yf = fused_model(x.to(DEV)).cpu()
+        ya = fused_model(x[:2].to(DEV)).cpu()
+    for out in (y, yf):
+        err = float((out - y_ref).abs().max() / y_ref.abs().max())
+        assert err < 0.15, err
+        assert int((out.argmax(1) == y_ref.argmax(1)).sum()) >= 3
+    assert torch.equal(ya, yf[:2])
+    fwd = runtime.GraphedForward(fused_model, x.to(DEV))
+    assert torch.equal(fwd().cpu(), yf)
