@@ -426,3 +426,46 @@ def test_full_size_resnet18_ls2_headline_config():
     assert torch.equal(ya, yf[:2])
     fwd = runtime.GraphedForward(fused_model, x.to(DEV))
     assert torch.equal(fwd().cpu(), yf)
+
+
+def test_full_size_network_layer_by_layer_with_own_scales():
+    """Teacher-forced full-size check of the headline network (batch 2, 224 x 224): every one of the 16 QuantConv2d
+    layers, fed with the GPU's own input of that layer, must (a) pick a v1 that meets the solver contract against the
+    oracle, (b) reproduce the oracle's v2 for that v1 to 1e-6, and (c) produce the oracle's convolution output for
+    those scales to 1e-5 of max|y|.  Together with the exact kernels around them this pins the whole forward,
+    independent of the chaotic amplification of v1 tie-picks between layers."""
+    runtime_strict()
+    from ml_quant_b200 import runtime
+    from tests.test_gpu_quantizers import _solver_contract
+    model = runtime.build_model('imagenet_resnet18_ls1w_ls2a', torch.device(DEV))
+    runtime.calibrate(model, (3, 224, 224), batches=1, batch=8)
+    layers = runtime.quant_layers(model)
+    assert len(layers) == 16
+    rec = {}
+    for i, m in enumerate(layers):
+        orig = m.quantize_input
+
+        def wrapped(x, g, prologue=None, _i=i, _orig=orig):
+            planes, table = _orig(x, g, prologue)
+            rec[_i] = [x.detach().cpu(), table.detach().cpu(), None]
+            return planes, table
+        m.quantize_input = wrapped
+        m.register_forward_hook(lambda mod, inp, out, _i=i: rec[_i].__setitem__(2, out.detach().cpu()))
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        model(x.to(DEV))
+    for i, m in enumerate(layers):
+        xi, table, y = rec[i]
+        alpha = m.clamp_alpha
+        xin = xi.clamp(-alpha, alpha)
+        rows = xin.reshape(2, -1)
+        v1, v2 = table[0], table[1]
+        _solver_contract(rows, v1, O.solve_v1(rows, False, 3, chunk=1).view(-1), False, 3)
+        b1 = torch.where(xin >= 0, 1.0, -1.0)
+        v2_ref = (xin - v1.view(-1, 1, 1, 1) * b1).abs().mean(dim=(1, 2, 3))
+        assert torch.allclose(v2, v2_ref, rtol=1e-6, atol=0), (i, v2, v2_ref)
+        y_ref, _ = O.plane_conv_identity(xin, m.weight.detach().cpu(), m.bias.detach().cpu(), 'ls-2', [v1, v2],
+                                         m.w_approximate.v1.detach().cpu(), m.stride[0], m.padding[0])
+        err = float((y - y_ref).abs().max() / y_ref.abs().max())
+        assert err < 1e-5, (i, err)
