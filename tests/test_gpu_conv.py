@@ -469,3 +469,54 @@ def test_full_size_network_layer_by_layer_with_own_scales():
                                          m.w_approximate.v1.detach().cpu(), m.stride[0], m.padding[0])
         err = float((y - y_ref).abs().max() / y_ref.abs().max())
         assert err < 1e-5, (i, err)
+
+
+def test_full_size_fused_network_layer_by_layer():
+    """The same teacher-forced check for the path the benchmark runs (runtime.optimize_for_inference: BatchNorm
+    + clamp folded into the quantizer kernels, ReLU + residual into the convolution epilogue): every fused layer,
+    fed with the GPU's own input and residual, matches the oracle's composition for the GPU's scales to 1e-5 of
+    max|y|; BatchNorm is formed with one rounding (x * a + b in double, rounded), which is what the kernels' fmaf does."""
+    runtime_strict()
+    import torch.nn as nn
+    from ml_quant_b200 import runtime
+    from ml_quant_b200.binary.binary_conv import bn_affine
+    from tests.test_gpu_quantizers import _solver_contract
+    model = runtime.build_model('imagenet_resnet18_ls1w_ls2a', torch.device(DEV))
+    runtime.calibrate(model, (3, 224, 224), batches=1, batch=8)
+    runtime.optimize_for_inference(model)
+    layers = runtime.quant_layers(model)
+    rec = {}
+    for i, m in enumerate(layers):
+        oq, of = m.quantize_input, m.forward_fused
+
+        def q_wrapped(x, g, prologue=None, _i=i, _oq=oq):
+            planes, table = _oq(x, g, prologue)
+            rec.setdefault(_i, {})['table'] = table.detach().cpu()
+            return planes, table
+
+        def f_wrapped(x, bn=None, nonlin=None, residual=None, residual_after_act=True, _i=i, _of=of):
+            out = _of(x, bn, nonlin, residual, residual_after_act)
+            rec.setdefault(_i, {}).update(x=x.detach().cpu(), bn=bn, nonlin=nonlin, after=residual_after_act,
+                                          res=None if residual is None else residual.detach().cpu(), y=out.detach().cpu())
+            return out
+        m.quantize_input, m.forward_fused = q_wrapped, f_wrapped
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        model(x.to(DEV))
+    assert len(rec) == 16
+    for i, m in enumerate(layers):
+        r = rec[i]
+        a, b = bn_affine(r['bn'])
+        xb = (r['x'].double() * a.cpu().double().view(1, -1, 1, 1) + b.cpu().double().view(1, -1, 1, 1)).float()
+        xin = xb.clamp(-m.clamp_alpha, m.clamp_alpha)
+        v1, v2 = r['table'][0], r['table'][1]
+        rows = xin.reshape(2, -1)
+        _solver_contract(rows, v1, O.solve_v1(rows, False, 3, chunk=1).view(-1), False, 3)
+        conv, _ = O.plane_conv_identity(xin, m.weight.detach().cpu(), m.bias.detach().cpu(), 'ls-2', [v1, v2],
+                                        m.w_approximate.v1.detach().cpu(), m.stride[0], m.padding[0])
+        assert isinstance(r['nonlin'], nn.ReLU)
+        res = r['res'] if r['res'] is not None else torch.zeros_like(conv)
+        want = F.relu(conv) + res if r['after'] else F.relu(conv + res)
+        err = float((r['y'] - want).abs().max() / want.abs().max())
+        assert err < 1e-5, (i, err)
