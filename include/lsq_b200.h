@@ -105,6 +105,23 @@ LSQ_API int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int skip, 
 LSQ_API int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
                     float* d_v1, int32_t* d_diag, const lsq_prologue* pro, void* stream);
 
+/* Multi-tensor forms for weight tensors (the WeightQuantizer* modules of a whole network solve every
+ * layer's scales per forward in train mode, quant/binary/weight_quantization.py:27-34,51-59,75-82; the
+ * BASELINE solver sweep runs 53 tensors): `tensors` is a HOST array of `ntensors` descriptors, each
+ * [rows][len] contiguous fp32 on the device with its own output vector float[rows].  All small-row tensors
+ * go into one grid (one CTA per row); the per-row arithmetic is that of lsq_solve_v1 / lsq_row_absmean
+ * (nscales = 0), so results are bit-identical to the single-tensor calls.  No prologue, no diagnostics. */
+typedef struct lsq_row_tensor {
+  const float* d_x;
+  float* d_out;
+  int32_t rows;
+  int32_t len;
+} lsq_row_tensor;
+
+LSQ_API int lsq_solve_v1_multi(const lsq_row_tensor* tensors, int ntensors, int skip, int ternary, float alpha,
+                       void* stream);
+LSQ_API int lsq_row_absmean_multi(const lsq_row_tensor* tensors, int ntensors, float alpha, void* stream);
+
 /* Dense fake-quant tensor  out = sum_j s_j b_j  in the reference's fp32 operation order
  * (quantization.py:56, :89-92, :113-115, :139-146).  ternary = 1: two planes, both scaled by s_1. */
 LSQ_API int lsq_fakequant(const float* d_x, int64_t rows, int64_t len, float alpha,
@@ -160,6 +177,16 @@ LSQ_API int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alp
  *   i8   : the tcgen05 shared-memory operand image (K-major, no swizzle), see lsq_bconv_tc.cu */
 LSQ_API size_t lsq_wpack_bytes(int cout, int cin, int kh, int kw);
 LSQ_API int lsq_pack_weights(const float* d_w, int cout, int cin, int kh, int kw, void* d_wpack, void* stream);
+
+/* Deployable packed weights: the first lsq_wbits_bytes() bytes of the lsq_pack_weights
+ * buffer (the `bits` image, uint32[cout][kh*kw][ceil(cin/32)], bit c&31 of word c>>5 set when W >= 0) together
+ * with the per-channel scale (the reference's `w_approximate.v1` buffer, weight_quantization.py:25) are all
+ * an ls-1 layer needs at inference.  lsq_unpack_weights rebuilds a dense weight tensor
+ * w[co][c][ky][kx] = +-d_scale[co] (d_scale NULL: +-1) from it, whose sign(W) and mean|W| per channel are
+ * exactly the exported ones, so the reference's own modules load it as an ordinary state_dict entry. */
+LSQ_API size_t lsq_wbits_bytes(int cout, int cin, int kh, int kw);
+LSQ_API int lsq_unpack_weights(const uint32_t* d_bits, const float* d_scale, int cout, int cin, int kh, int kw,
+                       float* d_w, void* stream);
 
 /* ---- binary convolution ---------------------------------------------------------------------- */
 

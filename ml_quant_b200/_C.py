@@ -18,6 +18,7 @@ EXPORTS = [
     'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex', 'lsq_stem_fwd',
     'lsq_stem_image_bytes', 'lsq_stem_workspace_bytes', 'lsq_stem_supported', 'lsq_stem_pack_weights',
     'lsq_pwconv_supported', 'lsq_pwconv_image_bytes', 'lsq_pwconv_pack_weights', 'lsq_pwconv_fwd',
+    'lsq_solve_v1_multi', 'lsq_row_absmean_multi', 'lsq_wbits_bytes', 'lsq_unpack_weights',
 ]
 
 
@@ -34,6 +35,10 @@ class Prologue(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [('d_residual', C.c_void_p), ('d_prelu', C.c_void_p), ('n_prelu', C.c_int32), ('act', C.c_int32),
                 ('residual_after_act', C.c_int32)]
+
+
+class RowTensor(C.Structure):
+    _fields_ = [('d_x', C.c_void_p), ('d_out', C.c_void_p), ('rows', C.c_int32), ('len', C.c_int32)]
 
 
 class LsqError(RuntimeError):
@@ -93,6 +98,15 @@ def lib():
             L.lsq_pwconv_pack_weights.argtypes = [vp, i32, i32, vp, vp]
             L.lsq_pwconv_fwd.restype = i32
             L.lsq_pwconv_fwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]
+            L.lsq_wbits_bytes.restype = sz
+            L.lsq_wbits_bytes.argtypes = [i32] * 4
+            L.lsq_unpack_weights.restype = i32
+            L.lsq_unpack_weights.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+            tp = C.POINTER(RowTensor)
+            L.lsq_solve_v1_multi.restype = i32
+            L.lsq_solve_v1_multi.argtypes = [tp, i32, i32, i32, f32, vp]
+            L.lsq_row_absmean_multi.restype = i32
+            L.lsq_row_absmean_multi.argtypes = [tp, i32, f32, vp]
             for name in ('lsq_row_absmean', 'lsq_solve_v1', 'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry',
                          'lsq_encode_act', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
                          'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex'):

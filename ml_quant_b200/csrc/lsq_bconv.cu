@@ -55,6 +55,20 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   }
 }
 
+// Inverse of the `bits` image: w[co][c][tap] = bit ? +scale[co] : -scale[co]  (scale == NULL: +-1).
+__global__ void unpack_weights_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ scale, int cout,
+                                      int cin, int taps, int cw, float* __restrict__ w) {
+  const long long total = (long long)cout * cin * taps;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(idx % taps);
+    const int c = (int)((idx / taps) % cin);
+    const int co = (int)(idx / ((long long)taps * cin));
+    const uint32_t word = __ldg(bits + ((long long)co * taps + tap) * cw + (c >> 5));
+    const float v = scale ? __ldg(scale + co) : 1.0f;
+    w[idx] = ((word >> (c & 31)) & 1u) ? v : -v;
+  }
+}
+
 // One thread per output element; all planes at once.  Used for shapes outside the tensor-core
 // kernel (few channels, 5x5 LeNet layer) and as the on-device cross-check of that kernel.
 template <int NPL>
@@ -129,6 +143,23 @@ int lsq_pack_weights(const float* d_w, int cout, int cin, int kh, int kw, void* 
   if (grid > 148 * 8) grid = 148 * 8;
   pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_w, cout, cin, taps, cw, bits, i8);
   LSQ_CUDA_LAUNCH_CHECK("pack_weights_kernel");
+  return LSQ_OK;
+}
+
+size_t lsq_wbits_bytes(int cout, int cin, int kh, int kw) {
+  if (cout <= 0 || cin <= 0 || kh <= 0 || kw <= 0) return 0;
+  return (size_t)cout * kh * kw * ((cin + 31) / 32) * 4;
+}
+
+int lsq_unpack_weights(const uint32_t* d_bits, const float* d_scale, int cout, int cin, int kh, int kw, float* d_w,
+                       void* stream) {
+  LSQ_CHECK_ARG(d_bits && d_w, "lsq_unpack_weights: null pointer");
+  LSQ_CHECK_ARG(cout > 0 && cin > 0 && kh > 0 && kw > 0, "lsq_unpack_weights: bad shape");
+  const long long total = (long long)cout * cin * kh * kw;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  unpack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_bits, d_scale, cout, cin, kh * kw, (cin + 31) / 32, d_w);
+  LSQ_CUDA_LAUNCH_CHECK("unpack_weights_kernel");
   return LSQ_OK;
 }
 

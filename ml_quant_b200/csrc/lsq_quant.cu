@@ -252,6 +252,38 @@ encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const flo
   }
 }
 
+// Multi-tensor ls-1 scale (mean |x| per row of several weight tensors in one grid).  One CTA per row walks the
+// row in the same kRowChunk pieces, with the same per-thread / block / chunk summation order as
+// row_absmean_kernel, so the two agree bit for bit.
+constexpr int kMultiMax = 112;
+struct MultiTab {
+  const float* x[kMultiMax];
+  float* out[kMultiMax];
+  int len[kMultiMax];
+  int first_row[kMultiMax + 1];
+  int n;
+};
+__global__ void __launch_bounds__(kRowThreads)
+row_absmean_multi_kernel(const __grid_constant__ MultiTab tab, float alpha) {
+  __shared__ double red[32];
+  int lo = 0, hi = tab.n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tab.first_row[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const int r = (int)blockIdx.x - tab.first_row[lo];
+  const long long len = tab.len[lo];
+  const float* xr = tab.x[lo] + (long long)r * len;
+  double t = 0.0;
+  for (long long beg = 0; beg < len; beg += kRowChunk) {
+    const long long end = min(beg + (long long)kRowChunk, len);
+    double acc = 0.0;
+    for (long long e = beg + threadIdx.x; e < end; e += kRowThreads) acc += (double)fabsf(clamp_sym(__ldg(xr + e), alpha));
+    t += block_sum(acc, red);
+  }
+  if (threadIdx.x == 0) tab.out[lo][r] = (float)(t / (double)len);
+}
+
 }  // namespace lsq
 
 using namespace lsq;
@@ -291,6 +323,40 @@ int lsq_row_absmean_ex(const float* d_x, int64_t rows, int64_t len, float alpha,
   row_absmean_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nscales,
                                                                      d_out, partial, counter, to_dev(pro));
   LSQ_CUDA_LAUNCH_CHECK("row_absmean_kernel");
+  return LSQ_OK;
+}
+
+int lsq_row_absmean_multi(const lsq_row_tensor* tensors, int ntensors, float alpha, void* stream) {
+  LSQ_CHECK_ARG(tensors && ntensors > 0, "lsq_row_absmean_multi: bad arguments");
+  for (int i = 0; i < ntensors; ++i)
+    LSQ_CHECK_ARG(tensors[i].d_x && tensors[i].d_out && tensors[i].rows > 0 && tensors[i].len > 0,
+                  "lsq_row_absmean_multi: tensor %d: null pointer or empty shape", i);
+  int done = 0;
+  while (done < ntensors) {
+    int order[kMultiMax];
+    int nb = 0;
+    int64_t rows = 0;
+    for (; done < ntensors && nb < kMultiMax && rows + tensors[done].rows <= (int64_t)0x7fffffff; ++done) {
+      rows += tensors[done].rows;
+      order[nb++] = done;
+    }
+    for (int i = 1; i < nb; ++i) {        // longest rows first
+      const int o = order[i];
+      int j = i - 1;
+      for (; j >= 0 && tensors[order[j]].len < tensors[o].len; --j) order[j + 1] = order[j];
+      order[j + 1] = o;
+    }
+    MultiTab tab;
+    tab.n = nb;
+    tab.first_row[0] = 0;
+    for (int i = 0; i < nb; ++i) {
+      const lsq_row_tensor& T = tensors[order[i]];
+      tab.x[i] = T.d_x; tab.out[i] = T.d_out; tab.len[i] = T.len;
+      tab.first_row[i + 1] = tab.first_row[i] + T.rows;
+    }
+    row_absmean_multi_kernel<<<(unsigned)rows, kRowThreads, 0, (cudaStream_t)stream>>>(tab, alpha);
+    LSQ_CUDA_LAUNCH_CHECK("row_absmean_multi_kernel");
+  }
   return LSQ_OK;
 }
 

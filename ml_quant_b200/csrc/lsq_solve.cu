@@ -993,21 +993,19 @@ struct SmallSmem {
   uint32_t best_pos[32], best_key[32], kmin, kmax, ncand;
 };
 
+// One row solved by one CTA.  xr = the row, v1_dst = where its scale goes, diag_row = its 16 diagnostics or NULL.
 template <bool TERN>
-__global__ void __launch_bounds__(kSmallThreads)
-solve_v1_small_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
-                      int* __restrict__ diag, Prologue pro) {
-  __shared__ SmallSmem sm;
-  const long long row = blockIdx.x;
-  const float* xr = x + row * len;
+__device__ __forceinline__ void solve_small_row(SmallSmem& sm, const float* __restrict__ xr, long long len, int skip,
+                                                float alpha, float* __restrict__ v1_dst, int* __restrict__ diag_row,
+                                                const Prologue& pro) {
   const uint32_t n = (uint32_t)((len + skip - 1) / skip);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) { sm.kmin = kNoKey; sm.kmax = 0u; sm.ncand = 0u; }
   __syncthreads();
   if (n < 3) {
     if (tid == 0) {
-      v1_out[row] = 0.0f;
-      if (diag) for (int i = 0; i < 16; ++i) diag[row * 16 + i] = 0;
+      *v1_dst = 0.0f;
+      if (diag_row) for (int i = 0; i < 16; ++i) diag_row[i] = 0;
     }
     return;
   }
@@ -1065,12 +1063,51 @@ solve_v1_small_kernel(const float* __restrict__ x, long long len, int skip, floa
         b.offer(closed_cost2<true>((double)half_mean, 0.0, 0.0, (double)n, s_tot, q_tot), n, __float_as_uint(half_mean));
       }
     }
-    v1_out[row] = (nc_tot > 0) ? key_val(b.key) : 0.0f;
-    if (diag) {
-      for (int i = 0; i < 16; ++i) diag[row * 16 + i] = 0;
-      diag[row * 16 + 0] = 1; diag[row * 16 + 2] = (int)nc_tot;
+    *v1_dst = (nc_tot > 0) ? key_val(b.key) : 0.0f;
+    if (diag_row) {
+      for (int i = 0; i < 16; ++i) diag_row[i] = 0;
+      diag_row[0] = 1; diag_row[2] = (int)nc_tot;
     }
   }
+}
+
+template <bool TERN>
+__global__ void __launch_bounds__(kSmallThreads)
+solve_v1_small_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
+                      int* __restrict__ diag, Prologue pro) {
+  __shared__ SmallSmem sm;
+  const long long row = blockIdx.x;
+  solve_small_row<TERN>(sm, x + row * len, len, skip, alpha, v1_out + row, diag ? diag + row * 16 : nullptr, pro);
+}
+
+// Multi-tensor launch (weight tensors of a whole network in ONE grid): the tensor table travels by value in the
+// kernel parameters, CTA b finds its tensor by bisection over the cumulative row counts.  Same per-row code as
+// the single-tensor kernel, so the results are bit-identical.
+constexpr int kMultiMax = 112;
+struct MultiTab {
+  const float* x[kMultiMax];
+  float* out[kMultiMax];
+  int len[kMultiMax];
+  int first_row[kMultiMax + 1];
+  int n;
+};
+__device__ __forceinline__ int multi_find(const MultiTab& tab, int row) {
+  int lo = 0, hi = tab.n;                 // first_row[lo] <= row < first_row[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tab.first_row[mid] <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+template <bool TERN>
+__global__ void __launch_bounds__(kSmallThreads)
+solve_v1_multi_kernel(const __grid_constant__ MultiTab tab, int skip, float alpha) {
+  __shared__ SmallSmem sm;
+  const int t = multi_find(tab, (int)blockIdx.x);
+  const int r = (int)blockIdx.x - tab.first_row[t];
+  const long long len = tab.len[t];
+  const Prologue none{nullptr, nullptr, 1, 1, 1ull << 40};
+  solve_small_row<TERN>(sm, tab.x[t] + (long long)r * len, len, skip, alpha, tab.out[t] + r, nullptr, none);
 }
 
 }  // namespace lsq
@@ -1118,5 +1155,53 @@ extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int 
     return LSQ_ERR_CUDA;
   }
   LSQ_CUDA_LAUNCH_CHECK("solve_v1_kernel");
+  return LSQ_OK;
+}
+
+// Several tensors, one launch per `kMultiMax` small-row tensors (host table, passed by value; nothing is read from
+// the table after the call returns).  Tensors whose sampled rows exceed the small-row kernel get their own launch.
+extern "C" int lsq_solve_v1_multi(const lsq_row_tensor* tensors, int ntensors, int skip, int ternary, float alpha,
+                                  void* stream) {
+  LSQ_CHECK_ARG(tensors && ntensors > 0 && skip >= 1, "lsq_solve_v1_multi: bad arguments");
+  for (int i = 0; i < ntensors; ++i)
+    LSQ_CHECK_ARG(tensors[i].d_x && tensors[i].d_out && tensors[i].rows > 0 && tensors[i].len > 0,
+                  "lsq_solve_v1_multi: tensor %d: null pointer or empty shape", i);
+  // longest rows first: the grid drains evenly
+  int order[kMultiMax];
+  int done = 0;
+  while (done < ntensors) {
+    MultiTab tab;
+    tab.n = 0;
+    tab.first_row[0] = 0;
+    for (; done < ntensors && tab.n < kMultiMax; ++done) {
+      const lsq_row_tensor& T = tensors[done];
+      if (((int64_t)T.len + skip - 1) / skip > (int64_t)kSmallRow) {
+        const int st = lsq_solve_v1_ex(T.d_x, T.rows, T.len, skip, ternary, alpha, T.d_out, nullptr, nullptr, stream);
+        if (st != LSQ_OK) return st;
+        continue;
+      }
+      if ((int64_t)tab.first_row[tab.n] + T.rows > (int64_t)0x7fffffff) break;
+      order[tab.n] = done;
+      ++tab.n;
+      tab.first_row[tab.n] = tab.first_row[tab.n - 1] + T.rows;
+    }
+    if (tab.n == 0) continue;
+    // insertion sort of the batch by row length, descending (stable)
+    for (int i = 1; i < tab.n; ++i) {
+      const int o = order[i];
+      int j = i - 1;
+      for (; j >= 0 && tensors[order[j]].len < tensors[o].len; --j) order[j + 1] = order[j];
+      order[j + 1] = o;
+    }
+    for (int i = 0; i < tab.n; ++i) {
+      const lsq_row_tensor& T = tensors[order[i]];
+      tab.x[i] = T.d_x; tab.out[i] = T.d_out; tab.len[i] = T.len;
+      tab.first_row[i + 1] = tab.first_row[i] + T.rows;
+    }
+    dim3 grid((unsigned)tab.first_row[tab.n]);
+    if (ternary) solve_v1_multi_kernel<true><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(tab, skip, alpha);
+    else solve_v1_multi_kernel<false><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(tab, skip, alpha);
+    LSQ_CUDA_LAUNCH_CHECK("solve_v1_multi_kernel");
+  }
   return LSQ_OK;
 }

@@ -130,6 +130,46 @@ def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[fl
     return (out, dg) if diag else out
 
 
+def _row_tensor_table(xs: Sequence[torch.Tensor]):
+    """Host descriptor table (include/lsq_b200.h: lsq_row_tensor) for 2-D tensors on one device + their outputs."""
+    if len(xs) == 0:
+        raise ValueError('need at least one tensor')
+    dev = xs[0].device
+    keep, outs = [], []
+    tab = (_C.RowTensor * len(xs))()
+    for i, x in enumerate(xs):
+        require_cuda(x)
+        if x.device != dev or x.dim() != 2:
+            raise ValueError('multi-tensor calls need 2-D tensors on one device')
+        x = x.detach().contiguous()
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=dev)
+        keep.append(x)
+        outs.append(out)
+        tab[i] = _C.RowTensor(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1])
+    return dev, tab, keep, outs
+
+
+def solve_v1_multi(xs: Sequence[torch.Tensor], ternary: bool, skip: int = 1,
+                   alpha: Optional[float] = None) -> List[torch.Tensor]:
+    """Optimal v1 per row of several [rows, len] tensors in one launch (lsq_solve_v1_multi); same values as
+    ``solve_v1`` on each tensor."""
+    dev, tab, keep, outs = _row_tensor_table(xs)
+    total = float(sum(x.numel() for x in keep))
+    with torch.cuda.device(dev), _launch('solve_v1_multi', 4.0 * total):
+        _C.check(_C.lib().lsq_solve_v1_multi(tab, len(keep), int(skip), int(bool(ternary)), _alpha(alpha), _stream()),
+                 'lsq_solve_v1_multi')
+    return outs
+
+
+def row_absmean_multi(xs: Sequence[torch.Tensor], alpha: Optional[float] = None) -> List[torch.Tensor]:
+    """mean |x| per row of several [rows, len] tensors in one launch (lsq_row_absmean_multi)."""
+    dev, tab, keep, outs = _row_tensor_table(xs)
+    total = float(sum(x.numel() for x in keep))
+    with torch.cuda.device(dev), _launch('row_absmean_multi', 4.0 * total):
+        _C.check(_C.lib().lsq_row_absmean_multi(tab, len(keep), _alpha(alpha), _stream()), 'lsq_row_absmean_multi')
+    return outs
+
+
 def fakequant(x2d: torch.Tensor, scales: Sequence[torch.Tensor], ternary: bool = False,
               alpha: Optional[float] = None) -> torch.Tensor:
     """Dense sum_j s_j b_j in the reference's operation order (lsq_fakequant)."""

@@ -48,6 +48,29 @@ for name, fn in [('ls-1 (row_absmean)', lambda w: ops.row_absmean(w)),
         best = min(best, e0.elapsed_time(e1))
     print(f'{name:20s} eager {ms:7.3f} ms {elems / ms / 1e3:8.0f} Melem/s | graph {best:7.3f} ms {elems / best / 1e3:8.0f} Melem/s '
           f'{4.0 * elems / best / 1e6:7.0f} GB/s (53 launches)')
+# all 53 tensors in ONE launch (lsq_solve_v1_multi / lsq_row_absmean_multi; skip 1 keeps own launches for the
+# tensors whose rows exceed the small-row kernel)
+for name, fn in [('ls-1 multi', lambda: ops.row_absmean_multi(ws)),
+                 ('ls-2 skip 3 multi', lambda: ops.solve_v1_multi(ws, False, 3)), ('ls-2 skip 1 multi', lambda: ops.solve_v1_multi(ws, False, 1)),
+                 ('ls-T skip 3 multi', lambda: ops.solve_v1_multi(ws, True, 3)), ('ls-T skip 1 multi', lambda: ops.solve_v1_multi(ws, True, 1))]:
+    fn(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); keep = fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        keep = fn()
+    gbest = 1e9
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); graph.replay(); e1.record(); torch.cuda.synchronize()
+        gbest = min(gbest, e0.elapsed_time(e1))
+    print(f'{name:20s} eager {best:7.3f} ms {elems / best / 1e3:8.0f} Melem/s | graph {gbest:7.3f} ms {elems / gbest / 1e3:8.0f} Melem/s '
+          f'{4.0 * elems / gbest / 1e6:7.0f} GB/s')
 if '--cpu' in sys.argv:
     import time
     from oracle import lsq_oracle as O          # checker used as the CPU baseline of this sweep (test infrastructure)

@@ -223,3 +223,27 @@ def test_solver_resnet50_weight_sweep(tern):
             v_ref = O.solve_v1(rows, tern, skip, chunk=32).view(-1)
             _solver_contract(rows, v, v_ref, tern, skip)
         assert _close(ops.row_absmean(rows.to(DEV)), rows.abs().mean(1))
+
+
+def test_multi_tensor_solver_is_bit_identical_to_single_launches():
+    """lsq_solve_v1_multi / lsq_row_absmean_multi over all 53 ResNet-50 weight tensors (one grid per call; tensors
+    whose sampled rows exceed the small-row kernel get their own launch inside): same bits as per-tensor calls."""
+    from ml_quant_b200 import ops
+    g = torch.Generator().manual_seed(51)
+    ws = [(torch.randn(s[0], s[1] * s[2] * s[3], generator=g) * 0.05).to(DEV) for s in RESNET50_WEIGHT_SHAPES]
+    ws.append(torch.randn(5, 2, generator=g).to(DEV))            # fewer than 3 solve elements: v1 = 0
+    ws.append(torch.randn(300, 7000, generator=g).to(DEV))       # long rows: own launch inside the multi call
+    for tern in (False, True):
+        for skip in (3, 1):
+            multi = ops.solve_v1_multi(ws, tern, skip)
+            for w, v in zip(ws, multi):
+                assert torch.equal(v, ops.solve_v1(w, tern, skip)), (tuple(w.shape), tern, skip)
+    for alpha in (None, 0.05):
+        multi = ops.row_absmean_multi(ws, alpha=alpha)
+        for w, v in zip(ws, multi):
+            assert torch.equal(v, ops.row_absmean(w, alpha=alpha)), tuple(w.shape)
+    # more tensors than one parameter table holds (112): two grids
+    many = [ws[i % 8][: 16 + i] for i in range(130)]
+    multi = ops.solve_v1_multi(many, False, 3)
+    for w, v in zip(many, multi):
+        assert torch.equal(v, ops.solve_v1(w.contiguous(), False, 3))
