@@ -64,7 +64,8 @@ __global__ void unpack_weights_kernel(const uint32_t* __restrict__ bits, const f
     const int c = (int)((idx / taps) % cin);
     const int co = (int)(idx / ((long long)taps * cin));
     const uint32_t word = __ldg(bits + ((long long)co * taps + tap) * cw + (c >> 5));
-    const float v = scale ? __ldg(scale + co) : 1.0f;
+    float v = scale ? __ldg(scale + co) : 1.0f;
+    if (!(v > 0.0f)) v = 1.0f;              // an unset scale must not erase the sign (-0.0 >= 0)
     w[idx] = ((word >> (c & 31)) & 1u) ? v : -v;
   }
 }

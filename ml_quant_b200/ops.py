@@ -243,6 +243,34 @@ def pack_weights(w: torch.Tensor) -> torch.Tensor:
     return view
 
 
+def weight_bits(w: torch.Tensor) -> torch.Tensor:
+    """The deployable sign image of a weight tensor: int32 [cout, kh*kw, ceil(cin/32)], bit c&31 of word c>>5 set
+    when W >= 0 (the `bits` part of lsq_pack_weights, include/lsq_b200.h)."""
+    cout, cin, kh, kw = w.shape
+    nbytes = _C.lib().lsq_wbits_bytes(cout, cin, kh, kw)
+    return pack_weights(w)[:nbytes].clone().view(torch.int32).view(cout, kh * kw, (cin + 31) // 32)
+
+
+def unpack_weights(bits: torch.Tensor, scale: Optional[torch.Tensor], shape) -> torch.Tensor:
+    """Dense fp32 weights +-scale[co] from a sign image (lsq_unpack_weights)."""
+    cout, cin, kh, kw = (int(v) for v in shape)
+    if not bits.is_cuda or bits.dtype != torch.int32:
+        raise _C.LsqError('ml_quant_b200: unpack_weights needs an int32 CUDA tensor')
+    bits = bits.contiguous()
+    if bits.numel() * 4 != _C.lib().lsq_wbits_bytes(cout, cin, kh, kw):
+        raise ValueError(f'sign image of {bits.numel() * 4} bytes does not match weight shape {(cout, cin, kh, kw)}')
+    if scale is not None:
+        require_cuda(scale, 'scale')
+        scale = scale.detach().contiguous()
+        if scale.numel() != cout:
+            raise ValueError(f'scale must have {cout} entries')
+    w = torch.empty(cout, cin, kh, kw, dtype=torch.float32, device=bits.device)
+    with torch.cuda.device(bits.device), _launch('unpack_weights', 4.0 * w.numel()):
+        _C.check(_C.lib().lsq_unpack_weights(bits.data_ptr(), _ptr(scale), cout, cin, kh, kw, w.data_ptr(), _stream()),
+                 'lsq_unpack_weights')
+    return w
+
+
 def bconv2d(planes: torch.Tensor, g: _C.ActGeom, nplanes: int, act_scales: torch.Tensor, wpack: torch.Tensor,
             w_scale: torch.Tensor, bias: Optional[torch.Tensor], cout: int, impl: int = 0,
             out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = 0,

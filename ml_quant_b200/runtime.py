@@ -270,6 +270,50 @@ class HostPipeline:
         return self.host_out
 
 
+PACKED_FORMAT = 'lsq_b200.packed.v1'
+
+
+def export_packed(model: nn.Module) -> Dict[str, torch.Tensor]:
+    """Deployable checkpoint: the model's ``state_dict`` with the fp32 weight of every ls-1
+    ``QuantConv2d`` (in eval mode the layer only uses sign(W) and the stored ``w_approximate.v1``,
+    quant/binary/weight_quantization.py:32-33) replaced by its sign image -- ``<layer>.weight_bits`` int32
+    [cout, kh*kw, ceil(cin/32)] plus ``<layer>.weight_shape`` -- 1 bit instead of 32 per quantized weight.
+    Everything else (scales, biases, BatchNorm, fp layers, moving averages) is copied unchanged, on the CPU."""
+    from . import ops
+    from .binary.binary_conv import QuantConv2d
+    out: Dict[str, torch.Tensor] = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for name, m in model.named_modules():
+        if isinstance(m, QuantConv2d) and m.w_quant == 'ls-1':
+            key = f'{name}.weight' if name else 'weight'
+            ops.require_cuda(m.weight, f'{key} (export packs on the GPU)')
+            out[f'{key}_bits'] = ops.weight_bits(m.weight).cpu()
+            out[f'{key}_shape'] = torch.tensor(tuple(m.weight.shape), dtype=torch.int64)
+            del out[key]
+    out['_format'] = torch.tensor(list(PACKED_FORMAT.encode()), dtype=torch.uint8)
+    return out
+
+
+def load_packed(model: nn.Module, packed: Dict[str, torch.Tensor], strict: bool = True):
+    """Load an ``export_packed`` checkpoint into ``model`` (already on its CUDA device): the sign images are
+    expanded to W = +-v1[co], whose sign(W) and per-channel mean|W| are exactly the exported ones, so eval-mode
+    outputs equal those of the original fp32 checkpoint bit for bit and a train-mode re-solve returns the same
+    v1.  Returns ``load_state_dict``'s result."""
+    from . import ops
+    fmt = packed.get('_format')
+    if fmt is None or bytes(fmt.tolist()).decode() != PACKED_FORMAT:
+        raise ValueError(f'not a {PACKED_FORMAT} checkpoint')
+    dev = next(model.parameters()).device
+    state = {k: v for k, v in packed.items() if k != '_format' and not k.endswith(('.weight_bits', '.weight_shape'))
+             and k not in ('weight_bits', 'weight_shape')}
+    for k, bits in packed.items():
+        if k.endswith('weight_bits'):
+            base = k[:-len('_bits')]
+            prefix = base[:-len('weight')]
+            v1 = packed[f'{prefix}w_approximate.v1'].to(dev, torch.float32)
+            state[base] = ops.unpack_weights(bits.to(dev), v1, packed[f'{base}_shape'].tolist())
+    return model.load_state_dict(state, strict=strict)
+
+
 def gather_logits(local: torch.Tensor, world: int) -> torch.Tensor:
     """The path's only collective: all ranks' logits (one NCCL all_gather over NVLink)."""
     if world == 1:

@@ -520,3 +520,44 @@ def test_full_size_fused_network_layer_by_layer():
         want = F.relu(conv) + res if r['after'] else F.relu(conv + res)
         err = float((r['y'] - want).abs().max() / want.abs().max())
         assert err < 1e-5, (i, err)
+
+
+def test_packed_checkpoint_round_trip():
+    """export_packed / load_packed: sign images + scales instead of fp32 weights; a fresh
+    model loaded from the packed form gives bit-identical logits, a train-mode weight re-solve returns the same
+    v1, and the quantized weights take 1/32 of their fp32 size.  The oracle runs the unpacked state too."""
+    from ml_quant_b200 import ops, runtime
+    cfg = 'cifar100_resnet18_ls1w_ls2a'
+    model = runtime.build_model(cfg, torch.device(DEV))
+    runtime.calibrate(model, (3, 32, 32), batches=1, batch=16)
+    x = torch.randn(8, 3, 32, 32).to(DEV)
+    with torch.no_grad():
+        want = model(x)
+    packed = runtime.export_packed(model)
+    assert all(not v.is_cuda for v in packed.values())
+    layers = runtime.quant_layers(model)
+    qbytes = sum(m.weight.numel() * 4 for m in layers)
+    pbytes = sum(v.numel() * 4 for k, v in packed.items() if k.endswith('weight_bits'))
+    assert len([k for k in packed if k.endswith('weight_bits')]) == len(layers) == 16
+    assert pbytes * 32 == qbytes
+    # the sign image is the documented layout: bit c&31 of word c>>5 of [cout, tap, word] is W >= 0
+    name, m0 = next((n, m) for n, m in model.named_modules() if m is layers[0])
+    bits = packed[f'{name}.weight_bits']
+    w = m0.weight.detach().cpu()
+    cout, cin, kh, kw = w.shape
+    got = torch.stack([(bits[:, :, c >> 5] >> (c & 31)) & 1 for c in range(cin)], 1).bool()     # [cout, cin, taps]
+    assert torch.equal(got, w.reshape(cout, cin, kh * kw) >= 0)
+    fresh = runtime.build_model(cfg, torch.device(DEV), seed=7)
+    res = runtime.load_packed(fresh, packed)
+    fresh.eval()
+    assert not res.missing_keys and not res.unexpected_keys
+    with torch.no_grad():
+        assert torch.equal(fresh(x), want)
+        fm = runtime.quant_layers(fresh)[3]
+        assert torch.equal(ops.row_absmean(fm.weight.detach().reshape(fm.out_channels, -1)), fm.w_approximate.v1)
+    runtime.optimize_for_inference(fresh)
+    runtime.optimize_for_inference(model)
+    with torch.no_grad():
+        assert torch.equal(fresh(x), model(x))
+    with pytest.raises(ValueError):
+        runtime.load_packed(fresh, {k: v for k, v in packed.items() if k != '_format'})
