@@ -172,9 +172,14 @@ class QuantConv2d(nn.Conv2d):
             planes, v1 = ops.encode_act(x, g, [], 1, alpha, True, buf, pro)
             table = [v1]
         elif self.x_quant in ('ls-2', 'ls-T'):
-            v1 = ops.solve_v1(rows, tern, 3, alpha, prologue=pro)
-            planes, v2 = ops.encode_act(x, g, [v1], 2, alpha, not tern, buf, pro)
-            table = [v1, v1] if tern else [v1, v2]
+            # the kernels write straight into the [2, n] table the convolution reads: no stack / copy launches
+            tab = torch.empty(2, n, dtype=torch.float32, device=x.device)
+            ops.solve_v1(rows, tern, 3, alpha, prologue=pro, out=tab[0])
+            planes, _ = ops.encode_act(x, g, tab[:1], 2, alpha, not tern, buf, pro, next_scale_out=tab[1])
+            if tern:
+                tab[1].copy_(tab[0])
+            self._planes_cache[dev] = planes
+            return planes, tab
         else:
             scales: List[torch.Tensor] = []
             for _ in range(npl - 1):

@@ -76,6 +76,10 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 def scale_table(scales: Sequence[torch.Tensor], rows: int, device) -> Optional[torch.Tensor]:
     if len(scales) == 0:
         return None
+    if isinstance(scales, torch.Tensor) and scales.dim() == 2:     # already a [nscales, rows] table: no copy kernel
+        if scales.shape[1] != rows or scales.dtype != torch.float32 or not scales.is_contiguous():
+            raise ValueError(f'scale table must be contiguous float32 [k, {rows}]')
+        return scales.detach()
     tab = torch.stack([s.detach().reshape(-1).to(device=device, dtype=torch.float32) for s in scales]).contiguous()
     if tab.shape[1] != rows:
         raise ValueError(f'scale vectors must have {rows} entries, got {tab.shape[1]}')
@@ -115,18 +119,44 @@ def row_absmean(x2d: torch.Tensor, scales: Sequence[torch.Tensor] = (), alpha: O
     return out
 
 
+# long rows: keep the sampled keys of pass 1 in a scratch buffer for pass 2 (lsq_solve_v1_ws).  Off by default: measured
+# on B200 the store slows pass 1 by as much as pass 2 gains (247 vs 250 us on 512 rows of 200 704 elements).
+SOLVE_SCRATCH = False
+
+
+def _solve_scratch(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
+    """Uninitialised scratch for the solver, cached per (thread, device, stream); holds nothing between calls."""
+    if nbytes == 0 or not SOLVE_SCRATCH:
+        return None
+    cache = getattr(_tls, 'solve_ws', None)
+    if cache is None:
+        cache = _tls.solve_ws = {}
+    key = (device.index, _stream())
+    buf = cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        cache[key] = buf
+    return buf
+
+
 def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[float] = None,
-             diag: bool = False, prologue=None):
+             diag: bool = False, prologue=None, out: Optional[torch.Tensor] = None):
     """Optimal v1 per row (lsq_solve_v1); returns [rows] (and the int32 [rows,4] diagnostics)."""
     require_cuda(x2d)
     x2d = x2d.contiguous()
     rows, length = x2d.shape
-    out = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    if out is None:
+        out = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    elif out.shape != (rows,) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x2d.device:
+        raise ValueError(f'out must be a contiguous float32 [{rows}] tensor on {x2d.device}')
     dg = torch.zeros(rows, 16, dtype=torch.int32, device=x2d.device) if diag else None
+    L = _C.lib()
     with torch.cuda.device(x2d.device), _launch('solve_v1', 4.0 * rows * length):
         keep = []
-        _C.check(_C.lib().lsq_solve_v1_ex(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
-                                          out.data_ptr(), _ptr(dg), _prologue(prologue, keep), _stream()), 'lsq_solve_v1')
+        ws = _solve_scratch(x2d.device, L.lsq_solve_workspace_bytes(rows, length, int(skip), _alpha(alpha)))
+        _C.check(L.lsq_solve_v1_ws(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
+                                   out.data_ptr(), _ptr(dg), _prologue(prologue, keep), _ptr(ws),
+                                   0 if ws is None else ws.numel(), _stream()), 'lsq_solve_v1')
     return (out, dg) if diag else out
 
 
@@ -208,7 +238,8 @@ def act_geometry(n: int, c: int, h: int, w: int, kh: int, kw: int, stride: int, 
 
 def encode_act(x: torch.Tensor, g: _C.ActGeom, scales: Sequence[torch.Tensor], nplanes: int,
                alpha: Optional[float] = None, want_next_scale: bool = False,
-               planes: Optional[torch.Tensor] = None, prologue=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               planes: Optional[torch.Tensor] = None, prologue=None,
+               next_scale_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """x [n,c,h,w] -> bit planes (int32 buffer) and optionally the next per-sample scale (lsq_encode_act)."""
     require_cuda(x)
     x = x.contiguous()
@@ -217,7 +248,11 @@ def encode_act(x: torch.Tensor, g: _C.ActGeom, scales: Sequence[torch.Tensor], n
     if planes is None or planes.numel() * 4 < nbytes:
         planes = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=x.device)
     tab = scale_table(scales, g.n, x.device)
-    nxt = torch.empty(g.n, dtype=torch.float32, device=x.device) if want_next_scale else None
+    nxt = None
+    if want_next_scale:
+        nxt = next_scale_out if next_scale_out is not None else torch.empty(g.n, dtype=torch.float32, device=x.device)
+        if nxt.shape != (g.n,) or nxt.dtype != torch.float32 or not nxt.is_contiguous() or nxt.device != x.device:
+            raise ValueError(f'next_scale_out must be a contiguous float32 [{g.n}] tensor on {x.device}')
     need = L.lsq_reduce_workspace_bytes(g.n, g.c * g.h * g.w)
     ws = workspace(x.device, need)
     with torch.cuda.device(x.device), _launch('encode_act', x.numel() * (4.0 + nplanes / 8.0)):
