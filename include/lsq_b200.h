@@ -105,16 +105,6 @@ LSQ_API int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int skip, 
 LSQ_API int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
                     float* d_v1, int32_t* d_diag, const lsq_prologue* pro, void* stream);
 
-/* Same with a scratch buffer of lsq_solve_workspace_bytes() bytes (0 when the rows fit shared memory and are
- * read once anyway): rows too long for shared memory take two streaming passes; with the scratch the first pass
- * leaves the sampled |clamp(x)| values there and the second reads those -- a third of the bytes, no prologue
- * arithmetic.  Results are bit-identical to lsq_solve_v1_ex; d_ws == NULL is lsq_solve_v1_ex.  The scratch
- * holds nothing between calls. */
-LSQ_API size_t lsq_solve_workspace_bytes(int64_t rows, int64_t len, int skip, float alpha);
-LSQ_API int lsq_solve_v1_ws(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
-                    float* d_v1, int32_t* d_diag, const lsq_prologue* pro, void* d_ws, size_t ws_bytes,
-                    void* stream);
-
 /* Multi-tensor forms for weight tensors (the WeightQuantizer* modules of a whole network solve every
  * layer's scales per forward in train mode, quant/binary/weight_quantization.py:27-34,51-59,75-82; the
  * BASELINE solver sweep runs 53 tensors): `tensors` is a HOST array of `ntensors` descriptors, each

@@ -20,7 +20,6 @@ EXPORTS = [
     'lsq_stem_image_bytes', 'lsq_stem_workspace_bytes', 'lsq_stem_supported', 'lsq_stem_pack_weights',
     'lsq_pwconv_supported', 'lsq_pwconv_image_bytes', 'lsq_pwconv_pack_weights', 'lsq_pwconv_fwd',
     'lsq_solve_v1_multi', 'lsq_row_absmean_multi', 'lsq_wbits_bytes', 'lsq_unpack_weights',
-    'lsq_solve_workspace_bytes', 'lsq_solve_v1_ws',
 ]
 
 
@@ -104,10 +103,6 @@ def lib():
             L.lsq_wbits_bytes.argtypes = [i32] * 4
             L.lsq_unpack_weights.restype = i32
             L.lsq_unpack_weights.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
-            L.lsq_solve_workspace_bytes.restype = sz
-            L.lsq_solve_workspace_bytes.argtypes = [i64, i64, i32, f32]
-            L.lsq_solve_v1_ws.restype = i32
-            L.lsq_solve_v1_ws.argtypes = [vp, i64, i64, i32, i32, f32, vp, vp, pp, vp, sz, vp]
             tp = C.POINTER(RowTensor)
             L.lsq_solve_v1_multi.restype = i32
             L.lsq_solve_v1_multi.argtypes = [tp, i32, i32, i32, f32, vp]

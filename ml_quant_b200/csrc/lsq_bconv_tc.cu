@@ -152,13 +152,19 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       if (!valid) return -1;
       return (((long long)pi.s * P.cout + (long long)ctile * 128) * g.ho + pi.a) * g.wo + pi.col;
     };
+    // item -> (position tile, channel tile); layers of up to 128 channels have one channel tile: no division
+    auto split_item = [&](int item, int& ptile, int& ctile) {
+      if (P.n_ctiles == 1) { ptile = item; ctile = 0; }
+      else { ptile = item / P.n_ctiles; ctile = item - ptile * P.n_ctiles; }
+    };
     struct Cursor { int item, step; };
     auto advance = [&](Cursor& c) {
       if (++c.step == spi) { c.step = 0; c.item += (int)gridDim.x; }
     };
     auto issue = [&](const Cursor& c, int slot) {      // always commits a group so the group count stays uniform
       if (has_res && c.item < n_items) {
-        const int ptile = c.item / P.n_ctiles, ctile = c.item - ptile * P.n_ctiles;
+        int ptile, ctile;
+        split_item(c.item, ptile, ctile);
         int sample;
         const long long off = out_offset(ptile, ctile, pbase + 32 * c.step + lane, sample);
         const uint32_t dst = smem_u32(res0 + slot * 1024 + lane);
@@ -182,7 +188,21 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       if (++islot == R) islot = 0;
     }
     float ws = 0.0f, bs = 0.0f;
+    long long off_first = -1;     // output offset of position `lane` of the item's first step (reused by its store phase)
     while (co.item < n_items) {
+      int ptile, ctile;
+      split_item(co.item, ptile, ctile);
+      // the activation scales of this lane's position are requested before the residual prefetch below is issued,
+      // so their latency is hidden behind it (they were the largest single stall of the epilogue warps)
+      float2 s_first = make_float2(0.0f, 0.0f);
+      if (co.step == 0) {
+        int sample;
+        off_first = out_offset(ptile, ctile, pbase + lane, sample);
+        if (off_first >= 0) {
+          s_first.x = __ldg(act_scales + sample);
+          if (P.npl > 1) s_first.y = __ldg(act_scales + g.n + sample);
+        }
+      }
       issue(is, islot);
       advance(is);
       if (++islot == R) islot = 0;
@@ -191,10 +211,10 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       else if (R == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else if (R == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      const int ptile = co.item / P.n_ctiles, ctile = co.item - ptile * P.n_ctiles;
       if (co.step == 0) {
         // per-position activation scales of this warp's positions, per-thread channel constants
-        for (int p = lane; p < tph; p += 32) {
+        scl[lane] = s_first;
+        for (int p = lane + 32; p < tph; p += 32) {
           int sample;
           const long long off = out_offset(ptile, ctile, pbase + p, sample);
           float2 s2 = make_float2(0.0f, 0.0f);
@@ -245,8 +265,11 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       __syncwarp();
       // ---- lane = position: activation, residual, one 128-byte row segment per channel ----
       {
-        int sample;
-        const long long off = out_offset(ptile, ctile, pbase + 32 * co.step + lane, sample);
+        long long off = off_first;
+        if (co.step != 0) {
+          int sample;
+          off = out_offset(ptile, ctile, pbase + 32 * co.step + lane, sample);
+        }
         if (off >= 0) {
           const float* rs_base = res0 + cslot * 1024 + lane;
           const float* ot = outt + lane;

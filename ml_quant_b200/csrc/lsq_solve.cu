@@ -33,17 +33,7 @@ constexpr int kMaxRanges = 4;
 constexpr int kMaxFlag = 64;
 constexpr int kStack = 24;
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
-// A/B switches of the row passes (scripts/dev/solver_diag_scratch.py): elements per thread and batch, and whether
-// the loads of the next batch are issued before the current one is processed.  Measured on 512 bare rows of 200 704
-// elements: 8/off 247 us, 8/on 248 us, 4/off 256 us, 4/on 240 us -- but inside the network (BatchNorm prologue,
-// resident rows of the later stages) 4/on is slower overall (2.83 vs 2.71 ms per forward), so 8/off stays.
-#ifndef LSQ_LOAD_BATCH
-#define LSQ_LOAD_BATCH 8
-#endif
-#ifndef LSQ_PREFETCH
-#define LSQ_PREFETCH 0
-#endif
-constexpr int kLoadBatch = LSQ_LOAD_BATCH;
+constexpr int kLoadBatch = 8;
 constexpr int kMaxGroups = 128;        // flagged 16-bin groups whose bins get the fine test in parallel
 constexpr int kMaxProChannels = 512;   // prologue tables up to this many channels are staged in shared memory
 constexpr int kFineShift = 14, kFineListShift = 16;   // bin width of a top window anchored at the clamp bound
@@ -138,70 +128,11 @@ static_assert(sizeof(LayoutSmall::Smem) <= 55 * 1024 + 768, "four CTAs per SM ne
 // (u < kLoadBatch, valid while e < e_end), v[u] = x[e * skip]; kLoadBatch independent loads are in flight per
 // thread.  Trip counts are warp uniform.  (A cp.async.bulk ring feeding the same loop was measured slower:
 // scripts/mb/mb_hist.cu, 3.4 vs 4.7 TB/s.)
-// Same batches over the row's compacted keys (|clamp(prologue(x))| of the sampled elements, written by this CTA in
-// its first pass): plain cache-global loads, not the read-only path -- the data was written by this kernel.
-template <int THREADS, class Body>
-__device__ __forceinline__ void sweep_keys(const float* kf, uint32_t n, Body&& body) {
-  const int tid = threadIdx.x;
-  constexpr uint32_t kBatch = THREADS * kLoadBatch;
-#if LSQ_PREFETCH
-  float nxt[kLoadBatch];
-#pragma unroll
-  for (int u = 0; u < kLoadBatch; ++u) {
-    const uint32_t e = tid + u * THREADS;
-    nxt[u] = (e < n) ? __ldcg(kf + e) : 0.0f;
-  }
-  for (uint32_t eb = 0; eb < n; eb += kBatch) {
-    float v[kLoadBatch];
-    const uint32_t e0 = eb + tid;
-#pragma unroll
-    for (int u = 0; u < kLoadBatch; ++u) {
-      v[u] = nxt[u];
-      const uint32_t e = e0 + kBatch + u * THREADS;
-      nxt[u] = (e < n) ? __ldcg(kf + e) : 0.0f;
-    }
-    body(v, e0, min(n, eb + kBatch));
-  }
-#else
-  for (uint32_t eb = 0; eb < n; eb += kBatch) {
-    float v[kLoadBatch];
-    const uint32_t e0 = eb + tid;
-#pragma unroll
-    for (int u = 0; u < kLoadBatch; ++u) {
-      const uint32_t e = e0 + u * THREADS;
-      v[u] = (e < n) ? __ldcg(kf + e) : 0.0f;
-    }
-    body(v, e0, min(n, eb + kBatch));
-  }
-#endif
-}
-
 template <int NSTAGE, int THREADS, class Body>
 __device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip, uint32_t n, float* stage, Body&& body) {
   const int tid = threadIdx.x;
   constexpr uint32_t kBatch = THREADS * kLoadBatch;
   if (NSTAGE == 0) {
-#if LSQ_PREFETCH
-    // the loads of batch i+1 are issued before batch i is processed: a warp never sits out a full memory
-    // latency between two batches (the row passes ran at 60 % issue utilisation without it)
-    float nxt[kLoadBatch];
-#pragma unroll
-    for (int u = 0; u < kLoadBatch; ++u) {
-      const uint32_t e = tid + u * THREADS;
-      nxt[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
-    }
-    for (uint32_t eb = 0; eb < n; eb += kBatch) {
-      float v[kLoadBatch];
-      const uint32_t e0 = eb + tid;
-#pragma unroll
-      for (int u = 0; u < kLoadBatch; ++u) {
-        v[u] = nxt[u];
-        const uint32_t e = e0 + kBatch + u * THREADS;
-        nxt[u] = (e < n) ? __ldg(xr + (long long)e * skip) : 0.0f;
-      }
-      body(v, e0, min(n, eb + kBatch));
-    }
-#else
     for (uint32_t eb = 0; eb < n; eb += kBatch) {
       float v[kLoadBatch];
       const uint32_t e0 = eb + tid;
@@ -212,7 +143,6 @@ __device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip
       }
       body(v, e0, min(n, eb + kBatch));
     }
-#endif
     return;
   }
   // staged: every thread copies its own elements of the next NSTAGE-1 batches into shared memory with cp.async
@@ -417,7 +347,7 @@ __device__ void evaluate_list(SM& sm, const uint32_t* keys, uint32_t L, int nseg
 template <bool TERN, class LAY>
 __global__ void __launch_bounds__(LAY::kThreads, LAY::kMinBlocks)
 solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
-                int* __restrict__ diag, Prologue pro, float* keys_ws) {
+                int* __restrict__ diag, Prologue pro) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SolveSmem = typename LAY::Smem;
   constexpr int kT = LAY::kThreads;
@@ -541,18 +471,15 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     double ls = 0.0, lq = 0.0, lb = 0.0;
     uint32_t kmn = kNoKey, kmx = 0u, cb = 0u, mab = kNoKey, kwin = kNoKey;
     if (!from_list) {
-      // keyed = true: v[] already holds |clamp(prologue(x))| (the compacted keys of this row)
-      auto hist_body = [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end, const bool keyed) {
+      sweep_row<LAY::kStages, kT>(xr, skip, n, sm.stage,
+                [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
           const uint32_t e = e0 + u * kT;
           if (e >= e_end) break;
-          const float a = keyed ? v[u] : fabsf(clamp_sym(prologue(v[u], (long long)e * skip), alpha));
+          const float a = fabsf(clamp_sym(prologue(v[u], (long long)e * skip), alpha));
           const uint32_t k = __float_as_uint(a);
-          if (first) {
-            ls += (double)a; lq += (double)a * (double)a; kmn = min(kmn, k); kmx = max(kmx, k);
-            if (keys_ws) __stcg(keys_ws + (long long)row * n + e, a);
-          }
+          if (first) { ls += (double)a; lq += (double)a * (double)a; kmn = min(kmn, k); kmx = max(kmx, k); }
           if (k < klo) { ++cb; lb += (double)a; }
           else if (k > khi_incl) { mab = min(mab, k); }
           else {
@@ -562,13 +489,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
             if (sum_mode == 1) atomicAdd(&blo_sum[b], (k & 0x7FFFFFu) >> 9);
           }
         }
-      };
-      if (keys_ws && !first)
-        sweep_keys<kT>(keys_ws + (long long)row * n, n,
-                       [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) { hist_body(v, e0, e_end, true); });
-      else
-        sweep_row<LAY::kStages, kT>(xr, skip, n, sm.stage,
-                  [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) { hist_body(v, e0, e_end, false); });
+      });
       ++passes;
     } else {
       const uint32_t la = sm.nlist_a;
@@ -882,13 +803,14 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
       }
       __syncthreads();
       if (!from_list) {
-        auto collect_body = [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end, const bool keyed) {
+        sweep_row<LAY::kStages, kT>(xr, skip, n, sm.stage,
+                  [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) {
           uint32_t matched = 0u;
           uint32_t keys[kLoadBatch];
 #pragma unroll
           for (int u = 0; u < kLoadBatch; ++u) {
             if (e0 + u * kT >= e_end) break;
-            const float a = keyed ? v[u] : fabsf(clamp_sym(prologue(v[u], (long long)(e0 + u * kT) * skip), alpha));
+            const float a = fabsf(clamp_sym(prologue(v[u], (long long)(e0 + u * kT) * skip), alpha));
             const uint32_t k = __float_as_uint(a);
             keys[u] = k;
 #pragma unroll
@@ -920,13 +842,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
                 ++pos;
               }
           }
-        };
-        if (keys_ws)
-          sweep_keys<kT>(keys_ws + (long long)row * n, n,
-                         [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) { collect_body(v, e0, e_end, true); });
-        else
-          sweep_row<LAY::kStages, kT>(xr, skip, n, sm.stage,
-                    [&](const float (&v)[kLoadBatch], uint32_t e0, uint32_t e_end) { collect_body(v, e0, e_end, false); });
+        });
         ++passes;
       } else {
         const uint32_t la = sm.nlist_a;
@@ -1205,24 +1121,6 @@ extern "C" int lsq_solve_v1(const float* d_x, int64_t rows, int64_t len, int ski
 
 extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
                                float* d_v1, int32_t* d_diag, const lsq_prologue* pro, void* stream) {
-  return lsq_solve_v1_ws(d_x, rows, len, skip, ternary, alpha, d_v1, d_diag, pro, nullptr, 0, stream);
-}
-
-// rows that take two streaming passes (longer than shared memory holds) can keep their sampled keys in a scratch
-// buffer: the second pass then reads a third of the bytes, coalesced, and skips the prologue / clamp arithmetic
-static bool solve_streams(int64_t len, int skip, float alpha) {
-  const int64_t n = (len + skip - 1) / skip;
-  return n > (int64_t)kSmallRow && n > (int64_t)LayoutBig::kSmallCap && alpha > 0.0f;
-}
-
-extern "C" size_t lsq_solve_workspace_bytes(int64_t rows, int64_t len, int skip, float alpha) {
-  if (rows <= 0 || len <= 0 || skip < 1 || !solve_streams(len, skip, alpha)) return 0;
-  return (size_t)rows * (size_t)((len + skip - 1) / skip) * sizeof(float);
-}
-
-extern "C" int lsq_solve_v1_ws(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha,
-                               float* d_v1, int32_t* d_diag, const lsq_prologue* pro, void* d_ws, size_t ws_bytes,
-                               void* stream) {
   LSQ_CHECK_ARG(d_x && d_v1, "lsq_solve_v1: null pointer");
   LSQ_CHECK_ARG(rows > 0 && len > 0 && skip >= 1, "lsq_solve_v1: bad shape rows=%lld len=%lld skip=%d", (long long)rows, (long long)len, skip);
   LSQ_CHECK_ARG((len + skip - 1) / skip < (1ll << 31), "lsq_solve_v1: row too long");
@@ -1241,21 +1139,13 @@ extern "C" int lsq_solve_v1_ws(const float* d_x, int64_t rows, int64_t len, int 
   // rows whose sampled elements fit shared memory take the layout that keeps them there (one pass over HBM)
   // (unclamped long rows keep the 8192-bin layout: their top window cannot be anchored and stays coarse)
   const bool big = (len + skip - 1) / skip <= (int64_t)LayoutBig::kSmallCap || !(alpha > 0.0f);
-  float* keys = nullptr;
-  if (d_ws && !big) {
-    if (ws_bytes < lsq_solve_workspace_bytes(rows, len, skip, alpha) || ((uintptr_t)d_ws & 3)) {
-      set_error("lsq_solve_v1_ws: workspace %zu < %zu (or misaligned)", ws_bytes, lsq_solve_workspace_bytes(rows, len, skip, alpha));
-      return LSQ_ERR_WORKSPACE;
-    }
-    keys = (float*)d_ws;
-  }
   const size_t smem = big ? sizeof(LayoutBig::Smem) : sizeof(LayoutSmall::Smem);
   cudaError_t e;
 #define LSQ_SOLVE(T, LAY)                                                                                          \
   do {                                                                                                             \
     e = cudaFuncSetAttribute(solve_v1_kernel<T, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     if (e == cudaSuccess)                                                                                          \
-      solve_v1_kernel<T, LAY><<<grid, LAY::kThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp, keys); \
+      solve_v1_kernel<T, LAY><<<grid, LAY::kThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp); \
   } while (0)
   if (ternary) { if (big) LSQ_SOLVE(true, LayoutBig); else LSQ_SOLVE(true, LayoutSmall); }
   else { if (big) LSQ_SOLVE(false, LayoutBig); else LSQ_SOLVE(false, LayoutSmall); }

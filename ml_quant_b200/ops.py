@@ -119,26 +119,6 @@ def row_absmean(x2d: torch.Tensor, scales: Sequence[torch.Tensor] = (), alpha: O
     return out
 
 
-# long rows: keep the sampled keys of pass 1 in a scratch buffer for pass 2 (lsq_solve_v1_ws).  Off by default: measured
-# on B200 the store slows pass 1 by as much as pass 2 gains (247 vs 250 us on 512 rows of 200 704 elements).
-SOLVE_SCRATCH = False
-
-
-def _solve_scratch(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
-    """Uninitialised scratch for the solver, cached per (thread, device, stream); holds nothing between calls."""
-    if nbytes == 0 or not SOLVE_SCRATCH:
-        return None
-    cache = getattr(_tls, 'solve_ws', None)
-    if cache is None:
-        cache = _tls.solve_ws = {}
-    key = (device.index, _stream())
-    buf = cache.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        cache[key] = buf
-    return buf
-
-
 def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[float] = None,
              diag: bool = False, prologue=None, out: Optional[torch.Tensor] = None):
     """Optimal v1 per row (lsq_solve_v1); returns [rows] (and the int32 [rows,4] diagnostics)."""
@@ -150,13 +130,10 @@ def solve_v1(x2d: torch.Tensor, ternary: bool, skip: int = 1, alpha: Optional[fl
     elif out.shape != (rows,) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x2d.device:
         raise ValueError(f'out must be a contiguous float32 [{rows}] tensor on {x2d.device}')
     dg = torch.zeros(rows, 16, dtype=torch.int32, device=x2d.device) if diag else None
-    L = _C.lib()
     with torch.cuda.device(x2d.device), _launch('solve_v1', 4.0 * rows * length):
         keep = []
-        ws = _solve_scratch(x2d.device, L.lsq_solve_workspace_bytes(rows, length, int(skip), _alpha(alpha)))
-        _C.check(L.lsq_solve_v1_ws(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
-                                   out.data_ptr(), _ptr(dg), _prologue(prologue, keep), _ptr(ws),
-                                   0 if ws is None else ws.numel(), _stream()), 'lsq_solve_v1')
+        _C.check(_C.lib().lsq_solve_v1_ex(x2d.data_ptr(), rows, length, int(skip), int(bool(ternary)), _alpha(alpha),
+                                          out.data_ptr(), _ptr(dg), _prologue(prologue, keep), _stream()), 'lsq_solve_v1')
     return (out, dg) if diag else out
 
 

@@ -209,8 +209,7 @@ class GraphedForward:
         # them alive for the life of the graph even if a later eager call with another shape replaces a cache entry
         from . import ops
         self._keepalive = [(dict(m._planes_cache), dict(m._wpack_cache)) for m in quant_layers(model)]
-        self._keepalive.append((dict(ops._stem_ws), dict(getattr(ops._tls, 'ws', None) or {}),
-                                dict(getattr(ops._tls, 'solve_ws', None) or {})))
+        self._keepalive.append((dict(ops._stem_ws), dict(getattr(ops._tls, 'ws', None) or {})))
 
     def __call__(self, x: Optional[torch.Tensor] = None) -> torch.Tensor:
         if x is not None and x.data_ptr() != self.static_in.data_ptr():

@@ -248,37 +248,3 @@ def test_multi_tensor_solver_is_bit_identical_to_single_launches():
     for w, v in zip(many, multi):
         assert torch.equal(v, ops.solve_v1(w.contiguous(), False, 3))
 
-
-@pytest.mark.parametrize('tern', [False, True])
-def test_solver_scratch_variant_is_bit_identical(tern):
-    """lsq_solve_v1_ws (second pass over the compacted keys of the first) against lsq_solve_v1_ex on rows that
-    stream (longer than shared memory holds), with and without the BatchNorm prologue; a too small scratch is an
-    error, rows that do not stream need none."""
-    import ctypes as C
-    from ml_quant_b200 import _C, ops
-    g = torch.Generator().manual_seed(77)
-    L = _C.lib()
-    for (rows, c, hw) in ((24, 64, 56 * 56), (16, 128, 28 * 28), (5, 37, 1999)):
-        x = (torch.randn(rows, c * hw, generator=g) * 1.7).to(DEV)
-        x[1] = 0.25                                  # constant row
-        x[2, ::3] = 5.0                              # every sampled element clamps
-        a = (torch.rand(c, generator=g) + 0.5).to(DEV)
-        b = torch.randn(c, generator=g).to(DEV)
-        for pro in (None, (a, b, hw)):
-            for alpha in (3.0, 2.0):
-                assert L.lsq_solve_workspace_bytes(rows, c * hw, 3, alpha) == rows * ((c * hw + 2) // 3) * 4
-                want = ops.solve_v1(x, tern, 3, alpha, prologue=pro)
-                ops.SOLVE_SCRATCH = True
-                try:
-                    got = ops.solve_v1(x, tern, 3, alpha, prologue=pro)
-                finally:
-                    ops.SOLVE_SCRATCH = False
-                assert torch.equal(got, want), (rows, c, hw, pro is not None, alpha)
-    assert L.lsq_solve_workspace_bytes(8, 512 * 49, 3, 3.0) == 0          # fits shared memory: read once anyway
-    assert L.lsq_solve_workspace_bytes(8, 64 * 3136, 3, 0.0) == 0         # unclamped rows keep the plain passes
-    x = torch.randn(4, 64 * 3136).to(DEV)
-    out = torch.empty(4, device=DEV)
-    small = torch.empty(1024, dtype=torch.uint8, device=DEV)
-    st = L.lsq_solve_v1_ws(x.data_ptr(), 4, 64 * 3136, 3, int(tern), 3.0, out.data_ptr(), None, None, small.data_ptr(),
-                           small.numel(), torch.cuda.current_stream().cuda_stream)
-    assert st == -2
