@@ -35,6 +35,29 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert L.lsq_act_geometry(1, 64, 8, 8, 3, 3, 3, 1, ctypes.byref(g)) == -4     # stride 3: not packed
 
 
+def test_multi_tensor_and_packed_weight_argument_checks_without_a_gpu():
+    """Entry points added for the weight sweep / packed checkpoint validate their arguments before any CUDA call."""
+    from ml_quant_b200 import _C, runtime
+    L = _C.lib()
+    assert L.lsq_solve_v1_multi(None, 1, 3, 0, 0.0, None) == -1
+    tab = (_C.RowTensor * 2)()
+    tab[0] = _C.RowTensor(0x1000, 0x2000, 4, 64)
+    tab[1] = _C.RowTensor(0x1000, None, 4, 64)                     # second tensor has no output vector
+    assert L.lsq_solve_v1_multi(tab, 2, 3, 0, 0.0, None) == -1
+    assert b'tensor 1' in L.lsq_last_error()
+    assert L.lsq_row_absmean_multi(tab, 2, 0.0, None) == -1
+    assert L.lsq_solve_v1_multi(tab, 1, 0, 0, 0.0, None) == -1     # skip < 1
+    assert L.lsq_wbits_bytes(64, 64, 3, 3) == 64 * 9 * 2 * 4
+    assert L.lsq_wbits_bytes(50, 20, 5, 5) == 50 * 25 * 1 * 4
+    assert L.lsq_wbits_bytes(0, 20, 5, 5) == 0
+    assert L.lsq_unpack_weights(None, None, 64, 64, 3, 3, None, None) == -1
+    model = runtime.build_model('mnist_lenet5_ls1w_fpa')
+    with pytest.raises(ValueError):
+        runtime.load_packed(model, {'conv2.weight_bits': torch.zeros(1, dtype=torch.int32)})      # no format tag
+    with pytest.raises(Exception):
+        runtime.export_packed(model)                               # packing runs on the GPU: CPU weights fail loudly
+
+
 @pytest.mark.parametrize('shape', [(512, 64, 56, 56, 3, 1, 1), (4, 64, 56, 56, 3, 2, 1), (2, 128, 7, 9, 3, 2, 1),
                                    (4, 20, 12, 12, 5, 1, 0), (3, 16, 9, 9, 3, 2, 1), (2, 32, 5, 5, 1, 1, 0)])
 def test_geometry_positions_are_unique_and_padding_is_shared(shape):
