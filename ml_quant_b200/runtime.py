@@ -270,6 +270,36 @@ class HostPipeline:
         return self.host_out
 
 
+@torch.no_grad()
+def refresh_weight_scales(model: nn.Module, skip: int = 3) -> nn.Module:
+    """Solve and store the weight-quantizer scales of every ``QuantConv2d`` / ``QuantLinear`` in ``model`` -- what one
+    train-mode forward does layer by layer (quant/binary/weight_quantization.py:27-34, :51-59, :75-82) -- with ONE
+    multi-tensor launch per scheme (``lsq_row_absmean_multi`` for ls-1, ``lsq_solve_v1_multi`` for ls-2 / ls-T; the
+    values are bit-identical to the per-layer solves).  gf-k weights keep their per-layer greedy solve."""
+    from . import ops
+    from .binary import quantization
+    groups: Dict[str, list] = {'ls-1': [], 'ls-2': [], 'ls-T': []}
+    for m in quant_layers(model):
+        if m.w_quant in groups:
+            ops.require_cuda(m.weight, 'weight')
+            groups[m.w_quant].append(m)
+        elif m.w_quant.startswith('gf'):
+            vs, _ = quantization.quantizer_gf(m.weight.detach(), k=m.w_approximate.k)
+            for buf, v in zip(m.w_approximate.scales(), vs):
+                buf.copy_(v)
+    rows = {k: [m.weight.detach().reshape(m.out_channels, -1) for m in ms] for k, ms in groups.items()}
+    if groups['ls-1']:
+        for m, v1 in zip(groups['ls-1'], ops.row_absmean_multi(rows['ls-1'])):
+            m.w_approximate.v1.copy_(v1)
+    for scheme, tern in (('ls-2', False), ('ls-T', True)):
+        if groups[scheme]:
+            for m, w, v1 in zip(groups[scheme], rows[scheme], ops.solve_v1_multi(rows[scheme], tern, skip)):
+                m.w_approximate.v1.copy_(v1)
+                if not tern:
+                    m.w_approximate.v2.copy_(ops.row_absmean(w, [v1]))
+    return model
+
+
 PACKED_FORMAT = 'lsq_b200.packed.v1'
 
 

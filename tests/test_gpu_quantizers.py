@@ -248,3 +248,29 @@ def test_multi_tensor_solver_is_bit_identical_to_single_launches():
     for w, v in zip(many, multi):
         assert torch.equal(v, ops.solve_v1(w.contiguous(), False, 3))
 
+
+
+def test_refresh_weight_scales_matches_train_mode_forward():
+    """runtime.refresh_weight_scales (one multi-tensor launch per weight scheme) stores exactly the buffers a
+    train-mode pass of each WeightQuantizer* stores (weight_quantization.py:27-34, :51-59, :75-82, :100-109)."""
+    import copy
+    import torch.nn as nn
+    from quant.binary.binary_conv import QuantConv2d
+    from ml_quant_b200 import runtime
+    torch.manual_seed(5)
+    specs = [('ls-1', 16, 32, 3), ('ls-2', 32, 64, 3), ('ls-T', 64, 64, 3), ('ls-2', 64, 128, 1), ('ls-1', 20, 50, 5),
+             ('gf-2', 16, 16, 3), ('fp', 8, 8, 3), ('ls-T', 128, 256, 3)]
+    net = nn.Sequential(*[QuantConv2d('fp', wq, cin, cout, k) for wq, cin, cout, k in specs]).to(DEV)
+    want = copy.deepcopy(net)
+    for m in want:
+        m.w_approximate.train()
+        with torch.no_grad():
+            m.w_approximate(m.weight)
+    runtime.refresh_weight_scales(net)
+    checked = 0
+    for a, b in zip(net, want):
+        for (name, x), (_, y) in zip(a.w_approximate.named_buffers(), b.w_approximate.named_buffers()):
+            assert torch.equal(x, y), (a.w_quant, name)
+            assert float(y.abs().sum()) > 0
+            checked += 1
+    assert checked == 1 + 2 + 1 + 2 + 1 + 2 + 0 + 1
