@@ -18,6 +18,7 @@ Forward has two routes, both on the GPU:
 from collections import defaultdict
 from functools import partial
 import re
+import warnings
 from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 
 import torch
@@ -70,7 +71,10 @@ class QuantConv2d(nn.Conv2d):
         self.packed_impl = 0            # 0 auto, 1 CUDA-core kernel, 2 tensor-core kernel (tests / profiling)
         self.allow_packed = True
         self._wpack_cache: Dict[int, Tuple[Tuple[int, int], torch.Tensor]] = {}
-        self._planes_cache: Dict[int, torch.Tensor] = {}
+        # bit-plane scratch, one per (device, stream): two streams / threads running this module concurrently
+        # (nn.DataParallel replicas share this dict; a graph on one stream next to eager calls on another)
+        # must not overwrite each other's planes between the encoder and the convolution
+        self._planes_cache: Dict[Tuple[int, int], torch.Tensor] = {}
 
     # ---- factories (same static methods as the reference) -----------------------------------
     @staticmethod
@@ -121,7 +125,15 @@ class QuantConv2d(nn.Conv2d):
         """Geometry when the packed route applies to this call, else None."""
         if not (self.allow_packed and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
             return None
-        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad
+                                        or (self.bias is not None and self.bias.requires_grad)):
+            # autograd needs the reference's graph (STESign terms): generic route.  In eval mode this is
+            # almost always a forgotten torch.no_grad() -- say so once, the generic route is several times slower.
+            if not self.training and not getattr(QuantConv2d, '_warned_grad_eval', False):
+                QuantConv2d._warned_grad_eval = True
+                warnings.warn('QuantConv2d: eval-mode forward with autograd enabled takes the generic (fake-quant + '
+                              'F.conv2d) route; wrap inference in torch.no_grad() for the packed tensor-core path.',
+                              RuntimeWarning, stacklevel=3)
             return None
         if self.w_quant != 'ls-1' or not 1 <= self._num_planes() <= _PACKED_MAX_PLANES:
             return None
@@ -159,7 +171,7 @@ class QuantConv2d(nn.Conv2d):
         xa, alpha, npl = self.x_approximate, self.clamp_alpha, self._num_planes()
         pro = prologue
         n = x.shape[0]
-        dev = x.device.index or 0
+        dev = (x.device.index or 0, torch.cuda.current_stream(x.device).cuda_stream)
         buf = self._planes_cache.get(dev)
         rows = x.reshape(n, -1)
         tern = self.x_quant == 'ls-T'
@@ -205,6 +217,11 @@ class QuantConv2d(nn.Conv2d):
         g = self._packed_geometry(x)
         kind = {nn.ReLU: 1, nn.PReLU: 2, nn.Identity: 0, type(None): 0}.get(type(nonlin))
         ok = g is not None and kind is not None and (bn is None or (not bn.training and bn.track_running_stats))
+        if ok and torch.is_grad_enabled():
+            # the fused kernels build no autograd graph: anything around the convolution that wants a gradient
+            # (BatchNorm affine, PReLU slope, the residual branch) sends the call to the unfused composition
+            extra = [residual] + [p for m in (bn, nonlin) if m is not None for p in m.parameters()]
+            ok = not any(t is not None and t.requires_grad for t in extra)
         if not ok:
             y = self.forward(x if bn is None else bn(x))
             if residual is not None and not residual_after_act:

@@ -4,6 +4,12 @@ Mirror of quant/binary/optimal.py.  ``opt_v1`` (:121-155) is one CUDA kernel lau
 sort-free, no host synchronisation).  ``compute_mask`` (:41-83) and ``cost_function`` (:16-38) are the
 reference's inspection helpers; they are kept as device-side torch expressions for API completeness and
 are not used by any forward pass here.
+
+Prefix sums: the reference calls ``values.cumsum(dim=1)`` on an fp32 tensor; on the CPU, where its results are
+pinned, ATen accumulates that in DOUBLE and rounds each prefix to fp32 (tests/test_oracle.py::
+test_cpu_cumsum_accumulates_in_double).  ``compute_mask`` therefore forms the prefix sums in fp64 and rounds them to
+fp32 -- the reference's CPU arithmetic, not a refinement of it -- and reproduces the golden candidate sets bit for
+bit on the GPU (tests/test_gpu_round2.py::test_compute_mask_and_cost_function_against_golden).
 """
 from typing import Tuple
 

@@ -35,12 +35,23 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     flags = [f for f in NVCC_FLAGS if not f.startswith('--use_fast_math')]
-    objs = []
-    for src in SOURCES:
+    flags += [f for f in os.environ.get('LSQ_NVCC_EXTRA', '').split() if f]      # e.g. -DLSQ_TC_DIAG (development builds)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')]
+    headers.append(os.path.join(HERE, '..', 'include', 'lsq_b200.h'))
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src[:-3] + '.o')
-        cmd = [_nvcc()] + flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), newest_header):
+            return obj
+        cmd = [_nvcc()] + flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', path, '-o', obj]
         subprocess.run(cmd, check=True)
-        objs.append(obj)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
     subprocess.run([_nvcc(), '-shared', '-o', LIB] + objs + ['-lcudart'], check=True)
     return LIB
 

@@ -83,7 +83,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
                 const int8_t* __restrict__ wi8, const float* __restrict__ w_scale, const float* __restrict__ bias,
                 float* __restrict__ y, int* __restrict__ err, Epilogue epi, long long* __restrict__ diag) {
   long long w0 = 0, w1 = 0, w2 = 0;
-  const long long t_start = clock64();
+  const long long t_start = LSQ_TC_CLOCK();
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -443,10 +443,14 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
     }
   }
 
+#ifdef LSQ_TC_DIAG
   if (diag && lane == 0 && blockIdx.x == 0) {
     long long* d = diag + warp * 4;
     d[0] = clock64() - t_start; d[1] = w0; d[2] = w1; d[3] = w2;
   }
+#else
+  (void)t_start; (void)w0; (void)w1; (void)w2; (void)diag;
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, 512);
@@ -564,17 +568,19 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   const size_t bits_bytes = ((size_t)cout * g->kh * g->kw * g->cw * 4 + 1023) / 1024 * 1024;
   const int8_t* wi8 = (const int8_t*)d_wpack + bits_bytes;
 
-  cudaError_t e = cudaFuncSetAttribute(bconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess) { set_error("bconv2d_tc: cudaFuncSetAttribute(%zu): %s", smem_bytes, cudaGetErrorString(e)); return LSQ_ERR_CUDA; }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static std::atomic<unsigned long long> smem_set{0ull};
+  const cudaError_t e = ensure_max_smem(bconv_tc_kernel, smem_set);
+  if (e != cudaSuccess) { set_error("bconv2d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return LSQ_ERR_CUDA; }
+  const int sms = device_sms();
   const int grid = n_items < sms ? n_items : sms;
-  static const bool want_diag = getenv("LSQ_TC_DIAG") != nullptr;     // development aid: per-role wait cycles of CTA 0
   long long* d_diag = nullptr;
+#ifdef LSQ_TC_DIAG
+  static const bool want_diag = getenv("LSQ_TC_DIAG") != nullptr;     // development build: per-role wait cycles of CTA 0
   if (want_diag) { cudaMalloc(&d_diag, 22 * 4 * sizeof(long long)); cudaMemsetAsync(d_diag, 0, 22 * 4 * sizeof(long long), stream); }
+#endif
   bconv_tc_kernel<<<grid, kTcThreads, smem_bytes, stream>>>(d_planes, P, d_act_scales, wi8, d_w_scale, d_bias, d_y, nullptr, epi, d_diag);
   LSQ_CUDA_LAUNCH_CHECK("bconv_tc_kernel");
+#ifdef LSQ_TC_DIAG
   if (want_diag) {
     long long h[22 * 4];
     cudaStreamSynchronize(stream);
@@ -587,6 +593,7 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
     for (int w = 0; w < kTcThreads / 32; ++w)
       fprintf(stderr, "   %-6s total %9lld  wait0 %9lld  wait1(p_full) %9lld  wait2(w_full) %9lld\n", role[w], h[w * 4], h[w * 4 + 1], h[w * 4 + 2], h[w * 4 + 3]);
   }
+#endif
   return LSQ_OK;
 }
 

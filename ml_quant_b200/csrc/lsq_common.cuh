@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/lsq_b200.h"
 
 namespace lsq {
@@ -25,6 +26,34 @@ void set_error(const char* fmt, ...);
       return LSQ_ERR_CUDA;                                                            \
     }                                                                                 \
   } while (0)
+
+// Per-device facts that never change, looked up once (immutable after initialisation: the library still
+// holds no mutable state that calls could race on).
+inline int device_index() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+inline int device_sms() {
+  static std::atomic<int> cache[64];
+  const int dev = device_index();
+  if (dev < 0 || dev >= 64) return 148;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// Opt a kernel into the full 227 KB of dynamic shared memory, once per device (`done` = one bit per device).
+template <class K>
+inline cudaError_t ensure_max_smem(K kernel, std::atomic<unsigned long long>& done) {
+  const unsigned long long bit = 1ull << (device_index() & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 // sign with sign(0) = +1, as a float (+-1).  quant/binary/ste.py:16-18
 __device__ __forceinline__ float sign_pm1(float x) { return x >= 0.0f ? 1.0f : -1.0f; }
@@ -68,20 +97,30 @@ struct Prologue {
   const float* b;
   int channels;
   long long inner;
-  unsigned long long magic;   // ceil(2^40 / inner): index / inner == (index * magic) >> 40 for index < 2^40 / inner
+  unsigned long long magic;   // ceil(2^40 / inner): index / inner == (index * magic) >> 40 while index * inner < 2^40;
+                              // 0 when the row is too long for that: the kernels then divide exactly
 };
+// channel of element `index_in_row` (row = channels * inner elements)
+__device__ __forceinline__ unsigned prologue_channel(const Prologue& p, long long index_in_row) {
+  const unsigned c = p.magic ? (unsigned)(((unsigned long long)index_in_row * p.magic) >> 40)
+                             : (unsigned)((unsigned long long)index_in_row / (unsigned long long)p.inner);
+  return min(c, (unsigned)p.channels - 1u);
+}
 __host__ inline Prologue to_dev(const lsq_prologue* p) {
   Prologue d{nullptr, nullptr, 1, 1, 1ull << 40};
   if (p && p->d_ch_scale && p->d_ch_shift && p->inner > 0) {
     d.a = p->d_ch_scale; d.b = p->d_ch_shift; d.channels = p->channels; d.inner = p->inner;
     d.magic = ((1ull << 40) + (unsigned long long)p->inner - 1ull) / (unsigned long long)p->inner;
+    // (index * magic) >> 40 is exact while index * (magic * inner - 2^40) < 2^40, i.e. surely while
+    // row_length * inner <= 2^40; longer rows (feature maps beyond ~1000 x 1000) take the exact division
+    if ((double)p->channels * (double)p->inner * (double)p->inner > 1099511627776.0) d.magic = 0ull;
   }
   return d;
 }
 // the caller guarantees row length == channels * inner (one row = one sample), so index / inner < channels
 __device__ __forceinline__ float apply_prologue(const Prologue& p, float x, long long index_in_row) {
   if (p.a == nullptr) return x;
-  const unsigned c = (unsigned)(((unsigned long long)index_in_row * p.magic) >> 40);
+  const unsigned c = prologue_channel(p, index_in_row);
   return fmaf(x, __ldg(p.a + c), __ldg(p.b + c));
 }
 struct Epilogue {

@@ -269,11 +269,10 @@ extern "C" int lsq_pwconv_fwd(const float* d_x, int n, int cin, int h, int w, in
   P.smem_bar = o; o += 256;
   P.smem_out = o; o += 8 * 32 * kPwOutPitch * 4;
   const size_t smem = o;
-  cudaError_t e = cudaFuncSetAttribute(pwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<unsigned long long> smem_set{0ull};
+  const cudaError_t e = ensure_max_smem(pwconv_kernel, smem_set);
   if (e != cudaSuccess) { set_error("lsq_pwconv_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return LSQ_ERR_CUDA; }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sms();
   const int n_items = P.p_tiles * P.n_ctiles;
   const int grid = n_items < sms ? n_items : sms;
   pwconv_kernel<<<grid, kPwThreads, smem, (cudaStream_t)stream>>>(d_x, P, d_image, d_bias, d_y);

@@ -29,6 +29,7 @@ constexpr int kEncThreads = 128;  // pixels per block in the encoder
 // fixed size so that the partials of one call can never land on the (zero at rest) counters of a later call
 // with more rows.
 constexpr size_t kCounterBytes = 65536 * sizeof(unsigned);
+constexpr int64_t kMaxGridRows = 65535;   // gridDim.y limit: launches are chunked over more rows than this
 
 struct ScaleTab {  // up to LSQ_MAX_PLANES per-row scales, passed by value
   const float* p[LSQ_MAX_PLANES];
@@ -46,10 +47,11 @@ __device__ __forceinline__ float fold_residual(float v, const float (&s)[MAXS], 
 __global__ void __launch_bounds__(kRowThreads)
 row_absmean_kernel(const float* __restrict__ x, long long len, float alpha, const float* __restrict__ scales,
                    long long rows, int ns, float* __restrict__ out, double* __restrict__ partial,
-                   unsigned* __restrict__ counter, Prologue pro) {
+                   unsigned* __restrict__ counter, Prologue pro, long long row0) {
   __shared__ double red[32];
   __shared__ bool last;
-  const long long r = blockIdx.y;
+  const long long r = row0 + blockIdx.y;      // row of the tensor; the workspace is indexed by the chunk-local row
+  const long long rl = blockIdx.y;
   const float* xr = x + r * len;
   float s[LSQ_MAX_PLANES];
 #pragma unroll
@@ -64,24 +66,24 @@ row_absmean_kernel(const float* __restrict__ x, long long len, float alpha, cons
   double tot = block_sum(acc, red);
   const unsigned nblk = gridDim.x;
   if (threadIdx.x == 0) {
-    partial[r * nblk + blockIdx.x] = tot;
+    partial[rl * nblk + blockIdx.x] = tot;
     __threadfence();
-    last = (atomicAdd(&counter[r], 1u) == nblk - 1);
+    last = (atomicAdd(&counter[rl], 1u) == nblk - 1);
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
     __threadfence();
     double t = 0.0;
-    for (unsigned b = 0; b < nblk; ++b) t += __ldcg(&partial[r * nblk + b]);
+    for (unsigned b = 0; b < nblk; ++b) t += __ldcg(&partial[rl * nblk + b]);
     out[r] = (float)(t / (double)len);
-    counter[r] = 0u;
+    counter[rl] = 0u;
   }
 }
 
 __global__ void __launch_bounds__(kRowThreads)
 fakequant_kernel(const float* __restrict__ x, long long len, float alpha, const float* __restrict__ scales,
-                 long long rows, int npl, int ternary, float* __restrict__ out) {
-  const long long r = blockIdx.y;
+                 long long rows, int npl, int ternary, float* __restrict__ out, long long row0) {
+  const long long r = row0 + blockIdx.y;
   float s[LSQ_MAX_PLANES];
 #pragma unroll
   for (int i = 0; i < LSQ_MAX_PLANES; ++i) {
@@ -191,11 +193,12 @@ template <int NPL, int VEC>
 __global__ void __launch_bounds__(kEncThreads, 8)
 encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const float* __restrict__ scales,
                   int ns, uint32_t* __restrict__ planes, double* __restrict__ partial,
-                  unsigned* __restrict__ counter, float* __restrict__ last_scale, Prologue pro) {
+                  unsigned* __restrict__ counter, float* __restrict__ last_scale, Prologue pro, int s0) {
   __shared__ double red[32];
   __shared__ bool last;
   extern __shared__ float2 ab[];            // per-channel (scale, shift), padded to a multiple of 32 channels
-  const int s = blockIdx.y;
+  const int s = s0 + blockIdx.y;            // sample; the workspace is indexed by the chunk-local sample
+  const int sl = blockIdx.y;
   const int hw = g.h * g.w;
   for (int c = threadIdx.x; c < g.cw * 32; c += kEncThreads) {
     float2 k = make_float2(1.0f, 0.0f);
@@ -238,17 +241,17 @@ encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const flo
   double tot = block_sum(acc_sum, red);
   const unsigned nblk = gridDim.x;
   if (threadIdx.x == 0) {
-    partial[(long long)s * nblk + blockIdx.x] = tot;
+    partial[(long long)sl * nblk + blockIdx.x] = tot;
     __threadfence();
-    last = (atomicAdd(&counter[s], 1u) == nblk - 1);
+    last = (atomicAdd(&counter[sl], 1u) == nblk - 1);
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
     __threadfence();
     double t = 0.0;
-    for (unsigned b = 0; b < nblk; ++b) t += __ldcg(&partial[(long long)s * nblk + b]);
+    for (unsigned b = 0; b < nblk; ++b) t += __ldcg(&partial[(long long)sl * nblk + b]);
     last_scale[s] = (float)(t / ((double)g.c * (double)hw));
-    counter[s] = 0u;
+    counter[sl] = 0u;
   }
 }
 
@@ -307,22 +310,26 @@ int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float alpha, co
 int lsq_row_absmean_ex(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales,
                        int nscales, float* d_out, void* d_ws, size_t ws_bytes, const lsq_prologue* pro, void* stream) {
   LSQ_CHECK_ARG(d_x && d_out && d_ws, "lsq_row_absmean: null pointer");
-  LSQ_CHECK_ARG(rows > 0 && len > 0 && rows <= 65535, "lsq_row_absmean: bad shape rows=%lld len=%lld", (long long)rows, (long long)len);
+  LSQ_CHECK_ARG(rows > 0 && len > 0, "lsq_row_absmean: bad shape rows=%lld len=%lld", (long long)rows, (long long)len);
   LSQ_CHECK_ARG(nscales >= 0 && nscales <= LSQ_MAX_PLANES && (nscales == 0 || d_scales), "lsq_row_absmean: bad nscales %d", nscales);
   if (ws_bytes < lsq_reduce_workspace_bytes(rows, len)) {
     set_error("lsq_row_absmean: workspace %zu < %zu", ws_bytes, lsq_reduce_workspace_bytes(rows, len));
     return LSQ_ERR_WORKSPACE;
   }
-  if (pro && pro->d_ch_scale && ((int64_t)pro->channels * pro->inner != len || len >= (1ll << 26))) {
-    set_error("lsq_row_absmean: prologue needs len == channels * inner (< 2^26)");
+  if (pro && pro->d_ch_scale && ((int64_t)pro->channels * pro->inner != len || len >= (1ll << 31))) {
+    set_error("lsq_row_absmean: prologue needs len == channels * inner (< 2^31)");
     return LSQ_ERR_ARG;
   }
   unsigned* counter = (unsigned*)d_ws;
   double* partial = (double*)((char*)d_ws + kCounterBytes);
-  dim3 grid((unsigned)((len + kRowChunk - 1) / kRowChunk), (unsigned)rows);
-  row_absmean_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nscales,
-                                                                     d_out, partial, counter, to_dev(pro));
-  LSQ_CUDA_LAUNCH_CHECK("row_absmean_kernel");
+  // rows ride on gridDim.y (<= 65535): more rows (a QuantLinear over batch x tokens) go in consecutive launches
+  for (int64_t r0 = 0; r0 < rows; r0 += kMaxGridRows) {
+    const int64_t nr = rows - r0 < kMaxGridRows ? rows - r0 : kMaxGridRows;
+    dim3 grid((unsigned)((len + kRowChunk - 1) / kRowChunk), (unsigned)nr);
+    row_absmean_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nscales,
+                                                                       d_out, partial, counter, to_dev(pro), r0);
+    LSQ_CUDA_LAUNCH_CHECK("row_absmean_kernel");
+  }
   return LSQ_OK;
 }
 
@@ -363,14 +370,17 @@ int lsq_row_absmean_multi(const lsq_row_tensor* tensors, int ntensors, float alp
 int lsq_fakequant(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales, int nplanes,
                   int ternary, float* d_out, void* stream) {
   LSQ_CHECK_ARG(d_x && d_out && d_scales, "lsq_fakequant: null pointer");
-  LSQ_CHECK_ARG(rows > 0 && len > 0 && rows <= 65535, "lsq_fakequant: bad shape");
+  LSQ_CHECK_ARG(rows > 0 && len > 0, "lsq_fakequant: bad shape");
   LSQ_CHECK_ARG(nplanes >= 1 && nplanes <= LSQ_MAX_PLANES, "lsq_fakequant: bad nplanes %d", nplanes);
   LSQ_CHECK_ARG(!ternary || nplanes == 2, "lsq_fakequant: ternary needs nplanes == 2");
   unsigned gx = (unsigned)((len + kRowThreads * 4 - 1) / (kRowThreads * 4));
   if (gx > 4096) gx = 4096;
-  dim3 grid(gx, (unsigned)rows);
-  fakequant_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nplanes, ternary, d_out);
-  LSQ_CUDA_LAUNCH_CHECK("fakequant_kernel");
+  for (int64_t r0 = 0; r0 < rows; r0 += kMaxGridRows) {
+    const int64_t nr = rows - r0 < kMaxGridRows ? rows - r0 : kMaxGridRows;
+    dim3 grid(gx, (unsigned)nr);
+    fakequant_kernel<<<grid, kRowThreads, 0, (cudaStream_t)stream>>>(d_x, len, alpha, d_scales, rows, nplanes, ternary, d_out, r0);
+    LSQ_CUDA_LAUNCH_CHECK("fakequant_kernel");
+  }
   return LSQ_OK;
 }
 
@@ -441,7 +451,6 @@ int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alpha, cons
   LSQ_CHECK_ARG(d_x && g && d_planes, "lsq_encode_act: null pointer");
   LSQ_CHECK_ARG(nplanes >= 1 && nplanes <= 4, "lsq_encode_act: nplanes %d not in [1,4]", nplanes);
   LSQ_CHECK_ARG(nscales >= 0 && nscales <= nplanes && (nscales == 0 || d_scales), "lsq_encode_act: bad nscales %d", nscales);
-  LSQ_CHECK_ARG(g->n <= 65535, "lsq_encode_act: batch too large");
   const int hw = g->h * g->w;
   double* partial = nullptr;
   unsigned* counter = nullptr;
@@ -460,23 +469,26 @@ int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alpha, cons
   // 16-byte loads need every channel plane of every sample to start 16-byte aligned
   const bool vec4 = (hw % 4 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0);
   const int nq = vec4 ? hw / 4 : hw;
-  dim3 grid((unsigned)(((long long)nq * g->cw + kEncThreads - 1) / kEncThreads), (unsigned)g->n);
   const size_t smem = (size_t)g->cw * 32 * sizeof(float2);
   LSQ_CHECK_ARG(smem <= 40 * 1024, "lsq_encode_act: too many channels (%d)", g->c);
   cudaStream_t st = (cudaStream_t)stream;
-#define LSQ_ENC(NPL, VEC) encode_act_kernel<NPL, VEC><<<grid, kEncThreads, smem, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp)
-  switch (nplanes * 2 + (vec4 ? 1 : 0)) {
-    case 2: LSQ_ENC(1, 1); break;
-    case 3: LSQ_ENC(1, 4); break;
-    case 4: LSQ_ENC(2, 1); break;
-    case 5: LSQ_ENC(2, 4); break;
-    case 6: LSQ_ENC(3, 1); break;
-    case 7: LSQ_ENC(3, 4); break;
-    case 8: LSQ_ENC(4, 1); break;
-    default: LSQ_ENC(4, 4); break;
-  }
+  for (int s0 = 0; s0 < g->n; s0 += (int)kMaxGridRows) {      // samples ride on gridDim.y (<= 65535)
+    const int ns_chunk = g->n - s0 < (int)kMaxGridRows ? g->n - s0 : (int)kMaxGridRows;
+    dim3 grid((unsigned)(((long long)nq * g->cw + kEncThreads - 1) / kEncThreads), (unsigned)ns_chunk);
+#define LSQ_ENC(NPL, VEC) encode_act_kernel<NPL, VEC><<<grid, kEncThreads, smem, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp, s0)
+    switch (nplanes * 2 + (vec4 ? 1 : 0)) {
+      case 2: LSQ_ENC(1, 1); break;
+      case 3: LSQ_ENC(1, 4); break;
+      case 4: LSQ_ENC(2, 1); break;
+      case 5: LSQ_ENC(2, 4); break;
+      case 6: LSQ_ENC(3, 1); break;
+      case 7: LSQ_ENC(3, 4); break;
+      case 8: LSQ_ENC(4, 1); break;
+      default: LSQ_ENC(4, 4); break;
+    }
 #undef LSQ_ENC
-  LSQ_CUDA_LAUNCH_CHECK("encode_act_kernel");
+    LSQ_CUDA_LAUNCH_CHECK("encode_act_kernel");
+  }
   return LSQ_OK;
 }
 

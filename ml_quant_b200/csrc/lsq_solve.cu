@@ -364,7 +364,7 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
     for (int c = tid; c < pro.channels; c += blockDim.x) sm.ab[c] = make_float2(__ldg(pro.a + c), __ldg(pro.b + c));
   auto prologue = [&](float v, long long index_in_row) -> float {
     if (!pro_on) return v;
-    const unsigned c = (unsigned)(((unsigned long long)index_in_row * pro.magic) >> 40);
+    const unsigned c = prologue_channel(pro, index_in_row);
     if (pro_smem) { const float2 k = sm.ab[c]; return fmaf(v, k.x, k.y); }
     return fmaf(v, __ldg(pro.a + c), __ldg(pro.b + c));
   };
@@ -1124,8 +1124,8 @@ extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int 
   LSQ_CHECK_ARG(d_x && d_v1, "lsq_solve_v1: null pointer");
   LSQ_CHECK_ARG(rows > 0 && len > 0 && skip >= 1, "lsq_solve_v1: bad shape rows=%lld len=%lld skip=%d", (long long)rows, (long long)len, skip);
   LSQ_CHECK_ARG((len + skip - 1) / skip < (1ll << 31), "lsq_solve_v1: row too long");
-  if (pro && pro->d_ch_scale && ((int64_t)pro->channels * pro->inner != len || len >= (1ll << 26))) {
-    set_error("lsq_solve_v1: prologue needs len == channels * inner (< 2^26)");
+  if (pro && pro->d_ch_scale && ((int64_t)pro->channels * pro->inner != len || len >= (1ll << 31))) {
+    set_error("lsq_solve_v1: prologue needs len == channels * inner (< 2^31)");
     return LSQ_ERR_ARG;
   }
   const Prologue dp = to_dev(pro);
@@ -1143,7 +1143,8 @@ extern "C" int lsq_solve_v1_ex(const float* d_x, int64_t rows, int64_t len, int 
   cudaError_t e;
 #define LSQ_SOLVE(T, LAY)                                                                                          \
   do {                                                                                                             \
-    e = cudaFuncSetAttribute(solve_v1_kernel<T, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    static std::atomic<unsigned long long> smem_set{0ull};                                                         \
+    e = ensure_max_smem(solve_v1_kernel<T, LAY>, smem_set);                                                        \
     if (e == cudaSuccess)                                                                                          \
       solve_v1_kernel<T, LAY><<<grid, LAY::kThreads, smem, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp); \
   } while (0)

@@ -108,7 +108,7 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ActGeom& g = P.g;
   long long w0 = 0, w1 = 0;
-  const long long t_start = clock64();
+  const long long t_start = LSQ_TC_CLOCK();
   // barriers: p_full[4] p_empty[4] acc_full[2] acc_empty[2] | tmem base
   const uint32_t bar0 = sbase + P.smem_bar;
   auto p_full = [&](int s) { return bar0 + 8u * s; };
@@ -278,7 +278,11 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
       }
     }
   }
+#ifdef LSQ_TC_DIAG
   if (diag && lane == 0 && blockIdx.x == 0) { diag[warp * 3] = clock64() - t_start; diag[warp * 3 + 1] = w0; diag[warp * 3 + 2] = w1; }
+#else
+  (void)t_start; (void)w0; (void)w1; (void)diag;
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem_base, 512);
@@ -420,17 +424,19 @@ extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* 
     set_error("lsq_stem_fwd: image %dx%d not supported (patch does not fit shared memory)", h, w);
     return LSQ_ERR_UNSUPPORTED;
   }
-  cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<unsigned long long> smem_set{0ull}, pool_set{0ull};
+  cudaError_t e = ensure_max_smem(stem_conv_kernel, smem_set);
   if (e != cudaSuccess) { set_error("lsq_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return LSQ_ERR_CUDA; }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sms();
   const int grid = P.p_tiles < sms ? P.p_tiles : sms;
-  static const bool want_diag = getenv("LSQ_TC_DIAG") != nullptr;     // development aid: wait cycles per warp of CTA 0
   long long* d_diag = nullptr;
+#ifdef LSQ_TC_DIAG
+  static const bool want_diag = getenv("LSQ_TC_DIAG") != nullptr;     // development build: wait cycles per warp of CTA 0
   if (want_diag) { cudaMalloc(&d_diag, 32 * 3 * sizeof(long long)); cudaMemsetAsync(d_diag, 0, 32 * 3 * sizeof(long long), (cudaStream_t)stream); }
+#endif
   stem_conv_kernel<<<grid, kStThreads, smem, (cudaStream_t)stream>>>(d_x, P, d_image, d_bias, d_conv_ws, d_diag);
   LSQ_CUDA_LAUNCH_CHECK("stem_conv_kernel");
+#ifdef LSQ_TC_DIAG
   if (want_diag) {
     long long h[32 * 3];
     cudaStreamSynchronize((cudaStream_t)stream);
@@ -441,10 +447,11 @@ extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* 
       fprintf(stderr, "   warp %2d (%s) total %9lld  wait0 %9lld  wait1(p_full) %9lld\n", w,
               w < 16 ? ((w & 3) < 2 ? "epi-main" : "epi-upper") : (w == 16 ? "mma" : "producer"), h[w * 3], h[w * 3 + 1], h[w * 3 + 2]);
   }
+#endif
   const int hp = (P.hc - 1) / 2 + 1, wp = (P.wc - 1) / 2 + 1;
   const size_t plane_bytes = (size_t)P.hc * P.wc * sizeof(float);
   if (plane_bytes <= 56 * 1024 && ((uintptr_t)d_conv_ws & 15) == 0) {
-    e = cudaFuncSetAttribute(stem_pool_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
+    e = ensure_max_smem(stem_pool_plane_kernel, pool_set);
     if (e != cudaSuccess) { set_error("lsq_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return LSQ_ERR_CUDA; }
     stem_pool_plane_kernel<<<(unsigned)(n * 64), 256, plane_bytes, (cudaStream_t)stream>>>(d_conv_ws, d_out, P.hc, P.wc, hp, wp);
   } else {

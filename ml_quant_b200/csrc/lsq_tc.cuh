@@ -38,12 +38,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
-// mbar_wait that also accumulates the cycles spent waiting (role diagnostics, LSQ_TC_DIAG=1)
+// mbar_wait that also accumulates the cycles spent waiting: role diagnostics, compiled in only with
+// -DLSQ_TC_DIAG (a development build; the product kernels pay no clock reads)
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int* err, int code, long long& acc) {
+#ifdef LSQ_TC_DIAG
   const long long t0 = clock64();      // try_wait itself may suspend the thread: time the first probe too
   mbar_wait(bar, parity, err, code);
   acc += clock64() - t0;
+#else
+  (void)acc;
+  mbar_wait(bar, parity, err, code);
+#endif
 }
+#ifdef LSQ_TC_DIAG
+#define LSQ_TC_CLOCK() clock64()
+#else
+#define LSQ_TC_CLOCK() 0ll
+#endif
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -170,8 +170,12 @@ def optimize_for_inference(model: nn.Module) -> nn.Module:
     for m in model.modules():
         if isinstance(m, XnorBasicBlock) and not hasattr(m, '_lsq_orig_forward'):
             m._lsq_orig_forward = m.forward
+            # the fused block (folded shortcut / BatchNorm kernels) builds no autograd graph: any call that may
+            # need gradients -- training, or eval with autograd on (frozen-BN fine-tuning, saliency, KD
+            # teachers) -- runs the original forward
             m.forward = types.MethodType(
-                lambda self, x: _xnor_block_fused(self, x) if not self.training else self._lsq_orig_forward(x), m)
+                lambda self, x: (_xnor_block_fused(self, x) if not (self.training or torch.is_grad_enabled())
+                                 else self._lsq_orig_forward(x)), m)
     if isinstance(model, QResNet) and not isinstance(model.blocks[0], _FusedStem):
         stem = _FusedStem(model.conv1, model.bn1, model.maxpool)
         object.__setattr__(model, '_lsq_stem', stem)      # not registered: state_dict stays the reference's

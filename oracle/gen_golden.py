@@ -117,6 +117,30 @@ def layers(bc):
     print('layers.pt', len(out))
 
 
+def ma_layers(bc):
+    """QuantConv2d with a moving-average activation policy (activation_quantization.py:68-102): two train-mode
+    steps track the per-batch mean scales, then the eval forward quantizes with the STORED scales (:90-98)."""
+    out = []
+    i = 0
+    for mode in ('eval_only', 'train_and_eval'):
+        for xs in ('ls-1', 'ls-2', 'ls-T', 'gf-2'):
+            torch.manual_seed(900 + i)
+            i += 1
+            m = bc.QuantConv2d(xs, 'ls-1', 64, 64, 3, {'kind': 'symmetric', 'alpha': 2.0}, mode, 0.9, padding=1)
+            xt = [torch.randn(4, 64, 9, 9) * 1.3 for _ in range(2)]
+            x = torch.randn(3, 64, 9, 9) * 1.3
+            with torch.no_grad():
+                m.train()
+                yt = [m(t) for t in xt]
+                m.eval()
+                y = m(x)
+            out.append({'spec': dict(x_quant=xs, mode=mode, momentum=0.9, alpha=2.0),
+                        'state': {kk: vv.clone() for kk, vv in m.state_dict().items()},
+                        'x_train': xt, 'y_train_last': yt[-1], 'x': x, 'y': y})
+    torch.save(out, os.path.join(OUT, 'ma_layers.pt'))
+    print('ma_layers.pt', len(out))
+
+
 def _calibrate(model, shape, seeds=(100, 101)):
     model.train()
     with torch.no_grad():
@@ -165,8 +189,14 @@ def nets(rn, ln):
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     q, o, bc, rn, ln = _ref()
-    functions(q, o)
-    layers(bc)
-    nets(rn, ln)
+    only = set(sys.argv[1:])         # e.g. `python oracle/gen_golden.py ma_layers` adds one fixture, leaves the rest
+    if not only or 'functions' in only:
+        functions(q, o)
+    if not only or 'layers' in only:
+        layers(bc)
+    if not only or 'nets' in only:
+        nets(rn, ln)
+    if not only or 'ma_layers' in only:
+        ma_layers(bc)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KiB')

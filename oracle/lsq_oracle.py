@@ -197,6 +197,21 @@ def bit_planes(x: Tensor, scheme: str, scales: Sequence[Tensor]) -> List[Tensor]
     return planes
 
 
+def quantize_activation_stored(x: Tensor, scheme: str, scales: Sequence[Tensor]) -> Tensor:
+    """Eval-mode activation quantizer with GIVEN per-sample scales: the moving-average path
+    (quant/binary/activation_quantization.py:90-98, _moving_average_quantization :141-145, :172-176,
+    :203-207, :234-239) and the public ``v1=`` / ``vs=`` arguments of the quantizer functions."""
+    if scheme == 'fp':
+        return x
+    if scheme == 'ls-1':
+        return quant_ls1(x, scales[0])[1]
+    if scheme == 'ls-2':
+        return quant_ls2(x, scales[0], scales[1])[2]
+    if scheme == 'ls-T':
+        return quant_lsT(x, scales[0])[1]
+    return quant_gf(x, int(scheme.split('-')[1]), list(scales))[1]
+
+
 def quantize_activation(x: Tensor, scheme: str, chunk: int = 16) -> Tuple[List[Tensor], Tensor]:
     """Eval-mode, moving_average_mode='off' activation quantizer: scales are re-solved per sample.
     quant/binary/activation_quantization.py:99-100 and the _batch_quantization methods."""
@@ -244,10 +259,17 @@ def ema_step(avg: Tensor, momentum: Tensor, x: Tensor, seen: int) -> Tensor:
 # --------------------------------------------------------------------------- QuantConv2d forward
 def quant_conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor], x_scheme: str, w_scheme: str,
                  w_scales: Optional[Sequence[Tensor]], alpha: Optional[float] = None,
-                 stride=1, padding=0, dilation=1, groups=1, chunk: int = 16) -> Tensor:
-    """Eval-mode QuantConv2d.forward.  quant/binary/binary_conv.py:161-173."""
+                 stride=1, padding=0, dilation=1, groups=1, chunk: int = 16,
+                 x_scales: Optional[Sequence[Tensor]] = None, record: Optional[list] = None) -> Tensor:
+    """Eval-mode QuantConv2d.forward.  quant/binary/binary_conv.py:161-173.  ``x_scales``: stored activation
+    scales (moving-average modes) instead of the per-sample solve; ``record``: receives the scales used."""
     xin = x if alpha is None else clamp_symmetric(x, alpha)
-    _, xq = quantize_activation(xin, x_scheme, chunk)
+    if x_scales is not None:
+        xq, used = quantize_activation_stored(xin, x_scheme, x_scales), list(x_scales)
+    else:
+        used, xq = quantize_activation(xin, x_scheme, chunk)
+    if record is not None:
+        record.append([u.clone() for u in used])
     _, wq = quantize_weight(weight, w_scheme, w_scales)
     return F.conv2d(xq, wq, bias, stride, padding, dilation, groups)
 
@@ -287,7 +309,8 @@ def _nonlin(x: Tensor, kind: str, sd: Dict[str, Tensor], p: str) -> Tensor:
     return x
 
 
-def _qconv(x: Tensor, sd: Dict[str, Tensor], p: str, cfg: dict, stride: int, padding: int) -> Tensor:
+def _qconv(x: Tensor, sd: Dict[str, Tensor], p: str, cfg: dict, stride: int, padding: int,
+           record: Optional[list] = None) -> Tensor:
     w_s = cfg['w_quant']
     nsc = {'fp': 0, 'ls-1': 1, 'ls-2': 2, 'ls-T': 1}.get(w_s)
     if nsc is None:
@@ -296,12 +319,13 @@ def _qconv(x: Tensor, sd: Dict[str, Tensor], p: str, cfg: dict, stride: int, pad
     clamp = cfg.get('clamp') or {'kind': 'identity'}
     alpha = clamp.get('alpha', 2) if clamp['kind'] == 'symmetric' else None
     return quant_conv2d(x, sd[p + '.weight'], sd.get(p + '.bias'), cfg['x_quant'], w_s, scales,
-                        alpha, stride, padding)
+                        alpha, stride, padding, record=record)
 
 
-def resnet_forward(sd: Dict[str, Tensor], arch: dict, x: Tensor) -> Tensor:
+def resnet_forward(sd: Dict[str, Tensor], arch: dict, x: Tensor, record: Optional[list] = None) -> Tensor:
     """Eval forward of QResNet from a state_dict and the YAML ``arch_config``.
-    quant/models/resnet.py:91-97 (regular), :180-190 (xnor), :283-340,393-397 (stem/classifier)."""
+    quant/models/resnet.py:91-97 (regular), :180-190 (xnor), :283-340,393-397 (stem/classifier).
+    ``record`` (a list) receives the activation scales of every QuantConv2d in call order."""
     l0 = arch['layer0']
     x = F.conv2d(x, sd['conv1.weight'], sd.get('conv1.bias'), l0['stride'], l0['padding'])
     x = F.relu(_bn_eval(x, sd, 'bn1'))
@@ -328,19 +352,19 @@ def resnet_forward(sd: Dict[str, Tensor], arch: dict, x: Tensor) -> Tensor:
                 return _bn_eval(t, sd, p + '.shortcut.1')
 
             if arch['block'] == 'xnor':
-                o1 = _nonlin(_qconv(_bn_eval(x, sd, p + '.bn1'), sd, p + '.conv1', cfg, stride, 1),
+                o1 = _nonlin(_qconv(_bn_eval(x, sd, p + '.bn1'), sd, p + '.conv1', cfg, stride, 1, record),
                              nl[0], sd, p + '.nonlin1')
                 if cfg.get('double_shortcut', False):
                     o1 = o1 + shortcut(x)
-                o2 = _qconv(_bn_eval(o1, sd, p + '.bn2'), sd, p + '.conv2', cfg, 1, 1)
+                o2 = _qconv(_bn_eval(o1, sd, p + '.bn2'), sd, p + '.conv2', cfg, 1, 1, record)
                 if cfg.get('double_shortcut', False):
                     x = _nonlin(o2, nl[1], sd, p + '.nonlin2') + o1
                 else:
                     x = _nonlin(o2 + shortcut(x), nl[1], sd, p + '.nonlin2')
             else:
-                o = _nonlin(_bn_eval(_qconv(x, sd, p + '.conv1', cfg, stride, 1), sd, p + '.bn1'),
+                o = _nonlin(_bn_eval(_qconv(x, sd, p + '.conv1', cfg, stride, 1, record), sd, p + '.bn1'),
                             nl[0], sd, p + '.nonlin1')
-                o = _bn_eval(_qconv(o, sd, p + '.conv2', cfg, 1, 1), sd, p + '.bn2')
+                o = _bn_eval(_qconv(o, sd, p + '.conv2', cfg, 1, 1, record), sd, p + '.bn2')
                 x = _nonlin(o + shortcut(x), nl[1], sd, p + '.nonlin2')
             planes = out_planes
             bi += 1

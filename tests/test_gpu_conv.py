@@ -317,7 +317,7 @@ def test_fused_stem_kernel_matches_torch():
         got = ops.stem_fwd(x, ops.stem_pack(wt), b)
         assert got.shape == want.shape
         err = float((got - want).abs().max() / want.abs().max())
-        assert err < 2e-5, (n, h, w, err)
+        assert err < 5e-6, (n, h, w, err)
 
 
 def test_pointwise_strided_conv_matches_torch():
@@ -335,7 +335,7 @@ def test_pointwise_strided_conv_matches_torch():
         got = ops.pwconv_fwd(x, ops.pwconv_pack(wt), b, cout, st)
         assert got.shape == want.shape
         err = float((got - want).abs().max() / want.abs().max())
-        assert err < 2e-5, (n, cin, cout, h, w, st, err)
+        assert err < 5e-6, (n, cin, cout, h, w, st, err)
 
 
 def test_quantlinear_matches_oracle():

@@ -1,0 +1,369 @@
+"""GPU parity tests added in round 2 (VERDICT r1 "what's missing" 1-4, 6 and the advisor's findings), all through
+the C ABI: stored-scale (moving-average) packed route, compute_mask / cost_function, injected-scale end-to-end
+logits of the headline network, the CIFAR configuration at full width, re-entrancy, large feature maps, many rows.
+"""
+import threading
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import lsq_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def runtime_strict():
+    from ml_quant_b200 import runtime
+    runtime.strict_fp32()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# QuantConv2d with moving_average_mode != 'off' (reference activation_quantization.py:68-102)
+# ---------------------------------------------------------------------------------------------------------------
+def test_moving_average_layers_against_golden():
+    """tests/golden/ma_layers.pt (made by oracle/gen_golden.py from the unmodified reference): QuantConv2d with
+    'eval_only' / 'train_and_eval' activation quantizers for ls-1 / ls-2 / ls-T / gf-2.
+      (a) reference state loaded, eval forward through forward() AND forward_fused(): the packed route with the
+          STORED scales (encode only, no solve) reproduces the reference output to 1e-5 of max|y|;
+      (b) the two train-mode steps re-run here track the same moving average (1e-5: the ls-2 / ls-T batch solve
+          picks a v1 under the staged solver contract, the tracked value is a mean over 4 samples and 2 steps)."""
+    runtime_strict()
+    from quant.binary.binary_conv import QuantConv2d
+    from ml_quant_b200 import ops
+    recs = load_golden('ma_layers.pt')
+    assert len(recs) == 8
+    for rec in recs:
+        sp = rec['spec']
+        m = QuantConv2d(sp['x_quant'], 'ls-1', 64, 64, 3, {'kind': 'symmetric', 'alpha': sp['alpha']}, sp['mode'],
+                        sp['momentum'], padding=1)
+        m.load_state_dict(rec['state'])
+        m = m.to(DEV).eval()
+        x = rec['x'].to(DEV)
+        ops.reset_counters()
+        with torch.no_grad():
+            y = m(x)
+            yf = m.forward_fused(x)
+        # the stored-scale branch ran: encoder + packed convolution, and NO solver launch
+        assert ops.LAUNCHES.get('encode_act', 0) + ops.LAUNCHES.get('quant_act', 0) >= 2, ops.LAUNCHES
+        assert ops.LAUNCHES.get('solve_v1', 0) == 0 and ops.LAUNCHES.get('row_absmean', 0) == 0, ops.LAUNCHES
+        assert ops.LAUNCHES.get('bconv_tc', 0) == 2, ops.LAUNCHES
+        want = rec['y']
+        for out in (y, yf):
+            err = float((out.cpu() - want).abs().max() / want.abs().max())
+            assert err < 1e-5, (sp, err)
+        # oracle with the stored scales agrees with the golden output bit for bit (pins the oracle function)
+        st = rec['state']
+        avg = st['x_approximate.moving_avg_module.moving_average']
+        scales = [avg[i].expand(x.shape[0]) for i in range(avg.numel())]
+        y_or = O.quant_conv2d(rec['x'], st['weight'], st['bias'], sp['x_quant'], 'ls-1', [st['w_approximate.v1']],
+                              sp['alpha'], 1, 1, x_scales=scales)
+        assert torch.equal(y_or, want)
+        # (b) tracking: fresh module with the reference's weights, the reference's two training batches
+        m2 = QuantConv2d(sp['x_quant'], 'ls-1', 64, 64, 3, {'kind': 'symmetric', 'alpha': sp['alpha']}, sp['mode'],
+                         sp['momentum'], padding=1)
+        with torch.no_grad():
+            m2.weight.copy_(st['weight'])
+            m2.bias.copy_(st['bias'])
+        m2 = m2.to(DEV).train()
+        with torch.no_grad():
+            for xt in rec['x_train']:
+                yt = m2(xt.to(DEV))
+        got_avg = m2.x_approximate.moving_avg_module.moving_average.cpu()
+        assert torch.allclose(got_avg, avg, rtol=2e-5, atol=0), (sp, got_avg, avg)
+        assert int(m2.x_approximate.moving_avg_module.num_batches_tracked) == 2
+        assert torch.allclose(m2.w_approximate.v1.cpu(), st['w_approximate.v1'], rtol=1e-6, atol=0)
+        if sp['mode'] == 'eval_only' and sp['x_quant'] in ('ls-1', 'gf-2'):
+            # train-mode output uses the batch scales; ls-1 / gf have no ill-posed pick: compare directly
+            err = float((yt.cpu() - rec['y_train_last']).abs().max() / rec['y_train_last'].abs().max())
+            assert err < 1e-5, (sp, err)
+
+
+def test_activation_quantizer_lst_moving_average_kat():
+    """Reference KAT tests/binary/test_activation_quantization.py (ternary, 1.0 -> 1.1 with momentum 0.9)."""
+    from quant.binary import quantization
+    from quant.binary.activation_quantization import ActivationQuantizerLST
+    torch.manual_seed(1234)
+    x = torch.ones(32, 16, 3, 3, device=DEV) * 2
+    x2 = torch.rand(32, 16, 3, 3, device=DEV)
+    x3 = torch.ones(32, 16, 3, 3, device=DEV) * 4
+    for mode in ('eval_only', 'train_and_eval'):
+        q = ActivationQuantizerLST(mode, 0.9).to(DEV)
+        q.train()
+        out = q(x)                       # all-equal rows: v1 = mean / 2 = 1.0 (optimal.py:86-118), x_q = 2 v1
+        assert torch.all(out == 2.0)
+        assert torch.allclose(q.moving_avg_module.moving_average.cpu(), torch.tensor([1.0]))
+        out = q(x3)                      # tracked v1 -> 1 * 0.9 + 2 * 0.1 = 1.1
+        assert torch.allclose(q.moving_avg_module.moving_average.cpu(), torch.tensor([1.1]))
+        if mode == 'eval_only':
+            assert torch.all(out == 4.0)
+        else:
+            assert torch.equal(out, quantization.quantizer_ls_ternary(x3, torch.tensor([1.1] * 32, device=DEV))[1])
+        q.eval()
+        want = quantization.quantizer_ls_ternary(x2, torch.tensor([1.1] * 32, device=DEV))[1]
+        assert torch.equal(q(x2), want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# compute_mask / cost_function (reference optimal.py:16-83) against the golden candidate sets
+# ---------------------------------------------------------------------------------------------------------------
+def test_compute_mask_and_cost_function_against_golden(golden_functions):
+    """compute_mask on the GPU returns the reference's candidate set -- per-row counts and the selected values bit
+    for bit (tests/golden/functions.pt: cand_*).  The prefix sums are accumulated in fp64 and rounded to fp32 per
+    position, which IS what the reference computes on the CPU: ATen's CPU cumsum accumulates a float tensor in
+    double (acc_type<float, false>) and rounds each prefix (checked bit-exactly in tests/test_oracle.py).
+    cost_function agrees with the reference formula evaluated by the oracle to 1e-6."""
+    from quant.binary import optimal
+    for rec in golden_functions:
+        rows = rec['x'].reshape(rec['x'].shape[0], -1)
+        for skip in (1, 3):
+            a = rows[..., ::skip].abs()
+            if a.shape[1] < 3:
+                continue
+            for tern in (False, True):
+                gold = rec[f'cand_s{skip}_t{int(tern)}']
+                mask, vals = optimal.compute_mask(a.to(DEV), tern)
+                assert mask.dtype == torch.bool and tuple(mask.shape) == (a.shape[0], a.shape[1] - 2)
+                assert torch.equal(mask.sum(1).cpu(), gold['counts']), (skip, tern)
+                assert torch.equal(vals.cpu(), gold['values']), (skip, tern)
+                # cost of every candidate: reference formula on the CPU (oracle) vs the device expression
+                if vals.numel() == 0:
+                    continue
+                ncand = int(gold['counts'].max())
+                table = torch.zeros(a.shape[0], max(ncand, 1))
+                off = 0
+                for r, c in enumerate(gold['counts'].tolist()):
+                    table[r, :c] = gold['values'][off:off + c]
+                    off += c
+                want = O.candidate_cost(a, table, tern)
+                got = optimal.cost_function(a.to(DEV), table.to(DEV), tern).cpu()
+                assert torch.allclose(got, want, rtol=2e-6, atol=1e-6), (skip, tern, float((got - want).abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# end-to-end logits with the oracle's v1 injected per layer
+# ---------------------------------------------------------------------------------------------------------------
+def _inject_v1(model, per_layer_v1):
+    """Make every ls-2 QuantConv2d of ``model`` quantize with a GIVEN v1 (the public ``v1=`` argument of
+    quantizer_ls_2, quantization.py:61-62) instead of solving; v2 and the planes are computed by the kernels."""
+    from ml_quant_b200 import ops, runtime
+    used = []
+    for i, m in enumerate(runtime.quant_layers(model)):
+        def q_given(x, g, prologue=None, _m=m, _i=i):
+            n = x.shape[0]
+            tab = torch.empty(2, n, dtype=torch.float32, device=x.device)
+            tab[0].copy_(per_layer_v1[_i].to(x.device))
+            planes, _ = ops.encode_act(x, g, tab[:1], 2, _m.clamp_alpha, True, None, prologue, next_scale_out=tab[1])
+            used.append(tab.detach().cpu())
+            return planes, tab
+        m.quantize_input = q_given
+    return used
+
+
+@pytest.mark.parametrize('cfg,hw', [('imagenet_resnet18_ls1w_ls2a', 224), ('cifar100_resnet18_ls1w_ls2a', 32)])
+def test_logits_with_injected_oracle_scales(cfg, hw):
+    """With the oracle's v1 of every layer injected, the ill-posed arg-min is out of the loop and the
+    whole forward -- stem, 16 x (BatchNorm, clamp, encode, v2, binary convolution, ReLU, shortcuts), classifier --
+    must reproduce the oracle's logits: <= 1e-5 of max|logit| (plain and fused-for-inference graph), v2 of every
+    layer to 1e-6."""
+    runtime_strict()
+    from ml_quant_b200 import configs, runtime
+    model = runtime.build_model(cfg, torch.device(DEV))
+    runtime.calibrate(model, (3, hw, hw), batches=1, batch=8)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(4321)
+    x = torch.randn(2, 3, hw, hw, generator=g)
+    rec = []
+    y_ref = O.resnet_forward(sd, configs.arch(cfg), x, record=rec)
+    assert len(rec) == 16
+    used = _inject_v1(model, [r[0] for r in rec])
+    with torch.no_grad():
+        y = model(x.to(DEV)).cpu()
+    assert len(used) == 16
+    for i, (tab, r) in enumerate(zip(used, rec)):
+        assert torch.equal(tab[0], r[0])
+        assert torch.allclose(tab[1], r[1], rtol=1e-6, atol=0), (i, tab[1], r[1])
+    err = float((y - y_ref).abs().max() / y_ref.abs().max())
+    assert err < 1e-5, err
+    used.clear()
+    fused = runtime.optimize_for_inference(model)
+    with torch.no_grad():
+        yf = fused(x.to(DEV)).cpu()
+    errf = float((yf - y_ref).abs().max() / y_ref.abs().max())
+    assert errf < 1e-5, errf
+
+
+def test_cifar_full_width_layer_by_layer():
+    """BASELINE config 2 (CIFAR-100 ResNet-18, ls-1 weights / ls-2 activations, clamp 2, full width) teacher-forced
+    like the headline network: every layer, fed with the GPU's own input, meets the solver contract, reproduces the
+    oracle's v2 for that v1 to 1e-6 and the oracle's convolution output for those scales to 1e-5 of max|y|."""
+    runtime_strict()
+    from ml_quant_b200 import runtime
+    from tests.test_gpu_quantizers import _solver_contract
+    model = runtime.build_model('cifar100_resnet18_ls1w_ls2a', torch.device(DEV))
+    runtime.calibrate(model, (3, 32, 32), batches=1, batch=16)
+    layers = runtime.quant_layers(model)
+    assert len(layers) == 16
+    rec = {}
+    for i, m in enumerate(layers):
+        orig = m.quantize_input
+
+        def wrapped(x, g, prologue=None, _i=i, _orig=orig):
+            planes, table = _orig(x, g, prologue)
+            rec[_i] = [x.detach().cpu(), table.detach().cpu(), None]
+            return planes, table
+        m.quantize_input = wrapped
+        m.register_forward_hook(lambda mod, inp, out, _i=i: rec[_i].__setitem__(2, out.detach().cpu()))
+    g = torch.Generator().manual_seed(79)
+    x = torch.randn(4, 3, 32, 32, generator=g)
+    with torch.no_grad():
+        model(x.to(DEV))
+    for i, m in enumerate(layers):
+        xi, table, y = rec[i]
+        xin = xi.clamp(-m.clamp_alpha, m.clamp_alpha)
+        rows = xin.reshape(4, -1)
+        v1, v2 = table[0], table[1]
+        _solver_contract(rows, v1, O.solve_v1(rows, False, 3, chunk=1).view(-1), False, 3)
+        b1 = torch.where(xin >= 0, 1.0, -1.0)
+        v2_ref = (xin - v1.view(-1, 1, 1, 1) * b1).abs().mean(dim=(1, 2, 3))
+        assert torch.allclose(v2, v2_ref, rtol=1e-6, atol=0), (i, v2, v2_ref)
+        y_ref, _ = O.plane_conv_identity(xin, m.weight.detach().cpu(), m.bias.detach().cpu(), 'ls-2', [v1, v2],
+                                         m.w_approximate.v1.detach().cpu(), m.stride[0], m.padding[0])
+        err = float((y - y_ref).abs().max() / y_ref.abs().max())
+        assert err < 1e-5, (i, err)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# re-entrancy: replicas / threads / streams sharing one module
+# ---------------------------------------------------------------------------------------------------------------
+def test_two_threads_two_streams_share_a_module():
+    """nn.DataParallel replicas are shallow copies that share the module's caches (packed weights, plane scratch)
+    and run concurrently, one host thread each.  Here: two threads, each on its own stream, push different batches
+    through the SAME QuantConv2d 20 times; every result must equal the serial result bit for bit."""
+    from quant.binary.binary_conv import QuantConv2d
+    torch.manual_seed(3)
+    m = QuantConv2d('ls-2', 'ls-1', 64, 64, 3, {'kind': 'symmetric', 'alpha': 3.0}, padding=1).to(DEV)
+    with torch.no_grad():
+        m.train(); m(torch.randn(2, 64, 28, 28, device=DEV)); m.eval()
+    xs = [torch.randn(8, 64, 28, 28, device=DEV) * (1 + 0.1 * i) for i in range(2)]
+    with torch.no_grad():
+        want = [m(x).clone() for x in xs]
+    torch.cuda.synchronize()
+    bad = []
+
+    def worker(i):
+        st = torch.cuda.Stream(device=DEV)
+        with torch.cuda.stream(st), torch.no_grad():
+            for _ in range(20):
+                y = m(xs[i])
+                if not torch.equal(y, want[i]):
+                    bad.append(i)
+        st.synchronize()
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not bad, bad
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='requires >= 2 GPUs')
+def test_data_parallel_two_gpus():
+    """Counterpart of the reference's only multi-GPU test (tests/utils/test_moving_average.py:125-166): a
+    QuantConv2d with an eval_only moving average under nn.DataParallel on 2 GPUs -- statistics tracked on replica
+    0, eval output equal to the single-GPU module's."""
+    from quant.binary.binary_conv import QuantConv2d
+    torch.manual_seed(4)
+    m = QuantConv2d('ls-1', 'ls-1', 64, 64, 3, {'kind': 'symmetric', 'alpha': 2.0}, 'eval_only', 0.9, padding=1).to(DEV)
+    dp = nn.DataParallel(m, device_ids=[0, 1])
+    dp.train()
+    with torch.no_grad():
+        for i in range(3):
+            dp(torch.randn(8, 64, 14, 14, device=DEV))
+    assert int(m.x_approximate.moving_avg_module.num_batches_tracked) == 3
+    dp.eval()
+    x = torch.randn(8, 64, 14, 14, device=DEV)
+    with torch.no_grad():
+        y_dp, y_single = dp(x), m(x)
+    assert torch.equal(y_dp, y_single)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# advisor findings
+# ---------------------------------------------------------------------------------------------------------------
+def test_fused_prologue_on_large_feature_map():
+    """The fused BatchNorm prologue maps an element to its channel by a reciprocal multiplication that is exact only
+    while row_length * inner < 2^40; 64 channels of 500 x 500 (inner = 250 000, not a power of two) is beyond that
+    and takes the exact division.  Scales with the fused prologue must equal the scales of the materialised affine
+    map (same fmaf) bit for bit."""
+    from ml_quant_b200 import ops
+    torch.manual_seed(6)
+    c, inner = 64, 500 * 500
+    x = torch.randn(2, c * inner, device=DEV)
+    a = (torch.rand(c, device=DEV) + 0.5)
+    b = torch.randn(c, device=DEV)
+    xb = torch.addcmul(b.repeat_interleave(inner).unsqueeze(0), x, a.repeat_interleave(inner).unsqueeze(0))   # fma
+    pro = (a, b, inner)
+    assert torch.equal(ops.row_absmean(x, [], 2.0, pro), ops.row_absmean(xb, [], 2.0))
+    assert torch.equal(ops.solve_v1(x, False, 3, 2.0, prologue=pro), ops.solve_v1(xb, False, 3, 2.0))
+    assert torch.equal(ops.solve_v1(x, True, 3, 2.0, prologue=pro), ops.solve_v1(xb, True, 3, 2.0))
+
+
+def test_quantlinear_many_rows_and_solver_contract():
+    """QuantLinear flattens every leading dimension into rows: more than 65 535 rows (the gridDim.y limit of the row
+    kernels) must work on both routes; the ls-2 / ls-T activation scales obey the solver contract and, with OUR
+    scales, the output equals the oracle's composition to 1e-5."""
+    from quant.binary.binary_conv import QuantLinear
+    from tests.test_gpu_quantizers import _solver_contract
+    torch.manual_seed(13)
+    for xs, fin, fout, alpha in [('ls-2', 512, 256, 3.0), ('ls-T', 192, 64, 3.0), ('ls-2', 100, 10, None)]:
+        clamp = None if alpha is None else {'kind': 'symmetric', 'alpha': alpha}
+        m = QuantLinear(xs, 'ls-1', fin, fout, clamp=clamp).to(DEV)
+        x = torch.randn(33, fin) * 1.5
+        with torch.no_grad():
+            m.train(); m(x.to(DEV)); m.eval()
+            y = m(x.to(DEV)).cpu()
+        xin = x if alpha is None else x.clamp(-alpha, alpha)
+        tern = xs == 'ls-T'
+        from ml_quant_b200 import ops
+        v1 = ops.solve_v1(xin.to(DEV), tern, 3).cpu()
+        _solver_contract(xin, v1, O.solve_v1(xin, tern, 3, chunk=8).view(-1), tern, 3)
+        x4 = xin.view(33, fin, 1, 1)
+        xq = (O.quant_lsT(x4, v1)[1] if tern else O.quant_ls2(x4, v1)[2]).view(33, fin)
+        w = m.weight.detach().cpu()
+        wq = w.abs().mean(1, keepdim=True) * torch.where(w >= 0, 1.0, -1.0)
+        want = F.linear(xq, wq, m.bias.detach().cpu())
+        err = float((y - want).abs().max() / want.abs().max())
+        assert err < 1e-5, (xs, fin, fout, err)
+    big = QuantLinear('ls-1', 'ls-1', 64, 64, clamp={'kind': 'symmetric', 'alpha': 2.0}).to(DEV)
+    x = torch.randn(70000, 64, device=DEV)
+    with torch.no_grad():
+        big.train(); big(x[:16]); big.eval()
+        y = big(x)
+        y_head = big(x[:100])
+        y_tail = big(x[-100:])
+    assert y.shape == (70000, 64)
+    assert torch.equal(y[:100], y_head) and torch.equal(y[-100:], y_tail)
+
+
+def test_eval_with_grad_enabled_keeps_gradients_and_warns():
+    """optimize_for_inference'd blocks in eval mode WITH autograd on (frozen-BN fine-tuning, saliency) must build the
+    reference's graph: the input and the shortcut convolution receive gradients; a RuntimeWarning names the slow route."""
+    import warnings
+    from ml_quant_b200 import runtime
+    from ml_quant_b200.binary.binary_conv import QuantConv2d
+    model = runtime.build_model('cifar100_resnet18_ls1w_ls2a', torch.device(DEV))
+    runtime.calibrate(model, (3, 32, 32), batches=1, batch=8)
+    runtime.optimize_for_inference(model)
+    x = torch.randn(2, 3, 32, 32, device=DEV, requires_grad=True)
+    QuantConv2d._warned_grad_eval = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        model(x).sum().backward()
+    assert any('torch.no_grad' in str(i.message) for i in w)
+    assert x.grad is not None and float(x.grad.abs().sum()) > 0
+    sc = [m for m in model.modules() if hasattr(m, 'shortcut') and len(m.shortcut) == 2]
+    assert sc and all(b.shortcut[0].weight.grad is not None and float(b.shortcut[0].weight.grad.abs().sum()) > 0 for b in sc)

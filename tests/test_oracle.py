@@ -111,6 +111,37 @@ def test_nets_bit_exact(golden_nets):
         assert torch.equal(y, rec['y']), name
 
 
+def test_moving_average_layers_bit_exact():
+    """tests/golden/ma_layers.pt: eval forward of QuantConv2d with STORED activation scales (moving-average modes,
+    activation_quantization.py:90-98) -- the oracle's quant_conv2d(x_scales=...) reproduces it bit for bit, and the
+    tracked averages follow ema_step over the per-batch mean scales of the two training batches."""
+    from tests.conftest import load_golden
+    for rec in load_golden('ma_layers.pt'):
+        sp, st, x = rec['spec'], rec['state'], rec['x']
+        avg = st['x_approximate.moving_avg_module.moving_average']
+        scales = [avg[i].expand(x.shape[0]) for i in range(avg.numel())]
+        y = O.quant_conv2d(x, st['weight'], st['bias'], sp['x_quant'], 'ls-1', [st['w_approximate.v1']], sp['alpha'], 1, 1,
+                           x_scales=scales)
+        assert torch.equal(y, rec['y']), sp
+        mom = st['x_approximate.moving_avg_module.momentum']
+        track = torch.zeros_like(avg)
+        for i, xt in enumerate(rec['x_train']):
+            vs, _ = O.quantize_activation(O.clamp_symmetric(xt, sp['alpha']), sp['x_quant'], chunk=4)
+            track = O.ema_step(track, mom, torch.stack(vs).mean(1), i)
+        assert torch.equal(track, avg), (sp, track, avg)
+
+
+def test_cpu_cumsum_accumulates_in_double():
+    """ATen's CPU cumsum of a float tensor accumulates in double and rounds every prefix to fp32 (acc_type<float,
+    /*is_cuda=*/false> = double): the reference's `values.cumsum(dim=1)` (optimal.py:56) on the CPU is therefore
+    bit-identical to an fp64 prefix sum cast to fp32 -- which is what the mirror's compute_mask and the CUDA
+    solver's candidate test ((float) of an fp64 prefix) compute."""
+    torch.manual_seed(0)
+    for n in (100, 5000, 66902):
+        s = torch.sort(torch.randn(4, n).abs(), dim=1).values
+        assert torch.equal(s.cumsum(1), s.double().cumsum(1).float())
+
+
 def test_ema():
     m = torch.tensor([0.9])
     a = O.ema_step(torch.zeros(1), m, torch.tensor([2.0]), 0)
@@ -143,6 +174,46 @@ torch.save(out, sys.argv[1])
         assert torch.equal(a, b)
     assert torch.equal(O.quant_gf(x, 3)[1], ref['gf3'][1])
     assert torch.equal(O.quant_ls1(x)[1], ref['ls1'][1])
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/quant'), reason='reference not mounted')
+def test_live_reference_stored_scales_and_moving_average_conv():
+    """The stored-scale (moving-average) eval path of the live reference -- QuantConv2d built with
+    moving_average_mode='eval_only', one train-mode step to track the scales, then eval
+    (activation_quantization.py:68-102, binary_conv.py:161-173) -- against the oracle's
+    quantize_activation_stored / quant_conv2d(x_scales=...), bit for bit, for every activation scheme."""
+    import subprocess
+    import tempfile
+    code = r'''
+import sys, torch
+sys.path.insert(0, "/root/reference")
+from quant.binary.binary_conv import QuantConv2d
+out = {}
+for scheme in ("ls-1", "ls-2", "ls-T", "gf-2"):
+    torch.manual_seed(5)
+    m = QuantConv2d(scheme, "ls-1", 8, 16, 3, clamp={"kind": "symmetric", "alpha": 2.0},
+                    moving_average_mode="eval_only", moving_average_momentum=0.9, padding=1)
+    m.train()
+    with torch.no_grad():
+        m(torch.randn(4, 8, 9, 9))
+        m(torch.randn(4, 8, 9, 9))
+    m.eval()
+    x = torch.randn(3, 8, 9, 9)
+    with torch.no_grad():
+        y = m(x)
+    out[scheme] = {"state": m.state_dict(), "x": x, "y": y}
+torch.save(out, sys.argv[1])
+'''
+    with tempfile.NamedTemporaryFile(suffix='.pt') as f:
+        subprocess.run([sys.executable, '-c', code, f.name], check=True, cwd='/tmp')
+        ref = torch.load(f.name, weights_only=False)
+    for scheme, rec in ref.items():
+        st, x = rec['state'], rec['x']
+        avg = st['x_approximate.moving_avg_module.moving_average']
+        scales = [avg[i].expand(x.shape[0]) for i in range(avg.numel())]
+        y = O.quant_conv2d(x, st['weight'], st['bias'], scheme, 'ls-1', [st['w_approximate.v1']], 2.0, 1, 1,
+                           x_scales=scales)
+        assert torch.equal(y, rec['y']), scheme
 
 
 def test_sort_free_solver_model_matches_oracle():
