@@ -20,6 +20,7 @@ EXPORTS = [
     'lsq_stem_image_bytes', 'lsq_stem_workspace_bytes', 'lsq_stem_supported', 'lsq_stem_pack_weights',
     'lsq_pwconv_supported', 'lsq_pwconv_image_bytes', 'lsq_pwconv_pack_weights', 'lsq_pwconv_fwd',
     'lsq_solve_v1_multi', 'lsq_row_absmean_multi', 'lsq_wbits_bytes', 'lsq_unpack_weights',
+    'lsq_quantize_act_workspace_bytes', 'lsq_quantize_act',
 ]
 
 
@@ -108,6 +109,10 @@ def lib():
             L.lsq_solve_v1_multi.argtypes = [tp, i32, i32, i32, f32, vp]
             L.lsq_row_absmean_multi.restype = i32
             L.lsq_row_absmean_multi.argtypes = [tp, i32, f32, vp]
+            L.lsq_quantize_act_workspace_bytes.restype = sz
+            L.lsq_quantize_act_workspace_bytes.argtypes = [gp]
+            L.lsq_quantize_act.restype = i32
+            L.lsq_quantize_act.argtypes = [vp, gp, f32, i32, i32, vp, vp, vp, sz, pp, vp, vp]
             for name in ('lsq_row_absmean', 'lsq_solve_v1', 'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry',
                          'lsq_encode_act', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
                          'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex'):

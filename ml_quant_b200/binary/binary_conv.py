@@ -184,12 +184,9 @@ class QuantConv2d(nn.Conv2d):
             planes, v1 = ops.encode_act(x, g, [], 1, alpha, True, buf, pro)
             table = [v1]
         elif self.x_quant in ('ls-2', 'ls-T'):
-            # the kernels write straight into the [2, n] table the convolution reads: no stack / copy launches
-            tab = torch.empty(2, n, dtype=torch.float32, device=x.device)
-            ops.solve_v1(rows, tern, 3, alpha, prologue=pro, out=tab[0])
-            planes, _ = ops.encode_act(x, g, tab[:1], 2, alpha, not tern, buf, pro, next_scale_out=tab[1])
-            if tern:
-                tab[1].copy_(tab[0])
+            # one fused launch (csrc/lsq_qact.cu): clamp + BatchNorm prologue + v1 solve + v2 + both sign planes with a
+            # single read of x from HBM, written straight into the [2, n] table the convolution reads
+            planes, tab = ops.quantize_act(x, g, tern, alpha, 3, buf, pro)
             self._planes_cache[dev] = planes
             return planes, tab
         else:

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liblsq_b200.so')
-SOURCES = ['lsq_quant.cu', 'lsq_solve.cu', 'lsq_bconv.cu', 'lsq_bconv_tc.cu', 'lsq_stem.cu', 'lsq_pwconv.cu']
+SOURCES = ['lsq_quant.cu', 'lsq_solve.cu', 'lsq_qact.cu', 'lsq_bconv.cu', 'lsq_bconv_tc.cu', 'lsq_stem.cu', 'lsq_pwconv.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--use_fast_math=false']
 

@@ -1,0 +1,644 @@
+// Fused activation quantizer for the 2-bit (ls-2) and ternary (ls-T) schemes: ONE read of the fp32 input from HBM.
+//
+// Replaces, on the QuantConv2d input (quant/binary/binary_conv.py:163 -> activation_quantization.py:99-100 ->
+// quantization.py:59-115 -> optimal.py:121-155), the chain  clamp -> opt_v1 (sort, cumsum, masks, cost tensor,
+// .tolist() sync) -> v2 = mean|x - v1 sign(x)| -> binarize / residual / binarize  and, fused in front of it, the
+// eval-mode BatchNorm of the caller (quant/models/resnet.py:180-190).  Round 1 ran this as three kernels that each
+// streamed the tensor from HBM (histogram pass, collection pass, encoder); here a row (= one sample) is handled by
+// one thread-block cluster that keeps it hot in L2:
+//
+//   sweep 1 (HBM)  every 3rd element (optimal.py:134) of |clamp(bn(x))|: float bit patterns are monotone keys;
+//                  bins of 2^14 keys anchored at the clamp bound (512 bins per octave, 8 octaves), count + exact
+//                  integer sum of the low 14 key bits per bin (native shared-memory atomics, order independent);
+//                  the bin index of every sampled element is kept in shared memory (2 bytes per sample);
+//   merge          the CTAs of the cluster add up their histograms through distributed shared memory;
+//   flag           rank 0: prefix counts / EXACT prefix sums at the bin edges bound both threshold functions of
+//                  optimal.py:63-80 over every bin (may_hold, conservative): a handful of bins can hold a candidate;
+//   collect        every CTA walks its bin indices, re-reads the few hundred flagged elements (L2 hits) and sends
+//                  their exact keys to rank 0;
+//   solve          rank 0 sorts them, gives every one the reference's own fp32 candidate test on (float) prefix sums
+//                  and the closed-form cost in fp64; first minimum wins (torch.argmin) -> v1;
+//   sweep 2 (L2)   the encoder's work item (lsq_encode_core.cuh): both sign planes in the convolution's raster and
+//                  sum |x - v1 sign(x)| -> v2 (fp64, fixed summation tree, deterministic and batch invariant).
+//
+// The cluster size is chosen on the host so that the rows in flight (2 CTAs per SM) fit in L2 and a CTA's share of
+// the sampled row fits its bin-index buffer.  Rows the fast path cannot decide (a candidate may sit below the bin
+// window, too many flagged elements, ...) are marked in d_row_status and redone by the generic kernels of
+// lsq_solve.cu / lsq_quant.cu, launched behind this one on the marked rows only.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include "lsq_common.cuh"
+#include "lsq_encode_core.cuh"
+#include "lsq_solve_core.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace lsq {
+
+constexpr int kQThreads = 512;
+constexpr int kQBins = 4096, kQShift = 14;
+constexpr int kQBinsPerThread = kQBins / kQThreads;   // 8 consecutive bins per thread in the scan
+constexpr int kQIdsCap = 17408;                       // sampled elements of a row handled by one CTA
+constexpr int kQListCap = 2048;                       // collected elements (sorted and tested one by one)
+constexpr int kQMaxFlag = 64;
+constexpr int kQMaxGroups = 128;
+constexpr int kQMaxCluster = 8;
+constexpr int kQMaxChannels = 512;
+constexpr uint32_t kIdBelow = 0xFFFFu, kIdNone = 0xFFFEu;
+
+struct QParams {
+  long long len;          // elements per row (= c * h * w)
+  uint32_t n_s;           // sampled elements per row: ceil(len / 3)
+  uint32_t groups;        // 12-element groups per row: ceil(len / 12)
+  uint32_t klo;           // first key of the bin window
+  uint32_t hw, nq, nitems;
+  unsigned long long hw_magic;   // ceil(2^40 / hw), or 0: divide exactly
+};
+
+struct QSmem {
+  uint32_t hcnt[kQBins];
+  uint32_t hrem[kQBins];
+  uint16_t ids[kQIdsCap];
+  uint32_t list[kQListCap];        // rank 0: collected keys; during the scan: per-thread group prefixes
+  float2 ab[kQMaxChannels];
+  double red[32];
+  double wsum[32];
+  uint32_t wcnt[32];
+  uint32_t wfirst[32];
+  // per-rank partial results, written into rank 0's copy through distributed shared memory
+  double part_sb[kQMaxCluster];
+  double part_v2[kQMaxCluster];
+  uint32_t part_cb[kQMaxCluster], part_kmin[kQMaxCluster], part_kmax[kQMaxCluster];
+  uint32_t kmin, kmax, cb;
+  int nflag, ngroup;
+  uint16_t glist[kQMaxGroups];
+  uint16_t fbin[kQMaxFlag];
+  uint32_t fexcl[kQMaxFlag], fnb[kQMaxFlag];
+  double fsumb[kQMaxFlag];
+  int ford[kQMaxFlag];
+  int nrange;
+  Range rng[kMaxRanges];
+  double seg_base[kMaxRanges];
+  uint32_t nlist, want_list;
+  int status;                      // 0 = solved here, != 0: reason the row goes to the generic kernels
+  float v1;
+  double s_tot, q_tot;
+  double best_cost[32];
+  uint32_t best_pos[32], best_key[32], ncand;
+};
+static_assert(sizeof(QSmem) <= 113 * 1024, "two CTAs per SM");
+static_assert(kQThreads * 16 <= kQListCap * 4, "group prefix records are parked in the list");
+
+__device__ __forceinline__ uint32_t q_channel(const QParams& qp, unsigned long long idx) {
+  return qp.hw_magic ? (uint32_t)((idx * qp.hw_magic) >> 40) : (uint32_t)(idx / qp.hw);
+}
+
+// exact sum of the `cnt` keys of bin b (all share the exponent and the upper mantissa bits of the bin's first key)
+__device__ __forceinline__ double q_bin_sum(uint32_t klo, uint32_t b, uint32_t cnt, uint32_t rem) {
+  const uint32_t kb = klo + (b << kQShift);
+  const int e = (int)(kb >> 23);
+  const double msum = (double)cnt * (double)(kb & 0x7FFFFFu) + (double)rem;
+  if (e == 0) return msum * pow2d(-149);
+  return ((double)cnt * 8388608.0 + msum) * pow2d(e - 150);
+}
+
+template <bool TERN, int VEC>
+__global__ void __launch_bounds__(kQThreads, 2)
+quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue pro, int cs, QParams qp,
+                 uint32_t* __restrict__ planes, float* __restrict__ scales, int* __restrict__ row_status,
+                 int* __restrict__ diag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  QSmem& sm = *reinterpret_cast<QSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int rank = (cs > 1) ? (int)cluster.block_rank() : 0;
+  const long long row = (long long)blockIdx.x / cs;
+  QSmem* const r0 = (cs > 1) ? cluster.map_shared_rank(&sm, 0) : &sm;
+  const float* xr = x + row * qp.len;
+  const uint32_t klo = qp.klo, n = qp.n_s;
+  auto csync = [&]() { if (cs > 1) cluster.sync(); else __syncthreads(); };
+
+  // ---- setup --------------------------------------------------------------------------------------------------
+  for (int b = tid; b < kQBins; b += kQThreads) { sm.hcnt[b] = 0u; sm.hrem[b] = 0u; }
+  for (int c = tid; c < g.cw * 32; c += kQThreads) {
+    float2 k = make_float2(1.0f, 0.0f);
+    if (pro.a && c < g.c) k = make_float2(__ldg(pro.a + c), __ldg(pro.b + c) + 0.0f);
+    sm.ab[c] = k;
+  }
+  if (tid == 0) {
+    sm.kmin = kNoKey; sm.kmax = 0u; sm.cb = 0u; sm.nflag = 0; sm.ngroup = 0; sm.nrange = 0; sm.nlist = 0u;
+    sm.want_list = 0u; sm.status = 0; sm.v1 = 0.0f; sm.ncand = 0u;
+  }
+  __syncthreads();
+
+  // ---- sweep 1: histogram of the sampled keys of this CTA's share of the row -------------------------------------
+  const uint32_t g_lo = (uint32_t)(((unsigned long long)qp.groups * (unsigned)rank) / (unsigned)cs);
+  const uint32_t g_hi = (uint32_t)(((unsigned long long)qp.groups * (unsigned)(rank + 1)) / (unsigned)cs);
+  {
+    uint32_t kmn = kNoKey, kmx = 0u, cb = 0u;
+    double lb = 0.0;
+    auto sample = [&](float raw, uint32_t c) -> uint32_t {
+      const float2 k = sm.ab[c];
+      const float a = fabsf(clamp_sym(fmaf(raw, k.x, k.y), alpha));
+      const uint32_t key = __float_as_uint(a);
+      kmn = min(kmn, key); kmx = max(kmx, key);
+      if (key >= klo) {
+        const uint32_t b = min((key - klo) >> kQShift, (uint32_t)(kQBins - 1));
+        atomicAdd(&sm.hcnt[b], 1u);
+        atomicAdd(&sm.hrem[b], key & ((1u << kQShift) - 1u));
+        return b;
+      }
+      ++cb; lb += (double)a;
+      return kIdBelow;
+    };
+    constexpr int kU = 3;   // groups per thread and trip: 12 independent loads in flight
+    for (uint32_t gb = g_lo + tid; gb < g_hi; gb += kU * kQThreads) {
+      float raw[kU][4];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t gi = gb + u * kQThreads;
+        const long long i0 = (long long)gi * 12;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long idx = i0 + 3 * j;
+          raw[u][j] = (gi < g_hi && idx < qp.len) ? __ldg(xr + idx) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t gi = gb + u * kQThreads;
+        if (gi >= g_hi) break;
+        const unsigned long long i0 = (unsigned long long)gi * 12ull;
+        uint32_t c = q_channel(qp, i0);
+        uint32_t r = (uint32_t)(i0 - (unsigned long long)c * qp.hw);
+        uint32_t id[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((long long)(i0 + 3 * j) < qp.len) {
+            while (r >= qp.hw) { r -= qp.hw; ++c; }
+            id[j] = sample(raw[u][j], c);
+          } else {
+            id[j] = kIdNone;
+          }
+          r += 3;
+        }
+        *reinterpret_cast<uint2*>(&sm.ids[4 * (gi - g_lo)]) = make_uint2(id[0] | (id[1] << 16), id[2] | (id[3] << 16));
+      }
+    }
+    const double sb = block_sum(lb, sm.red);
+    cb = (uint32_t)__reduce_add_sync(0xffffffffu, cb);
+    kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
+    if (lane == 0) { atomicAdd(&sm.cb, cb); atomicMin(&sm.kmin, kmn); atomicMax(&sm.kmax, kmx); }
+    __syncthreads();
+    if (tid == 0) {
+      r0->part_sb[rank] = sb; r0->part_cb[rank] = sm.cb; r0->part_kmin[rank] = sm.kmin; r0->part_kmax[rank] = sm.kmax;
+    }
+  }
+  csync();
+
+  // ---- merge: CTA r sums slice r of all histograms into rank 0's ---------------------------------------------------
+  if (cs > 1) {
+    const int slice = kQBins / cs;
+    for (int b = rank * slice + tid; b < (rank + 1) * slice; b += kQThreads) {
+      uint32_t c = 0u, r = 0u;
+      for (int q = 0; q < cs; ++q) {
+        const QSmem* p = cluster.map_shared_rank(&sm, q);
+        c += p->hcnt[b]; r += p->hrem[b];
+      }
+      r0->hcnt[b] = c; r0->hrem[b] = r;
+    }
+    cluster.sync();
+  }
+
+  // ---- rank 0: scan the bins, flag those that can hold a candidate, build the ranges to collect ----------------------
+  if (rank == 0) {
+    double sum_below = 0.0;
+    uint32_t cnt_below = 0u, kmin = kNoKey, kmax = 0u;
+    for (int q = 0; q < cs; ++q) {
+      sum_below += sm.part_sb[q]; cnt_below += sm.part_cb[q];
+      kmin = min(kmin, sm.part_kmin[q]); kmax = max(kmax, sm.part_kmax[q]);
+    }
+    uint32_t ct = 0u, fn = kNoKey;
+    double stt = 0.0, stq = 0.0;
+#pragma unroll
+    for (int j = 0; j < kQBinsPerThread; ++j) {
+      const uint32_t b = tid * kQBinsPerThread + j, cnt = sm.hcnt[b];
+      if (cnt != 0u) {
+        const double s = q_bin_sum(klo, b, cnt, sm.hrem[b]);
+        ct += cnt; stt += s; stq += s * s / (double)cnt;
+        if (fn == kNoKey) fn = b;
+      }
+    }
+    uint32_t ci = ct;
+    double si = stt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t tc = __shfl_up_sync(0xffffffffu, ci, o);
+      const double ts = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) { ci += tc; si += ts; }
+    }
+    uint32_t sfx = fn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_down_sync(0xffffffffu, sfx, o);
+      if (lane + o < 32) sfx = min(sfx, t);
+    }
+    uint32_t nxt_in_warp = __shfl_down_sync(0xffffffffu, sfx, 1);
+    if (lane == 31) nxt_in_warp = kNoKey;
+    if (lane == 31) { sm.wcnt[wid] = ci; sm.wsum[wid] = si; }
+    if (lane == 0) sm.wfirst[wid] = sfx;
+    __syncthreads();
+    uint32_t coff = 0u;
+    double soff = 0.0, s_bins = 0.0;
+    for (int w = 0; w < kQThreads / 32; ++w) {
+      if (w < wid) { coff += sm.wcnt[w]; soff += sm.wsum[w]; }
+      s_bins += sm.wsum[w];
+    }
+    uint32_t nxt_after = nxt_in_warp;
+    for (int w = wid + 1; w < kQThreads / 32 && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
+    const double s_tot = sum_below + s_bins;
+    const double q_tot = block_sum(stq, sm.red);      // sum of squares up to the spread inside a bin: a constant
+                                                      // shared by every candidate's cost, it cannot move the arg-min
+    const uint32_t excl0 = cnt_below + coff + ci - ct;
+    const double pref0 = sum_below + soff + si - stt;
+
+    auto bin_upper = [&](uint32_t b) -> float {       // largest value a key of bin b can have
+      const uint32_t nh = min(klo + ((b + 1u) << kQShift) - 1u, kmax);
+      return fmaxf(key_val(nh), key_val(klo + (b << kQShift)));
+    };
+    auto test_bin = [&](uint32_t b, uint32_t cnt, double s, uint32_t excl, double pref, uint32_t nb) {
+      const uint32_t elo_k = klo + (b << kQShift);
+      const uint32_t ehi_k = min(klo + ((b + 1u) << kQShift) - 1u, kmax);
+      const float nxt_hi = (nb != kNoKey) ? bin_upper(nb) : key_val(kmax);
+      if (!may_hold<TERN>(elo_k, ehi_k, cnt, s, excl, pref, nxt_hi, n, s_tot, kmax, 0.0f)) return;
+      const int slot = atomicAdd(&sm.nflag, 1);
+      if (slot < kQMaxFlag) { sm.fbin[slot] = (uint16_t)b; sm.fexcl[slot] = excl; sm.fsumb[slot] = pref; sm.fnb[slot] = nb; }
+    };
+    // two levels: one coarse test per thread on the union of its bins, the fine test only for flagged groups
+    uint32_t* const gexcl = sm.list;
+    uint32_t* const gnext = sm.list + kQThreads;
+    double* const gpref = reinterpret_cast<double*>(sm.list + 2 * kQThreads);
+    gexcl[tid] = excl0; gnext[tid] = nxt_after; gpref[tid] = pref0;
+    if (ct != 0u) {
+      const uint32_t b0 = tid * kQBinsPerThread;
+      const uint32_t elo_k = klo + (b0 << kQShift);
+      const uint32_t ehi_k = min(klo + ((b0 + kQBinsPerThread) << kQShift) - 1u, kmax);
+      const float nxt_hi = (nxt_after != kNoKey) ? bin_upper(nxt_after) : key_val(kmax);
+      if (may_hold<TERN>(elo_k, ehi_k, ct, stt, excl0, pref0, nxt_hi, n, s_tot, kmax, 0.0f)) {
+        const int slot = atomicAdd(&sm.ngroup, 1);
+        if (slot < kQMaxGroups) sm.glist[slot] = (uint16_t)tid;
+      }
+    }
+    __syncthreads();
+    const int ngroup = sm.ngroup;
+    const uint32_t nfine = (uint32_t)min(ngroup, kQMaxGroups) * (uint32_t)kQBinsPerThread;
+    for (uint32_t idx = tid; idx < nfine; idx += kQThreads) {
+      const uint32_t gid = sm.glist[idx / kQBinsPerThread], j = idx % kQBinsPerThread;
+      const uint32_t b = gid * kQBinsPerThread + j, cnt = sm.hcnt[b];
+      if (cnt == 0u) continue;
+      uint32_t excl = gexcl[gid];
+      double pref = gpref[gid];
+      for (uint32_t j1 = 0; j1 < j; ++j1) {
+        const uint32_t b1 = gid * kQBinsPerThread + j1, c1 = sm.hcnt[b1];
+        if (c1 != 0u) { excl += c1; pref += q_bin_sum(klo, b1, c1, sm.hrem[b1]); }
+      }
+      uint32_t nb = kNoKey;
+      for (uint32_t j2 = kQBinsPerThread - 1; j2 > j; --j2)
+        if (sm.hcnt[gid * kQBinsPerThread + j2] != 0u) nb = gid * kQBinsPerThread + j2;
+      if (nb == kNoKey) nb = gnext[gid];
+      test_bin(b, cnt, q_bin_sum(klo, b, cnt, sm.hrem[b]), excl, pref, nb);
+    }
+    __syncthreads();
+    const int nflag = sm.nflag;
+    if (nflag > 1 && nflag <= kQMaxFlag && tid < nflag) {
+      const uint32_t mine = sm.fbin[tid];
+      int rk = 0;
+      for (int i = 0; i < nflag; ++i) rk += (sm.fbin[i] < mine) ? 1 : 0;   // bins are distinct
+      sm.ford[rk] = tid;
+    } else if (nflag == 1 && tid == 0) {
+      sm.ford[0] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sm.s_tot = s_tot; sm.q_tot = q_tot; sm.kmin = kmin; sm.kmax = kmax;
+      int status = 0;
+      if (n < 3u) status = 1;
+      if (ngroup > kQMaxGroups || nflag > kQMaxFlag) status = 2;
+      // everything below the bin window is one pseudo bin: if it could hold a candidate the row needs finer
+      // treatment there (never seen on clamped BatchNorm outputs)
+      if (status == 0 && cnt_below != 0u) {
+        uint32_t fb = kNoKey;
+        for (int w = 0; w < kQThreads / 32 && fb == kNoKey; ++w) fb = sm.wfirst[w];
+        const float nxt_hi = (fb != kNoKey) ? bin_upper(fb) : key_val(kmax);
+        if (may_hold<TERN>(0u, klo - 1u, cnt_below, sum_below, 0u, 0.0, nxt_hi, n, s_tot, kmax, 0.0f)) status = 3;
+      }
+      int nr = 0;
+      uint32_t total = 0u;
+      if (status == 0) {
+        // a flagged bin is collected together with the next non-empty bin, whose smallest key is the exact successor
+        // of the flagged bin's last element in the candidate test (the successor's own bin was tested and cannot hold
+        // a candidate whatever follows it)
+        Range* R = sm.rng;
+        for (int i = 0; i < nflag; ++i) {
+          const int sl = sm.ford[i];
+          const uint32_t b = sm.fbin[sl], ex = sm.fexcl[sl], nb = sm.fnb[sl];
+          const uint32_t hi = (nb != kNoKey) ? nb : b;
+          const uint32_t cnt = sm.hcnt[b] + ((nb != kNoKey) ? sm.hcnt[nb] : 0u);
+          if (nr > 0 && b <= R[nr - 1].bhi) {
+            // b is the successor bin of the previous flagged bin (already counted): extend by b's own successor
+            if (hi > R[nr - 1].bhi) { R[nr - 1].count += (nb != kNoKey) ? sm.hcnt[nb] : 0u; R[nr - 1].bhi = hi; }
+          } else if (nr < kMaxRanges) {
+            R[nr].blo = b; R[nr].bhi = hi; R[nr].cnt_below = ex; R[nr].count = cnt;
+            R[nr].span.sum_below = sm.fsumb[sl];
+            ++nr;
+          } else {
+            // more runs than ranges: extend the last one over the gap (it then also holds unflagged bins)
+            uint32_t extra = 0u;
+            for (uint32_t bb = R[nr - 1].bhi + 1u; bb <= hi; ++bb) extra += sm.hcnt[bb];
+            R[nr - 1].count += extra; R[nr - 1].bhi = hi;
+          }
+        }
+        for (int gi = 0; gi < nr; ++gi) {
+          Range& r = R[gi];
+          r.span.klo = (unsigned long long)klo + ((unsigned long long)r.blo << kQShift);
+          r.span.khi = (unsigned long long)klo + ((unsigned long long)(r.bhi + 1u) << kQShift);
+          r.span.cnt_below = r.cnt_below;
+          // any key <= the true successor of the range's last element keeps the test of that element conservative
+          // (it lies in an unflagged bin and cannot be a candidate)
+          r.span.next_key = (uint32_t)min(r.span.khi, 0x7F800000ull);
+          r.list_start = total;
+          total += r.count;
+        }
+        if (total > (uint32_t)kQListCap) status = 4;
+      }
+      sm.nrange = nr; sm.want_list = total; sm.status = status;
+    }
+    __syncthreads();
+  }
+  csync();
+
+  // ---- collect: exact keys of the sampled elements in the flagged ranges -> rank 0's list ---------------------------
+  int status = r0->status;
+  {
+    const int nr = (status == 0) ? r0->nrange : 0;
+    uint32_t blo[kMaxRanges], bhi[kMaxRanges];
+#pragma unroll
+    for (int gi = 0; gi < kMaxRanges; ++gi) {
+      blo[gi] = (gi < nr) ? r0->rng[gi].blo : 1u;
+      bhi[gi] = (gi < nr) ? r0->rng[gi].bhi : 0u;
+    }
+    if (nr > 0) {
+      const uint32_t ns_cta = 4u * (g_hi - g_lo);
+      for (uint32_t s4 = 4u * tid; s4 < ns_cta; s4 += 4u * kQThreads) {
+        const uint2 w = *reinterpret_cast<const uint2*>(&sm.ids[s4]);
+        const uint32_t id4[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t id = id4[j];
+          bool hit = false;
+#pragma unroll
+          for (int gi = 0; gi < kMaxRanges; ++gi) hit = hit || (id >= blo[gi] && id <= bhi[gi]);
+          if (hit) {
+            const unsigned long long idx = 3ull * (4ull * g_lo + s4 + j);
+            const uint32_t c = q_channel(qp, idx);
+            const float2 k = sm.ab[c];
+            const float a = fabsf(clamp_sym(fmaf(__ldg(xr + idx), k.x, k.y), alpha));
+            const uint32_t pos = atomicAdd(&r0->nlist, 1u);
+            if (pos < (uint32_t)kQListCap) r0->list[pos] = __float_as_uint(a);
+          }
+        }
+      }
+    }
+  }
+  csync();
+
+  // ---- rank 0: sort, the reference's candidate test on every collected element, closed-form cost -> v1 --------------
+  if (rank == 0) {
+    if (status == 0 && sm.nlist != sm.want_list) {     // cannot happen: the histogram and the bin indices disagree
+      status = 5;
+      if (tid == 0) sm.status = 5;
+    }
+    if (status == 0) {
+      const uint32_t L = sm.nlist;
+      Best best{1e300, 0xFFFFFFFFu, 0u};
+      uint32_t ncand = 0u;
+      const double s_tot = sm.s_tot, q_tot = sm.q_tot;
+      if (L > 0u) {
+        uint32_t lp = 2;
+        while (lp < L) lp <<= 1;
+        for (uint32_t e = L + tid; e < lp; e += kQThreads) sm.list[e] = kNoKey;
+        __syncthreads();
+        bitonic_sort(sm.list, lp);
+        evaluate_list<TERN>(sm, sm.list, L, sm.nrange, n, s_tot, q_tot, best, ncand);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double oc = __shfl_xor_sync(0xffffffffu, best.cost, o);
+        const uint32_t op = __shfl_xor_sync(0xffffffffu, best.pos, o);
+        const uint32_t ok = __shfl_xor_sync(0xffffffffu, best.key, o);
+        best.offer(oc, op, ok);
+      }
+      ncand = (uint32_t)__reduce_add_sync(0xffffffffu, ncand);
+      if (lane == 0) {
+        sm.best_cost[wid] = best.cost; sm.best_pos[wid] = best.pos; sm.best_key[wid] = best.key;
+        atomicAdd(&sm.ncand, ncand);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        Best b{1e300, 0xFFFFFFFFu, 0u};
+        for (int w = 0; w < kQThreads / 32; ++w) b.offer(sm.best_cost[w], sm.best_pos[w], sm.best_key[w]);
+        uint32_t nc_tot = sm.ncand;
+        if (TERN) {
+          // optimal.py:86-118: when min > mean/2 the value mean/2 (not a data element) is appended last
+          const float mean = (float)(s_tot / (double)n);
+          const float half_mean = __fmul_rn(0.5f, mean);
+          if (key_val(sm.kmin) > half_mean) {
+            ++nc_tot;
+            b.offer(closed_cost2<true>((double)half_mean, 0.0, 0.0, (double)n, s_tot, q_tot), n, __float_as_uint(half_mean));
+          }
+        }
+        const float v1 = (nc_tot > 0u) ? key_val(b.key) : 0.0f;
+        sm.v1 = v1;
+        scales[row] = v1;
+        if (TERN) scales[(long long)g.n + row] = v1;
+        sm.ncand = nc_tot;
+      }
+    }
+    if (tid == 0) {
+      row_status[row] = sm.status;
+      if (diag) {
+        int* d = diag + row * 8;
+        d[0] = sm.status; d[1] = sm.nflag; d[2] = (int)sm.nlist; d[3] = (int)sm.ncand; d[4] = sm.nrange; d[5] = cs;
+        d[6] = (int)sm.part_cb[0]; d[7] = sm.ngroup;
+      }
+    }
+    __syncthreads();
+  }
+  csync();
+  status = r0->status;
+  const float v1 = r0->v1;
+  csync();                          // rank 0 must not leave (and release its shared memory) before everyone has read
+  if (status != 0) return;          // the generic kernels redo this row (uniform over the cluster)
+
+  // ---- sweep 2 (L2): both sign planes and sum |x - v1 sign(x)| ----------------------------------------------------
+  {
+    const float sc[2] = {v1, 0.0f};
+    const int s = (int)row;
+    const uint32_t it_lo = (uint32_t)(((unsigned long long)qp.nitems * (unsigned)rank) / (unsigned)cs);
+    const uint32_t it_hi = (uint32_t)(((unsigned long long)qp.nitems * (unsigned)(rank + 1)) / (unsigned)cs);
+    double acc_sum = 0.0;
+    for (uint32_t item = it_lo + tid; item < it_hi; item += kQThreads) {
+      const int cgi = (int)(item / qp.nq), q = (int)(item - (uint32_t)cgi * qp.nq);
+      const int p0 = q * VEC;
+      const int cbase = cgi * 32;
+      const int cn = min(32, g.c - cbase);
+      const float* xp = xr + (long long)cbase * qp.hw + p0;
+      uint32_t word[VEC][2];
+      float gsum[VEC];
+      if (cn == 32) encode_group<2, VEC, true>(xp, (long long)qp.hw, cn, sm.ab + cbase, alpha, sc, 1, word, gsum);
+      else encode_group<2, VEC, false>(xp, (long long)qp.hw, cn, sm.ab + cbase, alpha, sc, 1, word, gsum);
+      int yi = p0 / g.w, xi = p0 - yi * g.w;
+#pragma unroll
+      for (int p = 0; p < VEC; ++p) {
+        if (p0 + p < (int)qp.hw) {
+          int phase = 0, a = yi, b = xi;
+          if (g.nphase == 4) { phase = ((yi & 1) << 1) | (xi & 1); a = yi >> 1; b = xi >> 1; }
+          const long long v = vpos(g, s, a, b);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            planes[(((long long)j * g.nphase + phase) * g.vtot + v) * g.cw + cgi] = word[p][j];
+          acc_sum += (double)gsum[p];
+        }
+        if (++xi == g.w) { xi = 0; ++yi; }
+      }
+    }
+    if (!TERN) {
+      const double tot = block_sum(acc_sum, sm.red);
+      if (tid == 0) r0->part_v2[rank] = tot;
+      csync();
+      if (rank == 0 && tid == 0) {
+        double t = 0.0;
+        for (int q = 0; q < cs; ++q) t += sm.part_v2[q];
+        scales[(long long)g.n + row] = (float)(t / (double)qp.len);
+      }
+    }
+  }
+}
+
+}  // namespace lsq
+
+using namespace lsq;
+
+// implemented in lsq_solve.cu / lsq_quant.cu: the generic kernels restricted to the rows marked in d_row_status
+namespace lsq {
+int solve_v1_marked_rows(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha, float* d_v1,
+                         float* d_v1_dup, const lsq_prologue* pro, const int* d_row_status, cudaStream_t stream);
+int encode_act_marked_rows(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
+                           int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
+                           const lsq_prologue* pro, const int* d_row_status, cudaStream_t stream);
+}
+
+// cluster size for rows of `len` elements: the CTA's share of the sampled row must fit its bin-index buffer, and the
+// rows in flight (two CTAs per SM) should stay L2 resident between the two sweeps
+static int qact_cluster_size(int64_t len, int sms) {
+  static const int forced = getenv("LSQ_QACT_CS") ? atoi(getenv("LSQ_QACT_CS")) : 0;   // development override
+  const int64_t groups = (len + 11) / 12;
+  int cs = 1;
+  while (cs < kQMaxCluster && 4 * ((groups + cs - 1) / cs + 1) > (int64_t)kQIdsCap) cs <<= 1;
+  const double l2_budget = 64.0 * 1024 * 1024;
+  while (cs < kQMaxCluster && (double)len * 4.0 * (2.0 * sms / cs) > l2_budget) cs <<= 1;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
+    if (4 * ((groups + forced - 1) / forced + 1) <= (int64_t)kQIdsCap) cs = forced;
+  }
+  return cs;
+}
+
+static bool qact_fast_path(const lsq_act_geom* g, float alpha, int skip) {
+  static const bool off = getenv("LSQ_QACT_OFF") != nullptr;      // development: always take the generic kernels
+  if (off) return false;
+  const int64_t len = (int64_t)g->c * g->h * g->w;
+  if (skip != 3 || !(alpha >= 1e-30f) || !(alpha < 3e38f)) return false;
+  if (len < 2048 || (len + 2) / 3 > 131071) return false;       // short rows: the sorting kernel; 32-bit bin sums
+  if (g->cw * 32 > kQMaxChannels) return false;
+  const int64_t groups = (len + 11) / 12;
+  if (4 * ((groups + kQMaxCluster - 1) / kQMaxCluster + 1) > (int64_t)kQIdsCap) return false;
+  return true;
+}
+
+extern "C" size_t lsq_quantize_act_workspace_bytes(const lsq_act_geom* g) {
+  if (!g) return 0;
+  return (size_t)g->n * sizeof(int) + 256 + lsq_reduce_workspace_bytes(g->n, (int64_t)g->c * g->h * g->w);
+}
+
+extern "C" int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float alpha, int ternary, int skip,
+                                uint32_t* d_planes, float* d_scales, void* d_ws, size_t ws_bytes,
+                                const lsq_prologue* pro, int32_t* d_diag, void* stream) {
+  LSQ_CHECK_ARG(d_x && g && d_planes && d_scales && d_ws, "lsq_quantize_act: null pointer");
+  LSQ_CHECK_ARG(skip >= 1, "lsq_quantize_act: bad skip %d", skip);
+  if (ws_bytes < lsq_quantize_act_workspace_bytes(g)) {
+    set_error("lsq_quantize_act: workspace %zu < %zu", ws_bytes, lsq_quantize_act_workspace_bytes(g));
+    return LSQ_ERR_WORKSPACE;
+  }
+  const int64_t len = (int64_t)g->c * g->h * g->w;
+  if (pro && pro->d_ch_scale && (pro->channels != g->c || pro->inner != (int64_t)g->h * g->w)) {
+    set_error("lsq_quantize_act: prologue must have %d channels of %d elements", g->c, g->h * g->w);
+    return LSQ_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // workspace: [reduce workspace of the encoder (arrival counters first, zero at rest)][row status, one int per row]
+  const size_t red_bytes = (lsq_reduce_workspace_bytes(g->n, len) + 255) / 256 * 256;
+  int* d_status = (int*)((char*)d_ws + red_bytes);
+  float* d_v2 = ternary ? nullptr : d_scales + g->n;
+  if (!qact_fast_path(g, alpha, skip)) {
+    // not the shape the fused kernel is built for: the generic kernels on every row (d_row_status = NULL)
+    int rc = solve_v1_marked_rows(d_x, g->n, len, skip, ternary, alpha, d_scales, ternary ? d_scales + g->n : nullptr,
+                                  pro, nullptr, st);
+    if (rc != LSQ_OK) return rc;
+    return encode_act_marked_rows(d_x, g, alpha, d_scales, 1, 2, d_planes, d_v2, d_ws, red_bytes, pro, nullptr, st);
+  }
+  const int sms = device_sms();
+  const int cs = qact_cluster_size(len, sms);
+  QParams qp;
+  qp.len = len; qp.n_s = (uint32_t)((len + 2) / 3); qp.groups = (uint32_t)((len + 11) / 12);
+  const uint32_t ka = __builtin_bit_cast(uint32_t, alpha) >> kQShift;
+  qp.klo = (ka + 1u - (uint32_t)kQBins) << kQShift;
+  qp.hw = (uint32_t)(g->h * g->w);
+  const bool vec4 = (qp.hw % 4 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0);
+  qp.nq = vec4 ? qp.hw / 4 : qp.hw;
+  qp.nitems = qp.nq * (uint32_t)g->cw;
+  qp.hw_magic = ((double)len * (double)qp.hw <= 1099511627776.0) ? ((1ull << 40) + qp.hw - 1ull) / qp.hw : 0ull;
+  const ActGeom dg = to_dev(*g);
+  const Prologue dp = to_dev(pro);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((int64_t)g->n * cs));
+  cfg.blockDim = dim3(kQThreads);
+  cfg.dynamicSmemBytes = sizeof(QSmem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
+  cudaError_t e = cudaSuccess;
+#define LSQ_QACT(T, V)                                                                                             \
+  do {                                                                                                             \
+    static std::atomic<unsigned long long> smem_set{0ull};                                                         \
+    e = ensure_max_smem(quant_act_kernel<T, V>, smem_set);                                                         \
+    if (e == cudaSuccess)                                                                                          \
+      e = cudaLaunchKernelEx(&cfg, quant_act_kernel<T, V>, d_x, dg, alpha, dp, cs, qp, d_planes, d_scales, d_status, \
+                             (int*)d_diag);                                                                        \
+  } while (0)
+  if (ternary) { if (vec4) LSQ_QACT(true, 4); else LSQ_QACT(true, 1); }
+  else { if (vec4) LSQ_QACT(false, 4); else LSQ_QACT(false, 1); }
+#undef LSQ_QACT
+  if (e != cudaSuccess) {
+    set_error("lsq_quantize_act: launch (cluster %d): %s", cs, cudaGetErrorString(e));
+    return LSQ_ERR_CUDA;
+  }
+  LSQ_CUDA_LAUNCH_CHECK("quant_act_kernel");
+  // rows the fused kernel could not decide (normally none): generic solve + encode on the marked rows only
+  int rc = solve_v1_marked_rows(d_x, g->n, len, skip, ternary, alpha, d_scales, ternary ? d_scales + g->n : nullptr,
+                                pro, d_status, st);
+  if (rc != LSQ_OK) return rc;
+  return encode_act_marked_rows(d_x, g, alpha, d_scales, 1, 2, d_planes, d_v2, d_ws, red_bytes, pro, d_status, st);
+}

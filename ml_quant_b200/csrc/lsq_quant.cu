@@ -11,6 +11,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include "lsq_common.cuh"
+#include "lsq_encode_core.cuh"
 
 namespace lsq {
 
@@ -121,79 +122,15 @@ __global__ void ste_backward_kernel(const float* __restrict__ x, const float* __
   }
 }
 
-// Activation encoder.  One work item = VEC consecutive pixels x one 32-channel group: the thread loads the
-// 32 channels (VEC = 4: one 16-byte load per channel, coalesced along W of the NCHW input, 8 loads in
-// flight), folds the per-channel affine prologue and the clamp, and shifts one sign bit per element and plane
-// into a register word with a funnel shift (channels are walked from 31 down to 0, so channel c lands on bit
-// c).  The sign bit IS the reference's sign(x) = [x >= 0] because no value tested here can be -0.0: the
-// prologue is always applied as fma(x, a, b) with b = -0.0 replaced by +0.0 (identity: a = 1, b = +0.0, which
-// maps -0.0 to +0.0 and every other float to itself), and u - v is never -0.0 for u != -0.0.
-// s * sign(d) is formed exactly by xor-ing d's sign bit into s.
-template <int NPL, int VEC, bool FULL>
-__device__ __forceinline__ void encode_group(const float* __restrict__ xp, long long cstride, int cn,
-                                             const float2* __restrict__ ab, float alpha, const float (&sc)[NPL], int ns,
-                                             uint32_t (&word)[VEC][NPL], float (&gsum)[VEC]) {
-#pragma unroll
-  for (int p = 0; p < VEC; ++p) {
-    gsum[p] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) word[p][j] = 0u;
-  }
-  constexpr int kBatch = 8;
-#pragma unroll 1
-  for (int c0 = 32 - kBatch; c0 >= 0; c0 -= kBatch) {
-    float raw[kBatch][VEC];
-#pragma unroll
-    for (int u = kBatch - 1; u >= 0; --u) {
-      const int cc = c0 + u;
-      if (FULL || cc < cn) {
-        if (VEC == 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(xp + (long long)cc * cstride));
-          raw[u][0] = t.x; raw[u][1 % VEC] = t.y; raw[u][2 % VEC] = t.z; raw[u][3 % VEC] = t.w;
-        } else {
-          raw[u][0] = __ldg(xp + (long long)cc * cstride);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = kBatch - 1; u >= 0; --u) {
-      const int cc = c0 + u;
-      const bool have = FULL || cc < cn;
-      const float2 k = have ? ab[cc] : make_float2(0.0f, 0.0f);
-#pragma unroll
-      for (int p = 0; p < VEC; ++p) {
-        if (!have) {   // channel beyond C: bit 0 in every plane, nothing added to the residual sum
-#pragma unroll
-          for (int j = 0; j < NPL; ++j) word[p][j] = __funnelshift_l(0x80000000u, word[p][j], 1);
-          continue;
-        }
-        const float val = clamp_sym(fmaf(raw[u][p], k.x, k.y), alpha);
-        float acc = 0.0f, res = val;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-          const float d = (j == 0) ? val : __fsub_rn(val, acc);
-          word[p][j] = __funnelshift_l(__float_as_uint(d), word[p][j], 1);
-          if (j < ns) {
-            const float t = __uint_as_float(__float_as_uint(sc[j]) ^ (__float_as_uint(d) & 0x80000000u));
-            acc = (j == 0) ? t : __fadd_rn(acc, t);
-            res = __fsub_rn(res, __uint_as_float(__float_as_uint(sc[j]) ^ (__float_as_uint(res) & 0x80000000u)));
-          }
-        }
-        gsum[p] += fabsf(res);
-      }
-    }
-  }
-#pragma unroll
-  for (int p = 0; p < VEC; ++p)
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) word[p][j] = ~word[p][j];
-}
-
 template <int NPL, int VEC>
 __global__ void __launch_bounds__(kEncThreads, 8)
 encode_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, const float* __restrict__ scales,
                   int ns, uint32_t* __restrict__ planes, double* __restrict__ partial,
-                  unsigned* __restrict__ counter, float* __restrict__ last_scale, Prologue pro, int s0) {
+                  unsigned* __restrict__ counter, float* __restrict__ last_scale, Prologue pro, int s0,
+                  const int* __restrict__ row_status) {
+  // row_status != NULL: only the samples marked non-zero are encoded (rows the fused quantizer of lsq_qact.cu left
+  // to the generic kernels)
+  if (row_status && row_status[s0 + blockIdx.y] == 0) return;
   __shared__ double red[32];
   __shared__ bool last;
   extern __shared__ float2 ab[];            // per-channel (scale, shift), padded to a multiple of 32 channels
@@ -445,9 +382,32 @@ int lsq_encode_act(const float* d_x, const lsq_act_geom* g, float alpha, const f
   return lsq_encode_act_ex(d_x, g, alpha, d_scales, nscales, nplanes, d_planes, d_last_scale, d_ws, ws_bytes, nullptr, stream);
 }
 
+static int encode_act_launch(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
+                             int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
+                             const lsq_prologue* pro, const int* d_row_status, void* stream);
+
 int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
                       int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
                       const lsq_prologue* pro, void* stream) {
+  return encode_act_launch(d_x, g, alpha, d_scales, nscales, nplanes, d_planes, d_last_scale, d_ws, ws_bytes, pro, nullptr, stream);
+}
+
+}  // extern "C"
+
+namespace lsq {
+int encode_act_marked_rows(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
+                           int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
+                           const lsq_prologue* pro, const int* d_row_status, cudaStream_t stream) {
+  return encode_act_launch(d_x, g, alpha, d_scales, nscales, nplanes, d_planes, d_last_scale, d_ws, ws_bytes, pro,
+                           d_row_status, (void*)stream);
+}
+}  // namespace lsq
+
+extern "C" {
+
+static int encode_act_launch(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
+                             int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
+                             const lsq_prologue* pro, const int* d_row_status, void* stream) {
   LSQ_CHECK_ARG(d_x && g && d_planes, "lsq_encode_act: null pointer");
   LSQ_CHECK_ARG(nplanes >= 1 && nplanes <= 4, "lsq_encode_act: nplanes %d not in [1,4]", nplanes);
   LSQ_CHECK_ARG(nscales >= 0 && nscales <= nplanes && (nscales == 0 || d_scales), "lsq_encode_act: bad nscales %d", nscales);
@@ -475,7 +435,7 @@ int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alpha, cons
   for (int s0 = 0; s0 < g->n; s0 += (int)kMaxGridRows) {      // samples ride on gridDim.y (<= 65535)
     const int ns_chunk = g->n - s0 < (int)kMaxGridRows ? g->n - s0 : (int)kMaxGridRows;
     dim3 grid((unsigned)(((long long)nq * g->cw + kEncThreads - 1) / kEncThreads), (unsigned)ns_chunk);
-#define LSQ_ENC(NPL, VEC) encode_act_kernel<NPL, VEC><<<grid, kEncThreads, smem, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp, s0)
+#define LSQ_ENC(NPL, VEC) encode_act_kernel<NPL, VEC><<<grid, kEncThreads, smem, st>>>(d_x, dg, alpha, d_scales, nscales, d_planes, partial, counter, d_last_scale, dp, s0, d_row_status)
     switch (nplanes * 2 + (vec4 ? 1 : 0)) {
       case 2: LSQ_ENC(1, 1); break;
       case 3: LSQ_ENC(1, 4); break;

@@ -240,6 +240,31 @@ def encode_act(x: torch.Tensor, g: _C.ActGeom, scales: Sequence[torch.Tensor], n
     return planes, nxt
 
 
+def quantize_act(x: torch.Tensor, g: _C.ActGeom, ternary: bool, alpha: Optional[float] = None, skip: int = 3,
+                 planes: Optional[torch.Tensor] = None, prologue=None, table: Optional[torch.Tensor] = None,
+                 diag: bool = False):
+    """Fused ls-2 / ls-T activation quantizer (lsq_quantize_act): x [n,c,h,w] -> (bit planes, scale table [2, n])
+    with one read of x from HBM; ``diag=True`` also returns the int32 [n, 8] per-row diagnostics."""
+    require_cuda(x)
+    x = x.contiguous()
+    L = _C.lib()
+    nbytes = L.lsq_act_planes_bytes(C.byref(g), 2)
+    if planes is None or planes.numel() * 4 < nbytes:
+        planes = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=x.device)
+    if table is None:
+        table = torch.empty(2, g.n, dtype=torch.float32, device=x.device)
+    elif tuple(table.shape) != (2, g.n) or table.dtype != torch.float32 or not table.is_contiguous() or table.device != x.device:
+        raise ValueError(f'table must be a contiguous float32 [2, {g.n}] tensor on {x.device}')
+    ws = workspace(x.device, L.lsq_quantize_act_workspace_bytes(C.byref(g)))
+    dg = torch.zeros(g.n, 8, dtype=torch.int32, device=x.device) if diag else None
+    with torch.cuda.device(x.device), _launch('quant_act', x.numel() * (4.0 + 2.0 / 8.0)):
+        keep = []
+        _C.check(L.lsq_quantize_act(x.data_ptr(), C.byref(g), _alpha(alpha), int(bool(ternary)), int(skip),
+                                    planes.data_ptr(), table.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _prologue(prologue, keep), _ptr(dg), _stream()), 'lsq_quantize_act')
+    return (planes, table, dg) if diag else (planes, table)
+
+
 def pack_weights(w: torch.Tensor) -> torch.Tensor:
     """sign(W) images for the convolution kernels (lsq_pack_weights)."""
     require_cuda(w, 'weight')
