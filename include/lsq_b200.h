@@ -178,8 +178,9 @@ LSQ_API int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alp
  *   v1 obeys the same solver contract, planes are bit-exact given v1, v2 agrees to fp32 rounding.
  * d_scales: float[2][n] (row 0 = v1; row 1 = v2, or v1 again for the ternary scheme) -- the table lsq_bconv2d_fwd reads.
  * d_ws: lsq_quantize_act_workspace_bytes(g) bytes whose first 256 KiB were zero-filled once (as for
- * lsq_reduce_workspace_bytes; the call leaves them zeroed).  d_diag (optional): int32[n][8] per-row diagnostics
- * {status, flagged bins, collected elements, candidates, ranges, cluster size, elements below the bin window, groups}.
+ * lsq_reduce_workspace_bytes; the call leaves them zeroed).  d_diag (optional): int32[n][16] per-row diagnostics
+ * {status, flagged bins, collected elements, candidates, ranges, cluster size, elements below the bin window, groups,
+ *  7 per-phase cycle counts of the cluster's first CTA, SM id}.
  * One thread-block cluster per sample keeps the row L2-resident between the histogram sweep and the encoding sweep;
  * samples the fused kernel cannot decide are redone by the generic kernels inside this call. */
 LSQ_API size_t lsq_quantize_act_workspace_bytes(const lsq_act_geom* g);

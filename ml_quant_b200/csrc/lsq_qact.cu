@@ -55,11 +55,16 @@ struct QParams {
   unsigned long long hw_magic;   // ceil(2^40 / hw), or 0: divide exactly
 };
 
+constexpr int kQSegMax = 256;                         // elements of one flagged bin a warp sorts
 struct QSmem {
   uint32_t hcnt[kQBins];
-  uint32_t hrem[kQBins];
+  union {
+    uint32_t hrem[kQBins];         // sweep 1 .. flagging: sum of the low key bits per bin
+    uint8_t fmap[kQBins];          // afterwards: bin -> 1 + flagged index, or 65 + index of the flagged bin it follows
+  };
   uint16_t ids[kQIdsCap];
-  uint32_t list[kQListCap];        // rank 0: collected keys; during the scan: per-thread group prefixes
+  uint32_t list[kQListCap];        // collected keys, one power-of-two padded segment per flagged bin (layout shared by
+                                   // all CTAs of the cluster); during the scan: per-thread group prefixes
   float2 ab[kQMaxChannels];
   double red[32];
   double wsum[32];
@@ -72,17 +77,20 @@ struct QSmem {
   uint32_t kmin, kmax, cb;
   int nflag, ngroup;
   uint16_t glist[kQMaxGroups];
+  // flagged bins as found (unordered) ...
   uint16_t fbin[kQMaxFlag];
   uint32_t fexcl[kQMaxFlag], fnb[kQMaxFlag];
   double fsumb[kQMaxFlag];
   int ford[kQMaxFlag];
-  int nrange;
-  Range rng[kMaxRanges];
-  double seg_base[kMaxRanges];
-  uint32_t nlist, want_list;
+  // ... and in ascending order, with their list segments
+  uint16_t sbin[kQMaxFlag], snb[kQMaxFlag];       // bin, next non-empty bin (0xFFFF: none)
+  uint32_t sexcl[kQMaxFlag], seg_start[kQMaxFlag], seg_cnt[kQMaxFlag];
+  double spref[kQMaxFlag];
+  uint32_t lfill[kQMaxFlag], lsmin[kQMaxFlag];    // this CTA: elements collected per segment, smallest key of the follower bin
+  uint32_t nlist;
   int status;                      // 0 = solved here, != 0: reason the row goes to the generic kernels
   float v1;
-  double s_tot, q_tot;
+  double s_tot;
   double best_cost[32];
   uint32_t best_pos[32], best_key[32], ncand;
 };
@@ -93,13 +101,17 @@ __device__ __forceinline__ uint32_t q_channel(const QParams& qp, unsigned long l
   return qp.hw_magic ? (uint32_t)((idx * qp.hw_magic) >> 40) : (uint32_t)(idx / qp.hw);
 }
 
-// exact sum of the `cnt` keys of bin b (all share the exponent and the upper mantissa bits of the bin's first key)
-__device__ __forceinline__ double q_bin_sum(uint32_t klo, uint32_t b, uint32_t cnt, uint32_t rem) {
+// exact sum of the `cnt` keys of bin b as an integer multiple of the bin's ulp 2^(e-150): all keys of a bin share the
+// exponent e and the upper mantissa bits of the bin's first key; `rem` is the sum of their low 14 bits
+__device__ __forceinline__ unsigned long long q_bin_isum(uint32_t klo, uint32_t b, uint32_t cnt, uint32_t rem) {
   const uint32_t kb = klo + (b << kQShift);
-  const int e = (int)(kb >> 23);
-  const double msum = (double)cnt * (double)(kb & 0x7FFFFFu) + (double)rem;
-  if (e == 0) return msum * pow2d(-149);
-  return ((double)cnt * 8388608.0 + msum) * pow2d(e - 150);
+  return (unsigned long long)cnt * (unsigned long long)(0x800000u | (kb & 0x7FFFFFu)) + rem;
+}
+__device__ __forceinline__ double q_bin_scale(uint32_t klo, uint32_t b) {       // 2^(e-150) of bin b (e >= 1)
+  return pow2d((int)((klo + (b << kQShift)) >> 23) - 150);
+}
+__device__ __forceinline__ double q_bin_sum(uint32_t klo, uint32_t b, uint32_t cnt, uint32_t rem) {
+  return (double)q_bin_isum(klo, b, cnt, rem) * q_bin_scale(klo, b);
 }
 
 template <bool TERN, int VEC>
@@ -117,6 +129,11 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
   const float* xr = x + row * qp.len;
   const uint32_t klo = qp.klo, n = qp.n_s;
   auto csync = [&]() { if (cs > 1) cluster.sync(); else __syncthreads(); };
+  // phase cycle counters of rank 0 (diagnostics only: one clock read per phase by one thread)
+  long long tprev = 0, tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool timing = diag != nullptr && tid == 0 && rank == 0;
+  if (timing) tprev = clock64();
+#define LSQ_QTICK(i) do { if (timing) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; } } while (0)
 
   // ---- setup --------------------------------------------------------------------------------------------------
   for (int b = tid; b < kQBins; b += kQThreads) { sm.hcnt[b] = 0u; sm.hrem[b] = 0u; }
@@ -126,8 +143,8 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     sm.ab[c] = k;
   }
   if (tid == 0) {
-    sm.kmin = kNoKey; sm.kmax = 0u; sm.cb = 0u; sm.nflag = 0; sm.ngroup = 0; sm.nrange = 0; sm.nlist = 0u;
-    sm.want_list = 0u; sm.status = 0; sm.v1 = 0.0f; sm.ncand = 0u;
+    sm.kmin = kNoKey; sm.kmax = 0u; sm.cb = 0u; sm.nflag = 0; sm.ngroup = 0; sm.nlist = 0u;
+    sm.status = 0; sm.v1 = 0.0f; sm.ncand = 0u;
   }
   __syncthreads();
 
@@ -151,7 +168,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       ++cb; lb += (double)a;
       return kIdBelow;
     };
-    constexpr int kU = 3;   // groups per thread and trip: 12 independent loads in flight
+    constexpr int kU = 5;   // groups per thread and trip: 20 independent loads in flight
     for (uint32_t gb = g_lo + tid; gb < g_hi; gb += kU * kQThreads) {
       float raw[kU][4];
 #pragma unroll
@@ -194,7 +211,9 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       r0->part_sb[rank] = sb; r0->part_cb[rank] = sm.cb; r0->part_kmin[rank] = sm.kmin; r0->part_kmax[rank] = sm.kmax;
     }
   }
+  LSQ_QTICK(0);   // setup + sweep 1
   csync();
+  LSQ_QTICK(1);   // first cluster barrier (waits for the slowest CTA's sweep)
 
   // ---- merge: CTA r sums slice r of all histograms into rank 0's ---------------------------------------------------
   if (cs > 1) {
@@ -209,8 +228,9 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     }
     cluster.sync();
   }
+  LSQ_QTICK(2);   // merge
 
-  // ---- rank 0: scan the bins, flag those that can hold a candidate, build the ranges to collect ----------------------
+  // ---- rank 0: scan the bins, flag those that can hold a candidate, lay out one list segment per flagged bin -------
   if (rank == 0) {
     double sum_below = 0.0;
     uint32_t cnt_below = 0u, kmin = kNoKey, kmax = 0u;
@@ -218,17 +238,18 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       sum_below += sm.part_sb[q]; cnt_below += sm.part_cb[q];
       kmin = min(kmin, sm.part_kmin[q]); kmax = max(kmax, sm.part_kmax[q]);
     }
+    // a thread's 8 consecutive bins lie in one octave (512 bins, aligned): their sums add up as integers
     uint32_t ct = 0u, fn = kNoKey;
-    double stt = 0.0, stq = 0.0;
+    unsigned long long it = 0ull;
 #pragma unroll
     for (int j = 0; j < kQBinsPerThread; ++j) {
       const uint32_t b = tid * kQBinsPerThread + j, cnt = sm.hcnt[b];
       if (cnt != 0u) {
-        const double s = q_bin_sum(klo, b, cnt, sm.hrem[b]);
-        ct += cnt; stt += s; stq += s * s / (double)cnt;
+        ct += cnt; it += q_bin_isum(klo, b, cnt, sm.hrem[b]);
         if (fn == kNoKey) fn = b;
       }
     }
+    const double stt = (double)it * q_bin_scale(klo, tid * kQBinsPerThread);
     uint32_t ci = ct;
     double si = stt;
 #pragma unroll
@@ -257,8 +278,6 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     uint32_t nxt_after = nxt_in_warp;
     for (int w = wid + 1; w < kQThreads / 32 && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
     const double s_tot = sum_below + s_bins;
-    const double q_tot = block_sum(stq, sm.red);      // sum of squares up to the spread inside a bin: a constant
-                                                      // shared by every candidate's cost, it cannot move the arg-min
     const uint32_t excl0 = cnt_below + coff + ci - ct;
     const double pref0 = sum_below + soff + si - stt;
 
@@ -297,11 +316,12 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       const uint32_t b = gid * kQBinsPerThread + j, cnt = sm.hcnt[b];
       if (cnt == 0u) continue;
       uint32_t excl = gexcl[gid];
-      double pref = gpref[gid];
+      unsigned long long ib = 0ull;
       for (uint32_t j1 = 0; j1 < j; ++j1) {
         const uint32_t b1 = gid * kQBinsPerThread + j1, c1 = sm.hcnt[b1];
-        if (c1 != 0u) { excl += c1; pref += q_bin_sum(klo, b1, c1, sm.hrem[b1]); }
+        if (c1 != 0u) { excl += c1; ib += q_bin_isum(klo, b1, c1, sm.hrem[b1]); }
       }
+      const double pref = gpref[gid] + (double)ib * q_bin_scale(klo, b);
       uint32_t nb = kNoKey;
       for (uint32_t j2 = kQBinsPerThread - 1; j2 > j; --j2)
         if (sm.hcnt[gid * kQBinsPerThread + j2] != 0u) nb = gid * kQBinsPerThread + j2;
@@ -310,126 +330,169 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     }
     __syncthreads();
     const int nflag = sm.nflag;
-    if (nflag > 1 && nflag <= kQMaxFlag && tid < nflag) {
-      const uint32_t mine = sm.fbin[tid];
-      int rk = 0;
-      for (int i = 0; i < nflag; ++i) rk += (sm.fbin[i] < mine) ? 1 : 0;   // bins are distinct
-      sm.ford[rk] = tid;
-    } else if (nflag == 1 && tid == 0) {
-      sm.ford[0] = 0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      sm.s_tot = s_tot; sm.q_tot = q_tot; sm.kmin = kmin; sm.kmax = kmax;
-      int status = 0;
-      if (n < 3u) status = 1;
-      if (ngroup > kQMaxGroups || nflag > kQMaxFlag) status = 2;
+    // warps 0-1: ascending order of the flagged bins and one power-of-two padded list segment for each (two lanes
+    // steps of a 64-entry scan); warp 2: the pseudo bin below the window; in parallel
+    if (tid == 0) { sm.s_tot = s_tot; sm.kmin = kmin; sm.kmax = kmax; sm.nlist = 0u; }
+    int bad = 0;
+    if (n < 3u) bad = 1;
+    if (ngroup > kQMaxGroups || nflag > kQMaxFlag) bad = 2;
+    if (bad == 0 && wid == 0) {
+      uint32_t run = 0u;
+      for (int base = 0; base < nflag; base += 32) {
+        const int t = base + lane;
+        uint32_t lp = 0u, cnt = 0u;
+        int rk = 0;
+        if (t < nflag) {
+          const uint32_t mine = sm.fbin[t];
+          for (int i = 0; i < nflag; ++i) rk += (sm.fbin[i] < mine) ? 1 : 0;   // bins are distinct
+          cnt = sm.hcnt[mine];
+          lp = 2u;
+          while (lp < cnt) lp <<= 1;
+          if (cnt > (uint32_t)kQSegMax) bad = 4;
+          sm.sbin[rk] = (uint16_t)mine;
+          sm.snb[rk] = (sm.fnb[t] != kNoKey) ? (uint16_t)sm.fnb[t] : (uint16_t)0xFFFFu;
+          sm.sexcl[rk] = sm.fexcl[t]; sm.spref[rk] = sm.fsumb[t];
+          sm.seg_cnt[rk] = cnt;
+          sm.ford[rk] = (int)lp;         // padded size by rank, turned into offsets below
+        }
+      }
+      __syncwarp();
+      for (int base = 0; base < nflag; base += 32) {
+        const int t = base + lane;
+        const uint32_t lp = (t < nflag) ? (uint32_t)sm.ford[t] : 0u;
+        uint32_t inc = lp;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        if (t < nflag) sm.seg_start[t] = run + inc - lp;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      bad = __reduce_max_sync(0xffffffffu, bad);
+      if (bad == 0 && run > (uint32_t)kQListCap) bad = 4;
+      if (lane == 0) { sm.nlist = run; if (bad) atomicMax(&sm.status, bad); }
+    } else if (bad == 0 && wid == 2 && lane == 0 && cnt_below != 0u) {
       // everything below the bin window is one pseudo bin: if it could hold a candidate the row needs finer
       // treatment there (never seen on clamped BatchNorm outputs)
-      if (status == 0 && cnt_below != 0u) {
-        uint32_t fb = kNoKey;
-        for (int w = 0; w < kQThreads / 32 && fb == kNoKey; ++w) fb = sm.wfirst[w];
-        const float nxt_hi = (fb != kNoKey) ? bin_upper(fb) : key_val(kmax);
-        if (may_hold<TERN>(0u, klo - 1u, cnt_below, sum_below, 0u, 0.0, nxt_hi, n, s_tot, kmax, 0.0f)) status = 3;
-      }
-      int nr = 0;
-      uint32_t total = 0u;
-      if (status == 0) {
-        // a flagged bin is collected together with the next non-empty bin, whose smallest key is the exact successor
-        // of the flagged bin's last element in the candidate test (the successor's own bin was tested and cannot hold
-        // a candidate whatever follows it)
-        Range* R = sm.rng;
-        for (int i = 0; i < nflag; ++i) {
-          const int sl = sm.ford[i];
-          const uint32_t b = sm.fbin[sl], ex = sm.fexcl[sl], nb = sm.fnb[sl];
-          const uint32_t hi = (nb != kNoKey) ? nb : b;
-          const uint32_t cnt = sm.hcnt[b] + ((nb != kNoKey) ? sm.hcnt[nb] : 0u);
-          if (nr > 0 && b <= R[nr - 1].bhi) {
-            // b is the successor bin of the previous flagged bin (already counted): extend by b's own successor
-            if (hi > R[nr - 1].bhi) { R[nr - 1].count += (nb != kNoKey) ? sm.hcnt[nb] : 0u; R[nr - 1].bhi = hi; }
-          } else if (nr < kMaxRanges) {
-            R[nr].blo = b; R[nr].bhi = hi; R[nr].cnt_below = ex; R[nr].count = cnt;
-            R[nr].span.sum_below = sm.fsumb[sl];
-            ++nr;
-          } else {
-            // more runs than ranges: extend the last one over the gap (it then also holds unflagged bins)
-            uint32_t extra = 0u;
-            for (uint32_t bb = R[nr - 1].bhi + 1u; bb <= hi; ++bb) extra += sm.hcnt[bb];
-            R[nr - 1].count += extra; R[nr - 1].bhi = hi;
-          }
-        }
-        for (int gi = 0; gi < nr; ++gi) {
-          Range& r = R[gi];
-          r.span.klo = (unsigned long long)klo + ((unsigned long long)r.blo << kQShift);
-          r.span.khi = (unsigned long long)klo + ((unsigned long long)(r.bhi + 1u) << kQShift);
-          r.span.cnt_below = r.cnt_below;
-          // any key <= the true successor of the range's last element keeps the test of that element conservative
-          // (it lies in an unflagged bin and cannot be a candidate)
-          r.span.next_key = (uint32_t)min(r.span.khi, 0x7F800000ull);
-          r.list_start = total;
-          total += r.count;
-        }
-        if (total > (uint32_t)kQListCap) status = 4;
-      }
-      sm.nrange = nr; sm.want_list = total; sm.status = status;
+      uint32_t fb = kNoKey;
+      for (int w = 0; w < kQThreads / 32 && fb == kNoKey; ++w) fb = sm.wfirst[w];
+      const float nxt_hi = (fb != kNoKey) ? bin_upper(fb) : key_val(kmax);
+      if (may_hold<TERN>(0u, klo - 1u, cnt_below, sum_below, 0u, 0.0, nxt_hi, n, s_tot, kmax, 0.0f)) atomicMax(&sm.status, 3);
     }
+    if (bad != 0 && tid == 0) atomicMax(&sm.status, bad);
     __syncthreads();
   }
+  LSQ_QTICK(3);   // scan + flag + segments
   csync();
 
-  // ---- collect: exact keys of the sampled elements in the flagged ranges -> rank 0's list ---------------------------
+  // ---- collect: exact keys of the sampled elements of the flagged bins -> this CTA's copy of the segments ------------
   int status = r0->status;
-  {
-    const int nr = (status == 0) ? r0->nrange : 0;
-    uint32_t blo[kMaxRanges], bhi[kMaxRanges];
+  const int nflag = (status == 0) ? r0->nflag : 0;
+  if (nflag > 0) {
+    // every CTA: bin -> segment map (the histogram's remainder sums are dead by now)
+    for (int b = tid; b < kQBins / 4; b += kQThreads) reinterpret_cast<uint32_t*>(sm.fmap)[b] = 0u;
+    if (rank != 0 && tid < nflag) { sm.sbin[tid] = r0->sbin[tid]; sm.snb[tid] = r0->snb[tid]; sm.seg_start[tid] = r0->seg_start[tid]; }
+    if (tid < kQMaxFlag) { sm.lfill[tid] = 0u; sm.lsmin[tid] = kNoKey; }
+    __syncthreads();
+    if (tid < nflag && sm.snb[tid] != 0xFFFFu) sm.fmap[sm.snb[tid]] = (uint8_t)(65 + tid);
+    __syncthreads();
+    if (tid < nflag) sm.fmap[sm.sbin[tid]] = (uint8_t)(1 + tid);     // a flagged bin that follows another one is a segment
+    __syncthreads();
+    const uint32_t ns_cta = 4u * (g_hi - g_lo);
+    for (uint32_t s4 = 4u * tid; s4 < ns_cta; s4 += 4u * kQThreads) {
+      const uint2 w = *reinterpret_cast<const uint2*>(&sm.ids[s4]);
+      const uint32_t id4[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
-    for (int gi = 0; gi < kMaxRanges; ++gi) {
-      blo[gi] = (gi < nr) ? r0->rng[gi].blo : 1u;
-      bhi[gi] = (gi < nr) ? r0->rng[gi].bhi : 0u;
-    }
-    if (nr > 0) {
-      const uint32_t ns_cta = 4u * (g_hi - g_lo);
-      for (uint32_t s4 = 4u * tid; s4 < ns_cta; s4 += 4u * kQThreads) {
-        const uint2 w = *reinterpret_cast<const uint2*>(&sm.ids[s4]);
-        const uint32_t id4[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t id = id4[j];
-          bool hit = false;
-#pragma unroll
-          for (int gi = 0; gi < kMaxRanges; ++gi) hit = hit || (id >= blo[gi] && id <= bhi[gi]);
-          if (hit) {
-            const unsigned long long idx = 3ull * (4ull * g_lo + s4 + j);
-            const uint32_t c = q_channel(qp, idx);
-            const float2 k = sm.ab[c];
-            const float a = fabsf(clamp_sym(fmaf(__ldg(xr + idx), k.x, k.y), alpha));
-            const uint32_t pos = atomicAdd(&r0->nlist, 1u);
-            if (pos < (uint32_t)kQListCap) r0->list[pos] = __float_as_uint(a);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t id = id4[j];
+        const uint32_t m = (id < (uint32_t)kQBins) ? sm.fmap[id] : 0u;
+        if (m != 0u) {
+          const unsigned long long idx = 3ull * (4ull * g_lo + s4 + j);
+          const uint32_t c = q_channel(qp, idx);
+          const float2 k = sm.ab[c];
+          const uint32_t key = __float_as_uint(fabsf(clamp_sym(fmaf(__ldg(xr + idx), k.x, k.y), alpha)));
+          if (m <= 64u) {
+            const uint32_t pos = atomicAdd(&sm.lfill[m - 1u], 1u);
+            if (pos < (uint32_t)kQSegMax) sm.list[sm.seg_start[m - 1u] + pos] = key;
+          } else {
+            atomicMin(&sm.lsmin[m - 65u], key);
           }
         }
       }
     }
   }
   csync();
+  LSQ_QTICK(4);   // collect (incl. the barriers around it)
 
-  // ---- rank 0: sort, the reference's candidate test on every collected element, closed-form cost -> v1 --------------
+  // ---- rank 0: gather the segments, sort each in one warp, the reference's candidate test, closed-form cost -> v1 ---
   if (rank == 0) {
-    if (status == 0 && sm.nlist != sm.want_list) {     // cannot happen: the histogram and the bin indices disagree
-      status = 5;
-      if (tid == 0) sm.status = 5;
-    }
+    Best best{1e300, 0xFFFFFFFFu, 0u};
+    uint32_t ncand = 0u;
+    const double s_tot = sm.s_tot;
     if (status == 0) {
-      const uint32_t L = sm.nlist;
-      Best best{1e300, 0xFFFFFFFFu, 0u};
-      uint32_t ncand = 0u;
-      const double s_tot = sm.s_tot, q_tot = sm.q_tot;
-      if (L > 0u) {
+      for (int i = wid; i < nflag; i += kQThreads / 32) {
+        const uint32_t base = sm.seg_start[i], cnt = sm.seg_cnt[i];
+        uint32_t fill = sm.lfill[i], smin = sm.lsmin[i];
+        for (int q = 1; q < cs; ++q) {
+          const QSmem* p = cluster.map_shared_rank(&sm, q);
+          const uint32_t cq = p->lfill[i];
+          for (uint32_t e = lane; e < cq && fill + e < (uint32_t)kQSegMax; e += 32) sm.list[base + fill + e] = p->list[base + e];
+          fill += cq;
+          smin = min(smin, p->lsmin[i]);
+        }
         uint32_t lp = 2;
-        while (lp < L) lp <<= 1;
-        for (uint32_t e = L + tid; e < lp; e += kQThreads) sm.list[e] = kNoKey;
-        __syncthreads();
-        bitonic_sort(sm.list, lp);
-        evaluate_list<TERN>(sm, sm.list, L, sm.nrange, n, s_tot, q_tot, best, ncand);
+        while (lp < cnt) lp <<= 1;
+        for (uint32_t e = cnt + lane; e < lp; e += 32) sm.list[base + e] = kNoKey;
+        if (lane == 0) {
+          sm.lsmin[i] = smin;
+          if (fill != cnt) sm.status = 5;        // cannot happen: the histogram and the bin indices disagree
+        }
+        __syncwarp();
+        uint32_t* keys = sm.list + base;
+        for (uint32_t k = 2; k <= lp; k <<= 1)
+          for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = lane; t < (lp >> 1); t += 32) {
+              const uint32_t a0 = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+              const uint32_t p1 = a0 | j;
+              const uint32_t ka = keys[a0], kb = keys[p1];
+              const bool up = ((a0 & k) == 0);
+              if ((ka > kb) == up) { keys[a0] = kb; keys[p1] = ka; }
+            }
+            __syncwarp();
+          }
+      }
+    }
+    __syncthreads();
+    status = sm.status;
+    if (status == 0) {
+      for (int i = wid; i < nflag; i += kQThreads / 32) {
+        const uint32_t base = sm.seg_start[i], cnt = sm.seg_cnt[i];
+        const uint32_t* keys = sm.list + base;
+        // successor of the segment's last element: the smallest key of the next non-empty bin
+        uint32_t succ = sm.kmax;
+        const uint32_t nb = sm.snb[i];
+        if (nb != 0xFFFFu) {
+          const uint32_t m = sm.fmap[nb];
+          succ = (m >= 1u && m <= 64u) ? sm.list[sm.seg_start[m - 1u]] : sm.lsmin[i];
+        }
+        const uint32_t per = (cnt + 31u) / 32u;
+        const uint32_t j0 = min((uint32_t)lane * per, cnt), j1 = min(j0 + per, cnt);
+        double loc = 0.0;
+        for (uint32_t j = j0; j < j1; ++j) loc += (double)key_val(keys[j]);
+        double inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        double run = sm.spref[i] + inc - loc;
+        const uint32_t excl = sm.sexcl[i];
+        for (uint32_t j = j0; j < j1; ++j) {
+          const uint32_t kj = keys[j];
+          run += (double)key_val(kj);
+          try_position<TERN>(best, ncand, kj, (j + 1u < cnt) ? keys[j + 1u] : succ, excl + j, run, n, s_tot, 0.0);
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -454,7 +517,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
           const float half_mean = __fmul_rn(0.5f, mean);
           if (key_val(sm.kmin) > half_mean) {
             ++nc_tot;
-            b.offer(closed_cost2<true>((double)half_mean, 0.0, 0.0, (double)n, s_tot, q_tot), n, __float_as_uint(half_mean));
+            b.offer(closed_cost2<true>((double)half_mean, 0.0, 0.0, (double)n, s_tot, 0.0), n, __float_as_uint(half_mean));
           }
         }
         const float v1 = (nc_tot > 0u) ? key_val(b.key) : 0.0f;
@@ -467,13 +530,14 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     if (tid == 0) {
       row_status[row] = sm.status;
       if (diag) {
-        int* d = diag + row * 8;
-        d[0] = sm.status; d[1] = sm.nflag; d[2] = (int)sm.nlist; d[3] = (int)sm.ncand; d[4] = sm.nrange; d[5] = cs;
+        int* d = diag + row * 16;
+        d[0] = sm.status; d[1] = sm.nflag; d[2] = (int)sm.nlist; d[3] = (int)sm.ncand; d[4] = 0; d[5] = cs;
         d[6] = (int)sm.part_cb[0]; d[7] = sm.ngroup;
       }
     }
     __syncthreads();
   }
+  LSQ_QTICK(5);   // sort + evaluate
   csync();
   status = r0->status;
   const float v1 = r0->v1;
@@ -523,6 +587,15 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       }
     }
   }
+  LSQ_QTICK(6);   // sweep 2 (+ barriers)
+  if (timing) {
+    int* d = diag + row * 16;
+    for (int i = 0; i < 7; ++i) d[8 + i] = (int)tph[i];
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    d[15] = (int)smid;
+  }
+#undef LSQ_QTICK
 }
 
 }  // namespace lsq
@@ -601,7 +674,9 @@ extern "C" int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float a
   QParams qp;
   qp.len = len; qp.n_s = (uint32_t)((len + 2) / 3); qp.groups = (uint32_t)((len + 11) / 12);
   const uint32_t ka = __builtin_bit_cast(uint32_t, alpha) >> kQShift;
-  qp.klo = (ka + 1u - (uint32_t)kQBins) << kQShift;
+  // window of kQBins bins whose last bin holds key(alpha); its first bin is rounded up to a multiple of 8 absolute
+  // bins so that the 8 consecutive bins a thread scans never straddle an octave (exponent) boundary
+  qp.klo = (((ka + 1u - (uint32_t)kQBins) + 7u) & ~7u) << kQShift;
   qp.hw = (uint32_t)(g->h * g->w);
   const bool vec4 = (qp.hw % 4 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0);
   qp.nq = vec4 ? qp.hw / 4 : qp.hw;

@@ -244,7 +244,7 @@ def quantize_act(x: torch.Tensor, g: _C.ActGeom, ternary: bool, alpha: Optional[
                  planes: Optional[torch.Tensor] = None, prologue=None, table: Optional[torch.Tensor] = None,
                  diag: bool = False):
     """Fused ls-2 / ls-T activation quantizer (lsq_quantize_act): x [n,c,h,w] -> (bit planes, scale table [2, n])
-    with one read of x from HBM; ``diag=True`` also returns the int32 [n, 8] per-row diagnostics."""
+    with one read of x from HBM; ``diag=True`` also returns the int32 [n, 16] per-row diagnostics."""
     require_cuda(x)
     x = x.contiguous()
     L = _C.lib()
@@ -256,7 +256,7 @@ def quantize_act(x: torch.Tensor, g: _C.ActGeom, ternary: bool, alpha: Optional[
     elif tuple(table.shape) != (2, g.n) or table.dtype != torch.float32 or not table.is_contiguous() or table.device != x.device:
         raise ValueError(f'table must be a contiguous float32 [2, {g.n}] tensor on {x.device}')
     ws = workspace(x.device, L.lsq_quantize_act_workspace_bytes(C.byref(g)))
-    dg = torch.zeros(g.n, 8, dtype=torch.int32, device=x.device) if diag else None
+    dg = torch.zeros(g.n, 16, dtype=torch.int32, device=x.device) if diag else None
     with torch.cuda.device(x.device), _launch('quant_act', x.numel() * (4.0 + 2.0 / 8.0)):
         keep = []
         _C.check(L.lsq_quantize_act(x.data_ptr(), C.byref(g), _alpha(alpha), int(bool(ternary)), int(skip),

@@ -1,25 +1,43 @@
-"""Rank source lines of an .ncu-rep by warp-stall samples: python scripts/ncu_lines.py rep [top]"""
-import csv, subprocess, sys
-rep, top = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv'], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr, fname, data = None, '', []
+"""Aggregate an `ncu --page source --csv --print-source cuda,sass` export by CUDA source line:
+    ncu -i rep.ncu-rep --page source --csv --print-source cuda,sass > src.csv ; python scripts/ncu_lines.py src.csv [top]
+Prints the lines with the most warp-stall samples (all samples), their share, executed instructions and the dominant
+stall reasons -- what a kernel's time is spent on, line by line."""
+import collections
+import csv
+import sys
+
+rows = list(csv.reader(open(sys.argv[1])))
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+fname, hdr = None, None
+agg = collections.OrderedDict()
 for r in rows:
-    if len(r) == 2 and r[0] == 'File Path':
+    if not r:
+        continue
+    if r[0] == 'File Path':
         fname = r[1].split('/')[-1]
-    elif r and r[0] == 'Line No':
+        continue
+    if r[0] == 'Line No':
         hdr = r
-    elif hdr and len(r) == len(hdr) and r[0].strip().isdigit():
-        try:
-            data.append((int(r[4]), fname, r))
-        except ValueError:
-            pass
-H = hdr
-idx = {n: i for i, n in enumerate(H)}
-tot = sum(d[0] for d in data)
-print('total samples', tot)
-cols = ['stall_long_sb', 'stall_short_sb', 'stall_barrier', 'stall_wait', 'stall_mio', 'stall_lg', 'stall_math', 'stall_branch_resolving', 'stall_no_inst', 'stall_not_selected', 'stall_selected']
-print('   n     %   file:line  ' + ' '.join(c.replace('stall_', '')[:7] for c in cols))
-for n, f, r in sorted(data, key=lambda t: -t[0])[:top]:
-    st = ' '.join(f'{r[idx[c]]:>7s}' for c in cols if c in idx)
-    print(f'{n:6d} {100 * n / tot:5.1f}% {f}:{r[0]:>4s} {st} | {r[1].strip()[:90]}')
+        continue
+    if hdr is None or r[0] == 'Function Name' or r[0] == '':
+        continue
+    d = {k: ('0' if v in ('-', '') else v) for k, v in zip(hdr, r)}
+    if not r[0].isdigit():
+        continue
+    key = (fname, int(r[0]))
+    try:
+        samples = int(d.get('Warp Stall Sampling (All Samples)', '0') or 0)
+        inst = int(d.get('Instructions Executed', '0') or 0)
+        stalls = {k[6:]: int(v or 0) for k, v in d.items() if k.startswith('stall_') and 'Not Issued' not in k}
+    except ValueError:      # a source line with unescaped quotes (inline asm) shifted the columns: skip it
+        continue
+    e = agg.setdefault(key, {'src': r[1].strip(), 'samples': 0, 'inst': 0, 'stalls': collections.Counter()})
+    e['samples'] += samples
+    e['inst'] += inst
+    e['stalls'].update(stalls)
+total = sum(e['samples'] for e in agg.values()) or 1
+tinst = sum(e['inst'] for e in agg.values()) or 1
+print(f'total samples {total}, warp instructions {tinst}')
+for (f, ln), e in sorted(agg.items(), key=lambda kv: -kv[1]['samples'])[:top]:
+    st = ', '.join(f'{k} {v * 100 // max(e["samples"], 1)}%' for k, v in e['stalls'].most_common(3) if v)
+    print(f'{e["samples"] * 100.0 / total:5.1f}%  inst {e["inst"] * 100.0 / tinst:5.1f}%  {f}:{ln:<4d} {e["src"][:90]:90s} | {st}')
