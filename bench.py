@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: ImageNet ResNet-18, ls-1 weights / ls-2 activations, forward images/s.
+"""Benchmark of the hot path (BASELINE.json): forward images/s of the binary-quantized ResNet-18 and the solver sweep.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c4|c2|c3|c5] [--batch B]
   (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
-One step = one forward of a [B,3,224,224] synthetic batch per GPU through QResNet (reference
-examples/imagenet/imagenet_ls1_weight_ls2_activation_kd.yaml, random-init weights, calibrated
-buffers).  Rank 0 prints ONE JSON line:
-  value         images/s over all GPUs, inputs resident in HBM, whole forward as one CUDA graph,
-                followed (N>1) by the NCCL all_gather of logits; CUDA events, max over ranks
-  e2e           the same through ml_quant_b200.runtime.HostPipeline with HOST batches: pinned H2D of
-                every batch and D2H of the logits inside the timed region (copy/compute overlapped)
-  roofline      dominant kernel of the step (share from a per-launch CUDA-event pass)
-  cpu_baseline  the oracle (torch-CPU restatement of the reference) on this box's host cores, bounded
---impl reference times that CPU restatement itself (the reference is pure PyTorch and cannot travel).
+--config (BASELINE.json `configs`):
+  c4 (default, the headline)  ImageNet ResNet-18, ls-1 weights / ls-2 activations, 512 images per GPU, 224 x 224
+  c2                          CIFAR-100 ResNet-18, ls-1 / ls-2, batch 256, 32 x 32
+  c3                          ImageNet ResNet-18, ls-1 / ls-1 (XNOR), batch 512
+  c5                          least-squares solver sweep over the 53 conv weights of a ResNet-50, k in {ls-1, ls-2, ls-T}
+One step = one forward of a synthetic batch per GPU through QResNet (random-init weights, calibrated buffers) or one
+solve of every tensor for the three quantizers.  Rank 0 prints ONE JSON line:
+  value         units/s over all GPUs, inputs resident in HBM, the step as one CUDA graph, followed (N > 1) by the NCCL
+                all_gather of logits; CUDA events, max over ranks
+  e2e           the same through the public pipeline with HOST batches: pinned H2D of every batch and D2H of the result
+                inside the timed region
+  roofline      dominant kernel of the step + `kernels`: every kernel of this repository with achieved / peak / frac and
+                measured DRAM bytes over algorithmic bytes (ncu, profiles/roofline_traffic.json)
+  cpu_baseline  the reference on this box's host cores, bounded sample
+--impl reference times the UNMODIFIED reference package (oracle/_ref/reference_full, staged by oracle/make_ref.py;
+kind "reference") on the host cores -- the oracle port (kind "port") only if the staged copy is missing.
 """
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -28,8 +35,20 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-CONFIG = 'imagenet_resnet18_ls1w_ls2a'
-METRIC = 'resnet18_ls1w_ls2a_fwd_images_per_sec'
+CONFIGS = {
+    'c4': dict(net='imagenet_resnet18_ls1w_ls2a', batch=512, image=224, metric='resnet18_ls1w_ls2a_fwd_images_per_sec',
+               planes=2, mb_per_image=29.5),
+    'c2': dict(net='cifar100_resnet18_ls1w_ls2a', batch=256, image=32, metric='cifar_resnet18_ls1w_ls2a_fwd_images_per_sec',
+               planes=2, mb_per_image=None),
+    'c3': dict(net='imagenet_resnet18_ls1w_ls1a', batch=512, image=224, metric='resnet18_ls1w_ls1a_fwd_images_per_sec',
+               planes=1, mb_per_image=29.1),
+    'c5': dict(net='resnet50_conv_weights', metric='ls_solver_weight_sweep_elements_per_sec'),
+}
+# the 53 convolution weights of torchvision's resnet50: (cout, cin, k) x count
+R50 = [((64, 3, 7), 1), ((64, 64, 1), 1), ((64, 64, 3), 3), ((64, 256, 1), 2), ((128, 128, 3), 4), ((128, 256, 1), 1),
+       ((128, 512, 1), 3), ((256, 64, 1), 4), ((256, 256, 3), 6), ((256, 512, 1), 1), ((256, 1024, 1), 5),
+       ((512, 128, 1), 4), ((512, 256, 1), 1), ((512, 512, 3), 3), ((512, 1024, 1), 1), ((512, 2048, 1), 2),
+       ((1024, 256, 1), 6), ((1024, 512, 1), 1), ((2048, 512, 1), 3), ((2048, 1024, 1), 1)]
 
 
 def peaks():
@@ -38,6 +57,20 @@ def peaks():
         d = json.load(open(p))
         return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
     return 6650.0, 1590.0, 1400.0, 'fallback'
+
+
+def int8_peak():
+    """Back-to-back tcgen05.mma kind::i8 M128 N256 K32 on all SMs (scripts/mb/mb_umma, built by __graft_entry__.build):
+    the tensor pipe's own integer peak, measured in this run.  None when the binary is missing or fails."""
+    exe = os.path.join(ROOT, 'scripts', 'mb', 'mb_umma')
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+        m = re.search(r'i8 M128 N256 aligned.*?([0-9.]+) POP/s', out)
+        return float(m.group(1)) * 1e3 if m else None          # TOP/s
+    except Exception:  # noqa: BLE001
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -71,29 +104,86 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
-def cpu_reference_arm(batch, steps, warmup):
-    """The reference's algorithm on the host cores (oracle/, torch CPU ops, all threads)."""
+def cpu_reference(net, images, steps, warmup):
+    """The reference (or, without the staged copy, the oracle port) on the host cores, in its own process."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'ref_arm.py'), net, str(images), str(steps), str(warmup)],
+                         capture_output=True, text=True, timeout=3000)
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith('{')]
+    if not lines:
+        raise RuntimeError('reference arm failed: ' + out.stderr[-2000:])
+    return json.loads(lines[-1])
+
+
+def r50_weights(device, seed=0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    ws = []
+    for (co, ci, k), cnt in R50:
+        for _ in range(cnt):
+            ws.append(torch.randn(co, ci * k * k, generator=g) * (2.0 / (ci * k * k)) ** 0.5)
+    return [w.to(device) for w in ws] if device is not None else ws
+
+
+def solver_sweep_cpu(sample_tensors, steps):
+    """Oracle restatement of the three weight quantizers on a bounded sample of the sweep (host cores)."""
     from oracle import lsq_oracle as O
-    from ml_quant_b200 import configs, runtime
     torch.set_num_threads(os.cpu_count() or 1)
-    model = runtime.build_model(CONFIG)
-    # buffers a checkpoint would carry: weight scales from the weights, BN stats left at init + noise
-    sd = {k: v.clone() for k, v in model.state_dict().items()}
-    for k in list(sd):
-        if k.endswith('w_approximate.v1'):
-            w = sd[k[:-len('w_approximate.v1')] + 'weight']
-            sd[k] = w.abs().mean(dim=(1, 2, 3))
-    arch = configs.arch(CONFIG)
-    g = torch.Generator().manual_seed(1234)
-    x = torch.randn(batch, 3, 224, 224, generator=g)
-    with torch.no_grad():
-        for _ in range(warmup):
-            O.resnet_forward(sd, arch, x)
-        t = time.time()
+    ws = [w for i, w in enumerate(r50_weights(None)) if i in sample_tensors]
+    n = sum(w.numel() for w in ws) * 3
+    t = time.perf_counter()
+    for _ in range(steps):
+        for w in ws:
+            w4 = w.view(w.shape[0], -1, 1, 1)
+            O.quant_ls1(w4)
+            O.solve_v1(w, False, 3, chunk=64)
+            O.solve_v1(w, True, 3, chunk=64)
+    dt = time.perf_counter() - t
+    return n * steps / dt, dt / steps, n
+
+
+def timed_steps(step, steps, flush, barrier, dist_max):
+    """K steps, CUDA events around each (L2 flushed between steps when the inputs fit in L2), summed; max over ranks."""
+    barrier()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for _ in range(steps):
-            O.resnet_forward(sd, arch, x)
-        dt = time.time() - t
-    return batch * steps / dt, dt / steps
+            out = step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+    else:
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = step()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+    return dist_max(ms), out
+
+
+def kernel_table(agg, hbm_peak, i8_peak, i8_src, tf32_peak, traffic):
+    rows = []
+    for name, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
+        sec = d['ms'] / 1e3
+        if name.startswith('bconv_tc'):
+            ach, peak, unit, bound, src = d['ops'] / sec / 1e12, i8_peak, 'TOP/s', 'tensor', i8_src
+        elif name in ('stem', 'pwconv'):
+            ach, peak, unit, bound, src = d['ops'] / sec / 1e12, tf32_peak, 'TFLOP/s', 'tensor', \
+                'useful fp32 flops against the tf32 pipe (MEASURED_PEAKS.json bf16_tflops / 2); the fp32-accurate split costs ' \
+                '2-3 tf32 products per fp32 product'
+        else:
+            ach, peak, unit, bound, src = d['bytes'] / sec / 1e9, hbm_peak, 'GB/s', 'hbm', 'MEASURED_PEAKS.json hbm_gbs'
+        t = traffic.get(name)
+        rows.append({'kernel': name, 'launches': d['launches'], 'ms': round(d['ms'], 4), 'bound': bound,
+                     'achieved': round(ach, 2), 'peak': round(peak, 1), 'unit': unit, 'frac': round(ach / peak, 4),
+                     'peak_source': src,
+                     'dram_over_algorithmic': None if not t else round(t['dram_bytes'] / t['algorithmic_bytes'], 3),
+                     'traffic_instance': None if not t else t.get('instance')})
+    return rows
 
 
 def main():
@@ -102,7 +192,8 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=512, help='images per GPU per step')
+    ap.add_argument('--config', default='c4', choices=sorted(CONFIGS))
+    ap.add_argument('--batch', type=int, default=0, help='images per GPU per step (default: the config\'s)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-fuse', action='store_true', help='keep BatchNorm / ReLU / residual adds as separate torch ops')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -110,25 +201,37 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    cfg = CONFIGS[args.config]
     hbm_peak, bf16_burst, bf16_sust, peak_src = peaks()
-    base_cfg = {'workload': CONFIG + '_b%d_224' % args.batch, 'batch_per_gpu': args.batch, 'image': 224,
+    cores = os.cpu_count() or 1
+    if args.config == 'c5':
+        return sweep_main(args, rank, world, local, cfg, hbm_peak, peak_src, cores)
+    B = args.batch or cfg['batch']
+    img = cfg['image']
+    in_mb = B * 3 * img * img * 4 / 2 ** 20
+    base_cfg = {'workload': '%s_b%d_%d' % (cfg['net'], B, img), 'config': args.config, 'batch_per_gpu': B, 'image': img,
                 'sharding': 'batch' if world > 1 else 'none',
-                'l2': 'per-step input (%d MB) and every activation tensor exceed the 126 MB L2' % (args.batch * 3 * 224 * 224 * 4 >> 20)}
+                'l2': ('per-step input (%d MB) and every large activation tensor exceed the 126 MB L2' % in_mb) if in_mb > 126
+                else 'L2 flushed (256 MB written) between timed steps: the %.0f MB input fits in L2' % in_mb}
+    ref_images = 64 if img >= 224 else 256
 
     if args.impl == 'reference':
         if rank != 0:
             return
-        cores = os.cpu_count() or 1
-        steps = max(1, min(args.steps, 3))
-        sample = 64
-        ips, sec = cpu_reference_arm(sample, steps, min(args.warmup, 1))
+        steps = max(1, args.steps)
+        # a step of the CPU arm is a bounded sample of the workload: `ref_images` images of the same distribution
+        per_step = ref_images if steps <= 3 else max(8, ref_images // 4)
+        r = cpu_reference(cfg['net'], per_step, steps, min(args.warmup, 1))
+        base_cfg['reference_step_images'] = per_step
         print(json.dumps({
-            'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
-            'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+            'impl': 'reference', 'metric': cfg['metric'], 'value': r['images_per_s'], 'unit': 'images/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': r['s_per_step'] * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': base_cfg,
-            'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{steps} forwards of {sample} images (oracle/lsq_oracle.py, torch CPU, {cores} threads)'},
-            'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+            'cpu_baseline': {'value': r['images_per_s'], 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'],
+                             'sample': f'{steps} forwards of {per_step} images each (not the {B} of the GPU step; CPU throughput '
+                                       f'does not depend on the batch), {"unmodified reference package" if r["kind"] == "reference" else "oracle port"}, '
+                                       f'torch CPU, {r["cores"]} threads'},
+            'e2e': {'value': r['images_per_s'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 
     if not torch.cuda.is_available():
@@ -141,19 +244,25 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     torch.backends.cudnn.benchmark = True
 
-    model = runtime.build_model(CONFIG, dev)
-    runtime.calibrate(model, (3, 224, 224))
+    model = runtime.build_model(cfg['net'], dev)
+    runtime.calibrate(model, (3, img, img))
     if not args.no_fuse:
         runtime.optimize_for_inference(model)
-    B = args.batch
     g = torch.Generator(device='cpu').manual_seed(1234 + rank)
-    host_x = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    host_x = torch.randn(B, 3, img, img, generator=g).pin_memory()
     x = host_x.to(dev)
+    flush = None if in_mb > 126 else torch.empty(256 * 2 ** 20 // 4, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def dist_max(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     with torch.no_grad():
         ops.reset_counters()
@@ -170,48 +279,31 @@ def main():
 
     for _ in range(2):
         step()
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        logits = step()
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    ms, _ = timed_steps(step, args.steps, flush, barrier, dist_max)
     clocks = sampler.summary() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end: host batches through the public pipeline (H2D + forward + D2H every step) ----
-    pipe = runtime.HostPipeline(model, (B, 3, 224, 224), dev, use_graph=not args.no_graph)
+    pipe = runtime.HostPipeline(model, (B, 3, img, img), dev, use_graph=not args.no_graph)
     batches = [host_x] * args.steps
     pipe.run(batches[:2])
     barrier()
     t0 = time.perf_counter()
     pipe.run(batches)
     if world > 1:
-        runtime.gather_logits(pipe.bufs[0][:1].new_zeros(B, 1000), world)
+        runtime.gather_logits(pipe.bufs[0][:1].new_zeros(B, pipe.host_out.shape[1]), world)
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(e2e_s.item())
+    e2e_value = world * B * args.steps / dist_max(time.perf_counter() - t0)
 
     # ---- per-launch timing of our kernels (eager pass, CUDA events on the launching stream) ----
     ops.PROFILE = []
     torch.cuda.synchronize()
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.no_grad():
-        pe0.record()
         model(x)
-        pe1.record()
     torch.cuda.synchronize()
-    eager_ms = pe0.elapsed_time(pe1)
     agg = {}
     for name, a, b, nbytes, nops in ops.PROFILE:
         d = agg.setdefault(name, {'ms': 0.0, 'launches': 0, 'bytes': 0.0, 'ops': 0.0})
@@ -220,55 +312,181 @@ def main():
         d['bytes'] += nbytes
         d['ops'] += nops
     ops.PROFILE = None
-    stem_ms = None
-    if hasattr(model, '_lsq_stem'):
-        se0, se1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.no_grad():
-            model._lsq_stem(x)
-            se0.record()
-            model._lsq_stem(x)
-            se1.record()
-        torch.cuda.synchronize()
-        stem_ms = se0.elapsed_time(se1)
-    ours_ms = sum(d['ms'] for d in agg.values())
-    top = max(agg, key=lambda k: agg[k]['ms'])
-    td = agg[top]
-    traffic, traffic_instance = None, None
-    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic, traffic_instance = tj.get(top), tj.get(top + '_instance')
-    if top.startswith('bconv_tc'):
-        # kind::i8 issues at twice the bf16 rate: denominator = 2 x measured bf16 (sustained, MEASURED_PEAKS.json).
-        # (scripts/mb/mb_umma.cu measures 4.3 POP/s for back-to-back M128 N256 K32 tcgen05.mma on this part.)
-        peak = 2.0 * bf16_sust
-        ach = td['ops'] / (td['ms'] / 1e3) / 1e12
-        roof = {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TOP/s', 'frac': ach / peak}
-    else:
-        ach = td['bytes'] / (td['ms'] / 1e3) / 1e9
-        roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak}
-    roof.update({'traffic': traffic, 'traffic_instance': traffic_instance, 'kernel': top, 'launches': td['launches'], 'avg_ms': td['ms'] / td['launches'],
-                 'share_of_step': td['ms'] / (ms / args.steps), 'peak_source': peak_src,
-                 'kernels_ms': {k: round(v['ms'], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])},
-                 'graph_step_ms': ms / args.steps, 'our_kernels_share': ours_ms / (ms / args.steps), 'fp32_stem_ms': stem_ms})
-    # whole-forward HBM roofline (29.5 MB/image with ideal fusion)
-    roof['forward_hbm_frac'] = (value / world) * 29.5e6 / (hbm_peak * 1e9)
-
     out = {
-        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+        'metric': cfg['metric'], 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
         'config': base_cfg, 'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': B * 3 * 224 * 224 * 4,
-                'd2h_bytes_per_step': B * 1000 * 4},
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': B * 3 * img * img * 4,
+                'd2h_bytes_per_step': B * pipe.host_out.shape[1] * 4},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
-        'roofline': roof, 'cuda_graph': not args.no_graph, 'fused_blocks': not args.no_fuse,
+        'cuda_graph': not args.no_graph, 'fused_blocks': not args.no_fuse,
     }
+    if rank == 0:
+        # the tensor pipe's integer peak, measured in this run (falls back to 2 x the measured bf16 burst figure)
+        i8 = int8_peak() if world == 1 else None
+        i8_peak, i8_src = (i8, 'scripts/mb/mb_umma: back-to-back tcgen05.mma kind::i8 M128 N256 K32 on 148 SMs, this run') \
+            if i8 else (2.0 * bf16_burst, '2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate)')
+        tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        traffic = json.load(open(tpath)).get('kernels', {}) if os.path.exists(tpath) else {}
+        kernels = kernel_table(agg, hbm_peak, i8_peak, i8_src, bf16_burst / 2.0, traffic)
+        top = kernels[0]
+        ours_ms = sum(d['ms'] for d in agg.values())
+        roof = {'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'], 'unit': top['unit'], 'frac': top['frac'],
+                'traffic': (traffic.get(top['kernel']) or {}).get('dram_bytes'),
+                'traffic_source': 'ncu --set full capture of one launch, kept in profiles/ (see profiles/roofline_traffic.json); '
+                                  'not re-measured by this run',
+                'kernel': top['kernel'], 'launches': top['launches'], 'avg_ms': top['ms'] / top['launches'],
+                'share_of_step': top['ms'] / (ms / args.steps), 'peak_source': top['peak_source'] + '; hbm: ' + peak_src,
+                'kernels': kernels, 'graph_step_ms': ms / args.steps,
+                'our_kernels_share': ours_ms / (ms / args.steps)}
+        if cfg['mb_per_image']:
+            # whole-forward HBM roofline (MB per image with ideal layer fusion)
+            roof['forward_hbm_frac'] = (value / world) * cfg['mb_per_image'] * 1e6 / (hbm_peak * 1e9)
+            roof['forward_hbm_frac_note'] = '%.1f MB/image x images/s / measured HBM copy bandwidth' % cfg['mb_per_image']
+        # bit-GEMM throughput of the binary convolutions (BASELINE.json metric, second half)
+        bc = [k for k in kernels if k['kernel'].startswith('bconv_tc')]
+        if bc:
+            roof['bit_gemm_tops'] = bc[0]['achieved']
+            roof['bit_gemm_frac_of_int8_peak'] = bc[0]['frac']
+        out['roofline'] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        ips, sec = cpu_reference_arm(64, 4, 1)      # ~5-10 s of CPU work on the box's host cores
-        out['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                               'sample': f'4 forwards of 64 images (oracle/lsq_oracle.py, torch CPU, {cores} threads)'}
+        r = cpu_reference(cfg['net'], ref_images, 3, 1)       # ~5-15 s of CPU work on the box's host cores
+        out['cpu_baseline'] = {'value': r['images_per_s'], 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'],
+                               'sample': f'3 forwards of {ref_images} images ('
+                                         f'{"unmodified reference package, oracle/_ref" if r["kind"] == "reference" else "oracle port"}, '
+                                         f'torch CPU, {r["cores"]} threads)'}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sweep_main(args, rank, world, local, cfg, hbm_peak, peak_src, cores):
+    """BASELINE.json configs[4]: the three weight quantizers over the 53 conv weights of a ResNet-50 (23.45 M elements in
+    26 560 rows; one multi-tensor launch per quantizer, the step captured as one CUDA graph).  N > 1: every rank solves
+    its own replica of the sweep (weights are replicated in the path; weak scaling, no collective)."""
+    elems = sum(co * ci * k * k * cnt for (co, ci, k), cnt in R50)
+    base_cfg = {'workload': 'resnet50_conv_weights_53_tensors_ls1_ls2_lsT_skip3', 'config': 'c5', 'elements': elems,
+                'rows': sum(co * cnt for (co, _, _), cnt in R50), 'sharding': 'replicas' if world > 1 else 'none',
+                'l2': 'L2 flushed (256 MB written) between timed steps: the 93.8 MB of weights fit in L2'}
+    unit_per_step = 3 * elems
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        sample = [0, 2, 5, 20, 27, 35, 40, 45]          # a bounded sample of the 53 tensors, every row-length class
+        steps = max(1, min(args.steps, 3))
+        eps, sec, n = solver_sweep_cpu(sample, steps)
+        base_cfg['reference_step_elements'] = n
+        print(json.dumps({
+            'impl': 'reference', 'metric': cfg['metric'], 'value': eps, 'unit': 'elements/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': 0, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': base_cfg,
+            'cpu_baseline': {'value': eps, 'unit': 'elements/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{steps} passes over {len(sample)} of the 53 tensors ({n // 3} elements) for ls-1, ls-2 and '
+                                       f'ls-T (oracle/lsq_oracle.py, torch CPU, {cores} threads)'},
+            'e2e': {'value': eps, 'unit': 'elements/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)')
+    from ml_quant_b200 import ops
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    host_w = [w.pin_memory() for w in r50_weights(None)]
+    ws = [w.to(dev) for w in host_w]
+    flush = torch.empty(256 * 2 ** 20 // 4, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dist_max(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def solve_all():
+        return ops.row_absmean_multi(ws), ops.solve_v1_multi(ws, False, 3), ops.solve_v1_multi(ws, True, 3)
+
+    ops.reset_counters()
+    for _ in range(max(args.warmup, 3)):
+        res = solve_all()
+    launches_per_step = sum(ops.LAUNCHES.values()) // max(args.warmup, 3)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        solve_all()
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph):
+        res = solve_all()
+
+    def step():
+        graph.replay()
+        return res
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, _ = timed_steps(step, args.steps, flush, barrier, dist_max)
+    clocks = sampler.summary() if sampler else None
+    value = world * unit_per_step * args.steps / (ms / 1e3)
+    # e2e: weights from pinned host memory, scales back to the host, every step
+    host_out = [torch.empty(w.shape[0], pin_memory=True) for w in host_w for _ in range(3)]
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for d, h in zip(ws, host_w):
+            d.copy_(h, non_blocking=True)
+        graph.replay()
+        k = 0
+        for group in res:
+            for v in group:
+                host_out[k].copy_(v, non_blocking=True)
+                k += 1
+        torch.cuda.synchronize()
+    e2e_value = world * unit_per_step * args.steps / dist_max(time.perf_counter() - t0)
+    # per-quantizer timing (graphs of one quantizer each would hide nothing: time the eager multi-tensor launches)
+    per = {}
+    for name, fn in (('ls-1', lambda: ops.row_absmean_multi(ws)), ('ls-2', lambda: ops.solve_v1_multi(ws, False, 3)),
+                     ('ls-T', lambda: ops.solve_v1_multi(ws, True, 3))):
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        per[name] = sorted(ts)[2]
+    out = {
+        'metric': cfg['metric'], 'value': value, 'unit': 'elements/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': base_cfg, 'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'elements/s', 'h2d_bytes_per_step': elems * 4,
+                'd2h_bytes_per_step': 3 * base_cfg['rows'] * 4},
+        'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step, 'cuda_graph': True,
+    }
+    if rank == 0:
+        ach = unit_per_step * 4 / (ms / args.steps / 1e3) / 1e9
+        out['roofline'] = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                           'traffic': None, 'kernel': 'solve_v1_multi + row_absmean_multi', 'peak_source': peak_src,
+                           'note': '4 bytes per element and quantizer (one algorithmic read each), whole step',
+                           'eager_ms': {k: round(v, 4) for k, v in per.items()},
+                           'eager_gbs': {k: round(elems * 4 / (v / 1e3) / 1e9, 1) for k, v in per.items()}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = [0, 2, 5, 20, 27, 35, 40, 45]
+        eps, sec, n = solver_sweep_cpu(sample, 1)
+        out['cpu_baseline'] = {'value': eps, 'unit': 'elements/s', 'cores': cores, 'kind': 'port',
+                               'sample': f'1 pass over {len(sample)} of the 53 tensors ({n // 3} elements) x 3 quantizers '
+                                         f'(oracle/lsq_oracle.py, torch CPU, {cores} threads)'}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
