@@ -56,6 +56,7 @@ struct QParams {
 };
 
 constexpr int kQSegMax = 256;                         // elements of one flagged bin a warp sorts
+constexpr int kQWarpQueue = 96;                       // hits a warp may queue in the collection walk
 struct QSmem {
   uint32_t hcnt[kQBins];
   union {
@@ -87,6 +88,7 @@ struct QSmem {
   uint32_t sexcl[kQMaxFlag], seg_start[kQMaxFlag], seg_cnt[kQMaxFlag];
   double spref[kQMaxFlag];
   uint32_t lfill[kQMaxFlag], lsmin[kQMaxFlag];    // this CTA: elements collected per segment, smallest key of the follower bin
+  uint32_t wq[kQThreads / 32][kQWarpQueue];       // per warp: (sample index << 8 | segment code) of the hits of the index walk
   uint32_t nlist;
   int status;                      // 0 = solved here, != 0: reason the row goes to the generic kernels
   float v1;
@@ -219,11 +221,18 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
   if (cs > 1) {
     const int slice = kQBins / cs;
     for (int b = rank * slice + tid; b < (rank + 1) * slice; b += kQThreads) {
-      uint32_t c = 0u, r = 0u;
-      for (int q = 0; q < cs; ++q) {
-        const QSmem* p = cluster.map_shared_rank(&sm, q);
-        c += p->hcnt[b]; r += p->hrem[b];
+      uint32_t cq[kQMaxCluster], rq[kQMaxCluster];
+#pragma unroll
+      for (int q = 0; q < kQMaxCluster; ++q) {       // all remote loads in flight together (one round trip)
+        cq[q] = 0u; rq[q] = 0u;
+        if (q < cs) {
+          const QSmem* p = cluster.map_shared_rank(&sm, q);
+          cq[q] = p->hcnt[b]; rq[q] = p->hrem[b];
+        }
       }
+      uint32_t c = 0u, r = 0u;
+#pragma unroll
+      for (int q = 0; q < kQMaxCluster; ++q) { c += cq[q]; r += rq[q]; }
       r0->hcnt[b] = c; r0->hrem[b] = r;
     }
     cluster.sync();
@@ -399,26 +408,41 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     __syncthreads();
     if (tid < nflag) sm.fmap[sm.sbin[tid]] = (uint8_t)(1 + tid);     // a flagged bin that follows another one is a segment
     __syncthreads();
+    // phase A: walk the bin indices; a warp queues its hits (sample, segment) without touching global memory ...
     const uint32_t ns_cta = 4u * (g_hi - g_lo);
-    for (uint32_t s4 = 4u * tid; s4 < ns_cta; s4 += 4u * kQThreads) {
-      const uint2 w = *reinterpret_cast<const uint2*>(&sm.ids[s4]);
+    uint32_t* const wq = sm.wq[wid];
+    uint32_t nq = 0u;                                  // warp uniform
+    for (uint32_t base = 128u * wid; base < ns_cta; base += 4u * kQThreads) {
+      const uint32_t s4 = base + 4u * lane;
+      uint2 w = make_uint2(0xFFFEFFFEu, 0xFFFEFFFEu);
+      if (s4 < ns_cta) w = *reinterpret_cast<const uint2*>(&sm.ids[s4]);
       const uint32_t id4[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t id = id4[j];
         const uint32_t m = (id < (uint32_t)kQBins) ? sm.fmap[id] : 0u;
-        if (m != 0u) {
-          const unsigned long long idx = 3ull * (4ull * g_lo + s4 + j);
-          const uint32_t c = q_channel(qp, idx);
-          const float2 k = sm.ab[c];
-          const uint32_t key = __float_as_uint(fabsf(clamp_sym(fmaf(__ldg(xr + idx), k.x, k.y), alpha)));
-          if (m <= 64u) {
-            const uint32_t pos = atomicAdd(&sm.lfill[m - 1u], 1u);
-            if (pos < (uint32_t)kQSegMax) sm.list[sm.seg_start[m - 1u] + pos] = key;
-          } else {
-            atomicMin(&sm.lsmin[m - 65u], key);
-          }
+        const uint32_t hit = __ballot_sync(0xffffffffu, m != 0u);
+        if (hit != 0u) {
+          const uint32_t pos = nq + __popc(hit & ((1u << lane) - 1u));
+          if (m != 0u && pos < (uint32_t)kQWarpQueue) wq[pos] = ((s4 + j) << 8) | m;
+          nq += __popc(hit);
         }
+      }
+    }
+    if (nq > (uint32_t)kQWarpQueue) { if (lane == 0) atomicMax(&r0->status, 6); nq = kQWarpQueue; }
+    __syncwarp();
+    // ... phase B: the exact keys of all queued hits, their loads in flight together (one trip to L2)
+    for (uint32_t e = lane; e < nq; e += 32u) {
+      const uint32_t ent = wq[e], m = ent & 0xFFu;
+      const unsigned long long idx = 3ull * (4ull * g_lo + (ent >> 8));
+      const uint32_t c = q_channel(qp, idx);
+      const float2 k = sm.ab[c];
+      const uint32_t key = __float_as_uint(fabsf(clamp_sym(fmaf(__ldg(xr + idx), k.x, k.y), alpha)));
+      if (m <= 64u) {
+        const uint32_t pos = atomicAdd(&sm.lfill[m - 1u], 1u);
+        if (pos < (uint32_t)kQSegMax) sm.list[sm.seg_start[m - 1u] + pos] = key;
+      } else {
+        atomicMin(&sm.lsmin[m - 65u], key);
       }
     }
   }
@@ -434,12 +458,37 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       for (int i = wid; i < nflag; i += kQThreads / 32) {
         const uint32_t base = sm.seg_start[i], cnt = sm.seg_cnt[i];
         uint32_t fill = sm.lfill[i], smin = sm.lsmin[i];
-        for (int q = 1; q < cs; ++q) {
-          const QSmem* p = cluster.map_shared_rank(&sm, q);
-          const uint32_t cq = p->lfill[i];
-          for (uint32_t e = lane; e < cq && fill + e < (uint32_t)kQSegMax; e += 32) sm.list[base + fill + e] = p->list[base + e];
-          fill += cq;
-          smin = min(smin, p->lsmin[i]);
+        if (cs > 1) {
+          // lane q (1 <= q < cs) fetches CTA q's count and follower minimum, then the warp copies all remote
+          // elements with independent loads: two round trips through distributed shared memory per segment
+          uint32_t cq = 0u, sq = kNoKey;
+          if (lane >= 1 && lane < cs) {
+            const QSmem* p = cluster.map_shared_rank(&sm, lane);
+            cq = p->lfill[i]; sq = p->lsmin[i];
+          }
+          uint32_t inc = cq;
+#pragma unroll
+          for (int o = 1; o < kQMaxCluster; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+          }
+          const uint32_t total_remote = __shfl_sync(0xffffffffu, inc, kQMaxCluster - 1);
+          smin = min(smin, warp_min_u32(sq));
+          uint32_t endt[kQMaxCluster];                 // inclusive prefix of CTA t, known to every lane
+#pragma unroll
+          for (int t = 0; t < kQMaxCluster; ++t) endt[t] = __shfl_sync(0xffffffffu, inc, t);
+          for (uint32_t e = lane; e < total_remote; e += 32u) {
+            int q = 1;
+            uint32_t off = 0u;
+#pragma unroll
+            for (int t = 1; t < kQMaxCluster; ++t)
+              if (e >= endt[t]) { q = t + 1; off = endt[t]; }
+            if (q < cs && fill + e < (uint32_t)kQSegMax) {
+              const QSmem* p = cluster.map_shared_rank(&sm, q);
+              sm.list[base + fill + e] = p->list[base + (e - off)];
+            }
+          }
+          fill += total_remote;
         }
         uint32_t lp = 2;
         while (lp < cnt) lp <<= 1;
