@@ -243,6 +243,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
     torch.backends.cudnn.benchmark = True
+    numa = runtime.bind_host_to_gpu(local) if world > 1 else None     # before any pinned allocation (first touch)
 
     model = runtime.build_model(cfg['net'], dev)
     runtime.calibrate(model, (3, img, img))
@@ -320,7 +321,7 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': B * 3 * img * img * 4,
                 'd2h_bytes_per_step': B * pipe.host_out.shape[1] * 4},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
-        'cuda_graph': not args.no_graph, 'fused_blocks': not args.no_fuse,
+        'cuda_graph': not args.no_graph, 'fused_blocks': not args.no_fuse, 'host_affinity': numa,
     }
     if rank == 0:
         # the tensor pipe's integer peak, measured in this run (falls back to 2 x the measured bf16 burst figure)
@@ -438,7 +439,7 @@ def sweep_main(args, rank, world, local, cfg, hbm_peak, peak_src, cores):
     clocks = sampler.summary() if sampler else None
     value = world * unit_per_step * args.steps / (ms / 1e3)
     # e2e: weights from pinned host memory, scales back to the host, every step
-    host_out = [torch.empty(w.shape[0], pin_memory=True) for w in host_w for _ in range(3)]
+    host_out = [torch.empty(w.shape[0], pin_memory=True) for _ in range(3) for w in host_w]      # res = 3 groups of 53
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

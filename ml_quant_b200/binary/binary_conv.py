@@ -71,6 +71,7 @@ class QuantConv2d(nn.Conv2d):
         self.packed_impl = 0            # 0 auto, 1 CUDA-core kernel, 2 tensor-core kernel (tests / profiling)
         self.allow_packed = True
         self._wpack_cache: Dict[int, Tuple[Tuple[int, int], torch.Tensor]] = {}
+        self._wplanes_cache: Dict[int, Tuple[tuple, list]] = {}
         # bit-plane scratch, one per (device, stream): two streams / threads running this module concurrently
         # (nn.DataParallel replicas share this dict; a graph on one stream next to eager calls on another)
         # must not overwrite each other's planes between the encoder and the convolution
@@ -135,8 +136,10 @@ class QuantConv2d(nn.Conv2d):
                               'F.conv2d) route; wrap inference in torch.no_grad() for the packed tensor-core path.',
                               RuntimeWarning, stacklevel=3)
             return None
-        if self.w_quant != 'ls-1' or not 1 <= self._num_planes() <= _PACKED_MAX_PLANES:
+        if self.w_quant == 'fp' or not 1 <= self._num_planes() <= _PACKED_MAX_PLANES:
             return None
+        if self.w_quant != 'ls-1' and self.w_approximate.training:
+            return None          # multi-plane weight scales are being solved: the reference's composition does that
         if self.groups != 1 or tuple(self.dilation) != (1, 1) or self.padding_mode != 'zeros':
             return None
         if isinstance(self.padding, str) or self.stride[0] != self.stride[1] or self.padding[0] != self.padding[1]:
@@ -156,6 +159,30 @@ class QuantConv2d(nn.Conv2d):
         if hit is None or hit[0] != key:
             hit = (key, ops.pack_weights(w))
             self._wpack_cache[dev] = hit
+        return hit[1]
+
+    def packed_weight_planes(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        """Multi-plane weight schemes (ls-2, ls-T, gf-k; quant/binary/weight_quantization.py:37-109 in eval mode):
+        W_q = sum_i v_i b_i with b_i = sign(W - sum_{l<i} v_l b_l) per output channel (quantization.py:89-92,
+        :113-115, :139-146).  Returns [(packed sign image of b_i, v_i)], cached until the weight or a scale buffer
+        changes; every plane runs through the same binary convolution kernels as an ls-1 weight."""
+        w, wa = self.weight, self.w_approximate
+        scales = list(wa.scales())
+        if self.w_quant == 'ls-T':
+            scales = [scales[0], scales[0]]
+        dev = w.device.index or 0
+        key = (w.data_ptr(), w._version) + tuple((v.data_ptr(), v._version) for v in scales)
+        hit = self._wplanes_cache.get(dev)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                acc = torch.zeros_like(w)
+                planes = []
+                for v in scales:
+                    b = torch.where(w - acc >= 0, 1.0, -1.0).to(w.dtype)       # sign with sign(0) = +1 (ste.py:16-18)
+                    planes.append((ops.pack_weights(b), v.detach()))
+                    acc = acc + v.view(-1, 1, 1, 1) * b
+            hit = (key, planes)
+            self._wplanes_cache[dev] = hit
         return hit[1]
 
     def _weight_scale(self) -> torch.Tensor:
@@ -202,9 +229,26 @@ class QuantConv2d(nn.Conv2d):
                         residual_after_act: bool = True) -> torch.Tensor:
         x = x.contiguous()
         planes, table = self.quantize_input(x, g, prologue)
-        return ops.bconv2d(planes, g, self._num_planes(), table, self.packed_weights(), self._weight_scale(),
-                           self.bias, self.out_channels, self.packed_impl, None, residual, act, prelu,
-                           residual_after_act)
+        if self.w_quant == 'ls-1':
+            return ops.bconv2d(planes, g, self._num_planes(), table, self.packed_weights(), self._weight_scale(),
+                               self.bias, self.out_channels, self.packed_impl, None, residual, act, prelu,
+                               residual_after_act)
+        # multi-plane weights: y = sum_i v_i[c] * sum_j s_j[n] * conv(b_j, wb_i) + bias -- one binary convolution per
+        # weight plane, each adding to the previous through the residual input of the epilogue (exact integer
+        # accumulators per plane pair); the block's own activation / residual, if any, on the way out of the last one
+        wplanes = self.packed_weight_planes()
+        y = None
+        for i, (wpack, v) in enumerate(wplanes):
+            lastp = i == len(wplanes) - 1
+            res_in = y
+            if lastp and residual is not None and not residual_after_act:
+                res_in = residual if y is None else y + residual          # act(sum + residual)
+            y = ops.bconv2d(planes, g, self._num_planes(), table, wpack, v, self.bias if i == 0 else None,
+                            self.out_channels, self.packed_impl, None, res_in, act if lastp else 0,
+                            prelu if lastp else None, False)
+        if residual is not None and residual_after_act:                   # act(sum) + residual
+            y = y + residual
+        return y
 
     def forward_fused(self, x: torch.Tensor, bn: Optional[nn.BatchNorm2d] = None, nonlin: Optional[nn.Module] = None,
                       residual: Optional[torch.Tensor] = None, residual_after_act: bool = True) -> torch.Tensor:

@@ -515,3 +515,73 @@ def test_fused_activation_quantizer_hands_odd_rows_to_the_generic_kernels():
         xx = x[:, :, :4, :4].contiguous() if alpha else x
         v1 = ops.solve_v1(xx.reshape(4, -1), False, 3, alpha)
         assert torch.equal(tab[0], v1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi-plane weight schemes on the packed route (reference weight_quantization.py:37-109)
+# ---------------------------------------------------------------------------------------------------------------
+def test_multi_plane_weight_schemes_take_the_packed_route(golden_layers):
+    """w_quant in {ls-2, ls-T, gf-2, gf-3} with binary activations: one tensor-core binary convolution per weight sign
+    plane (no dense fake-quant weights, no F.conv2d), output equal to the oracle's composition -- scales solved by the
+    oracle's own train-mode call, so only exact integer accumulators and fp32 epilogues differ: <= 1e-5 of max|y|;
+    plain forward and the fused BatchNorm / ReLU / residual forms."""
+    runtime_strict()
+    from quant.binary.binary_conv import QuantConv2d
+    from ml_quant_b200 import ops
+    torch.manual_seed(41)
+    for xs, ws, cin, cout, st in [('ls-2', 'ls-2', 64, 64, 1), ('ls-1', 'ls-T', 64, 128, 2), ('ls-2', 'gf-2', 128, 128, 1),
+                                  ('ls-T', 'gf-3', 64, 64, 1)]:
+        m = QuantConv2d(xs, ws, cin, cout, 3, {'kind': 'symmetric', 'alpha': 2.0}, stride=st, padding=1)
+        x = torch.randn(3, cin, 14, 14) * 1.2
+        w = m.weight.detach()
+        wsc, wq = O.quantize_weight(w, ws)                       # the reference's train-mode solve of the weight scales
+        names = [f'v{i + 1}' for i in range(len(wsc))]
+        with torch.no_grad():
+            for nme, v in zip(names, wsc):
+                getattr(m.w_approximate, nme).copy_(v)
+        m = m.to(DEV).eval()
+        xin = x.clamp(-2.0, 2.0)
+        ops.reset_counters()
+        with torch.no_grad():
+            y = m(x.to(DEV))
+        nplanes_w = {'ls-2': 2, 'ls-T': 2, 'gf-2': 2, 'gf-3': 3}[ws]
+        assert ops.LAUNCHES.get('bconv_tc', 0) == nplanes_w and 'fakequant' not in ops.LAUNCHES, ops.LAUNCHES
+        # the oracle's convolution with OUR activation scales (the ls-2 / ls-T pick is under the solver contract)
+        g = ops.act_geometry(3, cin, 14, 14, 3, 3, st, 1)
+        if xs in ('ls-2', 'ls-T'):
+            _, tab = ops.quantize_act(x.to(DEV), g, xs == 'ls-T', 2.0)
+            xsc = [tab[0].cpu(), tab[1].cpu()] if xs == 'ls-2' else [tab[0].cpu()]
+        else:
+            xsc = [ops.row_absmean(xin.reshape(3, -1).to(DEV)).cpu()]
+        xq = O.quantize_activation_stored(xin, xs, xsc)
+        want = F.conv2d(xq.double(), wq.double(), m.bias.detach().cpu().double(), st, 1).float()
+        err = float((y.cpu() - want).abs().max() / want.abs().max())
+        assert err < 1e-5, (xs, ws, err)
+        # fused forms: BatchNorm prologue, ReLU, residual before / after the activation
+        bn = nn.BatchNorm2d(cin).to(DEV).eval()
+        with torch.no_grad():
+            bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5); bn.weight.normal_(1, 0.1); bn.bias.normal_(0, 0.1)
+        res = torch.randn_like(y)
+        with torch.no_grad():
+            for after in (True, False):
+                got = m.forward_fused(x.to(DEV), bn, nn.ReLU(), res, after)
+                conv = m(bn(x.to(DEV)))
+                ref = F.relu(conv) + res if after else F.relu(conv + res)
+                e2 = float((got - ref).abs().max() / ref.abs().max())
+                assert e2 < 1e-5, (xs, ws, after, e2)
+    # golden layers with multi-plane weights (reference outputs; 32 input channels: CUDA-core kernel)
+    for rec in golden_layers:
+        sp = rec['spec']
+        if sp['w_quant'] in ('ls-1', 'fp') or sp['x_quant'] == 'fp':
+            continue
+        clamp = None if sp['alpha'] is None else {'kind': 'symmetric', 'alpha': sp['alpha']}
+        m = QuantConv2d(sp['x_quant'], sp['w_quant'], sp['cin'], sp['cout'], sp['k'], clamp, stride=sp['stride'],
+                        padding=sp['padding'], bias=sp['bias'])
+        m.load_state_dict(rec['state'])
+        m = m.to(DEV).eval()
+        ops.reset_counters()
+        with torch.no_grad():
+            y = m(rec['x'].to(DEV)).cpu()
+        assert 'fakequant' not in ops.LAUNCHES and ops.LAUNCHES.get('bconv_simple', 0) >= 2, ops.LAUNCHES
+        err = float((y - rec['y']).abs().max() / rec['y'].abs().max())
+        assert err < (1e-5 if sp['x_quant'] in ('ls-1',) or sp['x_quant'].startswith('gf') else 5e-2), (sp, err)
