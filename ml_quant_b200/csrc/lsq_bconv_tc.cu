@@ -18,10 +18,10 @@
 // so any row shift is a 16-byte multiple).
 //
 // Warp roles (448 threads, one CTA per SM, persistent over (position tile, channel tile) items):
-//   warps 0-3, 10-13  epilogue : thread = output channel (TMEM lane).  tcgen05.ld 16 positions x planes ->
+//   warps 0-3, 10-13  epilogue : thread = output channel (TMEM lane).  tcgen05.ld 16 accumulator columns ->
 //                     vw[c] * (s1[n] I1 + s2[n] I2) + bias[c] -> transposed through shared memory so that
-//                     global accesses run along positions (NCHW rows); activation and residual (prefetched
-//                     with cp.async several steps ahead) are applied on the way out
+//                     global accesses run along positions (NCHW rows); activation and residual (requested at the
+//                     start of the step, held in registers) are applied on the way out
 //   warp  4           MMA      : one thread issues tcgen05.mma / tcgen05.commit; owns the TMEM allocation
 //   warp  5           weights  : cp.async.bulk (TMA engine, 1-D) of pre-packed operand slabs, mbarrier tx
 //   warps 6-9         patches  : plane bits (L2) -> int8 patch in shared memory, fence.proxy.async
@@ -138,9 +138,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
     const int pbase = part * tph;
     const int spi = tph >> 5;                           // steps per item
     const bool has_res = epi.residual != nullptr;
-    const int R = P.r_stages;
     const long long cstride = (long long)g.ho * g.wo;
-    float* const res0 = reinterpret_cast<float*>(smem + P.smem_res) + (size_t)ewarp * R * 1024;
     float* const outt = reinterpret_cast<float*>(smem + P.smem_out) + (size_t)ewarp * 32 * kOutPitch;
     float2* const scl = reinterpret_cast<float2*>(smem + P.smem_scl) + (size_t)ewarp * 128;
 
@@ -152,141 +150,98 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       if (!valid) return -1;
       return (((long long)pi.s * P.cout + (long long)ctile * 128) * g.ho + pi.a) * g.wo + pi.col;
     };
-    // item -> (position tile, channel tile); layers of up to 128 channels have one channel tile: no division
-    auto split_item = [&](int item, int& ptile, int& ctile) {
-      if (P.n_ctiles == 1) { ptile = item; ctile = 0; }
-      else { ptile = item / P.n_ctiles; ctile = item - ptile * P.n_ctiles; }
-    };
-    struct Cursor { int item, step; };
-    auto advance = [&](Cursor& c) {
-      if (++c.step == spi) { c.step = 0; c.item += (int)gridDim.x; }
-    };
-    auto issue = [&](const Cursor& c, int slot) {      // always commits a group so the group count stays uniform
-      if (has_res && c.item < n_items) {
-        int ptile, ctile;
-        split_item(c.item, ptile, ctile);
-        int sample;
-        const long long off = out_offset(ptile, ctile, pbase + 32 * c.step + lane, sample);
-        const uint32_t dst = smem_u32(res0 + slot * 1024 + lane);
-        const int sz = off >= 0 ? 4 : 0;
-        const float* src = epi.residual + (off >= 0 ? off + (long long)chb * cstride : 0);
-        const long long s1 = off >= 0 ? cstride : 0;
-#pragma unroll
-        for (int ch = 0; ch < 32; ++ch) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)ch * 128u), "l"(src), "r"(sz) : "memory");
-          src += s1;
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
+    // exact int32 -> float for |i| < 2^22 with full-rate instructions (I2F issues at a quarter of the rate)
+    auto i2f = [](uint32_t i) -> float { return __uint_as_float(0x4B400000u + i) - 12582912.0f; };
     Ring acc(kAccStages);
-    Cursor is{(int)blockIdx.x, 0}, co{(int)blockIdx.x, 0};
-    int islot = 0, cslot = 0;
-    for (int r = 0; r + 1 < R; ++r) {
-      issue(is, islot);
-      advance(is);
-      if (++islot == R) islot = 0;
-    }
     float ws = 0.0f, bs = 0.0f;
-    long long off_first = -1;     // output offset of position `lane` of the item's first step (reused by its store phase)
-    while (co.item < n_items) {
+    const int ppsub = 16 / P.npl;                       // positions per 16-column TMEM load
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int ptile, ctile;
-      split_item(co.item, ptile, ctile);
-      // the activation scales of this lane's position are requested before the residual prefetch below is issued,
-      // so their latency is hidden behind it (they were the largest single stall of the epilogue warps)
-      float2 s_first = make_float2(0.0f, 0.0f);
-      if (co.step == 0) {
+      if (P.n_ctiles == 1) { ptile = item; ctile = 0; }  // layers of up to 128 channels: no division
+      else { ptile = item / P.n_ctiles; ctile = item - ptile * P.n_ctiles; }
+      for (int step = 0; step < spi; ++step) {
         int sample;
-        off_first = out_offset(ptile, ctile, pbase + lane, sample);
-        if (off_first >= 0) {
-          s_first.x = __ldg(act_scales + sample);
-          if (P.npl > 1) s_first.y = __ldg(act_scales + g.n + sample);
+        const long long off = out_offset(ptile, ctile, pbase + 32 * step + lane, sample);
+        // the residual values of this lane's position (32 channels) are requested first and stay in registers: their
+        // latency hides behind the accumulator conversion below (round 1 staged them through shared memory with
+        // cp.async: one issue + one shared-memory read per element and a cursor to keep several steps in flight)
+        float rs[32];
+        if (has_res) {
+          const float* rp = epi.residual + (off >= 0 ? off + (long long)chb * cstride : 0);
+          const long long st = off >= 0 ? cstride : 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rs[i] = __ldg(rp + i * st);
         }
-      }
-      issue(is, islot);
-      advance(is);
-      if (++islot == R) islot = 0;
-      // all but the R-1 most recent groups are complete -> the step being consumed has landed
-      if (R >= 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
-      else if (R == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
-      else if (R == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      if (co.step == 0) {
-        // per-position activation scales of this warp's positions, per-thread channel constants
-        scl[lane] = s_first;
-        for (int p = lane + 32; p < tph; p += 32) {
-          int sample;
-          const long long off = out_offset(ptile, ctile, pbase + p, sample);
-          float2 s2 = make_float2(0.0f, 0.0f);
-          if (off >= 0) {
-            s2.x = __ldg(act_scales + sample);
-            if (P.npl > 1) s2.y = __ldg(act_scales + g.n + sample);
+        if (step == 0) {
+          // per-position activation scales of this warp's positions, per-thread channel constants
+          for (int p = lane; p < tph; p += 32) {
+            int smp = sample;
+            const long long o2 = (p == lane) ? off : out_offset(ptile, ctile, pbase + p, smp);
+            float2 s2 = make_float2(0.0f, 0.0f);
+            if (o2 >= 0) {
+              s2.x = __ldg(act_scales + smp);
+              if (P.npl > 1) s2.y = __ldg(act_scales + g.n + smp);
+            }
+            scl[p] = s2;
           }
-          scl[p] = s2;
+          const float4 k = ctab[ctile * 128 + chb + lane];
+          ws = k.x; bs = k.y;
+          __syncwarp();
+          mbar_wait_t(acc_full(acc.stage), acc.phase, err, 1, w0);
+          tc_fence_after();
         }
-        const float4 k = ctab[ctile * 128 + chb + lane];
-        ws = k.x; bs = k.y;
+        // ---- thread = channel: 16 accumulator columns at a time from TMEM, scale, bias -> transposition tile ----
+        float* orow = outt + lane * kOutPitch;
+        for (int sub = 0; sub < 2 * P.npl; ++sub) {
+          const int pl0 = 32 * step + ppsub * sub;          // first position (within this warp's part) of the load
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc.stage * acc_cols +
+                                 (uint32_t)((pbase + pl0) * P.npl);
+          uint32_t rr[16];
+          tmem_ld16(taddr, rr);
+          const float4* sp = reinterpret_cast<const float4*>(scl + pl0);     // (s1, s2) of two positions per float4
+          if (P.npl > 1) {
+            float4 s4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s4[j] = sp[j];
+            tmem_ld_wait();
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float sx = (j & 1) ? s4[j >> 1].z : s4[j >> 1].x, sy = (j & 1) ? s4[j >> 1].w : s4[j >> 1].y;
+              o[j] = fmaf(ws, fmaf(sy, i2f(rr[2 * j + 1]), sx * i2f(rr[2 * j])), bs);
+            }
+            reinterpret_cast<float4*>(orow + 8 * sub)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<float4*>(orow + 8 * sub)[1] = make_float4(o[4], o[5], o[6], o[7]);
+          } else {
+            float4 s4[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s4[j] = sp[j];
+            tmem_ld_wait();
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float sx = (j & 1) ? s4[j >> 1].z : s4[j >> 1].x;
+              o[j] = fmaf(ws, sx * i2f(rr[j]), bs);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(orow + 16 * sub)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        }
         __syncwarp();
-        mbar_wait_t(acc_full(acc.stage), acc.phase, err, 1, w0);
-        tc_fence_after();
-      }
-      // ---- thread = channel: two halves of 16 positions x planes from TMEM, scale, bias -> transposition tile ----
-      float4* orow = reinterpret_cast<float4*>(outt + lane * kOutPitch);
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int p0 = pbase + 32 * co.step + 16 * sub;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc.stage * acc_cols + (uint32_t)(p0 * P.npl);
-        uint32_t rr[32];                                   // 16 positions x planes (interleaved)
-        tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&rr[0]));
-        if (P.npl > 1) tmem_ld16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(&rr[16]));
-        const float4* sp = reinterpret_cast<const float4*>(scl + 32 * co.step + 16 * sub);     // (s1, s2) of two positions
-        float4 s4[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s4[j] = sp[j];
-        tmem_ld_wait();
-        float o[16];
-        if (P.npl > 1) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float sx = (j & 1) ? s4[j >> 1].z : s4[j >> 1].x, sy = (j & 1) ? s4[j >> 1].w : s4[j >> 1].y;
-            const float t = fmaf(sy, (float)(int)rr[2 * j + 1], sx * (float)(int)rr[2 * j]);
-            o[j] = __fadd_rn(__fmul_rn(ws, t), bs);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float sx = (j & 1) ? s4[j >> 1].z : s4[j >> 1].x;
-            o[j] = __fadd_rn(__fmul_rn(ws, sx * (float)(int)rr[j]), bs);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) orow[4 * sub + j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-      }
-      __syncwarp();
-      // ---- lane = position: activation, residual, one 128-byte row segment per channel ----
-      {
-        long long off = off_first;
-        if (co.step != 0) {
-          int sample;
-          off = out_offset(ptile, ctile, pbase + 32 * co.step + lane, sample);
-        }
+        // ---- lane = position: activation, residual, one 128-byte row segment per channel ----
         if (off >= 0) {
-          const float* rs_base = res0 + cslot * 1024 + lane;
           const float* ot = outt + lane;
           const float4* tab = ctab + ctile * 128 + chb;
           float* yp = y + off + (long long)chb * cstride;
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
-            // all shared-memory reads first, then the arithmetic, then the stores (16 independent chains)
-            float v[16], rs[16];
+            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[i] = ot[(c0 + i) * kOutPitch];
-              rs[i] = has_res ? rs_base[(c0 + i) * 32] : 0.0f;
-            }
-            if (!epi.residual_after_act) {
+            for (int i = 0; i < 16; ++i) v[i] = ot[(c0 + i) * kOutPitch];
+            if (has_res && !epi.residual_after_act) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += rs[i];
+              for (int i = 0; i < 16; ++i) v[i] += rs[c0 + i];
             }
             if (epi.act == 1) {
 #pragma unroll
@@ -295,9 +250,9 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.0f ? v[i] : v[i] * tab[c0 + i].z;
             }
-            if (epi.residual_after_act) {
+            if (has_res && epi.residual_after_act) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += rs[i];
+              for (int i = 0; i < 16; ++i) v[i] += rs[c0 + i];
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -306,18 +261,13 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
             }
           }
         }
-      }
-      __syncwarp();
-      if (co.step == spi - 1) {
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(acc.stage));
-        acc.advance();
       }
-      advance(co);
-      if (++cslot == R) cslot = 0;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(acc.stage));
+      acc.advance();
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == 4) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
@@ -545,14 +495,14 @@ bool bconv2d_tc_supported(const lsq_act_geom* g, int nplanes, int cout) {
   if (g->stride != 1 && g->stride != 2) return false;
   if ((long long)g->n * g->rows_per_sample * g->pitch > (1ll << 31) - 4096) return false;
   TcParams P;
-  return tc_pick_tile(g, nplanes, cout, true, P) != 0;
+  return tc_pick_tile(g, nplanes, cout, false, P) != 0;
 }
 
 int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplanes, const float* d_act_scales,
                       const void* d_wpack, const float* d_w_scale, const float* d_bias, int cout, float* d_y,
                       const Epilogue& epi, cudaStream_t stream) {
   TcParams P;
-  if (tc_pick_tile(g, nplanes, cout, epi.residual != nullptr, P) == 0) {
+  if (tc_pick_tile(g, nplanes, cout, false, P) == 0) {      // residual values travel through registers: no staging area
     set_error("bconv2d_tc: patch does not fit shared memory");
     return LSQ_ERR_UNSUPPORTED;
   }
@@ -562,7 +512,7 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   const long long qspan = (long long)g->n * g->rows_per_sample * g->pitch;
   P.p_tiles = (int)((qspan + P.tp - 1) / P.tp);
   const int n_items = P.p_tiles * P.n_ctiles;
-  const size_t smem_bytes = (size_t)P.smem_res + (epi.residual ? (size_t)8 * P.r_stages * 4096 : 0);
+  const size_t smem_bytes = (size_t)P.smem_res;
 
   // the weight image follows the bit image inside d_wpack (lsq_bconv.cu)
   const size_t bits_bytes = ((size_t)cout * g->kh * g->kw * g->cw * 4 + 1023) / 1024 * 1024;

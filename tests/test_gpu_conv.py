@@ -207,7 +207,13 @@ def test_full_size_resnet18_against_live_oracle():
         y = model(x.to(DEV)).cpu()
     y_ref = O.resnet_forward(sd, configs.arch('imagenet_resnet18_ls1w_ls1a'), x)
     err = float((y - y_ref).abs().max() / y_ref.abs().max())
-    assert err < 5e-3, err
+    # End to end this network is chaotic too, if less than the ls-2 one: every layer takes sign(bn(x)) of ~10^6 values
+    # per sample and the few within fp32 rounding of zero flip.  Round 1's epilogue (fmul, fadd) happened to land at
+    # 4e-3 for this seed, round 2's (one fma: one rounding less) at 3.7e-2 -- both are "a handful of flipped signs,
+    # amplified by 16 random-init layers".  The strict statement is the teacher-forced per-layer test below
+    # (test_full_size_network_layer_by_layer_with_own_scales[imagenet_resnet18_ls1w_ls1a]).
+    assert err < 0.15, err
+    assert int((y.argmax(1) == y_ref.argmax(1)).sum()) >= 3
     # batch sharding is result preserving (per-sample scales, eval BN): bit-identical halves
     with torch.no_grad():
         a = model(x[:2].to(DEV)).cpu()
@@ -428,8 +434,10 @@ def test_full_size_resnet18_ls2_headline_config():
     assert torch.equal(fwd().cpu(), yf)
 
 
-def test_full_size_network_layer_by_layer_with_own_scales():
-    """Teacher-forced full-size check of the headline network (batch 2, 224 x 224): every one of the 16 QuantConv2d
+@pytest.mark.parametrize('cfg', ['imagenet_resnet18_ls1w_ls2a', 'imagenet_resnet18_ls1w_ls1a'])
+def test_full_size_network_layer_by_layer_with_own_scales(cfg):
+    """Teacher-forced full-size check of the headline network and of the XNOR network (BASELINE config 3; ls-1
+    activations: v1 = mean|x| to 1e-6, one plane) (batch 2, 224 x 224): every one of the 16 QuantConv2d
     layers, fed with the GPU's own input of that layer, must (a) pick a v1 that meets the solver contract against the
     oracle, (b) reproduce the oracle's v2 for that v1 to 1e-6, and (c) produce the oracle's convolution output for
     those scales to 1e-5 of max|y|.  Together with the exact kernels around them this pins the whole forward,
@@ -437,10 +445,11 @@ def test_full_size_network_layer_by_layer_with_own_scales():
     runtime_strict()
     from ml_quant_b200 import runtime
     from tests.test_gpu_quantizers import _solver_contract
-    model = runtime.build_model('imagenet_resnet18_ls1w_ls2a', torch.device(DEV))
+    model = runtime.build_model(cfg, torch.device(DEV))
     runtime.calibrate(model, (3, 224, 224), batches=1, batch=8)
     layers = runtime.quant_layers(model)
     assert len(layers) == 16
+    xnor = cfg.endswith('ls1a')
     rec = {}
     for i, m in enumerate(layers):
         orig = m.quantize_input
@@ -460,13 +469,19 @@ def test_full_size_network_layer_by_layer_with_own_scales():
         alpha = m.clamp_alpha
         xin = xi.clamp(-alpha, alpha)
         rows = xin.reshape(2, -1)
-        v1, v2 = table[0], table[1]
-        _solver_contract(rows, v1, O.solve_v1(rows, False, 3, chunk=1).view(-1), False, 3)
-        b1 = torch.where(xin >= 0, 1.0, -1.0)
-        v2_ref = (xin - v1.view(-1, 1, 1, 1) * b1).abs().mean(dim=(1, 2, 3))
-        assert torch.allclose(v2, v2_ref, rtol=1e-6, atol=0), (i, v2, v2_ref)
-        y_ref, _ = O.plane_conv_identity(xin, m.weight.detach().cpu(), m.bias.detach().cpu(), 'ls-2', [v1, v2],
-                                         m.w_approximate.v1.detach().cpu(), m.stride[0], m.padding[0])
+        if xnor:
+            v1 = table[0]
+            assert torch.allclose(v1, rows.abs().mean(1), rtol=1e-6, atol=0), (i, v1)
+            y_ref, _ = O.plane_conv_identity(xin, m.weight.detach().cpu(), m.bias.detach().cpu(), 'ls-1', [v1],
+                                             m.w_approximate.v1.detach().cpu(), m.stride[0], m.padding[0])
+        else:
+            v1, v2 = table[0], table[1]
+            _solver_contract(rows, v1, O.solve_v1(rows, False, 3, chunk=1).view(-1), False, 3)
+            b1 = torch.where(xin >= 0, 1.0, -1.0)
+            v2_ref = (xin - v1.view(-1, 1, 1, 1) * b1).abs().mean(dim=(1, 2, 3))
+            assert torch.allclose(v2, v2_ref, rtol=1e-6, atol=0), (i, v2, v2_ref)
+            y_ref, _ = O.plane_conv_identity(xin, m.weight.detach().cpu(), m.bias.detach().cpu(), 'ls-2', [v1, v2],
+                                             m.w_approximate.v1.detach().cpu(), m.stride[0], m.padding[0])
         err = float((y - y_ref).abs().max() / y_ref.abs().max())
         assert err < 1e-5, (i, err)
 
