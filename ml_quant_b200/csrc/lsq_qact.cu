@@ -37,7 +37,6 @@ namespace lsq {
 
 constexpr int kQThreads = 512;
 constexpr int kQBins = 4096, kQShift = 14;
-constexpr int kQBinsPerThread = kQBins / kQThreads;   // 8 consecutive bins per thread in the scan
 constexpr int kQIdsCap = 17408;                       // sampled elements of a row handled by one CTA
 constexpr int kQListCap = 2048;                       // collected elements (sorted and tested one by one)
 constexpr int kQMaxFlag = 64;
@@ -56,15 +55,17 @@ struct QParams {
 };
 
 constexpr int kQSegMax = 256;                         // elements of one flagged bin a warp sorts
-constexpr int kQWarpQueue = 96;                       // hits a warp may queue in the collection walk
-struct QSmem {
+constexpr int kQQueueTotal = kQBins;                  // hits a CTA may queue in the collection walk (split over its warps;
+                                                      // the queue reuses the bin counters, dead by then)
+template <int T, int IDS>
+struct QSmemT {
   uint32_t hcnt[kQBins];
   union {
     uint32_t hrem[kQBins];         // sweep 1 .. flagging: sum of the low key bits per bin
     uint8_t fmap[kQBins];          // afterwards: bin -> 1 + flagged index, or 65 + index of the flagged bin it follows
   };
-  uint16_t ids[kQIdsCap];
-  uint32_t list[kQListCap];        // collected keys, one power-of-two padded segment per flagged bin (layout shared by
+  uint16_t ids[IDS];
+  uint32_t list[(T * 4 > kQListCap) ? T * 4 : kQListCap];   // collected keys, one power-of-two padded segment per flagged bin (layout shared by
                                    // all CTAs of the cluster); during the scan: per-thread group prefixes
   float2 ab[kQMaxChannels];
   double red[32];
@@ -88,7 +89,6 @@ struct QSmem {
   uint32_t sexcl[kQMaxFlag], seg_start[kQMaxFlag], seg_cnt[kQMaxFlag];
   double spref[kQMaxFlag];
   uint32_t lfill[kQMaxFlag], lsmin[kQMaxFlag];    // this CTA: elements collected per segment, smallest key of the follower bin
-  uint32_t wq[kQThreads / 32][kQWarpQueue];       // per warp: (sample index << 8 | segment code) of the hits of the index walk
   uint32_t nlist;
   int status;                      // 0 = solved here, != 0: reason the row goes to the generic kernels
   float v1;
@@ -96,8 +96,8 @@ struct QSmem {
   double best_cost[32];
   uint32_t best_pos[32], best_key[32], ncand;
 };
-static_assert(sizeof(QSmem) <= 113 * 1024, "two CTAs per SM");
-static_assert(kQThreads * 16 <= kQListCap * 4, "group prefix records are parked in the list");
+static_assert(sizeof(QSmemT<kQThreads, kQIdsCap>) <= 113 * 1024, "two CTAs per SM");
+static_assert(sizeof(QSmemT<256, 64>) <= 56 * 1024, "four CTAs per SM");
 
 __device__ __forceinline__ uint32_t q_channel(const QParams& qp, unsigned long long idx) {
   return qp.hw_magic ? (uint32_t)((idx * qp.hw_magic) >> 40) : (uint32_t)(idx / qp.hw);
@@ -116,12 +116,15 @@ __device__ __forceinline__ double q_bin_sum(uint32_t klo, uint32_t b, uint32_t c
   return (double)q_bin_isum(klo, b, cnt, rem) * q_bin_scale(klo, b);
 }
 
-template <bool TERN, int VEC>
-__global__ void __launch_bounds__(kQThreads, 2)
+template <bool TERN, int VEC, int T, int IDS>
+__global__ void __launch_bounds__(T, 1024 / T)
 quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue pro, int cs, QParams qp,
                  uint32_t* __restrict__ planes, float* __restrict__ scales, int* __restrict__ row_status,
-                 int* __restrict__ diag) {
+                 int* __restrict__ diag, uint16_t* __restrict__ gids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  using QSmem = QSmemT<T, IDS>;
+  constexpr int kBinsPerThread = kQBins / T;          // consecutive bins per thread in the scan (8 or 16)
+  constexpr int kQWarpQueue = kQQueueTotal / (T / 32);
   QSmem& sm = *reinterpret_cast<QSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -130,6 +133,9 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
   QSmem* const r0 = (cs > 1) ? cluster.map_shared_rank(&sm, 0) : &sm;
   const float* xr = x + row * qp.len;
   const uint32_t klo = qp.klo, n = qp.n_s;
+  // bin index of every sampled element: in shared memory when the CTA's share of the row fits, else (one CTA per
+  // long row) in a global scratch row that is written in sweep 1 and read back, L2 hot, by the collection walk
+  uint16_t* const ids = gids ? gids + row * ((4ll * qp.groups + 7ll) & ~7ll) : sm.ids;      // 16-byte aligned rows
   auto csync = [&]() { if (cs > 1) cluster.sync(); else __syncthreads(); };
   // phase cycle counters of rank 0 (diagnostics only: one clock read per phase by one thread)
   long long tprev = 0, tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -138,8 +144,8 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
 #define LSQ_QTICK(i) do { if (timing) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; } } while (0)
 
   // ---- setup --------------------------------------------------------------------------------------------------
-  for (int b = tid; b < kQBins; b += kQThreads) { sm.hcnt[b] = 0u; sm.hrem[b] = 0u; }
-  for (int c = tid; c < g.cw * 32; c += kQThreads) {
+  for (int b = tid; b < kQBins; b += T) { sm.hcnt[b] = 0u; sm.hrem[b] = 0u; }
+  for (int c = tid; c < g.cw * 32; c += T) {
     float2 k = make_float2(1.0f, 0.0f);
     if (pro.a && c < g.c) k = make_float2(__ldg(pro.a + c), __ldg(pro.b + c) + 0.0f);
     sm.ab[c] = k;
@@ -171,11 +177,11 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       return kIdBelow;
     };
     constexpr int kU = 5;   // groups per thread and trip: 20 independent loads in flight
-    for (uint32_t gb = g_lo + tid; gb < g_hi; gb += kU * kQThreads) {
+    for (uint32_t gb = g_lo + tid; gb < g_hi; gb += kU * T) {
       float raw[kU][4];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const uint32_t gi = gb + u * kQThreads;
+        const uint32_t gi = gb + u * T;
         const long long i0 = (long long)gi * 12;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -185,7 +191,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const uint32_t gi = gb + u * kQThreads;
+        const uint32_t gi = gb + u * T;
         if (gi >= g_hi) break;
         const unsigned long long i0 = (unsigned long long)gi * 12ull;
         uint32_t c = q_channel(qp, i0);
@@ -201,7 +207,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
           }
           r += 3;
         }
-        *reinterpret_cast<uint2*>(&sm.ids[4 * (gi - g_lo)]) = make_uint2(id[0] | (id[1] << 16), id[2] | (id[3] << 16));
+        *reinterpret_cast<uint2*>(&ids[4 * (gi - g_lo)]) = make_uint2(id[0] | (id[1] << 16), id[2] | (id[3] << 16));
       }
     }
     const double sb = block_sum(lb, sm.red);
@@ -220,7 +226,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
   // ---- merge: CTA r sums slice r of all histograms into rank 0's ---------------------------------------------------
   if (cs > 1) {
     const int slice = kQBins / cs;
-    for (int b = rank * slice + tid; b < (rank + 1) * slice; b += kQThreads) {
+    for (int b = rank * slice + tid; b < (rank + 1) * slice; b += T) {
       uint32_t cq[kQMaxCluster], rq[kQMaxCluster];
 #pragma unroll
       for (int q = 0; q < kQMaxCluster; ++q) {       // all remote loads in flight together (one round trip)
@@ -251,14 +257,14 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     uint32_t ct = 0u, fn = kNoKey;
     unsigned long long it = 0ull;
 #pragma unroll
-    for (int j = 0; j < kQBinsPerThread; ++j) {
-      const uint32_t b = tid * kQBinsPerThread + j, cnt = sm.hcnt[b];
+    for (int j = 0; j < kBinsPerThread; ++j) {
+      const uint32_t b = tid * kBinsPerThread + j, cnt = sm.hcnt[b];
       if (cnt != 0u) {
         ct += cnt; it += q_bin_isum(klo, b, cnt, sm.hrem[b]);
         if (fn == kNoKey) fn = b;
       }
     }
-    const double stt = (double)it * q_bin_scale(klo, tid * kQBinsPerThread);
+    const double stt = (double)it * q_bin_scale(klo, tid * kBinsPerThread);
     uint32_t ci = ct;
     double si = stt;
 #pragma unroll
@@ -280,12 +286,12 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     __syncthreads();
     uint32_t coff = 0u;
     double soff = 0.0, s_bins = 0.0;
-    for (int w = 0; w < kQThreads / 32; ++w) {
+    for (int w = 0; w < T / 32; ++w) {
       if (w < wid) { coff += sm.wcnt[w]; soff += sm.wsum[w]; }
       s_bins += sm.wsum[w];
     }
     uint32_t nxt_after = nxt_in_warp;
-    for (int w = wid + 1; w < kQThreads / 32 && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
+    for (int w = wid + 1; w < T / 32 && nxt_after == kNoKey; ++w) nxt_after = sm.wfirst[w];
     const double s_tot = sum_below + s_bins;
     const uint32_t excl0 = cnt_below + coff + ci - ct;
     const double pref0 = sum_below + soff + si - stt;
@@ -304,13 +310,13 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     };
     // two levels: one coarse test per thread on the union of its bins, the fine test only for flagged groups
     uint32_t* const gexcl = sm.list;
-    uint32_t* const gnext = sm.list + kQThreads;
-    double* const gpref = reinterpret_cast<double*>(sm.list + 2 * kQThreads);
+    uint32_t* const gnext = sm.list + T;
+    double* const gpref = reinterpret_cast<double*>(sm.list + 2 * T);
     gexcl[tid] = excl0; gnext[tid] = nxt_after; gpref[tid] = pref0;
     if (ct != 0u) {
-      const uint32_t b0 = tid * kQBinsPerThread;
+      const uint32_t b0 = tid * kBinsPerThread;
       const uint32_t elo_k = klo + (b0 << kQShift);
-      const uint32_t ehi_k = min(klo + ((b0 + kQBinsPerThread) << kQShift) - 1u, kmax);
+      const uint32_t ehi_k = min(klo + ((b0 + kBinsPerThread) << kQShift) - 1u, kmax);
       const float nxt_hi = (nxt_after != kNoKey) ? bin_upper(nxt_after) : key_val(kmax);
       if (may_hold<TERN>(elo_k, ehi_k, ct, stt, excl0, pref0, nxt_hi, n, s_tot, kmax, 0.0f)) {
         const int slot = atomicAdd(&sm.ngroup, 1);
@@ -319,21 +325,21 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     }
     __syncthreads();
     const int ngroup = sm.ngroup;
-    const uint32_t nfine = (uint32_t)min(ngroup, kQMaxGroups) * (uint32_t)kQBinsPerThread;
-    for (uint32_t idx = tid; idx < nfine; idx += kQThreads) {
-      const uint32_t gid = sm.glist[idx / kQBinsPerThread], j = idx % kQBinsPerThread;
-      const uint32_t b = gid * kQBinsPerThread + j, cnt = sm.hcnt[b];
+    const uint32_t nfine = (uint32_t)min(ngroup, kQMaxGroups) * (uint32_t)kBinsPerThread;
+    for (uint32_t idx = tid; idx < nfine; idx += T) {
+      const uint32_t gid = sm.glist[idx / kBinsPerThread], j = idx % kBinsPerThread;
+      const uint32_t b = gid * kBinsPerThread + j, cnt = sm.hcnt[b];
       if (cnt == 0u) continue;
       uint32_t excl = gexcl[gid];
       unsigned long long ib = 0ull;
       for (uint32_t j1 = 0; j1 < j; ++j1) {
-        const uint32_t b1 = gid * kQBinsPerThread + j1, c1 = sm.hcnt[b1];
+        const uint32_t b1 = gid * kBinsPerThread + j1, c1 = sm.hcnt[b1];
         if (c1 != 0u) { excl += c1; ib += q_bin_isum(klo, b1, c1, sm.hrem[b1]); }
       }
       const double pref = gpref[gid] + (double)ib * q_bin_scale(klo, b);
       uint32_t nb = kNoKey;
-      for (uint32_t j2 = kQBinsPerThread - 1; j2 > j; --j2)
-        if (sm.hcnt[gid * kQBinsPerThread + j2] != 0u) nb = gid * kQBinsPerThread + j2;
+      for (uint32_t j2 = kBinsPerThread - 1; j2 > j; --j2)
+        if (sm.hcnt[gid * kBinsPerThread + j2] != 0u) nb = gid * kBinsPerThread + j2;
       if (nb == kNoKey) nb = gnext[gid];
       test_bin(b, cnt, q_bin_sum(klo, b, cnt, sm.hrem[b]), excl, pref, nb);
     }
@@ -385,7 +391,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       // everything below the bin window is one pseudo bin: if it could hold a candidate the row needs finer
       // treatment there (never seen on clamped BatchNorm outputs)
       uint32_t fb = kNoKey;
-      for (int w = 0; w < kQThreads / 32 && fb == kNoKey; ++w) fb = sm.wfirst[w];
+      for (int w = 0; w < T / 32 && fb == kNoKey; ++w) fb = sm.wfirst[w];
       const float nxt_hi = (fb != kNoKey) ? bin_upper(fb) : key_val(kmax);
       if (may_hold<TERN>(0u, klo - 1u, cnt_below, sum_below, 0u, 0.0, nxt_hi, n, s_tot, kmax, 0.0f)) atomicMax(&sm.status, 3);
     }
@@ -400,7 +406,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
   const int nflag = (status == 0) ? r0->nflag : 0;
   if (nflag > 0) {
     // every CTA: bin -> segment map (the histogram's remainder sums are dead by now)
-    for (int b = tid; b < kQBins / 4; b += kQThreads) reinterpret_cast<uint32_t*>(sm.fmap)[b] = 0u;
+    for (int b = tid; b < kQBins / 4; b += T) reinterpret_cast<uint32_t*>(sm.fmap)[b] = 0u;
     if (rank != 0 && tid < nflag) { sm.sbin[tid] = r0->sbin[tid]; sm.snb[tid] = r0->snb[tid]; sm.seg_start[tid] = r0->seg_start[tid]; }
     if (tid < kQMaxFlag) { sm.lfill[tid] = 0u; sm.lsmin[tid] = kNoKey; }
     __syncthreads();
@@ -410,27 +416,44 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     __syncthreads();
     // phase A: walk the bin indices; a warp queues its hits (sample, segment) without touching global memory ...
     const uint32_t ns_cta = 4u * (g_hi - g_lo);
-    uint32_t* const wq = sm.wq[wid];
+    uint32_t* const wq = sm.hcnt + wid * kQWarpQueue;     // (sample index << 8 | segment code) of this warp's hits
     uint32_t nq = 0u;                                  // warp uniform
-    for (uint32_t base = 128u * wid; base < ns_cta; base += 4u * kQThreads) {
-      const uint32_t s4 = base + 4u * lane;
-      uint2 w = make_uint2(0xFFFEFFFEu, 0xFFFEFFFEu);
-      if (s4 < ns_cta) w = *reinterpret_cast<const uint2*>(&sm.ids[s4]);
-      const uint32_t id4[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+    // a lane takes 8 consecutive samples per 16-byte load (global scratch rows: L2 latency), two loads in flight
+    constexpr int kW = 2;
+    for (uint32_t base0 = 256u * wid; base0 < ns_cta; base0 += kW * 8u * T) {
+      uint4 wv[kW];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t id = id4[j];
-        const uint32_t m = (id < (uint32_t)kQBins) ? sm.fmap[id] : 0u;
-        const uint32_t hit = __ballot_sync(0xffffffffu, m != 0u);
-        if (hit != 0u) {
-          const uint32_t pos = nq + __popc(hit & ((1u << lane) - 1u));
-          if (m != 0u && pos < (uint32_t)kQWarpQueue) wq[pos] = ((s4 + j) << 8) | m;
-          nq += __popc(hit);
+      for (int u = 0; u < kW; ++u) {
+        const uint32_t s8 = base0 + u * 8u * T + 8u * lane;
+        wv[u] = make_uint4(0xFFFEFFFEu, 0xFFFEFFFEu, 0xFFFEFFFEu, 0xFFFEFFFEu);
+        if (s8 + 8u <= ns_cta) wv[u] = *reinterpret_cast<const uint4*>(&ids[s8]);
+        else if (s8 < ns_cta) { const uint2 h = *reinterpret_cast<const uint2*>(&ids[s8]); wv[u].x = h.x; wv[u].y = h.y; }
+      }
+#pragma unroll
+      for (int u = 0; u < kW; ++u) {
+        const uint32_t s8 = base0 + u * 8u * T + 8u * lane;
+        if (base0 + u * 8u * T >= ns_cta) break;       // warp uniform
+        const uint32_t w4[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+        uint32_t m8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                  // eight independent lookups, then the ballots
+          const uint32_t id = (j & 1) ? (w4[j >> 1] >> 16) : (w4[j >> 1] & 0xFFFFu);
+          m8[j] = (id < (uint32_t)kQBins) ? sm.fmap[id] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t hit = __ballot_sync(0xffffffffu, m8[j] != 0u);
+          if (hit != 0u) {
+            const uint32_t pos = nq + __popc(hit & ((1u << lane) - 1u));
+            if (m8[j] != 0u && pos < (uint32_t)kQWarpQueue) wq[pos] = ((s8 + j) << 8) | m8[j];
+            nq += __popc(hit);
+          }
         }
       }
     }
     if (nq > (uint32_t)kQWarpQueue) { if (lane == 0) atomicMax(&r0->status, 6); nq = kQWarpQueue; }
     __syncwarp();
+    if (timing && cs == 1) { const long long tn = clock64(); tph[7] = tn - tprev; }      // map build + index walk
     // ... phase B: the exact keys of all queued hits, their loads in flight together (one trip to L2)
     for (uint32_t e = lane; e < nq; e += 32u) {
       const uint32_t ent = wq[e], m = ent & 0xFFu;
@@ -455,7 +478,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     uint32_t ncand = 0u;
     const double s_tot = sm.s_tot;
     if (status == 0) {
-      for (int i = wid; i < nflag; i += kQThreads / 32) {
+      for (int i = wid; i < nflag; i += T / 32) {
         const uint32_t base = sm.seg_start[i], cnt = sm.seg_cnt[i];
         uint32_t fill = sm.lfill[i], smin = sm.lsmin[i];
         if (cs > 1) {
@@ -515,7 +538,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     __syncthreads();
     status = sm.status;
     if (status == 0) {
-      for (int i = wid; i < nflag; i += kQThreads / 32) {
+      for (int i = wid; i < nflag; i += T / 32) {
         const uint32_t base = sm.seg_start[i], cnt = sm.seg_cnt[i];
         const uint32_t* keys = sm.list + base;
         // successor of the segment's last element: the smallest key of the next non-empty bin
@@ -558,7 +581,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       __syncthreads();
       if (tid == 0) {
         Best b{1e300, 0xFFFFFFFFu, 0u};
-        for (int w = 0; w < kQThreads / 32; ++w) b.offer(sm.best_cost[w], sm.best_pos[w], sm.best_key[w]);
+        for (int w = 0; w < T / 32; ++w) b.offer(sm.best_cost[w], sm.best_pos[w], sm.best_key[w]);
         uint32_t nc_tot = sm.ncand;
         if (TERN) {
           // optimal.py:86-118: when min > mean/2 the value mean/2 (not a data element) is appended last
@@ -600,7 +623,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
     const uint32_t it_lo = (uint32_t)(((unsigned long long)qp.nitems * (unsigned)rank) / (unsigned)cs);
     const uint32_t it_hi = (uint32_t)(((unsigned long long)qp.nitems * (unsigned)(rank + 1)) / (unsigned)cs);
     double acc_sum = 0.0;
-    for (uint32_t item = it_lo + tid; item < it_hi; item += kQThreads) {
+    for (uint32_t item = it_lo + tid; item < it_hi; item += T) {
       const int cgi = (int)(item / qp.nq), q = (int)(item - (uint32_t)cgi * qp.nq);
       const int p0 = q * VEC;
       const int cbase = cgi * 32;
@@ -640,6 +663,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
   if (timing) {
     int* d = diag + row * 16;
     for (int i = 0; i < 7; ++i) d[8 + i] = (int)tph[i];
+    if (cs == 1) d[10] = (int)tph[7];       // single-CTA rows have no merge: the slot reports the index walk instead
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     d[15] = (int)smid;
@@ -660,11 +684,25 @@ int encode_act_marked_rows(const float* d_x, const lsq_act_geom* g, float alpha,
                            const lsq_prologue* pro, const int* d_row_status, cudaStream_t stream);
 }
 
-// cluster size for rows of `len` elements: the CTA's share of the sampled row must fit its bin-index buffer, and the
-// rows in flight (two CTAs per SM) should stay L2 resident between the two sweeps
-static int qact_cluster_size(int64_t len, int sms) {
+// Launch shape for rows of `len` elements.  Rows whose sampled third fits the bin-index buffer of a CTA (17 408
+// samples: every layer input of the CIFAR network, stages 3-4 of the ImageNet one) run one CTA per row with the indices
+// in shared memory.  Longer rows (64 x 56 x 56 and 128 x 28 x 28):
+//   default   still one CTA per row, two per SM, the bin indices in a global scratch row (2 bytes per sample, written
+//             in sweep 1, read back L2-hot by the collection walk): 296 rows in flight, every SM streams all the time,
+//             no cross-CTA traffic -- but the rows in flight (238 / 119 MB) exceed L2, so the second sweep comes from
+//             HBM again: 2 x the input in DRAM traffic;
+//   cluster   LSQ_QACT_MODE=cluster: a cluster of 2-8 CTAs per row, sized so that the rows in flight stay L2 resident:
+//             DRAM traffic 1.07 x the input, but three of four CTAs idle while rank 0 solves and seven cluster
+//             barriers per row (measured 1.3 x slower than the default: DESIGN.md section 5).
+struct QactShape { int cs; bool global_ids; bool t256; };
+static QactShape qact_shape(int64_t len, int sms) {
   static const int forced = getenv("LSQ_QACT_CS") ? atoi(getenv("LSQ_QACT_CS")) : 0;   // development override
+  static const bool want_cluster = getenv("LSQ_QACT_MODE") && getenv("LSQ_QACT_MODE")[0] == 'c';
+  static const int tmode = getenv("LSQ_QACT_T") ? atoi(getenv("LSQ_QACT_T")) : 0;      // development: 256-thread CTAs, 4 per SM
   const int64_t groups = (len + 11) / 12;
+  if (!want_cluster && forced == 0 && tmode == 256) return {1, true, true};
+  if (4 * (groups + 1) <= (int64_t)kQIdsCap && forced <= 1) return {1, false, false};
+  if (!want_cluster && forced == 0) return {1, true, false};
   int cs = 1;
   while (cs < kQMaxCluster && 4 * ((groups + cs - 1) / cs + 1) > (int64_t)kQIdsCap) cs <<= 1;
   const double l2_budget = 64.0 * 1024 * 1024;
@@ -672,7 +710,7 @@ static int qact_cluster_size(int64_t len, int sms) {
   if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
     if (4 * ((groups + forced - 1) / forced + 1) <= (int64_t)kQIdsCap) cs = forced;
   }
-  return cs;
+  return {cs, false, false};
 }
 
 static bool qact_fast_path(const lsq_act_geom* g, float alpha, int skip) {
@@ -682,14 +720,14 @@ static bool qact_fast_path(const lsq_act_geom* g, float alpha, int skip) {
   if (skip != 3 || !(alpha >= 1e-30f) || !(alpha < 3e38f)) return false;
   if (len < 2048 || (len + 2) / 3 > 131071) return false;       // short rows: the sorting kernel; 32-bit bin sums
   if (g->cw * 32 > kQMaxChannels) return false;
-  const int64_t groups = (len + 11) / 12;
-  if (4 * ((groups + kQMaxCluster - 1) / kQMaxCluster + 1) > (int64_t)kQIdsCap) return false;
   return true;
 }
 
 extern "C" size_t lsq_quantize_act_workspace_bytes(const lsq_act_geom* g) {
   if (!g) return 0;
-  return (size_t)g->n * sizeof(int) + 256 + lsq_reduce_workspace_bytes(g->n, (int64_t)g->c * g->h * g->w);
+  const int64_t len = (int64_t)g->c * g->h * g->w;
+  const size_t ids = (size_t)g->n * (size_t)((((len + 11) / 12) * 4 + 7) & ~7ll) * sizeof(uint16_t);   // bin indices of long rows
+  return (size_t)g->n * sizeof(int) + 512 + lsq_reduce_workspace_bytes(g->n, len) + ids;
 }
 
 extern "C" int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float alpha, int ternary, int skip,
@@ -710,6 +748,7 @@ extern "C" int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float a
   // workspace: [reduce workspace of the encoder (arrival counters first, zero at rest)][row status, one int per row]
   const size_t red_bytes = (lsq_reduce_workspace_bytes(g->n, len) + 255) / 256 * 256;
   int* d_status = (int*)((char*)d_ws + red_bytes);
+  uint16_t* d_ids = (uint16_t*)((char*)d_ws + red_bytes + ((size_t)g->n * sizeof(int) + 255) / 256 * 256);
   float* d_v2 = ternary ? nullptr : d_scales + g->n;
   if (!qact_fast_path(g, alpha, skip)) {
     // not the shape the fused kernel is built for: the generic kernels on every row (d_row_status = NULL)
@@ -719,13 +758,14 @@ extern "C" int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float a
     return encode_act_marked_rows(d_x, g, alpha, d_scales, 1, 2, d_planes, d_v2, d_ws, red_bytes, pro, nullptr, st);
   }
   const int sms = device_sms();
-  const int cs = qact_cluster_size(len, sms);
+  const QactShape shape = qact_shape(len, sms);
+  const int cs = shape.cs;
   QParams qp;
   qp.len = len; qp.n_s = (uint32_t)((len + 2) / 3); qp.groups = (uint32_t)((len + 11) / 12);
   const uint32_t ka = __builtin_bit_cast(uint32_t, alpha) >> kQShift;
-  // window of kQBins bins whose last bin holds key(alpha); its first bin is rounded up to a multiple of 8 absolute
-  // bins so that the 8 consecutive bins a thread scans never straddle an octave (exponent) boundary
-  qp.klo = (((ka + 1u - (uint32_t)kQBins) + 7u) & ~7u) << kQShift;
+  // window of kQBins bins whose last bin holds key(alpha); its first bin is rounded up to a multiple of 16 absolute
+  // bins so that the 8 or 16 consecutive bins a thread scans never straddle an octave (exponent) boundary
+  qp.klo = (((ka + 1u - (uint32_t)kQBins) + 15u) & ~15u) << kQShift;
   qp.hw = (uint32_t)(g->h * g->w);
   const bool vec4 = (qp.hw % 4 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 16 == 0);
   qp.nq = vec4 ? qp.hw / 4 : qp.hw;
@@ -735,8 +775,9 @@ extern "C" int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float a
   const Prologue dp = to_dev(pro);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((int64_t)g->n * cs));
-  cfg.blockDim = dim3(kQThreads);
-  cfg.dynamicSmemBytes = sizeof(QSmem);
+  cfg.blockDim = dim3(shape.t256 ? 256 : kQThreads);
+  cfg.dynamicSmemBytes = shape.t256 ? sizeof(QSmemT<256, 64>) : sizeof(QSmemT<kQThreads, kQIdsCap>);
+  uint16_t* gids = shape.global_ids ? d_ids : nullptr;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -744,16 +785,21 @@ extern "C" int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float a
   cfg.attrs = attr;
   cfg.numAttrs = cs > 1 ? 1 : 0;
   cudaError_t e = cudaSuccess;
-#define LSQ_QACT(T, V)                                                                                             \
+#define LSQ_QACT(TERNARY, V, THR, IDS)                                                                             \
   do {                                                                                                             \
     static std::atomic<unsigned long long> smem_set{0ull};                                                         \
-    e = ensure_max_smem(quant_act_kernel<T, V>, smem_set);                                                         \
+    e = ensure_max_smem(quant_act_kernel<TERNARY, V, THR, IDS>, smem_set);                                         \
     if (e == cudaSuccess)                                                                                          \
-      e = cudaLaunchKernelEx(&cfg, quant_act_kernel<T, V>, d_x, dg, alpha, dp, cs, qp, d_planes, d_scales, d_status, \
-                             (int*)d_diag);                                                                        \
+      e = cudaLaunchKernelEx(&cfg, quant_act_kernel<TERNARY, V, THR, IDS>, d_x, dg, alpha, dp, cs, qp, d_planes,   \
+                             d_scales, d_status, (int*)d_diag, gids);                                              \
   } while (0)
-  if (ternary) { if (vec4) LSQ_QACT(true, 4); else LSQ_QACT(true, 1); }
-  else { if (vec4) LSQ_QACT(false, 4); else LSQ_QACT(false, 1); }
+#define LSQ_QACT_V(TERNARY, V)                                                                                     \
+  do {                                                                                                             \
+    if (shape.t256) LSQ_QACT(TERNARY, V, 256, 64); else LSQ_QACT(TERNARY, V, kQThreads, kQIdsCap);                 \
+  } while (0)
+  if (ternary) { if (vec4) LSQ_QACT_V(true, 4); else LSQ_QACT_V(true, 1); }
+  else { if (vec4) LSQ_QACT_V(false, 4); else LSQ_QACT_V(false, 1); }
+#undef LSQ_QACT_V
 #undef LSQ_QACT
   if (e != cudaSuccess) {
     set_error("lsq_quantize_act: launch (cluster %d): %s", cs, cudaGetErrorString(e));
