@@ -176,7 +176,10 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       ++cb; lb += (double)a;
       return kIdBelow;
     };
-    constexpr int kU = 5;   // groups per thread and trip: 20 independent loads in flight
+#ifndef LSQ_QACT_KU
+#define LSQ_QACT_KU 2
+#endif
+    constexpr int kU = LSQ_QACT_KU;   // groups per thread and trip: 4 independent loads each in flight
     for (uint32_t gb = g_lo + tid; gb < g_hi; gb += kU * T) {
       float raw[kU][4];
 #pragma unroll
