@@ -169,8 +169,8 @@ LSQ_API int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alp
                       uint32_t* d_planes, float* d_last_scale,
                       void* d_ws, size_t ws_bytes, const lsq_prologue* pro, void* stream);
 
-/* Fused 2-bit / ternary activation quantizer of the QuantConv2d input: scales AND bit planes with ONE read of x from
- * HBM.  Replaces, for x_quant = 'ls-2' (ternary = 0) and 'ls-T' (ternary = 1) with moving_average_mode = 'off',
+/* Fused 2-bit / ternary activation quantizer of the QuantConv2d input: scales AND bit planes in one kernel.
+ * Replaces, for x_quant = 'ls-2' (ternary = 0) and 'ls-T' (ternary = 1) with moving_average_mode = 'off',
  * quantizer_ls_2 / quantizer_ls_ternary as called by ActivationQuantizerLS2 / LST._batch_quantization
  * (quant/binary/activation_quantization.py:99-100,165-168,196-199 -> quantization.py:59-115 -> optimal.py:121-155):
  *   v1 = opt_v1(|clamp(x)|[::skip]) per sample, v2 = mean |clamp(x) - v1 sign(x)| (2-bit), the two sign planes in the
@@ -181,7 +181,8 @@ LSQ_API int lsq_encode_act_ex(const float* d_x, const lsq_act_geom* g, float alp
  * lsq_reduce_workspace_bytes; the call leaves them zeroed).  d_diag (optional): int32[n][16] per-row diagnostics
  * {status, flagged bins, collected elements, candidates, ranges, cluster size, elements below the bin window, groups,
  *  7 per-phase cycle counts of the cluster's first CTA, SM id}.
- * One thread-block cluster per sample keeps the row L2-resident between the histogram sweep and the encoding sweep;
+ * One CTA per sample (or, with LSQ_QACT_MODE=cluster in the environment, one thread-block cluster per sample that
+ * keeps the row L2-resident between the histogram sweep and the encoding sweep: one HBM read, but slower);
  * samples the fused kernel cannot decide are redone by the generic kernels inside this call. */
 LSQ_API size_t lsq_quantize_act_workspace_bytes(const lsq_act_geom* g);
 LSQ_API int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float alpha, int ternary, int skip,

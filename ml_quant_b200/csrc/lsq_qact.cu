@@ -1,30 +1,30 @@
-// Fused activation quantizer for the 2-bit (ls-2) and ternary (ls-T) schemes: ONE read of the fp32 input from HBM.
+// Fused activation quantizer for the 2-bit (ls-2) and ternary (ls-T) schemes: one kernel per QuantConv2d input.
 //
 // Replaces, on the QuantConv2d input (quant/binary/binary_conv.py:163 -> activation_quantization.py:99-100 ->
 // quantization.py:59-115 -> optimal.py:121-155), the chain  clamp -> opt_v1 (sort, cumsum, masks, cost tensor,
 // .tolist() sync) -> v2 = mean|x - v1 sign(x)| -> binarize / residual / binarize  and, fused in front of it, the
 // eval-mode BatchNorm of the caller (quant/models/resnet.py:180-190).  Round 1 ran this as three kernels that each
-// streamed the tensor from HBM (histogram pass, collection pass, encoder); here a row (= one sample) is handled by
-// one thread-block cluster that keeps it hot in L2:
+// streamed the tensor from HBM (histogram pass, collection pass, encoder).  Here a row (= one sample) is handled by one
+// CTA (default) or by one thread-block cluster (LSQ_QACT_MODE=cluster, see qact_shape below):
 //
 //   sweep 1 (HBM)  every 3rd element (optimal.py:134) of |clamp(bn(x))|: float bit patterns are monotone keys;
 //                  bins of 2^14 keys anchored at the clamp bound (512 bins per octave, 8 octaves), count + exact
 //                  integer sum of the low 14 key bits per bin (native shared-memory atomics, order independent);
-//                  the bin index of every sampled element is kept in shared memory (2 bytes per sample);
-//   merge          the CTAs of the cluster add up their histograms through distributed shared memory;
-//   flag           rank 0: prefix counts / EXACT prefix sums at the bin edges bound both threshold functions of
+//                  the bin index of every sampled element is kept (2 bytes per sample; shared memory or, for rows
+//                  too long for that, a global scratch row that is read back L2-hot);
+//   merge          (cluster only) the CTAs add up their histograms through distributed shared memory;
+//   flag           prefix counts / EXACT prefix sums at the bin edges bound both threshold functions of
 //                  optimal.py:63-80 over every bin (may_hold, conservative): a handful of bins can hold a candidate;
-//   collect        every CTA walks its bin indices, re-reads the few hundred flagged elements (L2 hits) and sends
-//                  their exact keys to rank 0;
-//   solve          rank 0 sorts them, gives every one the reference's own fp32 candidate test on (float) prefix sums
-//                  and the closed-form cost in fp64; first minimum wins (torch.argmin) -> v1;
-//   sweep 2 (L2)   the encoder's work item (lsq_encode_core.cuh): both sign planes in the convolution's raster and
+//   collect        walk the bin indices, queue the hits, re-read the few hundred flagged elements in one go and file
+//                  their exact keys into one list segment per flagged bin;
+//   solve          one warp per segment sorts it, gives every element the reference's own fp32 candidate test on
+//                  (float) prefix sums and the closed-form cost in fp64; first minimum wins (torch.argmin) -> v1;
+//   sweep 2        the encoder's work item (lsq_encode_core.cuh): both sign planes in the convolution's raster and
 //                  sum |x - v1 sign(x)| -> v2 (fp64, fixed summation tree, deterministic and batch invariant).
 //
-// The cluster size is chosen on the host so that the rows in flight (2 CTAs per SM) fit in L2 and a CTA's share of
-// the sampled row fits its bin-index buffer.  Rows the fast path cannot decide (a candidate may sit below the bin
-// window, too many flagged elements, ...) are marked in d_row_status and redone by the generic kernels of
-// lsq_solve.cu / lsq_quant.cu, launched behind this one on the marked rows only.
+// Rows the fast path cannot decide (a candidate may sit below the bin window, too many flagged elements, ...) are
+// marked in d_row_status and redone by the generic kernels of lsq_solve.cu / lsq_quant.cu, launched behind this one on
+// the marked rows only.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "lsq_common.cuh"
