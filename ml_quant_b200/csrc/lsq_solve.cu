@@ -805,65 +805,75 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
 }
 
 // ---- short rows (<= 2048 sampled elements: every conv / linear weight row with skip 3) ---------------------
-// The whole sampled row is sorted in shared memory by a 128-thread CTA and every position gets the reference's
-// own candidate test -- the reference algorithm itself (optimal.py:41-83), without the histogram machinery whose
-// per-row latency dominated such rows (16 CTAs per SM instead of 2).
+// One WARP per row (round 2; round 1 used a 128-thread CTA per row whose ~60 block barriers per sort dominated):
+// the sampled row is sorted in the warp's slice of shared memory with __syncwarp-only bitonic steps and every
+// position gets the reference's own candidate test -- the reference algorithm itself (optimal.py:41-83), with no
+// histogram machinery and no block-wide synchronisation; 4 rows per CTA, up to 28 rows per SM in flight.
 constexpr int kSmallThreads = 128;
+constexpr int kSmallWarps = kSmallThreads / 32;
 constexpr int kSmallRow = 2048;
-struct SmallSmem {
-  uint32_t keys[kSmallRow];
-  double red[32];
-  double wsum[32];
-  Range rng[kMaxRanges];
-  double seg_base[kMaxRanges];
-  double best_cost[32];
-  uint32_t best_pos[32], best_key[32], kmin, kmax, ncand;
-};
 
-// One row solved by one CTA.  xr = the row, v1_dst = where its scale goes, diag_row = its 16 diagnostics or NULL.
+// One row solved by one warp.  keys = the warp's shared-memory slice (>= next power of two of the sampled length).
 template <bool TERN>
-__device__ __forceinline__ void solve_small_row(SmallSmem& sm, const float* __restrict__ xr, long long len, int skip,
-                                                float alpha, float* __restrict__ v1_dst, int* __restrict__ diag_row,
-                                                const Prologue& pro) {
+__device__ __forceinline__ void solve_row_warp(uint32_t* keys, const float* __restrict__ xr, long long len, int skip,
+                                               float alpha, float* __restrict__ v1_dst, float* __restrict__ v1_dup,
+                                               int* __restrict__ diag_row, const Prologue& pro) {
   const uint32_t n = (uint32_t)((len + skip - 1) / skip);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) { sm.kmin = kNoKey; sm.kmax = 0u; sm.ncand = 0u; }
-  __syncthreads();
+  const int lane = threadIdx.x & 31;
   if (n < 3) {
-    if (tid == 0) {
+    if (lane == 0) {
       *v1_dst = 0.0f;
+      if (v1_dup) *v1_dup = 0.0f;
       if (diag_row) for (int i = 0; i < 16; ++i) diag_row[i] = 0;
     }
     return;
   }
   double ls = 0.0, lq = 0.0;
   uint32_t kmn = kNoKey, kmx = 0u;
-  for (uint32_t e = tid; e < n; e += kSmallThreads) {
+  for (uint32_t e = lane; e < n; e += 32) {
     const long long idx = (long long)e * skip;
     const float a = fabsf(clamp_sym(apply_prologue(pro, __ldg(xr + idx), idx), alpha));
     const uint32_t k = __float_as_uint(a);
     ls += (double)a; lq += (double)a * (double)a;
     kmn = min(kmn, k); kmx = max(kmx, k);
-    sm.keys[e] = k;
+    keys[e] = k;
   }
   uint32_t lp = 2;
   while (lp < n) lp <<= 1;
-  for (uint32_t e = n + tid; e < lp; e += kSmallThreads) sm.keys[e] = kNoKey;
-  const double s_tot = block_sum(ls, sm.red);
-  const double q_tot = block_sum(lq, sm.red);
+  for (uint32_t e = n + lane; e < lp; e += 32) keys[e] = kNoKey;
+  const double s_tot = warp_sum(ls), q_tot = warp_sum(lq);
   kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
-  if (lane == 0) { atomicMin(&sm.kmin, kmn); atomicMax(&sm.kmax, kmx); }
-  __syncthreads();
-  if (tid == 0) {
-    Range r;
-    r.blo = 0u; r.bhi = 0u; r.cnt_below = 0u; r.count = n; r.list_start = 0u;
-    r.span.klo = 0ull; r.span.khi = 1ull << 32; r.span.sum_below = 0.0; r.span.cnt_below = 0u; r.span.next_key = sm.kmax;
-    sm.rng[0] = r;
+  __syncwarp();
+  for (uint32_t k = 2; k <= lp; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = lane; t < (lp >> 1); t += 32) {
+        const uint32_t a0 = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const uint32_t p1 = a0 | j;
+        const uint32_t ka = keys[a0], kb = keys[p1];
+        const bool up = ((a0 & k) == 0);
+        if ((ka > kb) == up) { keys[a0] = kb; keys[p1] = ka; }
+      }
+      __syncwarp();
+    }
+  // every position of the sorted row: contiguous chunk per lane, fp64 prefix sums by shuffle
+  const uint32_t per = (n + 31u) / 32u;
+  const uint32_t j0 = min((uint32_t)lane * per, n), j1 = min(j0 + per, n);
+  double loc = 0.0;
+  for (uint32_t j = j0; j < j1; ++j) loc += (double)key_val(keys[j]);
+  double inc = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
   }
-  bitonic_sort(sm.keys, lp);          // ends with a block barrier
+  double run = inc - loc;
   Best best{1e300, 0xFFFFFFFFu, 0u};
   uint32_t ncand = 0;
-  evaluate_list<TERN>(sm, sm.keys, n, 1, n, s_tot, q_tot, best, ncand);
+  for (uint32_t j = j0; j < j1; ++j) {
+    const uint32_t kj = keys[j];
+    run += (double)key_val(kj);
+    try_position<TERN>(best, ncand, kj, (j + 1u < n) ? keys[j + 1u] : kmx, j, run, n, s_tot, q_tot);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double oc = __shfl_xor_sync(0xffffffffu, best.cost, o);
@@ -873,24 +883,19 @@ __device__ __forceinline__ void solve_small_row(SmallSmem& sm, const float* __re
   }
   ncand = (uint32_t)__reduce_add_sync(0xffffffffu, ncand);
   if (lane == 0) {
-    sm.best_cost[wid] = best.cost; sm.best_pos[wid] = best.pos; sm.best_key[wid] = best.key;
-    atomicAdd(&sm.ncand, ncand);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    Best b{1e300, 0xFFFFFFFFu, 0u};
-    for (int w = 0; w < kSmallThreads / 32; ++w) b.offer(sm.best_cost[w], sm.best_pos[w], sm.best_key[w]);
-    uint32_t nc_tot = sm.ncand;
+    uint32_t nc_tot = ncand;
     if (TERN) {
       // optimal.py:86-118: when min > mean/2 the value mean/2 (not a data element) is appended last
       const float mean = (float)(s_tot / (double)n);
       const float half_mean = __fmul_rn(0.5f, mean);
-      if (key_val(sm.kmin) > half_mean) {
+      if (key_val(kmn) > half_mean) {
         ++nc_tot;
-        b.offer(closed_cost2<true>((double)half_mean, 0.0, 0.0, (double)n, s_tot, q_tot), n, __float_as_uint(half_mean));
+        best.offer(closed_cost2<true>((double)half_mean, 0.0, 0.0, (double)n, s_tot, q_tot), n, __float_as_uint(half_mean));
       }
     }
-    *v1_dst = (nc_tot > 0) ? key_val(b.key) : 0.0f;
+    const float v1 = (nc_tot > 0) ? key_val(best.key) : 0.0f;
+    *v1_dst = v1;
+    if (v1_dup) *v1_dup = v1;
     if (diag_row) {
       for (int i = 0; i < 16; ++i) diag_row[i] = 0;
       diag_row[0] = 1; diag_row[2] = (int)nc_tot;
@@ -900,17 +905,19 @@ __device__ __forceinline__ void solve_small_row(SmallSmem& sm, const float* __re
 
 template <bool TERN>
 __global__ void __launch_bounds__(kSmallThreads)
-solve_v1_small_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
-                      int* __restrict__ diag, Prologue pro, const int* __restrict__ row_status, float* __restrict__ v1_dup) {
-  __shared__ SmallSmem sm;
-  const long long row = blockIdx.x;
+solve_v1_small_kernel(const float* __restrict__ x, long long rows, long long len, int skip, float alpha,
+                      float* __restrict__ v1_out, int* __restrict__ diag, Prologue pro, const int* __restrict__ row_status,
+                      float* __restrict__ v1_dup, int lp_cap) {
+  extern __shared__ __align__(16) uint32_t small_keys[];
+  const long long row = (long long)blockIdx.x * kSmallWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
   if (row_status && row_status[row] == 0) return;
-  solve_small_row<TERN>(sm, x + row * len, len, skip, alpha, v1_out + row, diag ? diag + row * 16 : nullptr, pro);
-  if (v1_dup && threadIdx.x == 0) v1_dup[row] = v1_out[row];      // written by this thread just above
+  solve_row_warp<TERN>(small_keys + (size_t)(threadIdx.x >> 5) * lp_cap, x + row * len, len, skip, alpha, v1_out + row,
+                       v1_dup ? v1_dup + row : nullptr, diag ? diag + row * 16 : nullptr, pro);
 }
 
 // Multi-tensor launch (weight tensors of a whole network in ONE grid): the tensor table travels by value in the
-// kernel parameters, CTA b finds its tensor by bisection over the cumulative row counts.  Same per-row code as
+// kernel parameters, every warp finds its tensor by bisection over the cumulative row counts.  Same per-row code as
 // the single-tensor kernel, so the results are bit-identical.
 constexpr int kMultiMax = 112;
 struct MultiTab {
@@ -930,13 +937,16 @@ __device__ __forceinline__ int multi_find(const MultiTab& tab, int row) {
 }
 template <bool TERN>
 __global__ void __launch_bounds__(kSmallThreads)
-solve_v1_multi_kernel(const __grid_constant__ MultiTab tab, int skip, float alpha) {
-  __shared__ SmallSmem sm;
-  const int t = multi_find(tab, (int)blockIdx.x);
-  const int r = (int)blockIdx.x - tab.first_row[t];
+solve_v1_multi_kernel(const __grid_constant__ MultiTab tab, int skip, float alpha, int lp_cap) {
+  extern __shared__ __align__(16) uint32_t small_keys[];
+  const int grow = (int)blockIdx.x * kSmallWarps + (int)(threadIdx.x >> 5);
+  if (grow >= tab.first_row[tab.n]) return;
+  const int t = multi_find(tab, grow);
+  const int r = grow - tab.first_row[t];
   const long long len = tab.len[t];
   const Prologue none{nullptr, nullptr, 1, 1, 1ull << 40};
-  solve_small_row<TERN>(sm, tab.x[t] + (long long)r * len, len, skip, alpha, tab.out[t] + r, nullptr, none);
+  solve_row_warp<TERN>(small_keys + (size_t)(threadIdx.x >> 5) * lp_cap, tab.x[t] + (long long)r * len, len, skip, alpha,
+                       tab.out[t] + r, nullptr, nullptr, none);
 }
 
 }  // namespace lsq
@@ -977,8 +987,12 @@ static int solve_v1_launch(const float* d_x, int64_t rows, int64_t len, int skip
   const Prologue dp = to_dev(pro);
   dim3 grid((unsigned)rows);
   if ((len + skip - 1) / skip <= (int64_t)kSmallRow) {
-    if (ternary) solve_v1_small_kernel<true><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp, d_row_status, d_v1_dup);
-    else solve_v1_small_kernel<false><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(d_x, len, skip, alpha, d_v1, d_diag, dp, d_row_status, d_v1_dup);
+    int lp_cap = 2;
+    while (lp_cap < (int)((len + skip - 1) / skip)) lp_cap <<= 1;
+    const size_t sm_bytes = (size_t)kSmallWarps * lp_cap * sizeof(uint32_t);
+    const dim3 wgrid((unsigned)((rows + kSmallWarps - 1) / kSmallWarps));
+    if (ternary) solve_v1_small_kernel<true><<<wgrid, kSmallThreads, sm_bytes, (cudaStream_t)stream>>>(d_x, rows, len, skip, alpha, d_v1, d_diag, dp, d_row_status, d_v1_dup, lp_cap);
+    else solve_v1_small_kernel<false><<<wgrid, kSmallThreads, sm_bytes, (cudaStream_t)stream>>>(d_x, rows, len, skip, alpha, d_v1, d_diag, dp, d_row_status, d_v1_dup, lp_cap);
     LSQ_CUDA_LAUNCH_CHECK("solve_v1_small_kernel");
     return LSQ_OK;
   }
@@ -1045,9 +1059,12 @@ extern "C" int lsq_solve_v1_multi(const lsq_row_tensor* tensors, int ntensors, i
       tab.x[i] = T.d_x; tab.out[i] = T.d_out; tab.len[i] = T.len;
       tab.first_row[i + 1] = tab.first_row[i] + T.rows;
     }
-    dim3 grid((unsigned)tab.first_row[tab.n]);
-    if (ternary) solve_v1_multi_kernel<true><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(tab, skip, alpha);
-    else solve_v1_multi_kernel<false><<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(tab, skip, alpha);
+    int lp_cap = 2;                          // the longest sampled row of this batch (tab.len is sorted descending)
+    while (lp_cap < (tab.len[0] + skip - 1) / skip) lp_cap <<= 1;
+    const size_t sm_bytes = (size_t)kSmallWarps * lp_cap * sizeof(uint32_t);
+    dim3 grid((unsigned)((tab.first_row[tab.n] + kSmallWarps - 1) / kSmallWarps));
+    if (ternary) solve_v1_multi_kernel<true><<<grid, kSmallThreads, sm_bytes, (cudaStream_t)stream>>>(tab, skip, alpha, lp_cap);
+    else solve_v1_multi_kernel<false><<<grid, kSmallThreads, sm_bytes, (cudaStream_t)stream>>>(tab, skip, alpha, lp_cap);
     LSQ_CUDA_LAUNCH_CHECK("solve_v1_multi_kernel");
   }
   return LSQ_OK;
