@@ -140,7 +140,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
     const bool has_res = epi.residual != nullptr;
     const long long cstride = (long long)g.ho * g.wo;
     float* const outt = reinterpret_cast<float*>(smem + P.smem_out) + (size_t)ewarp * 32 * kOutPitch;
-    float2* const scl = reinterpret_cast<float2*>(smem + P.smem_scl) + (size_t)ewarp * 128;
+    float2* const scl = reinterpret_cast<float2*>(smem + P.smem_scl) + (size_t)ewarp * tph;     // tph entries per warp
 
     // where does position `p` of tile `ptile` land in the output?  (offset of channel 0 of the channel tile, or -1)
     auto out_offset = [&](int ptile, int ctile, int p, int& sample) -> long long {
@@ -445,7 +445,7 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   P.w_slab_bytes = 128u * 64u;
   const size_t total = 225 * 1024;
   const size_t bar_bytes = 512, tab_bytes = (size_t)cout * 16;
-  const size_t scl_bytes = 8 * 128 * sizeof(float2), out_bytes = 8 * 32 * kOutPitch * sizeof(float);
+  const size_t scl_bytes = (size_t)8 * (tp / (8 / (P.creal >> 5))) * sizeof(float2), out_bytes = 8 * 32 * kOutPitch * sizeof(float);
   const size_t slack = 0;
   const size_t fixed = bar_bytes + tab_bytes + scl_bytes + out_bytes + slack;
   // minimum: 2 patch stages (1 when there is a single channel block and nothing to overlap with is no option:
