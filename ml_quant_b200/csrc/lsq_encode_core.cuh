@@ -73,4 +73,43 @@ __device__ __forceinline__ void encode_group(const float* __restrict__ xp, long 
     for (int j = 0; j < NPL; ++j) word[p][j] = ~word[p][j];
 }
 
+// Both sign planes of the items [it_lo, it_hi) of sample `s` (item = 32-channel group x VEC-pixel group of the row xr)
+// for the 2-bit / ternary code with first scale v1, written in the convolution's raster; returns this thread's share of
+// sum |x - v1 sign(x)| (the v2 numerator).  Work is strided over the CTA's threads.  Shared by the fused quantizer
+// (lsq_qact.cu) and the generic fallback for the rows it marks (lsq_solve.cu).
+template <int VEC>
+__device__ __forceinline__ double encode2_row_part(const float* __restrict__ xr, const ActGeom& g, int s, uint32_t hw,
+                                                   uint32_t nq, uint32_t it_lo, uint32_t it_hi,
+                                                   const float2* __restrict__ ab, float alpha, float v1,
+                                                   uint32_t* __restrict__ planes) {
+  const float sc[2] = {v1, 0.0f};
+  double acc_sum = 0.0;
+  for (uint32_t item = it_lo + threadIdx.x; item < it_hi; item += blockDim.x) {
+    const int cgi = (int)(item / nq), q = (int)(item - (uint32_t)cgi * nq);
+    const int p0 = q * VEC;
+    const int cbase = cgi * 32;
+    const int cn = min(32, g.c - cbase);
+    const float* xp = xr + (long long)cbase * hw + p0;
+    uint32_t word[VEC][2];
+    float gsum[VEC];
+    if (cn == 32) encode_group<2, VEC, true>(xp, (long long)hw, cn, ab + cbase, alpha, sc, 1, word, gsum);
+    else encode_group<2, VEC, false>(xp, (long long)hw, cn, ab + cbase, alpha, sc, 1, word, gsum);
+    int yi = p0 / g.w, xi = p0 - yi * g.w;
+#pragma unroll
+    for (int p = 0; p < VEC; ++p) {
+      if (p0 + p < (int)hw) {
+        int phase = 0, a = yi, b = xi;
+        if (g.nphase == 4) { phase = ((yi & 1) << 1) | (xi & 1); a = yi >> 1; b = xi >> 1; }
+        const long long v = vpos(g, s, a, b);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          planes[(((long long)j * g.nphase + phase) * g.vtot + v) * g.cw + cgi] = word[p][j];
+        acc_sum += (double)gsum[p];
+      }
+      if (++xi == g.w) { xi = 0; ++yi; }
+    }
+  }
+  return acc_sum;
+}
+
 }  // namespace lsq

@@ -621,36 +621,9 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
 
   // ---- sweep 2 (L2): both sign planes and sum |x - v1 sign(x)| ----------------------------------------------------
   {
-    const float sc[2] = {v1, 0.0f};
-    const int s = (int)row;
     const uint32_t it_lo = (uint32_t)(((unsigned long long)qp.nitems * (unsigned)rank) / (unsigned)cs);
     const uint32_t it_hi = (uint32_t)(((unsigned long long)qp.nitems * (unsigned)(rank + 1)) / (unsigned)cs);
-    double acc_sum = 0.0;
-    for (uint32_t item = it_lo + tid; item < it_hi; item += T) {
-      const int cgi = (int)(item / qp.nq), q = (int)(item - (uint32_t)cgi * qp.nq);
-      const int p0 = q * VEC;
-      const int cbase = cgi * 32;
-      const int cn = min(32, g.c - cbase);
-      const float* xp = xr + (long long)cbase * qp.hw + p0;
-      uint32_t word[VEC][2];
-      float gsum[VEC];
-      if (cn == 32) encode_group<2, VEC, true>(xp, (long long)qp.hw, cn, sm.ab + cbase, alpha, sc, 1, word, gsum);
-      else encode_group<2, VEC, false>(xp, (long long)qp.hw, cn, sm.ab + cbase, alpha, sc, 1, word, gsum);
-      int yi = p0 / g.w, xi = p0 - yi * g.w;
-#pragma unroll
-      for (int p = 0; p < VEC; ++p) {
-        if (p0 + p < (int)qp.hw) {
-          int phase = 0, a = yi, b = xi;
-          if (g.nphase == 4) { phase = ((yi & 1) << 1) | (xi & 1); a = yi >> 1; b = xi >> 1; }
-          const long long v = vpos(g, s, a, b);
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            planes[(((long long)j * g.nphase + phase) * g.vtot + v) * g.cw + cgi] = word[p][j];
-          acc_sum += (double)gsum[p];
-        }
-        if (++xi == g.w) { xi = 0; ++yi; }
-      }
-    }
+    const double acc_sum = encode2_row_part<VEC>(xr, g, (int)row, qp.hw, qp.nq, it_lo, it_hi, sm.ab, alpha, v1, planes);
     if (!TERN) {
       const double tot = block_sum(acc_sum, sm.red);
       if (tid == 0) r0->part_v2[rank] = tot;
@@ -685,6 +658,9 @@ int solve_v1_marked_rows(const float* d_x, int64_t rows, int64_t len, int skip, 
 int encode_act_marked_rows(const float* d_x, const lsq_act_geom* g, float alpha, const float* d_scales, int nscales,
                            int nplanes, uint32_t* d_planes, float* d_last_scale, void* d_ws, size_t ws_bytes,
                            const lsq_prologue* pro, const int* d_row_status, cudaStream_t stream);
+// one small launch: generic solve + encode of the rows marked in d_row_status (lsq_solve.cu)
+int qact_fallback_launch(const float* d_x, const lsq_act_geom* g, float alpha, int ternary, int skip, uint32_t* d_planes,
+                         float* d_scales, const lsq_prologue* pro, const int* d_row_status, bool vec4, cudaStream_t stream);
 }
 
 // Launch shape for rows of `len` elements.  Rows whose sampled third fits the bin-index buffer of a CTA (17 408
@@ -809,9 +785,7 @@ extern "C" int lsq_quantize_act(const float* d_x, const lsq_act_geom* g, float a
     return LSQ_ERR_CUDA;
   }
   LSQ_CUDA_LAUNCH_CHECK("quant_act_kernel");
-  // rows the fused kernel could not decide (normally none): generic solve + encode on the marked rows only
-  int rc = solve_v1_marked_rows(d_x, g->n, len, skip, ternary, alpha, d_scales, ternary ? d_scales + g->n : nullptr,
-                                pro, d_status, st);
-  if (rc != LSQ_OK) return rc;
-  return encode_act_marked_rows(d_x, g, alpha, d_scales, 1, 2, d_planes, d_v2, d_ws, red_bytes, pro, d_status, st);
+  // rows the fused kernel could not decide (normally none): one small launch that looks at the marks and redoes the
+  // marked rows with the generic solver + encoder
+  return qact_fallback_launch(d_x, g, alpha, ternary, skip, d_planes, d_scales, pro, d_status, vec4, st);
 }

@@ -23,6 +23,7 @@
 //   is evaluated directly.  No host synchronisation (the reference does .tolist(), optimal.py:147).
 #include "lsq_common.cuh"
 #include "lsq_solve_core.cuh"
+#include "lsq_encode_core.cuh"
 
 namespace lsq {
 
@@ -166,19 +167,16 @@ __device__ __forceinline__ void sweep_row(const float* __restrict__ xr, int skip
 }
 
 
+// One row solved by one CTA of LAY::kThreads threads (smem_raw: LAY::Smem).  v1_dup != NULL receives a second copy of
+// v1 (ternary scale table).  Every thread of the CTA must call it (block barriers inside).
 template <bool TERN, class LAY>
-__global__ void __launch_bounds__(LAY::kThreads, LAY::kMinBlocks)
-solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
-                int* __restrict__ diag, Prologue pro, const int* __restrict__ row_status, float* __restrict__ v1_dup) {
-  // row_status != NULL: only the rows marked non-zero are solved (rows the fused activation quantizer of
-  // lsq_qact.cu left to this generic kernel); v1_dup != NULL receives a second copy of v1 (ternary scale table)
-  if (row_status && row_status[blockIdx.x] == 0) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ void solve_v1_row(unsigned char* smem_raw, const float* __restrict__ x, long long len, int skip, float alpha,
+                             float* __restrict__ v1_out, int* __restrict__ diag, const Prologue& pro, const long long row,
+                             float* __restrict__ v1_dup) {
   using SolveSmem = typename LAY::Smem;
   constexpr int kT = LAY::kThreads;
   constexpr int kBins = LAY::kBins, kBinsPerThread = LAY::kBinsPerThread, kCap = LAY::kCap, kSmallCap = LAY::kSmallCap, kTopShift = LAY::kTopShift;
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smem_raw);
-  const long long row = blockIdx.x;
   const float* xr = x + row * len;
   const uint32_t n = (uint32_t)((len + skip - 1) / skip);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -804,6 +802,51 @@ solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alph
   }
 }
 
+template <bool TERN, class LAY>
+__global__ void __launch_bounds__(LAY::kThreads, LAY::kMinBlocks)
+solve_v1_kernel(const float* __restrict__ x, long long len, int skip, float alpha, float* __restrict__ v1_out,
+                int* __restrict__ diag, Prologue pro, const int* __restrict__ row_status, float* __restrict__ v1_dup) {
+  // row_status != NULL: only the rows marked non-zero are solved
+  if (row_status && row_status[blockIdx.x] == 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  solve_v1_row<TERN, LAY>(smem_raw, x, len, skip, alpha, v1_out, diag, pro, (long long)blockIdx.x, v1_dup);
+}
+
+// Fallback of the fused activation quantizer (lsq_qact.cu): ONE small launch whose CTAs walk the samples, skip the
+// unmarked ones (normally all) and redo a marked sample with the generic solver above followed by the encoder's work
+// items -- the same arithmetic as lsq_solve_v1_ex + lsq_encode_act_ex (nscales = 1, nplanes = 2).
+template <bool TERN, int VEC>
+__global__ void __launch_bounds__(LayoutBig::kThreads, 1)
+qact_fallback_kernel(const float* __restrict__ x, ActGeom g, long long len, int skip, float alpha, Prologue pro,
+                     uint32_t* __restrict__ planes, float* __restrict__ scales, const int* __restrict__ row_status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* const ab = reinterpret_cast<float2*>(smem_raw + ((sizeof(LayoutBig::Smem) + 15) & ~(size_t)15));      // encoder's (scale, shift) table
+  double* const red = reinterpret_cast<double*>(ab + g.cw * 32);
+  const uint32_t hw = (uint32_t)(g.h * g.w), nq = VEC == 4 ? hw / 4 : hw, nitems = nq * (uint32_t)g.cw;
+  bool table_ready = false;
+  for (long long row = blockIdx.x; row < g.n; row += gridDim.x) {
+    if (row_status[row] == 0) continue;                 // uniform over the CTA
+    if (!table_ready) {
+      for (int c = threadIdx.x; c < g.cw * 32; c += blockDim.x) {
+        float2 k = make_float2(1.0f, 0.0f);
+        if (pro.a && c < g.c) k = make_float2(__ldg(pro.a + c), __ldg(pro.b + c) + 0.0f);
+        ab[c] = k;
+      }
+      table_ready = true;
+    }
+    __syncthreads();
+    solve_v1_row<TERN, LayoutBig>(smem_raw, x, len, skip, alpha, scales, nullptr, pro, row, TERN ? scales + g.n : nullptr);
+    __syncthreads();
+    const float v1 = *reinterpret_cast<volatile float*>(scales + row);       // written by thread 0 before the barrier
+    const double part = encode2_row_part<VEC>(x + row * len, g, (int)row, hw, nq, 0u, nitems, ab, alpha, v1, planes);
+    if (!TERN) {
+      const double tot = block_sum(part, red);
+      if (threadIdx.x == 0) scales[(long long)g.n + row] = (float)(tot / (double)len);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- short rows (<= 2048 sampled elements: every conv / linear weight row with skip 3) ---------------------
 // One WARP per row (round 2; round 1 used a 128-thread CTA per row whose ~60 block barriers per sort dominated):
 // the sampled row is sorted in the warp's slice of shared memory with __syncwarp-only bitonic steps and every
@@ -971,6 +1014,33 @@ namespace lsq {
 int solve_v1_marked_rows(const float* d_x, int64_t rows, int64_t len, int skip, int ternary, float alpha, float* d_v1,
                          float* d_v1_dup, const lsq_prologue* pro, const int* d_row_status, cudaStream_t stream) {
   return solve_v1_launch(d_x, rows, len, skip, ternary, alpha, d_v1, nullptr, pro, d_row_status, d_v1_dup, (void*)stream);
+}
+}  // namespace lsq
+
+namespace lsq {
+int qact_fallback_launch(const float* d_x, const lsq_act_geom* g, float alpha, int ternary, int skip, uint32_t* d_planes,
+                         float* d_scales, const lsq_prologue* pro, const int* d_row_status, bool vec4, cudaStream_t stream) {
+  const int64_t len = (int64_t)g->c * g->h * g->w;
+  const Prologue dp = to_dev(pro);
+  const ActGeom dg = to_dev(*g);
+  const size_t smem = ((sizeof(LayoutBig::Smem) + 15) & ~(size_t)15) + (size_t)g->cw * 32 * sizeof(float2) + 32 * sizeof(double);
+  int grid = device_sms();
+  if (grid > g->n) grid = g->n;
+  cudaError_t e = cudaSuccess;
+#define LSQ_FB(T, V)                                                                                               \
+  do {                                                                                                             \
+    static std::atomic<unsigned long long> smem_set{0ull};                                                         \
+    e = ensure_max_smem(qact_fallback_kernel<T, V>, smem_set);                                                     \
+    if (e == cudaSuccess)                                                                                          \
+      qact_fallback_kernel<T, V><<<grid, LayoutBig::kThreads, smem, stream>>>(d_x, dg, len, skip, alpha, dp, d_planes, \
+                                                                              d_scales, d_row_status);             \
+  } while (0)
+  if (ternary) { if (vec4) LSQ_FB(true, 4); else LSQ_FB(true, 1); }
+  else { if (vec4) LSQ_FB(false, 4); else LSQ_FB(false, 1); }
+#undef LSQ_FB
+  if (e != cudaSuccess) { set_error("lsq_quantize_act: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return LSQ_ERR_CUDA; }
+  LSQ_CUDA_LAUNCH_CHECK("qact_fallback_kernel");
+  return LSQ_OK;
 }
 }  // namespace lsq
 

@@ -484,29 +484,30 @@ def test_fused_activation_quantizer_hands_odd_rows_to_the_generic_kernels():
     bit-identical to lsq_solve_v1 + lsq_encode_act; ordinary rows of the same batch keep status 0."""
     from ml_quant_b200 import ops
     torch.manual_seed(32)
-    n, c, h, w = 8, 64, 28, 28
-    x = torch.randn(n, c, h, w, device=DEV)
-    x[1] = 0.75
-    x[2] = 0.0
-    x[3] *= 1e-6
-    x[4] = torch.randint(0, 3, (c, h, w), device=DEV).float() - 1.0
-    x[5] = x[5].abs() + 0.5
-    g = ops.act_geometry(n, c, h, w, 3, 3, 1, 1)
-    nwords = ops._C.lib().lsq_act_planes_bytes(ops.C.byref(g), 2) // 4
-    for tern in (False, True):
-        planes, tab, dg = ops.quantize_act(x, g, tern, 2.0, 3, torch.zeros(nwords, dtype=torch.int32, device=DEV), None, diag=True)
-        v1 = ops.solve_v1(x.reshape(n, -1), tern, 3, 2.0)
-        planes2, v2 = ops.encode_act(x, g, [v1], 2, 2.0, not tern)
-        st = dg[:, 0].cpu()
-        assert int(st[0]) == 0 and int(st[6]) == 0 and int(st[7]) == 0, st
-        assert int((st != 0).sum()) >= 3, st
-        odd = st != 0
-        assert torch.equal(tab[0].cpu()[odd], v1.cpu()[odd])
-        if not tern:
-            assert torch.equal(tab[1].cpu()[odd], v2.cpu()[odd])
-        # planes of the whole batch equal the generic encoder's for the scales in the table
-        planes3, _ = ops.encode_act(x, g, tab[:1].clone(), 2, 2.0, False, torch.zeros(nwords, dtype=torch.int32, device=DEV))
-        assert torch.equal(planes[:nwords], planes3[:nwords])
+    # (the second shape's rows are longer than the generic solver's in-shared-memory layout holds)
+    for n, c, h, w in ((8, 64, 28, 28), (8, 64, 56, 56), (8, 96, 14, 14), (8, 32, 10, 10)):
+        x = torch.randn(n, c, h, w, device=DEV)
+        x[1] = 0.75
+        x[2] = 0.0
+        x[3] *= 1e-6
+        x[4] = torch.randint(0, 3, (c, h, w), device=DEV).float() - 1.0
+        x[5] = x[5].abs() + 0.5
+        g = ops.act_geometry(n, c, h, w, 3, 3, 1, 1)
+        nwords = ops._C.lib().lsq_act_planes_bytes(ops.C.byref(g), 2) // 4
+        for tern in (False, True):
+            planes, tab, dg = ops.quantize_act(x, g, tern, 2.0, 3, torch.zeros(nwords, dtype=torch.int32, device=DEV), None, diag=True)
+            v1 = ops.solve_v1(x.reshape(n, -1), tern, 3, 2.0)
+            planes2, v2 = ops.encode_act(x, g, [v1], 2, 2.0, not tern)
+            st = dg[:, 0].cpu()
+            assert int(st[0]) == 0 and int(st[6]) == 0 and int(st[7]) == 0, st
+            assert int((st != 0).sum()) >= 3, st
+            odd = st != 0
+            assert torch.equal(tab[0].cpu()[odd], v1.cpu()[odd])
+            if not tern:
+                assert torch.equal(tab[1].cpu()[odd], v2.cpu()[odd])
+            # planes of the whole batch equal the generic encoder's for the scales in the table
+            planes3, _ = ops.encode_act(x, g, tab[:1].clone(), 2, 2.0, False, torch.zeros(nwords, dtype=torch.int32, device=DEV))
+            assert torch.equal(planes[:nwords], planes3[:nwords])
     # shapes outside the fused kernel's domain take the generic kernels for every row: no clamp, short rows
     x = torch.randn(4, 64, 8, 8, device=DEV)
     g = ops.act_geometry(4, 64, 8, 8, 3, 3, 1, 1)
