@@ -227,14 +227,18 @@ LSQ_API int lsq_bconv2d_fwd_ex(const uint32_t* d_planes, const lsq_act_geom* g, 
 /* ---- fp32 stem of QResNet (not part of the quantized path) ----------------------
  * out = maxpool3x3/s2/p1(relu(conv7x7/s2/p3(x, w) + bias)) for x [n,3,h,w] -> out [n,64,hp,wp]
  * (quant/models/resnet.py:283-308 with the eval BatchNorm folded into w / bias by the caller).
- * The convolution runs on the tcgen05 tensor cores (kind::tf32, 3xTF32 split: fp32-level accuracy).
+ * The convolution runs on the tcgen05 tensor cores with split operands (fp32-level accuracy, ~1e-6 of max|y|):
+ * images up to 250 pixels wide take ONE kernel (kind::f16, x and w as fp16 hi + lo pairs, max-pool folded into the
+ * epilogue, the convolution output never reaches HBM; |x| is clamped to the fp16 range 65504); wider images take
+ * the two-kernel route (kind::tf32 3xTF32 convolution, then a pool kernel).  lsq_stem_is_fused says which.
  *   lsq_stem_pack_weights: d_w float[64][147] (k = c*49 + ky*7 + kx) -> operand image of
  *                          lsq_stem_image_bytes() bytes (16-byte aligned), once per weight version
  *   lsq_stem_fwd:          d_conv_ws = scratch of lsq_stem_workspace_bytes(n, h, w) bytes (the rectified
- *                          convolution output [n,64,hc,wc]) */
+ *                          convolution output [n,64,hc,wc]; 256 bytes, unused, on the one-kernel route) */
 LSQ_API size_t lsq_stem_image_bytes(void);
 LSQ_API size_t lsq_stem_workspace_bytes(int n, int h, int w);
 LSQ_API int lsq_stem_supported(int n, int h, int w);
+LSQ_API int lsq_stem_is_fused(int n, int h, int w);
 LSQ_API int lsq_stem_pack_weights(const float* d_w, float* d_image, void* stream);
 LSQ_API int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_image, const float* d_bias,
                  float* d_conv_ws, float* d_out, void* stream);

@@ -19,6 +19,7 @@
 // per tap pair instead of three.  49 taps -> 25 pairs x 2 = 50 MMAs per tile; the epilogue adds the two lane
 // halves (warp pairs exchange through shared memory).  All weights (100 KB) stay in shared memory.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "lsq_common.cuh"
 #include "lsq_tc.cuh"
 
@@ -388,14 +389,342 @@ static bool stem_plan(int n, int h, int w, StemParams& P, size_t& smem_bytes) {
   return true;
 }
 
+// ================================================================================================================
+// Fused stem for images up to 250 pixels wide: conv 7x7 / 2 + bias + ReLU + max-pool 3x3 / 2 in ONE kernel.
+// The convolution output (1.6 GB at batch 512) never reaches HBM.
+//  * operands are fp16 pairs: x = hi + lo and w = hi + lo (11 + 11 significant bits; every weight row is first
+//    scaled by a power of two so that its largest entry sits in [2^13, 2^14) and its lo parts stay normal; the
+//    epilogue undoes the scale exactly).  A patch position holds 16 bytes [xh0 xh1 xh2 0 xl0 xl1 xl2 0], a weight
+//    row [w0 w1 w2 0 w0 w1 w2 0], so one K chunk of kind::f16 contracts w * (x_hi + x_lo) for one tap; the two K
+//    chunks of an instruction are two taps (two shifts of the same patch, as above); rows 0..63 carry W_hi and
+//    rows 64..127 W_lo as above.  All four product terms in 25 instructions per tile (the TF32 kernel: 50).
+//  * the kernel has its own raster: pitch pw = wc + 3 rounded up to 8, a tile = 2 * pw positions = the two
+//    convolution rows (2k, 2k+1) of one sample = exactly what pooled row k needs besides row 2k-1.  A CTA walks
+//    a contiguous range of tiles; the horizontal maxima of row 2k-1 stay in the epilogue threads' registers from
+//    the previous tile (a range that starts inside a sample recomputes one tile to get them).
+//  * epilogue: thread = channel (the accumulator's own layout), so both pooling directions are register maxima;
+//    the W_lo half of the accumulator is added through a shared-memory exchange between warp pairs first (the sum
+//    must precede the ReLU / max).  The pooled row (64 x wp) is transposed through shared memory and stored
+//    along px.
+constexpr int kSfXPitch = 20;                  // exchange tile: [32 channels][16 columns + left neighbour], float4 conflict-free
+constexpr int kSfPoolPitch = 65;               // pooled tile: [64 channels][<= 64 px], lane = channel conflict-free
+constexpr uint32_t kSfImageOffset = kStWeightBytes;          // fp16 image behind the TF32 image
+constexpr uint32_t kSfScaleOffset = 2 * kStWeightBytes;      // 64 x 2^-e (fp32)
+
+struct SfParams {
+  int n, h, w, hc, wc, hp, wp;
+  int pw, ncols, pp, nch, tiles;
+  uint32_t pw_magic;
+  int first[4], count[4];
+  int pair_off[kStPairs], pair_lbo[kStPairs];
+  uint32_t stage_bytes, smem_w, smem_p, smem_bar, smem_x, smem_pool;
+};
+
+__device__ __forceinline__ int stem_scale_exp(const float* __restrict__ w, int ch) {
+  float mx = 0.0f;
+  for (int j = 0; j < 147; ++j) mx = fmaxf(mx, fabsf(__ldg(w + ch * 147 + j)));
+  if (!(mx > 0.0f) || !(mx < 3.0e38f)) return 0;
+  const int e = 13 - ilogbf(mx);
+  return e < -100 ? -100 : (e > 100 ? 100 : e);
+}
+
+// fp16 image[pair][chunk][row][slot]: slots 0..2 and 4..6 = the three input channels of tap(pair, chunk) of output
+// channel row & 63, scaled by 2^e(channel); rows 0..63 the fp16 value, rows 64..127 the fp16 remainder
+__global__ void stem_pack_f16_kernel(const float* __restrict__ w, __half* __restrict__ image, float* __restrict__ inv_scale,
+                                     StemTaps T) {
+  const int total = kStPairs * 2 * 128 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int slot = i & 7, row = (i >> 3) & 127, chunk = (i >> 10) & 1, pair = i >> 11;
+    const int ch = row & 63, c = slot & 3;
+    const int tap = T.tap[pair][chunk];
+    const int e = stem_scale_exp(w, ch);
+    const float v = (c < 3 && tap >= 0) ? __ldg(w + ch * 147 + c * 49 + tap) * ldexpf(1.0f, e) : 0.0f;
+    const __half hi = __float2half_rn(v);
+    image[i] = row < 64 ? hi : __float2half_rn(__fsub_rn(v, __half2float(hi)));
+    if (i < 64) inv_scale[i] = ldexpf(1.0f, -stem_scale_exp(w, i));
+  }
+}
+
+__global__ void __launch_bounds__(kStThreads, 1)
+stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* __restrict__ wimage,
+                  const float* __restrict__ inv_scale, const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + P.smem_bar;
+  auto p_full = [&](int s) { return bar0 + 8u * s; };
+  auto p_empty = [&](int s) { return bar0 + 8u * (kStPStages + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kStPStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kStPStages + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * (2 * kStPStages + 4));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStPStages; ++s) { mbar_init(p_full(s), kStProducerWarps); mbar_init(p_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(wimage);
+    float4* dst = reinterpret_cast<float4*>(smem + P.smem_w);
+    for (int i = threadIdx.x; i < (int)(kStWeightBytes / 16); i += kStThreads) dst[i] = __ldg(src + i);
+  }
+  fence_proxy_async();
+  if (warp == 16) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  int* const err = nullptr;
+  // this CTA's tiles: [t_own, t_end) are stored; a range that starts inside a sample first redoes the tile before it
+  const int t_own = (int)((long long)P.tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long long)P.tiles * (blockIdx.x + 1) / gridDim.x);
+  const int t_begin = (t_own < t_end && (t_own % P.hp) != 0) ? t_own - 1 : t_own;
+
+  if (warp < 16) {
+    // ===================== epilogue (16 warps) =====================
+    const int qd = warp & 3, part = warp >> 2;
+    const bool upper = qd >= 2;
+    const int chg = qd & 1;
+    const int pairid = chg + 2 * part;
+    const int bar_id = 1 + pairid;                     // named barrier of the warp pair (64 threads)
+    float* const xt = reinterpret_cast<float*>(smem + P.smem_x) + (size_t)pairid * 2 * 32 * kSfXPitch + lane * kSfXPitch;
+    float* const pool = reinterpret_cast<float*>(smem + P.smem_pool);
+    const float bs = __ldg(bias + 32 * chg + lane), inv = __ldg(inv_scale + 32 * chg + lane);
+    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
+    const int pw = P.pw, wc = P.wc;
+    float carry[16];                                   // horizontal maxima of convolution row 2k-1, px = 8 (part nch + j) + i
+#pragma unroll
+    for (int i = 0; i < 16; ++i) carry[i] = 0.0f;
+    Ring acc(2);
+    uint32_t xbuf = 0, emitted = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int s = tile / P.hp, k = tile - s * P.hp;
+      const bool emit = tile >= t_own;
+      if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) carry[i] = 0.0f;  // no row -1 (outputs are >= 0: zero is neutral)
+      }
+      float* const ptile = pool + (size_t)(emitted & 1u) * 64 * kSfPoolPitch + (32 * chg + lane) * kSfPoolPitch;
+      mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cb = 16 * (part * P.nch + j);        // first convolution column of this chunk
+        if (j < P.nch && cb < pw) {
+          float m[17], c1[17];                         // [0] = column cb-1, [1 + i] = column cb + i
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            uint32_t a0[8], a1[8], am = 0u;
+            const uint32_t tcol = trow + (uint32_t)(acc.stage * 256 + r * pw + cb);
+            tmem_ld8(tcol, a0);
+            if (cb + 8 < pw) tmem_ld8(tcol + 8, a1);
+            else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a1[i] = 0u;
+            }
+            if (cb > 0) tmem_ld1(tcol - 1, am);
+            tmem_ld_wait();
+            float4* const xrow = reinterpret_cast<float4*>(xt + xbuf * 32 * kSfXPitch);
+            if (upper) {
+              xrow[0] = make_float4(__uint_as_float(a0[0]), __uint_as_float(a0[1]), __uint_as_float(a0[2]), __uint_as_float(a0[3]));
+              xrow[1] = make_float4(__uint_as_float(a0[4]), __uint_as_float(a0[5]), __uint_as_float(a0[6]), __uint_as_float(a0[7]));
+              xrow[2] = make_float4(__uint_as_float(a1[0]), __uint_as_float(a1[1]), __uint_as_float(a1[2]), __uint_as_float(a1[3]));
+              xrow[3] = make_float4(__uint_as_float(a1[4]), __uint_as_float(a1[5]), __uint_as_float(a1[6]), __uint_as_float(a1[7]));
+              reinterpret_cast<float*>(xrow)[16] = __uint_as_float(am);
+              asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // half parked (two tiles alternate)
+            } else {
+              asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+              const float4 u0 = xrow[0], u1 = xrow[1], u2 = xrow[2], u3 = xrow[3];
+              const float um = reinterpret_cast<const float*>(xrow)[16];
+              float v[17];
+              v[0] = __uint_as_float(am) + um;
+              v[1] = __uint_as_float(a0[0]) + u0.x; v[2] = __uint_as_float(a0[1]) + u0.y;
+              v[3] = __uint_as_float(a0[2]) + u0.z; v[4] = __uint_as_float(a0[3]) + u0.w;
+              v[5] = __uint_as_float(a0[4]) + u1.x; v[6] = __uint_as_float(a0[5]) + u1.y;
+              v[7] = __uint_as_float(a0[6]) + u1.z; v[8] = __uint_as_float(a0[7]) + u1.w;
+              v[9] = __uint_as_float(a1[0]) + u2.x; v[10] = __uint_as_float(a1[1]) + u2.y;
+              v[11] = __uint_as_float(a1[2]) + u2.z; v[12] = __uint_as_float(a1[3]) + u2.w;
+              v[13] = __uint_as_float(a1[4]) + u3.x; v[14] = __uint_as_float(a1[5]) + u3.y;
+              v[15] = __uint_as_float(a1[6]) + u3.z; v[16] = __uint_as_float(a1[7]) + u3.w;
+              const int lim = (2 * k + r < P.hc) ? wc : 0;               // columns (and rows) outside the map count as 0
+#pragma unroll
+              for (int i = 0; i < 17; ++i) {
+                const int col = cb - 1 + i;
+                float y = fmaxf(fmaf(v[i], inv, bs), 0.0f);
+                if (col >= lim || (i == 0 && cb == 0)) y = 0.0f;
+                if (r == 0) m[i] = y;
+                else { c1[i] = y; m[i] = fmaxf(m[i], y); }
+              }
+            }
+            xbuf ^= 1u;
+          }
+          if (!upper) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float hm = fmaxf(fmaxf(m[2 * i], m[2 * i + 1]), m[2 * i + 2]);
+              const float o = fmaxf(hm, carry[8 * j + i]);
+              carry[8 * j + i] = fmaxf(fmaxf(c1[2 * i], c1[2 * i + 1]), c1[2 * i + 2]);
+              if (emit) ptile[(cb >> 1) + i] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(acc.stage));
+      acc.advance();
+      if (emit) {
+        asm volatile("bar.sync 15, 512;" ::: "memory");                  // pooled row complete
+        const float* const pt = pool + (size_t)(emitted & 1u) * 64 * kSfPoolPitch;
+        const int wp = P.wp;
+        const long long chs = (long long)P.hp * wp;
+        float* const ob = out + ((long long)s * 64 * P.hp + k) * wp;
+        const int dch = 512 / wp, dpx = 512 - dch * wp;
+        int ch = (int)threadIdx.x / wp, px = (int)threadIdx.x - ch * wp;
+        while (ch < 64) {
+          ob[ch * chs + px] = pt[ch * kSfPoolPitch + px];
+          px += dpx; ch += dch;
+          if (px >= wp) { px -= wp; ++ch; }
+        }
+        ++emitted;
+      }
+    }
+  } else if (warp == 16) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      Ring acc(2), rp(kStPStages);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(P.ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32
+      const uint32_t wbase = sbase + P.smem_w;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(acc_empty(acc.stage), acc.phase ^ 1u, err, 2);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc.stage * 256);
+        for (int phase = 0; phase < 4; ++phase) {
+          mbar_wait(p_full(rp.stage), rp.phase, err, 3);
+          tc_fence_after();
+          const uint32_t pb = sbase + P.smem_p + (uint32_t)rp.stage * P.stage_bytes;
+          for (int kk = 0; kk < P.count[phase]; ++kk) {
+            const int pair = P.first[phase] + kk;
+            const uint64_t ad = make_desc(wbase + (uint32_t)pair * 4096u, 2048u, 128u);
+            const uint64_t bd = make_desc(pb + (uint32_t)P.pair_off[pair] * 16u, (uint32_t)P.pair_lbo[pair] * 16u, 128u);
+            umma_f16(d0, ad, bd, idesc, (phase | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(p_empty(rp.stage));
+          rp.advance();
+        }
+        umma_commit(acc_full(acc.stage));
+        acc.advance();
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== patch producers (warps 17-24) =====================
+    const int pt = (warp - 17) * 32 + lane;
+    const long long plane = (long long)P.h * P.w;
+    Ring rp(kStPStages);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int s = tile / P.hp, k = tile - s * P.hp;
+      const float* const xs = x + (long long)s * 3 * plane;
+      for (int phase = 0; phase < 4; ++phase) {
+        mbar_wait(p_empty(rp.stage), rp.phase ^ 1u, err, 6);
+        uint4* const patch = reinterpret_cast<uint4*>(smem + P.smem_p + (size_t)rp.stage * P.stage_bytes);
+        const int py = phase >> 1, px = phase & 1;
+        constexpr int kB = 3;
+        for (int pos0 = pt; pos0 < P.pp; pos0 += kB * kStProducerWarps * 32) {
+          float v[kB][3];
+#pragma unroll
+          for (int u = 0; u < kB; ++u) {
+            const int pos = pos0 + u * kStProducerWarps * 32;
+            v[u][0] = v[u][1] = v[u][2] = 0.0f;
+            if (pos < P.pp) {
+              const int prow = (int)(((uint32_t)pos * P.pw_magic) >> 20);
+              const int bcol = pos - prow * P.pw - 2;
+              const int a = 2 * k - 2 + prow;
+              const int iy = 2 * a + py, ix = 2 * bcol + px;
+              if (a >= 0 && bcol >= 0 && iy < P.h && ix < P.w) {
+                const float* xp = xs + (long long)iy * P.w + ix;
+                v[u][0] = __ldg(xp); v[u][1] = __ldg(xp + plane); v[u][2] = __ldg(xp + 2 * plane);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kB; ++u) {
+            const int pos = pos0 + u * kStProducerWarps * 32;
+            if (pos < P.pp) {
+              uint32_t hb[3], lb[3];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const float f = fminf(fmaxf(v[u][c], -65504.0f), 65504.0f);      // fp16 range (documented domain)
+                const __half hi = __float2half_rn(f);
+                const __half lo = __float2half_rn(__fsub_rn(f, __half2float(hi)));
+                hb[c] = (uint32_t)__half_as_ushort(hi);
+                lb[c] = (uint32_t)__half_as_ushort(lo);
+              }
+              patch[pos] = make_uint4(hb[0] | (hb[1] << 16), hb[2], lb[0] | (lb[1] << 16), lb[2]);
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(rp.stage));
+        rp.advance();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+static bool stem_fused_plan(int n, int h, int w, SfParams& P, size_t& smem_bytes) {
+  if (n <= 0 || h < 7 || w < 7) return false;
+  P.n = n; P.h = h; P.w = w;
+  P.hc = (h - 1) / 2 + 1; P.wc = (w - 1) / 2 + 1;
+  P.hp = (P.hc - 1) / 2 + 1; P.wp = (P.wc - 1) / 2 + 1;
+  P.pw = (P.wc + 3 + 7) / 8 * 8;
+  if (P.pw > 128) return false;                              // two convolution rows must fit one N = 256 tile
+  P.ncols = 2 * P.pw;
+  P.nch = (P.wp + 31) / 32;                                  // 4 epilogue parts x nch chunks x 8 px >= wp
+  if ((long long)n * P.hp > (1ll << 30)) return false;
+  P.tiles = n * P.hp;
+  P.pw_magic = ((1u << 20) + (uint32_t)P.pw - 1u) / (uint32_t)P.pw;
+  const StemTaps T = stem_taps();
+  int max_off = 0;
+  for (int ph = 0; ph < 4; ++ph) { P.first[ph] = T.first[ph]; P.count[ph] = T.count[ph]; }
+  for (int p = 0; p < kStPairs; ++p) {
+    const int o0 = (T.qy[p][0] + 2) * P.pw + T.qx[p][0] + 2, o1 = (T.qy[p][1] + 2) * P.pw + T.qx[p][1] + 2;
+    P.pair_off[p] = o0;
+    P.pair_lbo[p] = o1 - o0;
+    if (o0 < 0 || P.pair_lbo[p] <= 0 || P.pair_lbo[p] >= 0x3FFF) return false;
+    if (o1 > max_off) max_off = o1;
+  }
+  P.pp = (P.ncols + max_off + 7) / 8 * 8;
+  if ((long long)P.pp * P.pw_magic >= (1ll << 32)) return false;
+  P.stage_bytes = (uint32_t)P.pp * 16u;
+  uint32_t o = 0;
+  P.smem_w = o; o += kStWeightBytes;
+  P.smem_p = o; o += kStPStages * P.stage_bytes;
+  P.smem_bar = o; o += 256;
+  P.smem_x = o; o += 8 * 2 * 32 * kSfXPitch * 4;
+  P.smem_pool = o; o += 2 * 64 * kSfPoolPitch * 4;
+  smem_bytes = o;
+  return smem_bytes <= 227 * 1024;
+}
+
 }  // namespace lsq
 
 using namespace lsq;
 
-extern "C" size_t lsq_stem_image_bytes(void) { return kStWeightBytes; }
+extern "C" size_t lsq_stem_image_bytes(void) { return 2 * (size_t)kStWeightBytes + 64 * sizeof(float); }
+
+extern "C" int lsq_stem_is_fused(int n, int h, int w) {
+  SfParams F;
+  size_t smem = 0;
+  return stem_fused_plan(n, h, w, F, smem) ? 1 : 0;
+}
 
 extern "C" size_t lsq_stem_workspace_bytes(int n, int h, int w) {
   if (n <= 0 || h < 7 || w < 7) return 0;
+  if (lsq_stem_is_fused(n, h, w)) return 256;      // the fused kernel keeps the convolution output on chip
   const size_t hc = (size_t)(h - 1) / 2 + 1, wc = (size_t)(w - 1) / 2 + 1;
   return (size_t)n * 64 * hc * wc * sizeof(float);
 }
@@ -403,13 +732,18 @@ extern "C" size_t lsq_stem_workspace_bytes(int n, int h, int w) {
 extern "C" int lsq_stem_supported(int n, int h, int w) {
   StemParams P;
   size_t smem = 0;
-  return (n > 0 && h >= 7 && w >= 7 && stem_plan(n, h, w, P, smem)) ? 1 : 0;
+  return (n > 0 && h >= 7 && w >= 7 && (lsq_stem_is_fused(n, h, w) || stem_plan(n, h, w, P, smem))) ? 1 : 0;
 }
 
 extern "C" int lsq_stem_pack_weights(const float* d_w, float* d_image, void* stream) {
   LSQ_CHECK_ARG(d_w && d_image, "lsq_stem_pack_weights: null pointer");
+  LSQ_CHECK_ARG(((uintptr_t)d_image & 15) == 0, "lsq_stem_pack_weights: image must be 16-byte aligned");
   stem_pack_kernel<<<50, 256, 0, (cudaStream_t)stream>>>(d_w, d_image, stem_taps());
   LSQ_CUDA_LAUNCH_CHECK("stem_pack_kernel");
+  unsigned char* const base = reinterpret_cast<unsigned char*>(d_image);
+  stem_pack_f16_kernel<<<50, 256, 0, (cudaStream_t)stream>>>(d_w, reinterpret_cast<__half*>(base + kSfImageOffset),
+                                                           reinterpret_cast<float*>(base + kSfScaleOffset), stem_taps());
+  LSQ_CUDA_LAUNCH_CHECK("stem_pack_f16_kernel");
   return LSQ_OK;
 }
 
@@ -418,8 +752,23 @@ extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* 
   LSQ_CHECK_ARG(d_x && d_image && d_bias && d_conv_ws && d_out, "lsq_stem_fwd: null pointer");
   LSQ_CHECK_ARG(n > 0 && h >= 7 && w >= 7, "lsq_stem_fwd: bad shape");
   LSQ_CHECK_ARG(((uintptr_t)d_image & 15) == 0, "lsq_stem_fwd: weight image must be 16-byte aligned");
-  StemParams P;
   size_t smem = 0;
+  {
+    SfParams F;
+    static const bool no_fuse = getenv("LSQ_STEM_UNFUSED") != nullptr;     // development: force the two-kernel route
+    if (!no_fuse && stem_fused_plan(n, h, w, F, smem)) {
+      static std::atomic<unsigned long long> fused_set{0ull};
+      const cudaError_t fe = ensure_max_smem(stem_fused_kernel, fused_set);
+      if (fe != cudaSuccess) { set_error("lsq_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(fe)); return LSQ_ERR_CUDA; }
+      const int sms_f = device_sms();
+      const unsigned char* const base = reinterpret_cast<const unsigned char*>(d_image);
+      stem_fused_kernel<<<F.tiles < sms_f ? F.tiles : sms_f, kStThreads, smem, (cudaStream_t)stream>>>(
+          d_x, F, base + kSfImageOffset, reinterpret_cast<const float*>(base + kSfScaleOffset), d_bias, d_out);
+      LSQ_CUDA_LAUNCH_CHECK("stem_fused_kernel");
+      return LSQ_OK;
+    }
+  }
+  StemParams P;
   if (!stem_plan(n, h, w, P, smem)) {
     set_error("lsq_stem_fwd: image %dx%d not supported (patch does not fit shared memory)", h, w);
     return LSQ_ERR_UNSUPPORTED;

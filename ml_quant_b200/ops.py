@@ -361,7 +361,8 @@ _stem_ws = {}
 
 
 def stem_fwd(x: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """maxpool3x3s2p1(relu(conv7x7s2p3(x, w) + bias)) (lsq_stem_fwd); image comes from stem_pack."""
+    """maxpool3x3s2p1(relu(conv7x7s2p3(x, w) + bias)) (lsq_stem_fwd); image comes from stem_pack.
+    Images up to 250 pixels wide run as one kernel (|x| clamped to the fp16 range 65504)."""
     require_cuda(x, 'x')
     x = x.contiguous()
     n, c, h, w = x.shape
@@ -380,7 +381,8 @@ def stem_fwd(x: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.
     with torch.cuda.device(x.device), _launch('stem', 4.0 * (x.numel() + out.numel()), 2.0 * macs):
         _C.check(L.lsq_stem_fwd(x.data_ptr(), n, h, w, image.data_ptr(), bias.contiguous().data_ptr(), ws.data_ptr(),
                                 out.data_ptr(), _stream()), 'lsq_stem_fwd')
-    LAUNCHES['stem_pool'] = LAUNCHES.get('stem_pool', 0) + 1      # lsq_stem_fwd launches two kernels (conv, pool)
+    if not L.lsq_stem_is_fused(n, h, w):
+        LAUNCHES['stem_pool'] = LAUNCHES.get('stem_pool', 0) + 1      # the two-kernel route (conv, pool) of wide images
     return out
 
 
