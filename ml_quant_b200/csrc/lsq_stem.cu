@@ -407,13 +407,15 @@ static bool stem_plan(int n, int h, int w, StemParams& P, size_t& smem_bytes) {
 //    must precede the ReLU / max).  The pooled row (64 x wp) is transposed through shared memory and stored
 //    along px.
 constexpr int kSfXPitch = 20;                  // exchange tile: [32 channels][16 columns + left neighbour], float4 conflict-free
-constexpr int kSfPoolPitch = 65;               // pooled tile: [64 channels][<= 64 px], lane = channel conflict-free
+constexpr int kSfPoolPitch = 68;               // pooled tile: [64 channels][<= 64 px], rows 16-byte aligned for the float4 store
+constexpr int kSfProducerWarps = 6;
+constexpr int kSfThreads = (17 + kSfProducerWarps) * 32;     // 16 epilogue warps, MMA warp 16, producer warps 17-22
 constexpr uint32_t kSfImageOffset = kStWeightBytes;          // fp16 image behind the TF32 image
 constexpr uint32_t kSfScaleOffset = 2 * kStWeightBytes;      // 64 x 2^-e (fp32)
 
 struct SfParams {
   int n, h, w, hc, wc, hp, wp;
-  int pw, ncols, pp, nch, tiles;
+  int pw, ncols, pp, nch, tiles, dbg;
   uint32_t pw_magic;
   int first[4], count[4];
   int pair_off[kStPairs], pair_lbo[kStPairs];
@@ -445,27 +447,49 @@ __global__ void stem_pack_f16_kernel(const float* __restrict__ w, __half* __rest
   }
 }
 
-__global__ void __launch_bounds__(kStThreads, 1)
+__global__ void __launch_bounds__(kSfThreads, 1)
 stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* __restrict__ wimage,
-                  const float* __restrict__ inv_scale, const float* __restrict__ bias, float* __restrict__ out) {
+                  const float* __restrict__ inv_scale, const float* __restrict__ bias, float* __restrict__ out,
+                  long long* __restrict__ diag) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long w0 = 0, w1 = 0;
+  const long long t_start = LSQ_TC_CLOCK();
+#ifdef LSQ_TC_DIAG
+  long long sec[6] = {0, 0, 0, 0, 0, 0}, tq = 0;
+#define SF_T0() tq = clock64()
+#define SF_T(i) do { const long long tn = clock64(); sec[i] += tn - tq; tq = tn; } while (0)
+#else
+#define SF_T0()
+#define SF_T(i)
+#endif
+  // barriers: p_full[4] p_empty[4] (one ring stage per stride phase) acc_full[2] acc_empty[2] | tmem base
   const uint32_t bar0 = sbase + P.smem_bar;
   auto p_full = [&](int s) { return bar0 + 8u * s; };
-  auto p_empty = [&](int s) { return bar0 + 8u * (kStPStages + s); };
-  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kStPStages + s); };
-  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kStPStages + 2 + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * (2 * kStPStages + 4));
+  auto p_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (10 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * 12);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStPStages; ++s) { mbar_init(p_full(s), kStProducerWarps); mbar_init(p_empty(s), 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(p_full(s), kSfProducerWarps / 2); mbar_init(p_empty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
     const float4* src = reinterpret_cast<const float4*>(wimage);
     float4* dst = reinterpret_cast<float4*>(smem + P.smem_w);
-    for (int i = threadIdx.x; i < (int)(kStWeightBytes / 16); i += kStThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < (int)(kStWeightBytes / 16); i += kSfThreads) dst[i] = __ldg(src + i);
+  }
+  // operand descriptors of the 25 instructions of a tile: constant for the whole kernel (one ring stage per phase)
+  unsigned long long* const desc_tab = reinterpret_cast<unsigned long long*>(smem + P.smem_bar + 128);
+  if (threadIdx.x < kStPairs) {
+    const int pair = threadIdx.x;
+    int phase = 0;
+    while (phase < 3 && pair >= P.first[phase + 1]) ++phase;
+    const uint32_t pb = sbase + P.smem_p + (uint32_t)phase * P.stage_bytes;
+    desc_tab[2 * pair] = make_desc(sbase + P.smem_w + (uint32_t)pair * 4096u, 2048u, 128u);
+    desc_tab[2 * pair + 1] = make_desc(pb + (uint32_t)P.pair_off[pair] * 16u, (uint32_t)P.pair_lbo[pair] * 16u, 128u);
   }
   fence_proxy_async();
   if (warp == 16) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
@@ -481,195 +505,261 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
 
   if (warp < 16) {
     // ===================== epilogue (16 warps) =====================
+    // Warp pair (qd, qd + 2) of a part owns 32 channels x up to 32 convolution columns (two 16-column chunks) of
+    // both rows: the W_hi warp finishes chunk 0, the W_lo warp chunk 1, each after receiving the other's raw half
+    // of its chunk through the pair's exchange tile.  Pooling runs on the raw sums (the map acc -> relu(acc * 2^-e +
+    // bias) is monotone, so it commutes with max exactly); positions outside the map count as -inf.
     const int qd = warp & 3, part = warp >> 2;
-    const bool upper = qd >= 2;
+    const int mine = qd >> 1;                          // chunk this warp finishes (0: W_hi warp, 1: W_lo warp)
     const int chg = qd & 1;
     const int pairid = chg + 2 * part;
     const int bar_id = 1 + pairid;                     // named barrier of the warp pair (64 threads)
-    float* const xt = reinterpret_cast<float*>(smem + P.smem_x) + (size_t)pairid * 2 * 32 * kSfXPitch + lane * kSfXPitch;
+    float* const xpair = reinterpret_cast<float*>(smem + P.smem_x) + (size_t)pairid * 2 * 32 * kSfXPitch + lane * kSfXPitch;
+    float4* const xsend = reinterpret_cast<float4*>(xpair + mine * 32 * kSfXPitch);          // my half of the partner's chunk
+    const float4* const xrecv = reinterpret_cast<const float4*>(xpair + (mine ^ 1) * 32 * kSfXPitch);
     float* const pool = reinterpret_cast<float*>(smem + P.smem_pool);
     const float bs = __ldg(bias + 32 * chg + lane), inv = __ldg(inv_scale + 32 * chg + lane);
     const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const int pw = P.pw, wc = P.wc;
-    float carry[16];                                   // horizontal maxima of convolution row 2k-1, px = 8 (part nch + j) + i
+    const int pw = P.pw, wc = P.wc, wp = P.wp;
+    const int cb_m = 16 * (part * P.nch + mine), cb_o = 16 * (part * P.nch + (mine ^ 1));   // first columns of the chunks
+    const bool have_m = mine < P.nch && cb_m < pw, have_o = (mine ^ 1) < P.nch && cb_o < pw;
+    const float ninf = __int_as_float(0xff800000);
+    float carry[8];                                    // raw horizontal maxima of convolution row 2k-1, px = cb_m / 2 + i
+    // pooled row -> global: float4 units when rows are 16-byte multiples, else a scalar walk
+    const bool vec_store = (wp & 3) == 0;
+    const int wq = wp >> 2;
+    int so[2], go[2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) carry[i] = 0.0f;
+    for (int u = 0; u < 2; ++u) {
+      const int idx = (int)threadIdx.x + 512 * u;
+      const int ch = vec_store ? idx / wq : 64, q = vec_store ? idx - ch * wq : 0;
+      so[u] = ch < 64 ? ch * kSfPoolPitch + 4 * q : -1;
+      go[u] = ch * P.hp * wp + 4 * q;
+    }
     Ring acc(2);
-    uint32_t xbuf = 0, emitted = 0;
+    uint32_t emitted = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int s = tile / P.hp, k = tile - s * P.hp;
       const bool emit = tile >= t_own;
       if (k == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) carry[i] = 0.0f;  // no row -1 (outputs are >= 0: zero is neutral)
+        for (int i = 0; i < 8; ++i) carry[i] = ninf;   // no row -1
       }
-      float* const ptile = pool + (size_t)(emitted & 1u) * 64 * kSfPoolPitch + (32 * chg + lane) * kSfPoolPitch;
-      mbar_wait(acc_full(acc.stage), acc.phase, err, 1);
+      float* const ptile = pool + (size_t)(emitted & 1u) * 64 * kSfPoolPitch;
+      mbar_wait_t(acc_full(acc.stage), acc.phase, err, 1, w0);
       tc_fence_after();
+      // two 8-column halves of the chunk, both convolution rows at once (keeps the live registers few)
+      float left0 = ninf, left1 = ninf;                // column before the current half: row 2k, row 2k+1
+      const uint32_t tcol = trow + (uint32_t)(acc.stage * 256);
+      float* const prow = ptile + (32 * chg + lane) * kSfPoolPitch + (cb_m >> 1);
+      const bool row1 = 2 * k + 1 < P.hc;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int cb = 16 * (part * P.nch + j);        // first convolution column of this chunk
-        if (j < P.nch && cb < pw) {
-          float m[17], c1[17];                         // [0] = column cb-1, [1 + i] = column cb + i
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            uint32_t a0[8], a1[8], am = 0u;
-            const uint32_t tcol = trow + (uint32_t)(acc.stage * 256 + r * pw + cb);
-            tmem_ld8(tcol, a0);
-            if (cb + 8 < pw) tmem_ld8(tcol + 8, a1);
-            else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a1[i] = 0u;
-            }
-            if (cb > 0) tmem_ld1(tcol - 1, am);
-            tmem_ld_wait();
-            float4* const xrow = reinterpret_cast<float4*>(xt + xbuf * 32 * kSfXPitch);
-            if (upper) {
-              xrow[0] = make_float4(__uint_as_float(a0[0]), __uint_as_float(a0[1]), __uint_as_float(a0[2]), __uint_as_float(a0[3]));
-              xrow[1] = make_float4(__uint_as_float(a0[4]), __uint_as_float(a0[5]), __uint_as_float(a0[6]), __uint_as_float(a0[7]));
-              xrow[2] = make_float4(__uint_as_float(a1[0]), __uint_as_float(a1[1]), __uint_as_float(a1[2]), __uint_as_float(a1[3]));
-              xrow[3] = make_float4(__uint_as_float(a1[4]), __uint_as_float(a1[5]), __uint_as_float(a1[6]), __uint_as_float(a1[7]));
-              reinterpret_cast<float*>(xrow)[16] = __uint_as_float(am);
-              asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // half parked (two tiles alternate)
-            } else {
-              asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-              const float4 u0 = xrow[0], u1 = xrow[1], u2 = xrow[2], u3 = xrow[3];
-              const float um = reinterpret_cast<const float*>(xrow)[16];
-              float v[17];
-              v[0] = __uint_as_float(am) + um;
-              v[1] = __uint_as_float(a0[0]) + u0.x; v[2] = __uint_as_float(a0[1]) + u0.y;
-              v[3] = __uint_as_float(a0[2]) + u0.z; v[4] = __uint_as_float(a0[3]) + u0.w;
-              v[5] = __uint_as_float(a0[4]) + u1.x; v[6] = __uint_as_float(a0[5]) + u1.y;
-              v[7] = __uint_as_float(a0[6]) + u1.z; v[8] = __uint_as_float(a0[7]) + u1.w;
-              v[9] = __uint_as_float(a1[0]) + u2.x; v[10] = __uint_as_float(a1[1]) + u2.y;
-              v[11] = __uint_as_float(a1[2]) + u2.z; v[12] = __uint_as_float(a1[3]) + u2.w;
-              v[13] = __uint_as_float(a1[4]) + u3.x; v[14] = __uint_as_float(a1[5]) + u3.y;
-              v[15] = __uint_as_float(a1[6]) + u3.z; v[16] = __uint_as_float(a1[7]) + u3.w;
-              const int lim = (2 * k + r < P.hc) ? wc : 0;               // columns (and rows) outside the map count as 0
-#pragma unroll
-              for (int i = 0; i < 17; ++i) {
-                const int col = cb - 1 + i;
-                float y = fmaxf(fmaf(v[i], inv, bs), 0.0f);
-                if (col >= lim || (i == 0 && cb == 0)) y = 0.0f;
-                if (r == 0) m[i] = y;
-                else { c1[i] = y; m[i] = fmaxf(m[i], y); }
-              }
-            }
-            xbuf ^= 1u;
-          }
-          if (!upper) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float hm = fmaxf(fmaxf(m[2 * i], m[2 * i + 1]), m[2 * i + 2]);
-              const float o = fmaxf(hm, carry[8 * j + i]);
-              carry[8 * j + i] = fmaxf(fmaxf(c1[2 * i], c1[2 * i + 1]), c1[2 * i + 2]);
-              if (emit) ptile[(cb >> 1) + i] = o;
-            }
-          }
+      for (int hf = 0; hf < 2; ++hf) {
+        SF_T0();
+        const int cm = cb_m + 8 * hf, co = cb_o + 8 * hf;
+        const bool do_m = have_m && cm < pw && !(P.dbg & 1), do_o = have_o && co < pw && !(P.dbg & 1);
+        uint32_t a0[8], a1[8], b0[8], b1[8], al0 = 0u, al1 = 0u, bl0 = 0u, bl1 = 0u;
+        if (do_o && !(P.dbg & 16)) {
+          tmem_ld8(tcol + co, b0);
+          tmem_ld8(tcol + pw + co, b1);
+          if (hf == 0 && co > 0) { tmem_ld1(tcol + co - 1, bl0); tmem_ld1(tcol + pw + co - 1, bl1); }
         }
+        if (do_m && !(P.dbg & 16)) {
+          tmem_ld8(tcol + cm, a0);
+          tmem_ld8(tcol + pw + cm, a1);
+          if (hf == 0 && cm > 0) { tmem_ld1(tcol + cm - 1, al0); tmem_ld1(tcol + pw + cm - 1, al1); }
+        }
+        tmem_ld_wait();
+        SF_T(0);
+        if (do_o && !(P.dbg & 8)) {
+          xsend[0] = make_float4(__uint_as_float(b0[0]), __uint_as_float(b0[1]), __uint_as_float(b0[2]), __uint_as_float(b0[3]));
+          xsend[1] = make_float4(__uint_as_float(b0[4]), __uint_as_float(b0[5]), __uint_as_float(b0[6]), __uint_as_float(b0[7]));
+          xsend[2] = make_float4(__uint_as_float(b1[0]), __uint_as_float(b1[1]), __uint_as_float(b1[2]), __uint_as_float(b1[3]));
+          xsend[3] = make_float4(__uint_as_float(b1[4]), __uint_as_float(b1[5]), __uint_as_float(b1[6]), __uint_as_float(b1[7]));
+          if (hf == 0) reinterpret_cast<float2*>(xsend)[8] = make_float2(__uint_as_float(bl0), __uint_as_float(bl1));
+        }
+        if (!(P.dbg & 8)) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // halves parked
+        SF_T(1);
+        if (do_m) {
+          const float4 u0 = xrecv[0], u1 = xrecv[1], u2 = xrecv[2], u3 = xrecv[3];
+          float v0[8], v1[8];
+          v0[0] = __uint_as_float(a0[0]) + u0.x; v0[1] = __uint_as_float(a0[1]) + u0.y;
+          v0[2] = __uint_as_float(a0[2]) + u0.z; v0[3] = __uint_as_float(a0[3]) + u0.w;
+          v0[4] = __uint_as_float(a0[4]) + u1.x; v0[5] = __uint_as_float(a0[5]) + u1.y;
+          v0[6] = __uint_as_float(a0[6]) + u1.z; v0[7] = __uint_as_float(a0[7]) + u1.w;
+          v1[0] = __uint_as_float(a1[0]) + u2.x; v1[1] = __uint_as_float(a1[1]) + u2.y;
+          v1[2] = __uint_as_float(a1[2]) + u2.z; v1[3] = __uint_as_float(a1[3]) + u2.w;
+          v1[4] = __uint_as_float(a1[4]) + u3.x; v1[5] = __uint_as_float(a1[5]) + u3.y;
+          v1[6] = __uint_as_float(a1[6]) + u3.z; v1[7] = __uint_as_float(a1[7]) + u3.w;
+          if (hf == 0 && cm > 0) {
+            const float2 ul = reinterpret_cast<const float2*>(xrecv)[8];
+            left0 = __uint_as_float(al0) + ul.x;
+            left1 = __uint_as_float(al1) + ul.y;
+          }
+          if (cm + 8 > wc) {                                             // right edge of the map (uniform)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (cm + i >= wc) { v0[i] = ninf; v1[i] = ninf; }
+          }
+          if (!row1) {                                                   // odd map height: no row 2k+1
+            left1 = ninf;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v1[i] = ninf;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float p0 = i == 0 ? left0 : v0[2 * i - 1], p1 = i == 0 ? left1 : v1[2 * i - 1];
+            const float h1 = fmaxf(fmaxf(p1, v1[2 * i]), v1[2 * i + 1]);
+            const float h0 = fmaxf(fmaxf(p0, v0[2 * i]), v0[2 * i + 1]);
+            const float hm = fmaxf(fmaxf(h0, h1), carry[4 * hf + i]);
+            carry[4 * hf + i] = h1;
+            if (emit) prow[4 * hf + i] = fmaxf(fmaf(hm, inv, bs), 0.0f);
+          }
+          left0 = v0[7]; left1 = v1[7];
+        }
+        SF_T(2);
+        if (!(P.dbg & 8)) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // halves consumed
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(acc.stage));
       acc.advance();
-      if (emit) {
-        asm volatile("bar.sync 15, 512;" ::: "memory");                  // pooled row complete
-        const float* const pt = pool + (size_t)(emitted & 1u) * 64 * kSfPoolPitch;
-        const int wp = P.wp;
-        const long long chs = (long long)P.hp * wp;
+      SF_T(3);
+      if (emit && !(P.dbg & 4)) {
+#ifdef LSQ_TC_DIAG
+        const long long tb = clock64();
+#endif
+        if (!(P.dbg & 32)) asm volatile("bar.sync 15, 512;" ::: "memory");                  // pooled row complete
+#ifdef LSQ_TC_DIAG
+        w1 += clock64() - tb;
+#endif
+        SF_T0();
         float* const ob = out + ((long long)s * 64 * P.hp + k) * wp;
-        const int dch = 512 / wp, dpx = 512 - dch * wp;
-        int ch = (int)threadIdx.x / wp, px = (int)threadIdx.x - ch * wp;
-        while (ch < 64) {
-          ob[ch * chs + px] = pt[ch * kSfPoolPitch + px];
-          px += dpx; ch += dch;
-          if (px >= wp) { px -= wp; ++ch; }
+        if (vec_store) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (so[u] >= 0) *reinterpret_cast<float4*>(ob + go[u]) = *reinterpret_cast<const float4*>(ptile + so[u]);
+        } else {
+          const long long chs = (long long)P.hp * wp;
+          const int dch = 512 / wp, dpx = 512 - dch * wp;
+          int ch = (int)threadIdx.x / wp, px = (int)threadIdx.x - ch * wp;
+          while (ch < 64) {
+            ob[ch * chs + px] = ptile[ch * kSfPoolPitch + px];
+            px += dpx; ch += dch;
+            if (px >= wp) { px -= wp; ++ch; }
+          }
         }
+        SF_T(4);
         ++emitted;
       }
     }
   } else if (warp == 16) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      Ring acc(2), rp(kStPStages);
+      Ring acc(2);
+      uint32_t par = 0;
       const uint32_t idesc = (1u << 4) | ((uint32_t)(P.ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32
-      const uint32_t wbase = sbase + P.smem_w;
+      const ulonglong2* const dt = reinterpret_cast<const ulonglong2*>(desc_tab);
+      const int pfirst[5] = {P.first[0], P.first[1], P.first[2], P.first[3], kStPairs};
       for (int tile = t_begin; tile < t_end; ++tile) {
-        mbar_wait(acc_empty(acc.stage), acc.phase ^ 1u, err, 2);
+        mbar_wait_t(acc_empty(acc.stage), acc.phase ^ 1u, err, 2, w0);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc.stage * 256);
+#pragma unroll
         for (int phase = 0; phase < 4; ++phase) {
-          mbar_wait(p_full(rp.stage), rp.phase, err, 3);
+          mbar_wait_t(p_full(phase), par, err, 3, w1);
           tc_fence_after();
-          const uint32_t pb = sbase + P.smem_p + (uint32_t)rp.stage * P.stage_bytes;
-          for (int kk = 0; kk < P.count[phase]; ++kk) {
-            const int pair = P.first[phase] + kk;
-            const uint64_t ad = make_desc(wbase + (uint32_t)pair * 4096u, 2048u, 128u);
-            const uint64_t bd = make_desc(pb + (uint32_t)P.pair_off[pair] * 16u, (uint32_t)P.pair_lbo[pair] * 16u, 128u);
-            umma_f16(d0, ad, bd, idesc, (phase | kk) != 0 ? 1u : 0u);
+#pragma unroll 4
+          for (int pair = pfirst[phase]; pair < pfirst[phase + 1]; ++pair) {
+            const ulonglong2 d = dt[pair];
+            if (!(P.dbg & 2)) umma_f16(d0, d.x, d.y, idesc, pair != 0 ? 1u : 0u);
           }
-          umma_commit(p_empty(rp.stage));
-          rp.advance();
+          umma_commit(p_empty(phase));
         }
         umma_commit(acc_full(acc.stage));
         acc.advance();
+        par ^= 1u;
       }
     }
     __syncwarp();
   } else {
-    // ===================== patch producers (warps 17-24) =====================
-    const int pt = (warp - 17) * 32 + lane;
+    // ===================== patch producers (warps 17-22) =====================
+    // Three warps per input row parity py.  A lane loads pixel pairs (ix, ix + 1) = the px = 0 and px = 1 phase
+    // entries of one position (8 contiguous bytes when the row pitch allows), so every fetched sector is used once;
+    // the loads of the next tile are issued before waiting for the ring slots (their latency is what a tile waits for).
+    const int pwarp = warp - 17;
+    const int py = pwarp & 1, third = pwarp >> 1;
     const long long plane = (long long)P.h * P.w;
-    Ring rp(kStPStages);
+    uint4* const patch0 = reinterpret_cast<uint4*>(smem + P.smem_p + (size_t)(2 * py) * P.stage_bytes);
+    uint4* const patch1 = reinterpret_cast<uint4*>(smem + P.smem_p + (size_t)(2 * py + 1) * P.stage_bytes);
+    const bool pair_loads = (P.w & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+    uint32_t par = 0;
+    constexpr int kB = 7;                                // 96 * 7 >= the largest patch (648 positions)
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int s = tile / P.hp, k = tile - s * P.hp;
       const float* const xs = x + (long long)s * 3 * plane;
-      for (int phase = 0; phase < 4; ++phase) {
-        mbar_wait(p_empty(rp.stage), rp.phase ^ 1u, err, 6);
-        uint4* const patch = reinterpret_cast<uint4*>(smem + P.smem_p + (size_t)rp.stage * P.stage_bytes);
-        const int py = phase >> 1, px = phase & 1;
-        constexpr int kB = 3;
-        for (int pos0 = pt; pos0 < P.pp; pos0 += kB * kStProducerWarps * 32) {
-          float v[kB][3];
+      float2 v[kB][3];
 #pragma unroll
-          for (int u = 0; u < kB; ++u) {
-            const int pos = pos0 + u * kStProducerWarps * 32;
-            v[u][0] = v[u][1] = v[u][2] = 0.0f;
-            if (pos < P.pp) {
-              const int prow = (int)(((uint32_t)pos * P.pw_magic) >> 20);
-              const int bcol = pos - prow * P.pw - 2;
-              const int a = 2 * k - 2 + prow;
-              const int iy = 2 * a + py, ix = 2 * bcol + px;
-              if (a >= 0 && bcol >= 0 && iy < P.h && ix < P.w) {
-                const float* xp = xs + (long long)iy * P.w + ix;
-                v[u][0] = __ldg(xp); v[u][1] = __ldg(xp + plane); v[u][2] = __ldg(xp + 2 * plane);
-              }
-            }
-          }
+      for (int u = 0; u < kB; ++u) {
+        const int pos = third * 32 + lane + 96 * u;
+        v[u][0] = v[u][1] = v[u][2] = make_float2(0.0f, 0.0f);
+        if (pos < P.pp && !(P.dbg & 64)) {
+          const int prow = (int)(((uint32_t)pos * P.pw_magic) >> 20);
+          const int bcol = pos - prow * P.pw - 2;
+          const int a = 2 * k - 2 + prow;
+          const int iy = 2 * a + py, ix = 2 * bcol;
+          if (a >= 0 && bcol >= 0 && iy < P.h && ix < P.w) {
+            const float* xp = xs + (long long)iy * P.w + ix;
+            if (pair_loads) {                            // w even: ix + 1 < w
 #pragma unroll
-          for (int u = 0; u < kB; ++u) {
-            const int pos = pos0 + u * kStProducerWarps * 32;
-            if (pos < P.pp) {
-              uint32_t hb[3], lb[3];
+              for (int c = 0; c < 3; ++c) v[u][c] = __ldg(reinterpret_cast<const float2*>(xp + c * plane));
+            } else {
+              const bool second = ix + 1 < P.w;
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
-                const float f = fminf(fmaxf(v[u][c], -65504.0f), 65504.0f);      // fp16 range (documented domain)
-                const __half hi = __float2half_rn(f);
-                const __half lo = __float2half_rn(__fsub_rn(f, __half2float(hi)));
-                hb[c] = (uint32_t)__half_as_ushort(hi);
-                lb[c] = (uint32_t)__half_as_ushort(lo);
+                v[u][c].x = __ldg(xp + c * plane);
+                if (second) v[u][c].y = __ldg(xp + c * plane + 1);
               }
-              patch[pos] = make_uint4(hb[0] | (hb[1] << 16), hb[2], lb[0] | (lb[1] << 16), lb[2]);
             }
           }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(rp.stage));
-        rp.advance();
       }
+      mbar_wait_t(p_empty(2 * py), par ^ 1u, err, 6, w0);
+      mbar_wait_t(p_empty(2 * py + 1), par ^ 1u, err, 7, w0);
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int pos = third * 32 + lane + 96 * u;
+        if (pos < P.pp && !(P.dbg & 128)) {
+          uint32_t hb[2][3], lb[2][3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float f = fminf(fmaxf(e == 0 ? v[u][c].x : v[u][c].y, -65504.0f), 65504.0f);   // fp16 range (documented domain)
+              const __half hi = __float2half_rn(f);
+              const __half lo = __float2half_rn(__fsub_rn(f, __half2float(hi)));
+              hb[e][c] = (uint32_t)__half_as_ushort(hi);
+              lb[e][c] = (uint32_t)__half_as_ushort(lo);
+            }
+          }
+          patch0[pos] = make_uint4(hb[0][0] | (hb[0][1] << 16), hb[0][2], lb[0][0] | (lb[0][1] << 16), lb[0][2]);
+          patch1[pos] = make_uint4(hb[1][0] | (hb[1][1] << 16), hb[1][2], lb[1][0] | (lb[1][1] << 16), lb[1][2]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(p_full(2 * py)); mbar_arrive(p_full(2 * py + 1)); }
+      par ^= 1u;
     }
   }
+#ifdef LSQ_TC_DIAG
+  if (diag && lane == 0 && blockIdx.x == 0) { diag[warp * 3] = clock64() - t_start; diag[warp * 3 + 1] = w0; diag[warp * 3 + 2] = w1; }
+  if (diag && lane == 0 && blockIdx.x == 0 && warp == 0) for (int i = 0; i < 6; ++i) diag[75 + i] = sec[i];
+#else
+  (void)t_start; (void)w0; (void)w1; (void)diag;
+#endif
+#undef SF_T0
+#undef SF_T
   tc_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem_base, 512);
@@ -678,6 +768,8 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
 static bool stem_fused_plan(int n, int h, int w, SfParams& P, size_t& smem_bytes) {
   if (n <= 0 || h < 7 || w < 7) return false;
   P.n = n; P.h = h; P.w = w;
+  P.dbg = 0;
+  if (const char* d = getenv("LSQ_STEM_DBG")) P.dbg = atoi(d);
   P.hc = (h - 1) / 2 + 1; P.wc = (w - 1) / 2 + 1;
   P.hp = (P.hc - 1) / 2 + 1; P.wp = (P.wc - 1) / 2 + 1;
   P.pw = (P.wc + 3 + 7) / 8 * 8;
@@ -703,8 +795,9 @@ static bool stem_fused_plan(int n, int h, int w, SfParams& P, size_t& smem_bytes
   uint32_t o = 0;
   P.smem_w = o; o += kStWeightBytes;
   P.smem_p = o; o += kStPStages * P.stage_bytes;
-  P.smem_bar = o; o += 256;
+  P.smem_bar = o; o += 128 + kStPairs * 16 + 48;      // barriers + tmem slot, then the descriptor table
   P.smem_x = o; o += 8 * 2 * 32 * kSfXPitch * 4;
+  o = (o + 15u) & ~15u;
   P.smem_pool = o; o += 2 * 64 * kSfPoolPitch * 4;
   smem_bytes = o;
   return smem_bytes <= 227 * 1024;
@@ -762,9 +855,26 @@ extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* 
       if (fe != cudaSuccess) { set_error("lsq_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(fe)); return LSQ_ERR_CUDA; }
       const int sms_f = device_sms();
       const unsigned char* const base = reinterpret_cast<const unsigned char*>(d_image);
-      stem_fused_kernel<<<F.tiles < sms_f ? F.tiles : sms_f, kStThreads, smem, (cudaStream_t)stream>>>(
-          d_x, F, base + kSfImageOffset, reinterpret_cast<const float*>(base + kSfScaleOffset), d_bias, d_out);
+      long long* d_fdiag = nullptr;
+#ifdef LSQ_TC_DIAG
+      static const bool want_fdiag = getenv("LSQ_TC_DIAG") != nullptr;   // development build: wait cycles per warp of CTA 0
+      if (want_fdiag) { cudaMalloc(&d_fdiag, 32 * 3 * sizeof(long long)); cudaMemsetAsync(d_fdiag, 0, 32 * 3 * sizeof(long long), (cudaStream_t)stream); }
+#endif
+      stem_fused_kernel<<<F.tiles < sms_f ? F.tiles : sms_f, kSfThreads, smem, (cudaStream_t)stream>>>(
+          d_x, F, base + kSfImageOffset, reinterpret_cast<const float*>(base + kSfScaleOffset), d_bias, d_out, d_fdiag);
       LSQ_CUDA_LAUNCH_CHECK("stem_fused_kernel");
+#ifdef LSQ_TC_DIAG
+      if (want_fdiag) {
+        long long hd[32 * 3];
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(hd, d_fdiag, sizeof(hd), cudaMemcpyDeviceToHost);
+        cudaFree(d_fdiag);
+        fprintf(stderr, "[fused stem diag] tiles %d pw %d pp %d | warp 0 sections: tmem %lld pairbar %lld math %lld pool %lld store %lld\n", F.tiles, F.pw, F.pp, hd[75], hd[76], hd[77], hd[78], hd[79]);
+        for (int wi = 0; wi < kSfThreads / 32; ++wi)
+          fprintf(stderr, "   warp %2d (%s) total %9lld  wait0 %9lld  wait1 %9lld\n", wi,
+                  wi < 16 ? ((wi & 3) < 2 ? "epi-hi" : "epi-lo") : (wi == 16 ? "mma" : "producer"), hd[wi * 3], hd[wi * 3 + 1], hd[wi * 3 + 2]);
+      }
+#endif
       return LSQ_OK;
     }
   }
