@@ -415,7 +415,7 @@ constexpr uint32_t kSfScaleOffset = 2 * kStWeightBytes;      // 64 x 2^-e (fp32)
 
 struct SfParams {
   int n, h, w, hc, wc, hp, wp;
-  int pw, ncols, pp, nch, tiles, dbg;
+  int pw, ncols, pp, nch, tiles;
   uint32_t pw_magic;
   int first[4], count[4];
   int pair_off[kStPairs], pair_lbo[kStPairs];
@@ -464,15 +464,19 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
 #define SF_T0()
 #define SF_T(i)
 #endif
-  // barriers: p_full[4] p_empty[4] (one ring stage per stride phase) acc_full[2] acc_empty[2] | tmem base
+  // Barriers.  The patches have one buffer per stride phase; the phases of one input row parity (a "group": phases
+  // 2g, 2g+1) are produced and released together.  g_full[2]: patches of group g written; g_empty: the instructions
+  // of group 0 have read them; group 1 is released by acc_full (its instructions are the last of a tile) -- two
+  // tcgen05.commit per tile, each costs the issuing thread several hundred cycles.  acc_full[2] acc_empty[2] | tmem base
   const uint32_t bar0 = sbase + P.smem_bar;
-  auto p_full = [&](int s) { return bar0 + 8u * s; };
-  auto p_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto g_full = [&](int g) { return bar0 + 8u * g; };
+  const uint32_t g_empty = bar0 + 8u * 2;
   auto acc_full = [&](int s) { return bar0 + 8u * (8 + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (10 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * 12);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(p_full(s), kSfProducerWarps / 2); mbar_init(p_empty(s), 1); }
+    for (int g = 0; g < 2; ++g) mbar_init(g_full(g), kSfProducerWarps / 2);
+    mbar_init(g_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -557,28 +561,28 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
       for (int hf = 0; hf < 2; ++hf) {
         SF_T0();
         const int cm = cb_m + 8 * hf, co = cb_o + 8 * hf;
-        const bool do_m = have_m && cm < pw && !(P.dbg & 1), do_o = have_o && co < pw && !(P.dbg & 1);
+        const bool do_m = have_m && cm < pw, do_o = have_o && co < pw;
         uint32_t a0[8], a1[8], b0[8], b1[8], al0 = 0u, al1 = 0u, bl0 = 0u, bl1 = 0u;
-        if (do_o && !(P.dbg & 16)) {
+        if (do_o) {
           tmem_ld8(tcol + co, b0);
           tmem_ld8(tcol + pw + co, b1);
           if (hf == 0 && co > 0) { tmem_ld1(tcol + co - 1, bl0); tmem_ld1(tcol + pw + co - 1, bl1); }
         }
-        if (do_m && !(P.dbg & 16)) {
+        if (do_m) {
           tmem_ld8(tcol + cm, a0);
           tmem_ld8(tcol + pw + cm, a1);
           if (hf == 0 && cm > 0) { tmem_ld1(tcol + cm - 1, al0); tmem_ld1(tcol + pw + cm - 1, al1); }
         }
         tmem_ld_wait();
         SF_T(0);
-        if (do_o && !(P.dbg & 8)) {
+        if (do_o) {
           xsend[0] = make_float4(__uint_as_float(b0[0]), __uint_as_float(b0[1]), __uint_as_float(b0[2]), __uint_as_float(b0[3]));
           xsend[1] = make_float4(__uint_as_float(b0[4]), __uint_as_float(b0[5]), __uint_as_float(b0[6]), __uint_as_float(b0[7]));
           xsend[2] = make_float4(__uint_as_float(b1[0]), __uint_as_float(b1[1]), __uint_as_float(b1[2]), __uint_as_float(b1[3]));
           xsend[3] = make_float4(__uint_as_float(b1[4]), __uint_as_float(b1[5]), __uint_as_float(b1[6]), __uint_as_float(b1[7]));
           if (hf == 0) reinterpret_cast<float2*>(xsend)[8] = make_float2(__uint_as_float(bl0), __uint_as_float(bl1));
         }
-        if (!(P.dbg & 8)) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // halves parked
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // halves parked
         SF_T(1);
         if (do_m) {
           const float4 u0 = xrecv[0], u1 = xrecv[1], u2 = xrecv[2], u3 = xrecv[3];
@@ -618,18 +622,18 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
           left0 = v0[7]; left1 = v1[7];
         }
         SF_T(2);
-        if (!(P.dbg & 8)) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // halves consumed
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // halves consumed
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(acc.stage));
       acc.advance();
       SF_T(3);
-      if (emit && !(P.dbg & 4)) {
+      if (emit) {
 #ifdef LSQ_TC_DIAG
         const long long tb = clock64();
 #endif
-        if (!(P.dbg & 32)) asm volatile("bar.sync 15, 512;" ::: "memory");                  // pooled row complete
+        asm volatile("bar.sync 15, 512;" ::: "memory");                  // pooled row complete
 #ifdef LSQ_TC_DIAG
         w1 += clock64() - tb;
 #endif
@@ -666,15 +670,15 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc.stage * 256);
 #pragma unroll
-        for (int phase = 0; phase < 4; ++phase) {
-          mbar_wait_t(p_full(phase), par, err, 3, w1);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait_t(g_full(g), par, err, 3, w1);
           tc_fence_after();
 #pragma unroll 4
-          for (int pair = pfirst[phase]; pair < pfirst[phase + 1]; ++pair) {
+          for (int pair = pfirst[2 * g]; pair < pfirst[2 * g + 2]; ++pair) {
             const ulonglong2 d = dt[pair];
-            if (!(P.dbg & 2)) umma_f16(d0, d.x, d.y, idesc, pair != 0 ? 1u : 0u);
+            umma_f16(d0, d.x, d.y, idesc, pair != 0 ? 1u : 0u);
           }
-          umma_commit(p_empty(phase));
+          if (g == 0) umma_commit(g_empty);
         }
         umma_commit(acc_full(acc.stage));
         acc.advance();
@@ -694,6 +698,7 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
     uint4* const patch1 = reinterpret_cast<uint4*>(smem + P.smem_p + (size_t)(2 * py + 1) * P.stage_bytes);
     const bool pair_loads = (P.w & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
     uint32_t par = 0;
+    Ring prev(2);                                        // accumulator stage of the previous tile (group 1's release)
     constexpr int kB = 7;                                // 96 * 7 >= the largest patch (648 positions)
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int s = tile / P.hp, k = tile - s * P.hp;
@@ -703,7 +708,7 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
       for (int u = 0; u < kB; ++u) {
         const int pos = third * 32 + lane + 96 * u;
         v[u][0] = v[u][1] = v[u][2] = make_float2(0.0f, 0.0f);
-        if (pos < P.pp && !(P.dbg & 64)) {
+        if (pos < P.pp) {
           const int prow = (int)(((uint32_t)pos * P.pw_magic) >> 20);
           const int bcol = pos - prow * P.pw - 2;
           const int a = 2 * k - 2 + prow;
@@ -724,12 +729,13 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
           }
         }
       }
-      mbar_wait_t(p_empty(2 * py), par ^ 1u, err, 6, w0);
-      mbar_wait_t(p_empty(2 * py + 1), par ^ 1u, err, 7, w0);
+      // the previous tile's instructions of this group have read the patches
+      if (py == 0) mbar_wait_t(g_empty, par ^ 1u, err, 6, w0);
+      else if (tile > t_begin) { mbar_wait_t(acc_full(prev.stage), prev.phase, err, 7, w0); prev.advance(); }
 #pragma unroll
       for (int u = 0; u < kB; ++u) {
         const int pos = third * 32 + lane + 96 * u;
-        if (pos < P.pp && !(P.dbg & 128)) {
+        if (pos < P.pp) {
           uint32_t hb[2][3], lb[2][3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -748,7 +754,7 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(p_full(2 * py)); mbar_arrive(p_full(2 * py + 1)); }
+      if (lane == 0) mbar_arrive(g_full(py));
       par ^= 1u;
     }
   }
@@ -768,8 +774,6 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
 static bool stem_fused_plan(int n, int h, int w, SfParams& P, size_t& smem_bytes) {
   if (n <= 0 || h < 7 || w < 7) return false;
   P.n = n; P.h = h; P.w = w;
-  P.dbg = 0;
-  if (const char* d = getenv("LSQ_STEM_DBG")) P.dbg = atoi(d);
   P.hc = (h - 1) / 2 + 1; P.wc = (w - 1) / 2 + 1;
   P.hp = (P.hc - 1) / 2 + 1; P.wp = (P.wc - 1) / 2 + 1;
   P.pw = (P.wc + 3 + 7) / 8 * 8;

@@ -16,7 +16,7 @@ __device__ __forceinline__ uint64_t mkdesc(uint32_t saddr, uint32_t lbo, uint32_
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 // mode 0: A from shared memory; 1: A from tensor memory (columns 256..); 2: A from smem, both K chunks the same B (LBO = 0)
-__global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int iters, int per_tile, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int iters, int per_tile, long long* cycles, int bstep = 48, int lbo = 1920) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ unsigned long long bar;
   __shared__ uint32_t tslot;
@@ -41,9 +41,9 @@ __global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int iters, i
       for (int it = 0; it < iters; ++it) {
         for (int p = 0; p < per_tile; ++p) {
           // A: 25 pair images of 4 KB at 0; B: a 16-byte-per-position patch at 112 KB, taps = shifts
-          const uint32_t a0 = sb + (uint32_t)p * 4096u, b0 = sb + 114688u + (uint32_t)(it & 3) * 16384u + (uint32_t)p * 48u;
+          const uint32_t a0 = sb + (uint32_t)p * 4096u, b0 = sb + 114688u + (uint32_t)(it & 3) * 16384u + (uint32_t)p * (uint32_t)bstep;
           const uint64_t ad = mkdesc(a0, 2048u, 128u);
-          const uint64_t bd = mkdesc(b0, mode == 2 ? 0u : 1920u, 128u);
+          const uint64_t bd = mkdesc(b0, mode == 2 ? 0u : (uint32_t)lbo, 128u);
           const uint32_t acc = (it | p) != 0;
           if (mode == 1) {
             const uint32_t at = tbase + 256u + (uint32_t)p * 8u;
@@ -64,19 +64,26 @@ __global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int iters, i
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512) : "memory");
 }
-void run(const char* name, int M, int N, int mode, long long* dcyc) {
+void run(const char* name, int M, int N, int mode, long long* dcyc, int bstep = 48, int lbo = 1920) {
   const int iters = 400, per = 25;
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  k<<<148, 128, 200 * 1024>>>(M, N, mode, 40, per, dcyc);
+  k<<<148, 128, 200 * 1024>>>(M, N, mode, 40, per, dcyc, bstep, lbo);
   CK(cudaDeviceSynchronize());
-  k<<<148, 128, 200 * 1024>>>(M, N, mode, iters, per, dcyc);
+  k<<<148, 128, 200 * 1024>>>(M, N, mode, iters, per, dcyc, bstep, lbo);
   CK(cudaDeviceSynchronize());
   long long cyc; CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
   printf("%-44s M=%3d N=%3d  %7.1f clk/MMA  %6.0f MAC/clk/SM\n", name, M, N, (double)cyc / (iters * per), (double)M * N * 16 * iters * per / cyc);
 }
 int main() {
   long long* dcyc; CK(cudaMalloc(&dcyc, 8));
-  for (int N : {256, 240, 128, 64}) {
+  run("f16 A smem, B 128-B aligned, LBO 1920", 128, 240, 0, dcyc, 128, 1920);
+  run("f16 A smem, B +16 B steps, LBO 1920", 128, 240, 0, dcyc, 16, 1920);
+  run("f16 A smem, B 128-B aligned, LBO 16", 128, 240, 0, dcyc, 128, 16);
+  run("f16 A smem, B +16 B steps, LBO 16", 128, 240, 0, dcyc, 16, 16);
+  run("f16 A smem, B +48 B steps, LBO 32", 128, 240, 0, dcyc, 48, 32);
+  run("f16 A smem, B aligned, LBO 128", 128, 240, 0, dcyc, 128, 128);
+  run("f16 A tmem, B aligned, LBO 1920", 128, 240, 1, dcyc, 128, 1920);
+  for (int N : {240}) {
     run("f16 A smem", 128, N, 0, dcyc);
     run("f16 A tmem", 128, N, 1, dcyc);
     run("f16 A smem M64", 64, N, 0, dcyc);
