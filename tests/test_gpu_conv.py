@@ -309,21 +309,36 @@ def test_optimized_network_matches_plain_network():
 
 
 def test_fused_stem_kernel_matches_torch():
-    """lsq_stem_fwd (tcgen05 kind::tf32, 3xTF32 split) vs conv + bias + max-pool + ReLU in fp32 ATen (cuDNN off)."""
+    """lsq_stem_fwd vs conv + bias + max-pool + ReLU in fp32 ATen (cuDNN off): the one-kernel route (tcgen05 kind::f16,
+    fp16 hi/lo operand pairs, pooling in the epilogue) for images up to 250 pixels wide, the two-kernel route (kind::tf32
+    3xTF32 convolution + pool kernel) beyond; channels with tiny and huge weights exercise the per-row weight scaling."""
     import torch.nn.functional as F
     from ml_quant_b200 import ops
     runtime_strict()
     torch.manual_seed(9)
-    for n, h, w in [(3, 224, 224), (2, 64, 64), (2, 61, 75), (1, 32, 40)]:
+    L = ops._C.lib()
+    for n, h, w in [(3, 224, 224), (2, 64, 64), (2, 61, 75), (1, 32, 40), (2, 250, 250), (1, 260, 300), (5, 7, 7),
+                    (300, 96, 96), (2, 33, 223)]:
         x = torch.randn(n, 3, h, w, device=DEV)
         wt = torch.randn(64, 3, 7, 7, device=DEV) * 0.1
+        wt[5] *= 1e-3
+        wt[6] *= 300.0
+        wt[7] = 0.0
         b = torch.randn(64, device=DEV)
         want = F.relu(F.max_pool2d(F.conv2d(x, wt, b, 2, 3), 3, 2, 1))
         assert ops.stem_supported(n, h, w)
+        assert bool(L.lsq_stem_is_fused(n, h, w)) == (w <= 250)
         got = ops.stem_fwd(x, ops.stem_pack(wt), b)
         assert got.shape == want.shape
         err = float((got - want).abs().max() / want.abs().max())
         assert err < 5e-6, (n, h, w, err)
+        # per output channel as well (a channel with small weights must not inherit the error scale of a large one)
+        errc = float(((got - want).abs().amax(dim=(0, 2, 3)) / want.abs().amax(dim=(0, 2, 3)).clamp_min(1e-20)).max())
+        assert errc < 1e-5, (n, h, w, errc)
+    # out-of-range pixels are clamped to the fp16 range on the one-kernel route (documented domain): finite output
+    x = torch.randn(1, 3, 32, 32, device=DEV)
+    x[0, 0, 3, 3] = 1e30
+    assert bool(torch.isfinite(ops.stem_fwd(x, ops.stem_pack(wt), b)).all())
 
 
 def test_pointwise_strided_conv_matches_torch():
