@@ -49,6 +49,7 @@ struct TcParams {
   long long q_begin;             // first output position
   int pp;                        // patch positions per phase
   int p_stages, w_stages, r_stages;
+  int w_resident;                // all weight slabs of the layer stay in shared memory (one channel tile, they fit): loaded once per CTA
   int dmin[4];                   // per phase: smallest tap offset (positions)
   int tap_phase[kMaxTaps];
   int tap_off[kMaxTaps];         // tap offset relative to dmin of its phase (>= 0)
@@ -111,6 +112,24 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
   for (int c = threadIdx.x; c < P.cout; c += kTcThreads)
     ctab[c] = make_float4(__ldg(w_scale + c), bias ? __ldg(bias + c) : 0.0f,
                           epi.act == 2 ? __ldg(epi.prelu + (epi.n_prelu > 1 ? c : 0)) : 0.0f, 0.0f);
+  // Operand descriptors of every (weight stage, tap-in-stage, K half) and (patch stage, tap, K half): built once, so the
+  // issuing thread's loop is two shared-memory loads and one tcgen05.mma per instruction (indexed parameter loads and
+  // descriptor arithmetic in that single thread cost more than the instruction takes to execute).
+  unsigned long long* const atab = reinterpret_cast<unsigned long long*>(smem + P.smem_bar + 512);
+  unsigned long long* const btab = atab + kMaxWStages * 3 * 2;
+  for (int i = threadIdx.x; i < kMaxWStages * 3 * 2 + kMaxPStages * kMaxTaps * 2; i += kTcThreads) {
+    if (i < kMaxWStages * 3 * 2) {
+      const int h = i & 1, tt = (i >> 1) % 3, ws = (i >> 1) / 3;
+      const uint32_t a_addr = sbase + P.smem_w + (uint32_t)ws * P.w_stage_bytes + (uint32_t)tt * P.w_slab_bytes;
+      atab[i] = make_desc(a_addr + (uint32_t)(2 * h) * (128u * 16u), 128u * 16u, 128u);
+    } else {
+      const int j = i - kMaxWStages * 3 * 2;
+      const int h = j & 1, tap = (j >> 1) % kMaxTaps, ps = (j >> 1) / kMaxTaps;
+      const uint32_t b_addr = sbase + P.smem_p + (uint32_t)ps * P.p_stage_bytes + (uint32_t)P.tap_phase[tap] * P.phase_bytes +
+                              (uint32_t)(P.tap_off[tap] * P.npl) * 16u;
+      btab[j] = make_desc(b_addr + (uint32_t)(2 * h) * P.lbo_p, P.lbo_p, 128u);
+    }
+  }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -273,7 +292,6 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
     if (lane == 0) {
       Ring acc(kAccStages), rp(P.p_stages), rw(P.w_stages);
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((P.tp * P.npl) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t lbo_w = 128u * 16u, lbo_p = P.lbo_p;
       const int ngroups = P.taps / P.tps;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         mbar_wait_t(acc_empty(acc.stage), acc.phase ^ 1u, err, 2, w0);
@@ -282,23 +300,26 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
         for (int cb = 0; cb < P.ncb; ++cb) {
           mbar_wait_t(p_full(rp.stage), rp.phase, err, 3, w1);
           tc_fence_after();
-          const uint32_t patch = sbase + P.smem_p + (uint32_t)rp.stage * P.p_stage_bytes;
+          const ulonglong2* const bt = reinterpret_cast<const ulonglong2*>(btab + rp.stage * (kMaxTaps * 2));
           for (int tg = 0; tg < ngroups; ++tg) {
-            mbar_wait_t(w_full(rw.stage), rw.phase, err, 4, w2);
-            tc_fence_after();
-            const uint32_t wst = sbase + P.smem_w + (uint32_t)rw.stage * P.w_stage_bytes;
-            for (int tt = 0; tt < P.tps; ++tt) {
-              const int tap = tg * P.tps + tt;
-              const uint32_t b_addr = patch + (uint32_t)P.tap_phase[tap] * P.phase_bytes + (uint32_t)(P.tap_off[tap] * P.npl) * 16u;
-              const uint32_t a_addr = wst + (uint32_t)tt * P.w_slab_bytes;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint64_t ad = make_desc(a_addr + (uint32_t)(2 * h) * lbo_w, lbo_w, 128u);
-                const uint64_t bd = make_desc(b_addr + (uint32_t)(2 * h) * lbo_p, lbo_p, 128u);
-                umma_i8(d0, ad, bd, idesc, (cb | tap | h) != 0 ? 1u : 0u);
-              }
+            if (!P.w_resident || item == (int)blockIdx.x) {          // resident slabs: landed during the first item
+              mbar_wait_t(w_full(rw.stage), rw.phase, err, 4, w2);
+              tc_fence_after();
             }
-            umma_commit(w_empty(rw.stage));
+            const ulonglong2* const at = reinterpret_cast<const ulonglong2*>(atab + rw.stage * 6);
+            if (P.tps == 3) {
+#pragma unroll
+              for (int tt = 0; tt < 3; ++tt) {
+                const ulonglong2 ad = at[tt], bd = bt[tg * 3 + tt];
+                umma_i8(d0, ad.x, bd.x, idesc, (cb | tg | tt) != 0 ? 1u : 0u);
+                umma_i8(d0, ad.y, bd.y, idesc, 1u);
+              }
+            } else {
+              const ulonglong2 ad = at[0], bd = bt[tg];
+              umma_i8(d0, ad.x, bd.x, idesc, (cb | tg) != 0 ? 1u : 0u);
+              umma_i8(d0, ad.y, bd.y, idesc, 1u);
+            }
+            if (!P.w_resident) umma_commit(w_empty(rw.stage));
             rw.advance();
           }
           umma_commit(p_empty(rp.stage));
@@ -315,6 +336,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
     if (lane == 0) {
       const int ngroups = P.taps / P.tps;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (P.w_resident && item != (int)blockIdx.x) break;         // loaded once
         const int ctile = item % P.n_ctiles;
         const int8_t* wsrc = wi8 + (long long)ctile * P.ncb * P.taps * P.w_slab_bytes;
         for (int cb = 0; cb < P.ncb; ++cb)
@@ -444,7 +466,7 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   P.p_stage_bytes = (uint32_t)g->nphase * P.phase_bytes;
   P.w_slab_bytes = 128u * 64u;
   const size_t total = 225 * 1024;
-  const size_t bar_bytes = 512, tab_bytes = (size_t)cout * 16;
+  const size_t bar_bytes = 512 + (kMaxWStages * 3 * 2 + kMaxPStages * kMaxTaps * 2) * 8, tab_bytes = (size_t)cout * 16;
   const size_t scl_bytes = (size_t)8 * (tp / (8 / (P.creal >> 5))) * sizeof(float2), out_bytes = 8 * 32 * kOutPitch * sizeof(float);
   const size_t slack = 0;
   const size_t fixed = bar_bytes + tab_bytes + scl_bytes + out_bytes + slack;
@@ -453,11 +475,23 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   const size_t res_min = has_res ? (size_t)8 * 2 * 4096 : 0;
   if (fixed + 2 * (size_t)P.p_stage_bytes + 2 * (size_t)P.w_slab_bytes + res_min > total) return false;
   size_t left = total - fixed - res_min - 2 * (size_t)P.p_stage_bytes;
-  // weights: whole tap rows per stage when they fit twice (fewer commits), else single taps
-  P.tps = (P.taps % g->kw == 0 && 2 * (size_t)g->kw * P.w_slab_bytes <= left) ? g->kw : 1;
-  P.w_stage_bytes = (uint32_t)P.tps * P.w_slab_bytes;
-  P.w_stages = 2;
-  left -= 2 * (size_t)P.w_stage_bytes;
+  // weights: the whole layer when it fits (one channel tile: every item uses the same slabs -- streaming them again for
+  // every position tile costs ~1 GB of L2 -> shared-memory traffic per layer); else a ring of whole tap rows per stage when
+  // they fit twice (fewer commits), else of single taps
+  const size_t all_w = (size_t)P.ncb * P.taps * P.w_slab_bytes;
+  static const bool no_resident = getenv("LSQ_BCONV_STREAM_W") != nullptr;       // development: force the ring
+  P.w_resident = (!no_resident && P.n_ctiles == 1 && P.taps % g->kw == 0 && P.ncb * (P.taps / g->kw) <= kMaxWStages && all_w <= left) ? 1 : 0;
+  if (P.w_resident) {
+    P.tps = g->kw;
+    P.w_stage_bytes = (uint32_t)P.tps * P.w_slab_bytes;
+    P.w_stages = P.ncb * (P.taps / g->kw);
+    left -= all_w;
+  } else {
+    P.tps = (P.taps % g->kw == 0 && 2 * (size_t)g->kw * P.w_slab_bytes <= left) ? g->kw : 1;
+    P.w_stage_bytes = (uint32_t)P.tps * P.w_slab_bytes;
+    P.w_stages = 2;
+    left -= 2 * (size_t)P.w_stage_bytes;
+  }
   // then: deeper residual staging, a third patch stage, more weight stages
   P.r_stages = has_res ? 2 : 1;
   if (has_res) {
@@ -469,7 +503,7 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   }
   P.p_stages = 2;
   if (P.ncb >= 3 && P.p_stage_bytes <= left) { P.p_stages = 3; left -= P.p_stage_bytes; }
-  while (P.w_stages < kMaxWStages && P.w_stages * P.tps < 2 * P.taps && P.w_stage_bytes <= left) { ++P.w_stages; left -= P.w_stage_bytes; }
+  while (!P.w_resident && P.w_stages < kMaxWStages && P.w_stages * P.tps < 2 * P.taps && P.w_stage_bytes <= left) { ++P.w_stages; left -= P.w_stage_bytes; }
   uint32_t o = 0;
   P.smem_p = o; o += (uint32_t)P.p_stages * P.p_stage_bytes; o = (o + 127u) / 128u * 128u;
   P.smem_w = o; o += (uint32_t)P.w_stages * P.w_stage_bytes + (uint32_t)slack;
