@@ -14,7 +14,7 @@
 
 namespace lsq {
 
-constexpr int kPwThreads = 448;
+constexpr int kPwThreads = 576;        // warps 0-3, 10-13 epilogue; 4 MMA; 5 weights; 6-9, 14-17 producers
 constexpr int kPwTile = 256;          // output positions per tile = N
 constexpr int kPwStages = 3;          // patch / weight ring depth (per 16 input channels)
 constexpr int kPwOutPitch = 36;
@@ -61,7 +61,7 @@ pwconv_kernel(const float* __restrict__ x, PwParams P, const float* __restrict__
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.smem_bar + 8u * (4 * kPwStages + 4));
   if (threadIdx.x == 0) {
     for (int s = 0; s < kPwStages; ++s) {
-      mbar_init(p_full(s), 4); mbar_init(p_empty(s), 1); mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1);
+      mbar_init(p_full(s), 8); mbar_init(p_empty(s), 1); mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -75,7 +75,7 @@ pwconv_kernel(const float* __restrict__ x, PwParams P, const float* __restrict__
   const int n_items = P.p_tiles * P.n_ctiles;
   const int hwo = P.ho * P.wo;
 
-  if (warp < 4 || warp >= 10) {
+  if (warp < 4 || (warp >= 10 && warp < 14)) {
     // ===================== epilogue (8 warps): + bias, transposed, one 128-byte row segment per store ========
     const int quarter = warp & 3, half = warp < 4 ? 0 : 1;
     const int ewarp = quarter + 4 * half;
@@ -173,52 +173,63 @@ pwconv_kernel(const float* __restrict__ x, PwParams P, const float* __restrict__
       }
     }
   } else {
-    // ===================== producers (128 threads): strided gather of 16 channels x 256 positions ==========
+    // ===================== producers (256 threads): strided gather of 16 channels x 256 positions ==========
+    // thread = position.  The 16 loads of the NEXT stage are issued before the current one is converted and stored
+    // (two register buffers): the gather's latency, not its volume, is what a stage waits for.
     Ring rp(kPwStages);
-    const int pt = threadIdx.x - 6 * 32;
+    const int pt = warp < 10 ? threadIdx.x - 6 * 32 : threadIdx.x - 14 * 32 + 128;       // warps 6-9 and 14-17
     const long long plane = (long long)P.h * P.w;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int ptile = item / P.n_ctiles;
-      const float* src[2];
-      bool ok[2];
+    int item = blockIdx.x, ks = 0;
+    const float* src = x;
+    bool ok = false;
+    auto locate = [&]() {                               // this thread's pixel of channel 0 for `item`
+      const long long p = (long long)(item / P.n_ctiles) * kPwTile + pt;
+      ok = item < n_items && p < P.positions;
+      const long long pc = ok ? p : 0;
+      const unsigned sm = (unsigned)(((unsigned long long)pc * P.pos_magic) >> 40);
+      const unsigned rem = (unsigned)(pc - (long long)sm * hwo);
+      const unsigned oy = (unsigned)(((unsigned long long)rem * P.wo_magic) >> 40);
+      const unsigned ox = rem - oy * (unsigned)P.wo;
+      src = x + ((long long)sm * P.cin * P.h + (long long)P.stride * oy) * P.w + (long long)P.stride * ox;
+    };
+    auto issue = [&](float (&v)[16]) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const long long p = (long long)ptile * kPwTile + pt + u * 128;
-        ok[u] = p < P.positions;
-        const long long pc = ok[u] ? p : 0;
-        const unsigned s = (unsigned)(((unsigned long long)pc * P.pos_magic) >> 40);
-        const unsigned rem = (unsigned)(pc - (long long)s * hwo);
-        const unsigned oy = (unsigned)(((unsigned long long)rem * P.wo_magic) >> 40);
-        const unsigned ox = rem - oy * (unsigned)P.wo;
-        src[u] = x + ((long long)s * P.cin * P.h + (long long)P.stride * oy) * P.w + (long long)P.stride * ox;
+      for (int c = 0; c < 16; ++c) v[c] = ok ? __ldg(src + (long long)(ks * 16 + c) * plane) : 0.0f;
+    };
+    auto next = [&]() {
+      if (++ks == P.kstages) { ks = 0; item += gridDim.x; locate(); }
+    };
+    auto emit = [&](const float (&v)[16]) {
+      mbar_wait(p_empty(rp.stage), rp.phase ^ 1u, err, 6);
+      float4* hi = reinterpret_cast<float4*>(smem + P.smem_p + (size_t)rp.stage * kPwPatchBytes);
+      float4* lo = hi + kPwPatchBytes / 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float h4[4], l4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          h4[k] = __uint_as_float(__float_as_uint(v[4 * j + k]) & 0xFFFFE000u);
+          l4[k] = __fsub_rn(v[4 * j + k], h4[k]);
+        }
+        hi[j * kPwTile + pt] = make_float4(h4[0], h4[1], h4[2], h4[3]);
+        lo[j * kPwTile + pt] = make_float4(l4[0], l4[1], l4[2], l4[3]);
       }
-      for (int ks = 0; ks < P.kstages; ++ks) {
-        mbar_wait(p_empty(rp.stage), rp.phase ^ 1u, err, 6);
-        float4* hi = reinterpret_cast<float4*>(smem + P.smem_p + (size_t)rp.stage * kPwPatchBytes);
-        float4* lo = hi + kPwPatchBytes / 32;
-        float v[2][16];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int c = 0; c < 16; ++c) v[u][c] = ok[u] ? __ldg(src[u] + (long long)(ks * 16 + c) * plane) : 0.0f;
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float h4[4], l4[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              h4[k] = __uint_as_float(__float_as_uint(v[u][4 * j + k]) & 0xFFFFE000u);
-              l4[k] = __fsub_rn(v[u][4 * j + k], h4[k]);
-            }
-            hi[j * kPwTile + pt + u * 128] = make_float4(h4[0], h4[1], h4[2], h4[3]);
-            lo[j * kPwTile + pt + u * 128] = make_float4(l4[0], l4[1], l4[2], l4[3]);
-          }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(rp.stage));
-        rp.advance();
-      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(rp.stage));
+      rp.advance();
+    };
+    float va[16], vb[16];
+    locate();
+    if (item < n_items) issue(va);
+    while (item < n_items) {
+      next();
+      if (item < n_items) issue(vb);
+      emit(va);
+      if (item >= n_items) break;
+      next();
+      if (item < n_items) issue(va);
+      emit(vb);
     }
   }
   tc_fence_before();
