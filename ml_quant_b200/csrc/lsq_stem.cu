@@ -700,31 +700,36 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
     uint32_t par = 0;
     Ring prev(2);                                        // accumulator stage of the previous tile (group 1's release)
     constexpr int kB = 7;                                // 96 * 7 >= the largest patch (648 positions)
+    // tile-invariant part of the addressing: patch row and input column of this lane's positions (-1: nothing to load)
+    int prow_of[kB], ix_of[kB];
+#pragma unroll
+    for (int u = 0; u < kB; ++u) {
+      const int pos = third * 32 + lane + 96 * u;
+      const int prow = (int)(((uint32_t)pos * P.pw_magic) >> 20);
+      const int bcol = pos - prow * P.pw - 2;
+      prow_of[u] = prow;
+      ix_of[u] = (pos < P.pp && bcol >= 0 && 2 * bcol < P.w) ? 2 * bcol : -1;
+    }
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int s = tile / P.hp, k = tile - s * P.hp;
       const float* const xs = x + (long long)s * 3 * plane;
       float2 v[kB][3];
 #pragma unroll
       for (int u = 0; u < kB; ++u) {
-        const int pos = third * 32 + lane + 96 * u;
         v[u][0] = v[u][1] = v[u][2] = make_float2(0.0f, 0.0f);
-        if (pos < P.pp) {
-          const int prow = (int)(((uint32_t)pos * P.pw_magic) >> 20);
-          const int bcol = pos - prow * P.pw - 2;
-          const int a = 2 * k - 2 + prow;
-          const int iy = 2 * a + py, ix = 2 * bcol;
-          if (a >= 0 && bcol >= 0 && iy < P.h && ix < P.w) {
-            const float* xp = xs + (long long)iy * P.w + ix;
-            if (pair_loads) {                            // w even: ix + 1 < w
+        const int a = 2 * k - 2 + prow_of[u];
+        const int iy = 2 * a + py, ix = ix_of[u];
+        if (ix >= 0 && a >= 0 && iy < P.h) {
+          const float* xp = xs + (long long)iy * P.w + ix;
+          if (pair_loads) {                            // w even: ix + 1 < w
 #pragma unroll
-              for (int c = 0; c < 3; ++c) v[u][c] = __ldg(reinterpret_cast<const float2*>(xp + c * plane));
-            } else {
-              const bool second = ix + 1 < P.w;
+            for (int c = 0; c < 3; ++c) v[u][c] = __ldg(reinterpret_cast<const float2*>(xp + c * plane));
+          } else {
+            const bool second = ix + 1 < P.w;
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                v[u][c].x = __ldg(xp + c * plane);
-                if (second) v[u][c].y = __ldg(xp + c * plane + 1);
-              }
+            for (int c = 0; c < 3; ++c) {
+              v[u][c].x = __ldg(xp + c * plane);
+              if (second) v[u][c].y = __ldg(xp + c * plane + 1);
             }
           }
         }
@@ -736,20 +741,22 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
       for (int u = 0; u < kB; ++u) {
         const int pos = third * 32 + lane + 96 * u;
         if (pos < P.pp) {
-          uint32_t hb[2][3], lb[2][3];
+          // hi = fp16(x), lo = fp16(x - hi), two values per conversion instruction; |x| clamped to the fp16 range
+          uint4 q[2];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float f = fminf(fmaxf(e == 0 ? v[u][c].x : v[u][c].y, -65504.0f), 65504.0f);   // fp16 range (documented domain)
-              const __half hi = __float2half_rn(f);
-              const __half lo = __float2half_rn(__fsub_rn(f, __half2float(hi)));
-              hb[e][c] = (uint32_t)__half_as_ushort(hi);
-              lb[e][c] = (uint32_t)__half_as_ushort(lo);
-            }
+          for (int e = 0; e < 2; ++e) {
+            const float f0 = fminf(fmaxf(e == 0 ? v[u][0].x : v[u][0].y, -65504.0f), 65504.0f);
+            const float f1 = fminf(fmaxf(e == 0 ? v[u][1].x : v[u][1].y, -65504.0f), 65504.0f);
+            const float f2 = fminf(fmaxf(e == 0 ? v[u][2].x : v[u][2].y, -65504.0f), 65504.0f);
+            const __half2 h01 = __floats2half2_rn(f0, f1), h2z = __floats2half2_rn(f2, 0.0f);
+            const float2 b01 = __half22float2(h01), b2z = __half22float2(h2z);
+            const __half2 l01 = __floats2half2_rn(__fsub_rn(f0, b01.x), __fsub_rn(f1, b01.y));
+            const __half2 l2z = __floats2half2_rn(__fsub_rn(f2, b2z.x), 0.0f);
+            q[e] = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h2z),
+                              *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l2z));
           }
-          patch0[pos] = make_uint4(hb[0][0] | (hb[0][1] << 16), hb[0][2], lb[0][0] | (lb[0][1] << 16), lb[0][2]);
-          patch1[pos] = make_uint4(hb[1][0] | (hb[1][1] << 16), hb[1][2], lb[1][0] | (lb[1][1] << 16), lb[1][2]);
+          patch0[pos] = q[0];
+          patch1[pos] = q[1];
         }
       }
       fence_proxy_async();
