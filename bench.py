@@ -171,10 +171,15 @@ def kernel_table(agg, hbm_peak, i8_peak, i8_src, tf32_peak, traffic):
         sec = d['ms'] / 1e3
         if name.startswith('bconv_tc'):
             ach, peak, unit, bound, src = d['ops'] / sec / 1e12, i8_peak, 'TOP/s', 'tensor', i8_src
-        elif name in ('stem', 'pwconv'):
+        elif name == 'stem':
+            ach, peak, unit, bound, src = d['ops'] / sec / 1e12, 2.0 * tf32_peak, 'TFLOP/s', 'tensor', \
+                'useful fp32 flops against the f16 pipe (MEASURED_PEAKS.json bf16_tflops); the fp32-accurate fp16 hi/lo ' \
+                'split issues 5.8 f16 products per fp32 product (2 weight halves x 8 of 6 K slots x 120 of 112 columns), and ' \
+                'this K = 16 no-swizzle operand layout runs at 141 clocks per instruction, 0.43 of the pipe (profiles/r2_mb_umma_f16.txt)'
+        elif name == 'pwconv':
             ach, peak, unit, bound, src = d['ops'] / sec / 1e12, tf32_peak, 'TFLOP/s', 'tensor', \
                 'useful fp32 flops against the tf32 pipe (MEASURED_PEAKS.json bf16_tflops / 2); the fp32-accurate split costs ' \
-                '2-3 tf32 products per fp32 product'
+                '3 tf32 products per fp32 product'
         else:
             ach, peak, unit, bound, src = d['bytes'] / sec / 1e9, hbm_peak, 'GB/s', 'hbm', 'MEASURED_PEAKS.json hbm_gbs'
         t = traffic.get(name)

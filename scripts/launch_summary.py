@@ -20,6 +20,6 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 text = '\n'.join(lines)
 print(text)
 if len(sys.argv) > 2:
-    open(sys.argv[2], 'w').write('# Round 1 (final) - one forward step, ImageNet ResNet-18 ls1w/ls2a, batch 512, fused blocks, eager (no graph)\n\n'
+    open(sys.argv[2], 'w').write('# One forward step, ImageNet ResNet-18 ls1w/ls2a, batch 512, fused blocks, eager (no graph)\n\n'
                                  '`ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python profiles/profile_step.py` '
                                  '(cold-cache, serialised: compare shares)\n\n' + text + '\n')
