@@ -165,6 +165,9 @@ def timed_steps(step, steps, flush, barrier, dist_max):
     return dist_max(ms), out
 
 
+PIXEL_MEAN, PIXEL_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
 def kernel_table(agg, hbm_peak, i8_peak, i8_src, tf32_peak, traffic):
     rows = []
     for name, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
@@ -304,6 +307,21 @@ def main():
     barrier()
     e2e_value = world * B * args.steps / dist_max(time.perf_counter() - t0)
 
+    # ---- the same with uint8 pixel batches (the additional entry point runtime.set_pixel_input: ToTensor + Normalize
+    #      applied on the device, bit-identical to the host transform; 1 byte per pixel over PCIe instead of 4) ----
+    runtime.set_pixel_input(model, PIXEL_MEAN, PIXEL_STD)
+    host_u8 = torch.randint(0, 256, (B, 3, img, img), dtype=torch.uint8, generator=g).pin_memory()
+    pipe8 = runtime.HostPipeline(model, (B, 3, img, img), dev, use_graph=not args.no_graph, dtype=torch.uint8)
+    batches8 = [host_u8] * args.steps
+    pipe8.run(batches8[:2])
+    barrier()
+    t0 = time.perf_counter()
+    pipe8.run(batches8)
+    if world > 1:
+        runtime.gather_logits(pipe.bufs[0][:1].new_zeros(B, pipe8.host_out.shape[1]), world)
+    barrier()
+    e2e_u8_value = world * B * args.steps / dist_max(time.perf_counter() - t0)
+
     # ---- per-launch timing of our kernels (eager pass, CUDA events on the launching stream) ----
     ops.PROFILE = []
     torch.cuda.synchronize()
@@ -324,7 +342,12 @@ def main():
         'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
         'config': base_cfg, 'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': B * 3 * img * img * 4,
-                'd2h_bytes_per_step': B * pipe.host_out.shape[1] * 4},
+                'd2h_bytes_per_step': B * pipe.host_out.shape[1] * 4,
+                'input': 'fp32 tensors, normalised on the host (the reference\'s own input boundary, training.py:184-190)'},
+        'e2e_uint8': {'value': e2e_u8_value, 'unit': 'images/s', 'h2d_bytes_per_step': B * 3 * img * img,
+                      'd2h_bytes_per_step': B * pipe8.host_out.shape[1] * 4,
+                      'input': 'uint8 pixels; ToTensor + Normalize applied on the device through a 256-level table per channel '
+                               '(runtime.set_pixel_input: additional entry point, results bit-identical to the fp32 boundary)'},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
         'cuda_graph': not args.no_graph, 'fused_blocks': not args.no_fuse, 'host_affinity': numa,
     }

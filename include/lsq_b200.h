@@ -243,6 +243,21 @@ LSQ_API int lsq_stem_pack_weights(const float* d_w, float* d_image, void* stream
 LSQ_API int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_image, const float* d_bias,
                  float* d_conv_ws, float* d_out, void* stream);
 
+/* ---- uint8 pixel input (the data format in front of the path) ----------------------------------------
+ * The reference's loaders hand `evaluate` / `train` fp32 tensors that torchvision made from uint8 pixels on the host
+ * (ToTensor: x / 255, Normalize: (x - mean) / std; quant/common/training.py:184-190 then uploads them).  These two entry
+ * points take the uint8 pixels themselves (a quarter of the upload) and a table  lut[c][256]  with the fp32 value of every
+ * pixel level of every channel -- the caller evaluates its own transform once per level, so the result is bit-identical to
+ * transforming on the host:
+ *   lsq_u8_expand:    d_x uint8 [planes][inner] (planes = n * c, channel = plane % c)  ->  d_out fp32, out = lut[c][x]
+ *   lsq_stem_fwd_u8:  lsq_stem_fwd on lut[c][x] without materialising the fp32 image (one-kernel route only: images up to
+ *                     250 pixels wide, LSQ_ERR_UNSUPPORTED beyond -- expand first); padding is zero in the transformed
+ *                     domain, exactly as for the fp32 input. */
+LSQ_API int lsq_u8_expand(const unsigned char* d_x, int64_t planes, int c, int64_t inner, const float* d_lut, float* d_out,
+                  void* stream);
+LSQ_API int lsq_stem_fwd_u8(const unsigned char* d_x, int n, int h, int w, const float* d_lut, const float* d_image,
+                    const float* d_bias, float* d_out, void* stream);
+
 /* ---- fp32 pointwise strided convolution (downsampling shortcuts) ----------------
  * y[n,co,oy,ox] = sum_ci w[co,ci] * x[n,ci,stride*oy,stride*ox] + bias[co]  (quant/models/resnet.py:24-39,
  * Conv2d(kernel_size=1, stride) + eval BatchNorm2d folded into w / bias by the caller), tcgen05 kind::tf32

@@ -419,7 +419,7 @@ struct SfParams {
   uint32_t pw_magic;
   int first[4], count[4];
   int pair_off[kStPairs], pair_lbo[kStPairs];
-  uint32_t stage_bytes, smem_w, smem_p, smem_bar, smem_x, smem_pool;
+  uint32_t stage_bytes, smem_w, smem_p, smem_bar, smem_x, smem_pool, smem_lut;
 };
 
 __device__ __forceinline__ int stem_scale_exp(const float* __restrict__ w, int ch) {
@@ -447,8 +447,13 @@ __global__ void stem_pack_f16_kernel(const float* __restrict__ w, __half* __rest
   }
 }
 
+// U8: the input is uint8 pixels [n,3,h,w] and `lut` float[3][256] gives the fp32 value of every pixel level of every channel
+// (the caller's ToTensor + Normalize, evaluated once per level): the producers look the fp16 (hi, lo) pair of a pixel up in
+// a shared-memory table built from it, so the result equals the fp32 route on lut[c][pixel] bit for bit.
+template <bool U8>
 __global__ void __launch_bounds__(kSfThreads, 1)
-stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* __restrict__ wimage,
+stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__ xu8, const float* __restrict__ lut,
+                  SfParams P, const unsigned char* __restrict__ wimage,
                   const float* __restrict__ inv_scale, const float* __restrict__ bias, float* __restrict__ out,
                   long long* __restrict__ diag) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -494,6 +499,15 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
     const uint32_t pb = sbase + P.smem_p + (uint32_t)phase * P.stage_bytes;
     desc_tab[2 * pair] = make_desc(sbase + P.smem_w + (uint32_t)pair * 4096u, 2048u, 128u);
     desc_tab[2 * pair + 1] = make_desc(pb + (uint32_t)P.pair_off[pair] * 16u, (uint32_t)P.pair_lbo[pair] * 16u, 128u);
+  }
+  uint32_t* const lutp = reinterpret_cast<uint32_t*>(smem + P.smem_lut);      // U8: [3][256] fp16 hi | lo << 16
+  if (U8) {
+    for (int i = threadIdx.x; i < 768; i += kSfThreads) {
+      const float f = fminf(fmaxf(__ldg(lut + i), -65504.0f), 65504.0f);
+      const __half hi = __float2half_rn(f);
+      const __half lo = __float2half_rn(__fsub_rn(f, __half2float(hi)));
+      lutp[i] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+    }
   }
   fence_proxy_async();
   if (warp == 16) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
@@ -696,7 +710,7 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
     const long long plane = (long long)P.h * P.w;
     uint4* const patch0 = reinterpret_cast<uint4*>(smem + P.smem_p + (size_t)(2 * py) * P.stage_bytes);
     uint4* const patch1 = reinterpret_cast<uint4*>(smem + P.smem_p + (size_t)(2 * py + 1) * P.stage_bytes);
-    const bool pair_loads = (P.w & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+    const bool pair_loads = (P.w & 1) == 0 && (U8 ? (reinterpret_cast<uintptr_t>(xu8) & 1) == 0 : (reinterpret_cast<uintptr_t>(x) & 7) == 0);
     uint32_t par = 0;
     Ring prev(2);                                        // accumulator stage of the previous tile (group 1's release)
     constexpr int kB = 7;                                // 96 * 7 >= the largest patch (648 positions)
@@ -712,24 +726,45 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
     }
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int s = tile / P.hp, k = tile - s * P.hp;
-      const float* const xs = x + (long long)s * 3 * plane;
-      float2 v[kB][3];
+      const float* const xs = x + (U8 ? 0ll : (long long)s * 3 * plane);
+      const unsigned char* const us = xu8 + (U8 ? (long long)s * 3 * plane : 0ll);
+      float2 v[kB][3];                                   // fp32 route: pixel pairs of the three channels
+      uint32_t la[kB], lb[kB];                           // uint8 route: levels c0 | c1 << 8 | c2 << 16 of the px = 0 / px = 1 pixel; bit 31: outside
 #pragma unroll
       for (int u = 0; u < kB; ++u) {
-        v[u][0] = v[u][1] = v[u][2] = make_float2(0.0f, 0.0f);
         const int a = 2 * k - 2 + prow_of[u];
         const int iy = 2 * a + py, ix = ix_of[u];
-        if (ix >= 0 && a >= 0 && iy < P.h) {
-          const float* xp = xs + (long long)iy * P.w + ix;
-          if (pair_loads) {                            // w even: ix + 1 < w
+        const bool inside = ix >= 0 && a >= 0 && iy < P.h;
+        if (U8) {
+          la[u] = lb[u] = 0x80000000u;
+          if (inside) {
+            const unsigned char* up = us + (long long)iy * P.w + ix;
+            if (pair_loads) {                            // w even: ix + 1 < w
+              uchar2 q[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[u][c] = __ldg(reinterpret_cast<const float2*>(xp + c * plane));
-          } else {
-            const bool second = ix + 1 < P.w;
+              for (int c = 0; c < 3; ++c) q[c] = __ldg(reinterpret_cast<const uchar2*>(up + c * plane));
+              la[u] = (uint32_t)q[0].x | ((uint32_t)q[1].x << 8) | ((uint32_t)q[2].x << 16);
+              lb[u] = (uint32_t)q[0].y | ((uint32_t)q[1].y << 8) | ((uint32_t)q[2].y << 16);
+            } else {
+              la[u] = (uint32_t)__ldg(up) | ((uint32_t)__ldg(up + plane) << 8) | ((uint32_t)__ldg(up + 2 * plane) << 16);
+              if (ix + 1 < P.w)
+                lb[u] = (uint32_t)__ldg(up + 1) | ((uint32_t)__ldg(up + plane + 1) << 8) | ((uint32_t)__ldg(up + 2 * plane + 1) << 16);
+            }
+          }
+        } else {
+          v[u][0] = v[u][1] = v[u][2] = make_float2(0.0f, 0.0f);
+          if (inside) {
+            const float* xp = xs + (long long)iy * P.w + ix;
+            if (pair_loads) {                            // w even: ix + 1 < w
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              v[u][c].x = __ldg(xp + c * plane);
-              if (second) v[u][c].y = __ldg(xp + c * plane + 1);
+              for (int c = 0; c < 3; ++c) v[u][c] = __ldg(reinterpret_cast<const float2*>(xp + c * plane));
+            } else {
+              const bool second = ix + 1 < P.w;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                v[u][c].x = __ldg(xp + c * plane);
+                if (second) v[u][c].y = __ldg(xp + c * plane + 1);
+              }
             }
           }
         }
@@ -741,19 +776,31 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
       for (int u = 0; u < kB; ++u) {
         const int pos = third * 32 + lane + 96 * u;
         if (pos < P.pp) {
-          // hi = fp16(x), lo = fp16(x - hi), two values per conversion instruction; |x| clamped to the fp16 range
           uint4 q[2];
+          if (U8) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float f0 = fminf(fmaxf(e == 0 ? v[u][0].x : v[u][0].y, -65504.0f), 65504.0f);
-            const float f1 = fminf(fmaxf(e == 0 ? v[u][1].x : v[u][1].y, -65504.0f), 65504.0f);
-            const float f2 = fminf(fmaxf(e == 0 ? v[u][2].x : v[u][2].y, -65504.0f), 65504.0f);
-            const __half2 h01 = __floats2half2_rn(f0, f1), h2z = __floats2half2_rn(f2, 0.0f);
-            const float2 b01 = __half22float2(h01), b2z = __half22float2(h2z);
-            const __half2 l01 = __floats2half2_rn(__fsub_rn(f0, b01.x), __fsub_rn(f1, b01.y));
-            const __half2 l2z = __floats2half2_rn(__fsub_rn(f2, b2z.x), 0.0f);
-            q[e] = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h2z),
-                              *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l2z));
+            for (int e = 0; e < 2; ++e) {
+              const uint32_t l = e == 0 ? la[u] : lb[u];
+              q[e] = make_uint4(0u, 0u, 0u, 0u);         // outside the image: zero padding of the NORMALISED tensor
+              if (!(l & 0x80000000u)) {
+                const uint32_t e0 = lutp[l & 0xFFu], e1 = lutp[256 + ((l >> 8) & 0xFFu)], e2 = lutp[512 + ((l >> 16) & 0xFFu)];
+                q[e] = make_uint4((e0 & 0xFFFFu) | (e1 << 16), e2 & 0xFFFFu, (e0 >> 16) | (e1 & 0xFFFF0000u), e2 >> 16);
+              }
+            }
+          } else {
+            // hi = fp16(x), lo = fp16(x - hi), two values per conversion instruction; |x| clamped to the fp16 range
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float f0 = fminf(fmaxf(e == 0 ? v[u][0].x : v[u][0].y, -65504.0f), 65504.0f);
+              const float f1 = fminf(fmaxf(e == 0 ? v[u][1].x : v[u][1].y, -65504.0f), 65504.0f);
+              const float f2 = fminf(fmaxf(e == 0 ? v[u][2].x : v[u][2].y, -65504.0f), 65504.0f);
+              const __half2 h01 = __floats2half2_rn(f0, f1), h2z = __floats2half2_rn(f2, 0.0f);
+              const float2 b01 = __half22float2(h01), b2z = __half22float2(h2z);
+              const __half2 l01 = __floats2half2_rn(__fsub_rn(f0, b01.x), __fsub_rn(f1, b01.y));
+              const __half2 l2z = __floats2half2_rn(__fsub_rn(f2, b2z.x), 0.0f);
+              q[e] = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h2z),
+                                *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l2z));
+            }
           }
           patch0[pos] = q[0];
           patch1[pos] = q[1];
@@ -776,6 +823,33 @@ stem_fused_kernel(const float* __restrict__ x, SfParams P, const unsigned char* 
   tc_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+// out[p][i] = lut[(p % c) * 256 + x[p][i]]: uint8 planes -> fp32 through a per-channel table of the 256 pixel levels
+// (ToTensor + Normalize of the caller, evaluated once per level).  16 pixels per thread per step.
+__global__ void __launch_bounds__(256)
+u8_expand_kernel(const unsigned char* __restrict__ x, long long planes, int c, long long inner, const float* __restrict__ lut,
+                 float* __restrict__ out) {
+  extern __shared__ float slut[];
+  for (int i = threadIdx.x; i < c * 256; i += blockDim.x) slut[i] = __ldg(lut + i);
+  __syncthreads();
+  const long long total = planes * inner;
+  const bool vec = (inner & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec) {
+    const long long n16 = total >> 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x) + i);
+      const float* const t = slut + (int)(((i << 4) / inner) % c) * 256;
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      float4* o = reinterpret_cast<float4*>(out) + (i << 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] = make_float4(t[w[j] & 0xFFu], t[(w[j] >> 8) & 0xFFu], t[(w[j] >> 16) & 0xFFu], t[w[j] >> 24]);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+      out[i] = slut[(int)((i / inner) % c) * 256 + x[i]];
+  }
 }
 
 static bool stem_fused_plan(int n, int h, int w, SfParams& P, size_t& smem_bytes) {
@@ -810,6 +884,7 @@ static bool stem_fused_plan(int n, int h, int w, SfParams& P, size_t& smem_bytes
   P.smem_x = o; o += 8 * 2 * 32 * kSfXPitch * 4;
   o = (o + 15u) & ~15u;
   P.smem_pool = o; o += 2 * 64 * kSfPoolPitch * 4;
+  P.smem_lut = o; o += 3 * 256 * 4;
   smem_bytes = o;
   return smem_bytes <= 227 * 1024;
 }
@@ -851,6 +926,66 @@ extern "C" int lsq_stem_pack_weights(const float* d_w, float* d_image, void* str
   return LSQ_OK;
 }
 
+static int stem_fused_launch(const float* d_x, const unsigned char* d_xu8, const float* d_lut, int n, int h, int w,
+                             const float* d_image, const float* d_bias, float* d_out, void* stream) {
+  SfParams F;
+  size_t smem = 0;
+  if (!stem_fused_plan(n, h, w, F, smem)) { set_error("lsq_stem_fwd: image %dx%d does not fit the one-kernel route", h, w); return LSQ_ERR_UNSUPPORTED; }
+  static std::atomic<unsigned long long> fused_set{0ull}, fused_set_u8{0ull};
+  const cudaError_t fe = d_xu8 ? ensure_max_smem(stem_fused_kernel<true>, fused_set_u8) : ensure_max_smem(stem_fused_kernel<false>, fused_set);
+  if (fe != cudaSuccess) { set_error("lsq_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(fe)); return LSQ_ERR_CUDA; }
+  const int sms_f = device_sms();
+  const unsigned char* const base = reinterpret_cast<const unsigned char*>(d_image);
+  const int grid = F.tiles < sms_f ? F.tiles : sms_f;
+  long long* d_fdiag = nullptr;
+#ifdef LSQ_TC_DIAG
+  static const bool want_fdiag = getenv("LSQ_TC_DIAG") != nullptr;   // development build: wait cycles per warp of CTA 0
+  if (want_fdiag) { cudaMalloc(&d_fdiag, 32 * 3 * sizeof(long long)); cudaMemsetAsync(d_fdiag, 0, 32 * 3 * sizeof(long long), (cudaStream_t)stream); }
+#endif
+  if (d_xu8)
+    stem_fused_kernel<true><<<grid, kSfThreads, smem, (cudaStream_t)stream>>>(
+        nullptr, d_xu8, d_lut, F, base + kSfImageOffset, reinterpret_cast<const float*>(base + kSfScaleOffset), d_bias, d_out, d_fdiag);
+  else
+    stem_fused_kernel<false><<<grid, kSfThreads, smem, (cudaStream_t)stream>>>(
+        d_x, nullptr, nullptr, F, base + kSfImageOffset, reinterpret_cast<const float*>(base + kSfScaleOffset), d_bias, d_out, d_fdiag);
+  LSQ_CUDA_LAUNCH_CHECK("stem_fused_kernel");
+#ifdef LSQ_TC_DIAG
+  if (want_fdiag) {
+    long long hd[32 * 3];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(hd, d_fdiag, sizeof(hd), cudaMemcpyDeviceToHost);
+    cudaFree(d_fdiag);
+    fprintf(stderr, "[fused stem diag] tiles %d pw %d pp %d | warp 0 sections: tmem %lld pairbar %lld math %lld pool %lld store %lld\n", F.tiles, F.pw, F.pp, hd[75], hd[76], hd[77], hd[78], hd[79]);
+    for (int wi = 0; wi < kSfThreads / 32; ++wi)
+      fprintf(stderr, "   warp %2d (%s) total %9lld  wait0 %9lld  wait1 %9lld\n", wi,
+              wi < 16 ? ((wi & 3) < 2 ? "epi-hi" : "epi-lo") : (wi == 16 ? "mma" : "producer"), hd[wi * 3], hd[wi * 3 + 1], hd[wi * 3 + 2]);
+  }
+#endif
+  return LSQ_OK;
+}
+
+extern "C" int lsq_u8_expand(const unsigned char* d_x, int64_t planes, int c, int64_t inner, const float* d_lut, float* d_out,
+                             void* stream) {
+  LSQ_CHECK_ARG(d_x && d_lut && d_out, "lsq_u8_expand: null pointer");
+  LSQ_CHECK_ARG(planes > 0 && inner > 0 && c > 0 && c <= 32 && planes % c == 0, "lsq_u8_expand: bad shape planes=%lld c=%d inner=%lld",
+                (long long)planes, c, (long long)inner);
+  const long long work = (planes * inner + 15) / 16;
+  long long grid = (work + 255) / 256;
+  const long long cap = (long long)device_sms() * 8;
+  if (grid > cap) grid = cap;
+  u8_expand_kernel<<<(unsigned)grid, 256, (size_t)c * 256 * sizeof(float), (cudaStream_t)stream>>>(d_x, planes, c, inner, d_lut, d_out);
+  LSQ_CUDA_LAUNCH_CHECK("u8_expand_kernel");
+  return LSQ_OK;
+}
+
+extern "C" int lsq_stem_fwd_u8(const unsigned char* d_x, int n, int h, int w, const float* d_lut, const float* d_image,
+                               const float* d_bias, float* d_out, void* stream) {
+  LSQ_CHECK_ARG(d_x && d_lut && d_image && d_bias && d_out, "lsq_stem_fwd_u8: null pointer");
+  LSQ_CHECK_ARG(n > 0 && h >= 7 && w >= 7, "lsq_stem_fwd_u8: bad shape");
+  LSQ_CHECK_ARG(((uintptr_t)d_image & 15) == 0, "lsq_stem_fwd_u8: weight image must be 16-byte aligned");
+  return stem_fused_launch(nullptr, d_x, d_lut, n, h, w, d_image, d_bias, d_out, stream);
+}
+
 extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* d_image, const float* d_bias,
                             float* d_conv_ws, float* d_out, void* stream) {
   LSQ_CHECK_ARG(d_x && d_image && d_bias && d_conv_ws && d_out, "lsq_stem_fwd: null pointer");
@@ -858,36 +993,8 @@ extern "C" int lsq_stem_fwd(const float* d_x, int n, int h, int w, const float* 
   LSQ_CHECK_ARG(((uintptr_t)d_image & 15) == 0, "lsq_stem_fwd: weight image must be 16-byte aligned");
   size_t smem = 0;
   {
-    SfParams F;
     static const bool no_fuse = getenv("LSQ_STEM_UNFUSED") != nullptr;     // development: force the two-kernel route
-    if (!no_fuse && stem_fused_plan(n, h, w, F, smem)) {
-      static std::atomic<unsigned long long> fused_set{0ull};
-      const cudaError_t fe = ensure_max_smem(stem_fused_kernel, fused_set);
-      if (fe != cudaSuccess) { set_error("lsq_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(fe)); return LSQ_ERR_CUDA; }
-      const int sms_f = device_sms();
-      const unsigned char* const base = reinterpret_cast<const unsigned char*>(d_image);
-      long long* d_fdiag = nullptr;
-#ifdef LSQ_TC_DIAG
-      static const bool want_fdiag = getenv("LSQ_TC_DIAG") != nullptr;   // development build: wait cycles per warp of CTA 0
-      if (want_fdiag) { cudaMalloc(&d_fdiag, 32 * 3 * sizeof(long long)); cudaMemsetAsync(d_fdiag, 0, 32 * 3 * sizeof(long long), (cudaStream_t)stream); }
-#endif
-      stem_fused_kernel<<<F.tiles < sms_f ? F.tiles : sms_f, kSfThreads, smem, (cudaStream_t)stream>>>(
-          d_x, F, base + kSfImageOffset, reinterpret_cast<const float*>(base + kSfScaleOffset), d_bias, d_out, d_fdiag);
-      LSQ_CUDA_LAUNCH_CHECK("stem_fused_kernel");
-#ifdef LSQ_TC_DIAG
-      if (want_fdiag) {
-        long long hd[32 * 3];
-        cudaStreamSynchronize((cudaStream_t)stream);
-        cudaMemcpy(hd, d_fdiag, sizeof(hd), cudaMemcpyDeviceToHost);
-        cudaFree(d_fdiag);
-        fprintf(stderr, "[fused stem diag] tiles %d pw %d pp %d | warp 0 sections: tmem %lld pairbar %lld math %lld pool %lld store %lld\n", F.tiles, F.pw, F.pp, hd[75], hd[76], hd[77], hd[78], hd[79]);
-        for (int wi = 0; wi < kSfThreads / 32; ++wi)
-          fprintf(stderr, "   warp %2d (%s) total %9lld  wait0 %9lld  wait1 %9lld\n", wi,
-                  wi < 16 ? ((wi & 3) < 2 ? "epi-hi" : "epi-lo") : (wi == 16 ? "mma" : "producer"), hd[wi * 3], hd[wi * 3 + 1], hd[wi * 3 + 2]);
-      }
-#endif
-      return LSQ_OK;
-    }
+    if (!no_fuse && lsq_stem_is_fused(n, h, w)) return stem_fused_launch(d_x, nullptr, nullptr, n, h, w, d_image, d_bias, d_out, stream);
   }
   StemParams P;
   if (!stem_plan(n, h, w, P, smem)) {

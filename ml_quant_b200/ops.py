@@ -43,13 +43,13 @@ class _launch:
         return False
 
 
-def require_cuda(x: torch.Tensor, what: str = 'tensor') -> None:
+def require_cuda(x: torch.Tensor, what: str = 'tensor', dtype: torch.dtype = torch.float32) -> None:
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         raise _C.LsqError(
             f'ml_quant_b200: {what} must be a CUDA tensor -- the quantizer runs only as sm_100a CUDA kernels '
             '(no CPU fallback; the CPU restatement used for testing lives in oracle/).')
-    if x.dtype != torch.float32:
-        raise _C.LsqError(f'ml_quant_b200: {what} must be float32, got {x.dtype}')
+    if x.dtype != dtype:
+        raise _C.LsqError(f'ml_quant_b200: {what} must be {str(dtype).replace("torch.", "")}, got {x.dtype}')
 
 
 def _stream() -> int:
@@ -383,6 +383,48 @@ def stem_fwd(x: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.
                                 out.data_ptr(), _stream()), 'lsq_stem_fwd')
     if not L.lsq_stem_is_fused(n, h, w):
         LAUNCHES['stem_pool'] = LAUNCHES.get('stem_pool', 0) + 1      # the two-kernel route (conv, pool) of wide images
+    return out
+
+
+def u8_expand(x: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
+    """fp32 tensor lut[c][x] of a uint8 tensor [n, c, ...] (lsq_u8_expand): the caller's ToTensor + Normalize, evaluated
+    once per pixel level in ``lut`` float[c][256], applied on the device."""
+    if not isinstance(x, torch.Tensor) or x.dtype != torch.uint8 or x.dim() < 2:
+        raise ValueError('u8_expand takes a uint8 tensor [n, c, ...]')
+    require_cuda(x, 'x', torch.uint8)
+    x = x.contiguous()
+    n, c = x.shape[0], x.shape[1]
+    lut = lut.to(device=x.device, dtype=torch.float32).contiguous()
+    if tuple(lut.shape) != (c, 256):
+        raise ValueError(f'lut must be [{c}, 256]')
+    inner = x.numel() // max(n * c, 1)
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return out
+    with torch.cuda.device(x.device), _launch('u8_expand', 5.0 * x.numel()):
+        _C.check(_C.lib().lsq_u8_expand(x.data_ptr(), n * c, c, inner, lut.data_ptr(), out.data_ptr(), _stream()), 'lsq_u8_expand')
+    return out
+
+
+def stem_fwd_u8(x: torch.Tensor, lut: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """stem_fwd on lut[c][x] for uint8 pixels x [n, 3, h, w] without materialising the fp32 image (lsq_stem_fwd_u8; images up
+    to 250 pixels wide -- check with lsq_stem_is_fused -- else u8_expand + stem_fwd)."""
+    if not isinstance(x, torch.Tensor) or x.dtype != torch.uint8 or x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError('stem_fwd_u8 takes uint8 pixels [n, 3, h, w]')
+    require_cuda(x, 'x', torch.uint8)
+    x = x.contiguous()
+    n, _, h, w = x.shape
+    L = _C.lib()
+    lut = lut.to(device=x.device, dtype=torch.float32).contiguous()
+    if tuple(lut.shape) != (3, 256):
+        raise ValueError('lut must be [3, 256]')
+    hc, wc = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    hp, wp = (hc - 1) // 2 + 1, (wc - 1) // 2 + 1
+    out = torch.empty(n, 64, hp, wp, dtype=torch.float32, device=x.device)
+    macs = float(n) * 64 * hc * wc * 147
+    with torch.cuda.device(x.device), _launch('stem', 1.0 * x.numel() + 4.0 * out.numel(), 2.0 * macs):
+        _C.check(L.lsq_stem_fwd_u8(x.data_ptr(), n, h, w, lut.data_ptr(), image.data_ptr(), bias.contiguous().data_ptr(),
+                                   out.data_ptr(), _stream()), 'lsq_stem_fwd_u8')
     return out
 
 

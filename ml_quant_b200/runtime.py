@@ -115,6 +115,49 @@ def _xnor_block_fused(blk, x: torch.Tensor) -> torch.Tensor:
     return blk.conv2.forward_fused(first, blk.bn2, blk.nonlin2, sc, False)
 
 
+def pixel_lut(mean, std) -> torch.Tensor:
+    """float[c][256]: the value torchvision's ``ToTensor`` (x / 255) followed by ``Normalize(mean, std)`` ((x - mean) / std)
+    gives every uint8 pixel level of every channel, computed with the same fp32 operations on the host."""
+    m = torch.as_tensor(mean, dtype=torch.float32).reshape(-1, 1)
+    s = torch.as_tensor(std, dtype=torch.float32).reshape(-1, 1)
+    levels = torch.arange(256, dtype=torch.uint8).to(torch.float32).div(255)
+    return levels.reshape(1, 256).repeat(m.shape[0], 1).sub_(m).div_(s).contiguous()
+
+
+def _lut_on(model: nn.Module, device: torch.device) -> torch.Tensor:
+    cache = getattr(model, '_lsq_pixel_lut', None)
+    if cache is None:
+        raise RuntimeError('uint8 input: call runtime.set_pixel_input(model, mean, std) first')
+    key = (device.type, device.index)
+    if key not in cache:
+        cache[key] = cache['host'].to(device)
+    return cache[key]
+
+
+def set_pixel_input(model: nn.Module, mean, std) -> nn.Module:
+    """Let ``model`` take uint8 pixel batches [n, c, h, w] besides fp32 tensors: the host-side ``ToTensor`` + ``Normalize`` of the
+    reference's loaders (a per-channel map of 256 levels) is applied on the device -- inside the stem kernel for the ImageNet
+    stem, by ``lsq_u8_expand`` otherwise -- so a batch is uploaded as 1 byte per pixel instead of 4.  The fp32 input path is
+    unchanged and the results are bit-identical to transforming on the host (the same fp32 value per level)."""
+    import types
+    from . import ops
+    object.__setattr__(model, '_lsq_pixel_lut', {'host': pixel_lut(mean, std)})
+    if getattr(model, '_lsq_pixel_wrapped', False):
+        return model
+    inner = model.forward
+
+    def fwd(self, x):
+        if x.dtype == torch.uint8:
+            stem = getattr(self, '_lsq_stem', None)
+            fused = stem is not None and not (self.training or torch.is_grad_enabled()) and stem.takes_u8(x)
+            if not fused:
+                x = ops.u8_expand(x, _lut_on(self, x.device))
+        return inner(x)
+    model.forward = types.MethodType(fwd, model)
+    object.__setattr__(model, '_lsq_pixel_wrapped', True)
+    return model
+
+
 class _FusedStem(nn.Module):
     """conv1 -> bn1 -> relu -> maxpool of QResNet with the eval BatchNorm folded into the convolution
     weights and the max-pool taken before the ReLU (they commute), so the largest tensor of the network is
@@ -126,6 +169,7 @@ class _FusedStem(nn.Module):
         self._key = None
         self._image, self._image_key = None, None
         self.use_kernel = True
+        self.owner = None                 # weak reference to the network (its pixel table, set_pixel_input)
 
     def _folded(self):
         from .binary.binary_conv import bn_affine
@@ -139,13 +183,33 @@ class _FusedStem(nn.Module):
         return self._w, self._b
 
     def _kernel_ok(self, x: torch.Tensor) -> bool:
+        return x.is_cuda and x.dtype == torch.float32 and self._layers_ok()
+
+    def _layers_ok(self) -> bool:
         c, p = self.conv, self.pool
-        return (x.is_cuda and x.dtype == torch.float32 and c.in_channels == 3 and c.out_channels == 64
+        return (c.in_channels == 3 and c.out_channels == 64
                 and tuple(c.kernel_size) == (7, 7) and tuple(c.stride) == (2, 2) and tuple(c.padding) == (3, 3)
                 and tuple(c.dilation) == (1, 1) and c.groups == 1 and isinstance(p, nn.MaxPool2d)
                 and p.kernel_size == 3 and p.stride == 2 and p.padding == 1 and p.dilation == 1 and not p.ceil_mode)
 
+    def takes_u8(self, x: torch.Tensor) -> bool:
+        """uint8 pixels go straight into the stem kernel (no fp32 image in HBM) when its one-kernel route applies."""
+        from . import ops
+        return (self.use_kernel and x.is_cuda and x.dtype == torch.uint8 and x.dim() == 4 and x.shape[1] == 3
+                and self._layers_ok()
+                and bool(ops._C.lib().lsq_stem_is_fused(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
+        if x.dtype == torch.uint8:
+            from . import ops
+            lut = _lut_on(self.owner() if self.owner is not None else self, x.device)
+            if not (self.bn.training or torch.is_grad_enabled()) and self.takes_u8(x):
+                w, b = self._folded()
+                if self._image is None or self._image_key != self._key:
+                    self._image = ops.stem_pack(w)
+                    self._image_key = self._key
+                return ops.stem_fwd_u8(x, lut, self._image, b.contiguous())
+            x = ops.u8_expand(x, lut)
         if self.bn.training or torch.is_grad_enabled():
             return self.pool(F.relu(self.bn(self.conv(x))))
         w, b = self._folded()
@@ -177,12 +241,17 @@ def optimize_for_inference(model: nn.Module) -> nn.Module:
                 lambda self, x: (_xnor_block_fused(self, x) if not (self.training or torch.is_grad_enabled())
                                  else self._lsq_orig_forward(x)), m)
     if isinstance(model, QResNet) and not isinstance(model.blocks[0], _FusedStem):
+        import weakref
         stem = _FusedStem(model.conv1, model.bn1, model.maxpool)
+        stem.owner = weakref.ref(model)
         object.__setattr__(model, '_lsq_stem', stem)      # not registered: state_dict stays the reference's
         orig_forward = model.forward
 
         def fwd(self, x):
             if self.training or torch.is_grad_enabled():
+                if x.dtype == torch.uint8:
+                    from . import ops
+                    x = ops.u8_expand(x, _lut_on(self, x.device))
                 return orig_forward(x)
             x = self._lsq_stem(x)
             for blk in list(self.blocks)[1:]:
@@ -227,9 +296,11 @@ class HostPipeline:
 
     The upload of batch i+1 overlaps the forward of batch i (two device input buffers)."""
 
-    def __init__(self, model: nn.Module, batch_shape, device: torch.device, use_graph: bool = True):
+    def __init__(self, model: nn.Module, batch_shape, device: torch.device, use_graph: bool = True,
+                 dtype: torch.dtype = torch.float32):
+        # dtype=torch.uint8: pixel batches for a model prepared with set_pixel_input (1 byte per pixel over PCIe)
         self.device = device
-        self.bufs = [torch.empty(batch_shape, device=device) for _ in range(2)]
+        self.bufs = [torch.empty(batch_shape, device=device, dtype=dtype) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=device)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.freed = [torch.cuda.Event() for _ in range(2)]

@@ -586,3 +586,74 @@ def test_multi_plane_weight_schemes_take_the_packed_route(golden_layers):
         assert 'fakequant' not in ops.LAUNCHES and ops.LAUNCHES.get('bconv_simple', 0) >= 2, ops.LAUNCHES
         err = float((y - rec['y']).abs().max() / rec['y'].abs().max())
         assert err < (1e-5 if sp['x_quant'] in ('ls-1',) or sp['x_quant'].startswith('gf') else 5e-2), (sp, err)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# uint8 pixel input (the data format in front of the path; runtime.set_pixel_input)
+# ---------------------------------------------------------------------------------------------------------------
+def _host_transform(u8, mean, std):
+    """torchvision's ToTensor + Normalize on the host (quant/data loaders of the reference): x / 255, then (x - mean) / std."""
+    t = u8.to(torch.float32).div(255)
+    m = torch.tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+    return t.sub_(m).div_(s)
+
+
+def test_uint8_pixels_expand_like_the_host_transform():
+    """lsq_u8_expand and lsq_stem_fwd_u8 against ToTensor + Normalize evaluated on the host: bit-identical."""
+    from ml_quant_b200 import ops, runtime
+    runtime_strict()
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    lut = runtime.pixel_lut(mean, std)
+    g = torch.Generator().manual_seed(41)
+    for shape in [(3, 3, 224, 224), (2, 3, 61, 75), (1, 3, 7, 9), (5, 3, 32, 32), (2, 3, 33, 223)]:
+        u8 = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+        want = _host_transform(u8, mean, std).to(DEV)
+        got = ops.u8_expand(u8.to(DEV), lut)
+        assert torch.equal(got, want), shape
+        if shape[2] >= 7 and shape[3] >= 7:
+            wt = torch.randn(64, 3, 7, 7, device=DEV) * 0.1
+            b = torch.randn(64, device=DEV)
+            img = ops.stem_pack(wt)
+            assert bool(ops._C.lib().lsq_stem_is_fused(*[shape[0], shape[2], shape[3]]))
+            assert torch.equal(ops.stem_fwd_u8(u8.to(DEV), lut, img, b), ops.stem_fwd(want, img, b)), shape
+    # one channel, odd sizes (scalar path of the expand kernel)
+    u8 = torch.randint(0, 256, (4, 1, 13, 11), dtype=torch.uint8, generator=g)
+    lut1 = runtime.pixel_lut((0.1307,), (0.3081,))
+    assert torch.equal(ops.u8_expand(u8.to(DEV), lut1), _host_transform(u8, (0.1307,), (0.3081,)).to(DEV))
+    with pytest.raises(ValueError):
+        ops.u8_expand(torch.zeros(2, 3, 4, 4, device=DEV), lut)               # fp32 input
+    with pytest.raises(RuntimeError):
+        ops.stem_fwd_u8(torch.zeros(1, 3, 64, 300, dtype=torch.uint8, device=DEV), lut, img, b)   # wider than the one-kernel route
+
+
+@pytest.mark.parametrize('cfg,hw', [('imagenet_resnet18_ls1w_ls2a', (224, 224)), ('imagenet_resnet18_ls1w_ls2a', (64, 300)),
+                                    ('cifar100_resnet18_ls1w_ls2a', (32, 32))])
+def test_network_takes_uint8_pixel_batches(cfg, hw):
+    """A network prepared with runtime.set_pixel_input classifies uint8 pixel batches exactly as it classifies the fp32
+    tensors the host transform makes from them (fused stem, wide-image route, CIFAR stem; eager and as a CUDA graph)."""
+    from ml_quant_b200 import runtime
+    runtime_strict()
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    model = runtime.build_model(cfg, torch.device(DEV))
+    runtime.calibrate(model, (3,) + hw)
+    runtime.optimize_for_inference(model)
+    runtime.set_pixel_input(model, mean, std)
+    g = torch.Generator().manual_seed(43)
+    u8 = torch.randint(0, 256, (6, 3) + hw, dtype=torch.uint8, generator=g)
+    xf = _host_transform(u8, mean, std).to(DEV)
+    with torch.no_grad():
+        want = model(xf)
+        got = model(u8.to(DEV))
+    assert torch.equal(got, want)
+    graphed = runtime.GraphedForward(model, u8.to(DEV))
+    assert torch.equal(graphed(), want)
+    # host batches through the pipeline, 1 byte per pixel
+    pipe = runtime.HostPipeline(model, tuple(u8.shape), torch.device(DEV), use_graph=True, dtype=torch.uint8)
+    out = pipe.run([u8.pin_memory(), u8.pin_memory()])
+    assert torch.equal(out.to(DEV), want)
+    # without set_pixel_input a uint8 batch is an error, not a silent cast
+    other = runtime.build_model(cfg, torch.device(DEV))
+    runtime.optimize_for_inference(other).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        other(u8.to(DEV))
