@@ -856,6 +856,58 @@ constexpr int kSmallThreads = 128;
 constexpr int kSmallWarps = kSmallThreads / 32;
 constexpr int kSmallRow = 2048;
 
+// Sort keys[0, lp) (lp a power of two) with one warp.  Element e belongs to lane e & 31 ("column" ownership): a bitonic
+// compare-exchange at distance >= 32 pairs two elements of the SAME lane (plain loads / stores of the lane's own column, no
+// synchronisation), the five shorter distances of a stage are shuffles on a register.  No lane ever touches another lane's
+// column, so the whole sort needs no barrier; ~3 instructions per element and step (the network with one __syncwarp per
+// step and pair addressing through shared memory spent ~10).
+__device__ __forceinline__ void warp_sort_columns(uint32_t* keys, uint32_t lp, int lane) {
+  const uint32_t rows = (lp + 31u) >> 5;
+  for (uint32_t i = 0; i < rows; ++i) {                // stages k = 2 .. 32 inside every row of 32
+    const uint32_t e = i * 32u + (uint32_t)lane;
+    uint32_t r = e < lp ? keys[e] : kNoKey;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, r, j);
+        const bool lower = (lane & j) == 0;
+        const bool up = k < 32 ? ((lane & k) == 0) : ((i & 1u) == 0u);
+        r = (lower == up) ? min(r, o) : max(r, o);
+      }
+    }
+    if (e < lp) keys[e] = r;
+  }
+  for (uint32_t k = 64; k <= lp; k <<= 1) {
+    for (uint32_t j = k >> 1; j >= 32u; j >>= 1) {     // distances of whole rows: lane-private
+      const uint32_t jj = j >> 5;
+#pragma unroll 4
+      for (uint32_t t = 0; t < (rows >> 1); ++t) {
+        const uint32_t i = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u));
+        uint32_t* const pa = keys + i * 32u + lane;
+        uint32_t* const pb = pa + jj * 32u;
+        const uint32_t a = *pa, b2 = *pb;
+        const bool up = ((i << 5) & k) == 0u;
+        const uint32_t lo = min(a, b2), hi = max(a, b2);
+        *pa = up ? lo : hi;
+        *pb = up ? hi : lo;
+      }
+    }
+#pragma unroll 2
+    for (uint32_t i = 0; i < rows; ++i) {              // distances 16 .. 1 inside every row
+      uint32_t r = keys[i * 32u + lane];
+      const bool up = ((i << 5) & k) == 0u;
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, r, j);
+        const bool lower = (lane & j) == 0;
+        r = (lower == up) ? min(r, o) : max(r, o);
+      }
+      keys[i * 32u + lane] = r;
+    }
+  }
+}
+
 // One row solved by one warp.  keys = the warp's shared-memory slice (>= next power of two of the sampled length).
 template <bool TERN>
 __device__ __forceinline__ void solve_row_warp(uint32_t* keys, const float* __restrict__ xr, long long len, int skip,
@@ -887,17 +939,8 @@ __device__ __forceinline__ void solve_row_warp(uint32_t* keys, const float* __re
   const double s_tot = warp_sum(ls), q_tot = warp_sum(lq);
   kmn = warp_min_u32(kmn); kmx = warp_max_u32(kmx);
   __syncwarp();
-  for (uint32_t k = 2; k <= lp; k <<= 1)
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t t = lane; t < (lp >> 1); t += 32) {
-        const uint32_t a0 = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const uint32_t p1 = a0 | j;
-        const uint32_t ka = keys[a0], kb = keys[p1];
-        const bool up = ((a0 & k) == 0);
-        if ((ka > kb) == up) { keys[a0] = kb; keys[p1] = ka; }
-      }
-      __syncwarp();
-    }
+  warp_sort_columns(keys, lp, lane);
+  __syncwarp();
   // every position of the sorted row: contiguous chunk per lane, fp64 prefix sums by shuffle
   const uint32_t per = (n + 31u) / 32u;
   const uint32_t j0 = min((uint32_t)lane * per, n), j1 = min(j0 + per, n);
