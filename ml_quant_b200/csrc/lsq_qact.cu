@@ -519,6 +519,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
         uint32_t lp = 2;
         while (lp < cnt) lp <<= 1;
         for (uint32_t e = cnt + lane; e < lp; e += 32) sm.list[base + e] = kNoKey;
+        __syncwarp();                              // every lane has read lfill / lsmin of the segment (racecheck: WAR)
         if (lane == 0) {
           sm.lsmin[i] = smin;
           if (fill != cnt) sm.status = 5;        // cannot happen: the histogram and the bin indices disagree

@@ -163,33 +163,33 @@ stem_conv_kernel(const float* __restrict__ x, StemParams P, const float* __restr
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             orow[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // half parked
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // tile consumed: may be overwritten
-          continue;
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // half parked (both warps of the pair: one instruction)
+        if (!upper) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 u = orow[j];
-          orow[j] = make_float4(fmaxf(__uint_as_float(rr[4 * j]) + u.x + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 1]) + u.y + bs, 0.0f),
-                                fmaxf(__uint_as_float(rr[4 * j + 2]) + u.z + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 3]) + u.w + bs, 0.0f));
-        }
-        __syncwarp();
-        const StPos pi = st_decode(P, P.q_begin + (long long)tile * kStTile + p0 + pl16);
-        if (pi.in_range && pi.s < g.n && pi.a >= 0 && pi.a < P.hc && pi.col < P.wc) {
-          const float* ot = outt + (4 * ch_sub) * kStOutPitch + pl16;
-          float v[16];
+          for (int j = 0; j < 4; ++j) {
+            const float4 u = orow[j];
+            orow[j] = make_float4(fmaxf(__uint_as_float(rr[4 * j]) + u.x + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 1]) + u.y + bs, 0.0f),
+                                  fmaxf(__uint_as_float(rr[4 * j + 2]) + u.z + bs, 0.0f), fmaxf(__uint_as_float(rr[4 * j + 3]) + u.w + bs, 0.0f));
+          }
+          __syncwarp();
+          const StPos pi = st_decode(P, P.q_begin + (long long)tile * kStTile + p0 + pl16);
+          if (pi.in_range && pi.s < g.n && pi.a >= 0 && pi.a < P.hc && pi.col < P.wc) {
+            const float* ot = outt + (4 * ch_sub) * kStOutPitch + pl16;
+            float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = ot[(8 * (i >> 2) + (i & 3)) * kStOutPitch];
-          float* yp = conv + (((long long)pi.s * 64 + 32 * chg + 4 * ch_sub) * P.hc + pi.a) * P.wc + pi.col;
-          const long long s5 = 5 * cstride;
+            for (int i = 0; i < 16; ++i) v[i] = ot[(8 * (i >> 2) + (i & 3)) * kStOutPitch];
+            float* yp = conv + (((long long)pi.s * 64 + 32 * chg + 4 * ch_sub) * P.hc + pi.a) * P.wc + pi.col;
+            const long long s5 = 5 * cstride;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            *yp = v[i];
-            yp += ((i & 3) == 3) ? s5 : cstride;
+            for (int i = 0; i < 16; ++i) {
+              *yp = v[i];
+              yp += ((i & 3) == 3) ? s5 : cstride;
+            }
           }
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        __syncwarp();                                  // reconverge before the aligned barrier
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // tile consumed: may be overwritten
       }
       tc_fence_before();
       __syncwarp();
