@@ -262,6 +262,9 @@ def quantize_act(x: torch.Tensor, g: _C.ActGeom, ternary: bool, alpha: Optional[
         _C.check(L.lsq_quantize_act(x.data_ptr(), C.byref(g), _alpha(alpha), int(bool(ternary)), int(skip),
                                     planes.data_ptr(), table.data_ptr(), ws.data_ptr(), ws.numel(),
                                     _prologue(prologue, keep), _ptr(dg), _stream()), 'lsq_quantize_act')
+    # lsq_quantize_act launches two kernels either way: the fused kernel + its (normally empty) fallback pass, or the generic
+    # solver + encoder for shapes outside the fused kernel's domain
+    LAUNCHES['quant_act_second'] = LAUNCHES.get('quant_act_second', 0) + 1
     return (planes, table, dg) if diag else (planes, table)
 
 
