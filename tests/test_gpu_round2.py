@@ -657,3 +657,26 @@ def test_network_takes_uint8_pixel_batches(cfg, hw):
     runtime.optimize_for_inference(other).eval()
     with torch.no_grad(), pytest.raises(RuntimeError):
         other(u8.to(DEV))
+
+
+def test_reference_on_cuda_against_reference_on_cpu_second_witness():
+    """the unmodified reference's opt_v1 on CUDA and on the CPU over the same rows.  Their picks may differ
+    (the arg-min is decided among candidates whose fp32 costs tie to ~7 digits), but each pick satisfies the staged contract
+    this repository's solver is held to against the other: fp64 cost within (1 + 1e-5).  Runs the staged reference in its
+    own process (oracle/ref_witness.py); LSQ_WITNESS_OUT=<file> keeps the JSON line."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'oracle', 'ref_witness.py'), '24', '200704'],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith('{')][-1]
+    d = json.loads(line)
+    if 'unavailable' in d:
+        pytest.skip(d['unavailable'])
+    if os.environ.get('LSQ_WITNESS_OUT'):
+        open(os.environ['LSQ_WITNESS_OUT'], 'w').write(line + '\n')
+    for case in d['cases']:
+        assert case['max_fp64_cost_ratio_minus_1'] <= 1e-5, case
