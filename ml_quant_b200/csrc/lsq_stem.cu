@@ -544,16 +544,13 @@ stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__
     const float ninf = __int_as_float(0xff800000);
     float carry[8];                                    // raw horizontal maxima of convolution row 2k-1, px = cb_m / 2 + i
     // pooled row -> global: float4 units when rows are 16-byte multiples, else a scalar walk
+    // pooled row -> global: thread t stores channel t >> 3, 16-byte quads (t & 7) and (t & 7) + 8 of the row (rows are
+    // 16-byte multiples and at most 16 quads wide), else a scalar walk
     const bool vec_store = (wp & 3) == 0;
     const int wq = wp >> 2;
-    int so[2], go[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int idx = (int)threadIdx.x + 512 * u;
-      const int ch = vec_store ? idx / wq : 64, q = vec_store ? idx - ch * wq : 0;
-      so[u] = ch < 64 ? ch * kSfPoolPitch + 4 * q : -1;
-      go[u] = ch * P.hp * wp + 4 * q;
-    }
+    const int st_q = (int)threadIdx.x & 7, st_ch = (int)threadIdx.x >> 3;
+    const int so0 = st_ch * kSfPoolPitch + 4 * st_q;
+    const long long go0 = (long long)st_ch * P.hp * wp + 4 * st_q;
     Ring acc(2);
     uint32_t emitted = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -654,9 +651,8 @@ stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__
         SF_T0();
         float* const ob = out + ((long long)s * 64 * P.hp + k) * wp;
         if (vec_store) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-            if (so[u] >= 0) *reinterpret_cast<float4*>(ob + go[u]) = *reinterpret_cast<const float4*>(ptile + so[u]);
+          if (st_q < wq) *reinterpret_cast<float4*>(ob + go0) = *reinterpret_cast<const float4*>(ptile + so0);
+          if (st_q + 8 < wq) *reinterpret_cast<float4*>(ob + go0 + 32) = *reinterpret_cast<const float4*>(ptile + so0 + 32);
         } else {
           const long long chs = (long long)P.hp * wp;
           const int dch = 512 / wp, dpx = 512 - dch * wp;
@@ -714,16 +710,6 @@ stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__
     uint32_t par = 0;
     Ring prev(2);                                        // accumulator stage of the previous tile (group 1's release)
     constexpr int kB = 7;                                // 96 * 7 >= the largest patch (648 positions)
-    // tile-invariant part of the addressing: patch row and input column of this lane's positions (-1: nothing to load)
-    int prow_of[kB], ix_of[kB];
-#pragma unroll
-    for (int u = 0; u < kB; ++u) {
-      const int pos = third * 32 + lane + 96 * u;
-      const int prow = (int)(((uint32_t)pos * P.pw_magic) >> 20);
-      const int bcol = pos - prow * P.pw - 2;
-      prow_of[u] = prow;
-      ix_of[u] = (pos < P.pp && bcol >= 0 && 2 * bcol < P.w) ? 2 * bcol : -1;
-    }
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int s = tile / P.hp, k = tile - s * P.hp;
       const float* const xs = x + (U8 ? 0ll : (long long)s * 3 * plane);
@@ -732,9 +718,12 @@ stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__
       uint32_t la[kB], lb[kB];                           // uint8 route: levels c0 | c1 << 8 | c2 << 16 of the px = 0 / px = 1 pixel; bit 31: outside
 #pragma unroll
       for (int u = 0; u < kB; ++u) {
-        const int a = 2 * k - 2 + prow_of[u];
-        const int iy = 2 * a + py, ix = ix_of[u];
-        const bool inside = ix >= 0 && a >= 0 && iy < P.h;
+        const int pos = third * 32 + lane + 96 * u;
+        const int prow = (int)(((uint32_t)pos * P.pw_magic) >> 20);
+        const int bcol = pos - prow * P.pw - 2;
+        const int a = 2 * k - 2 + prow;
+        const int iy = 2 * a + py, ix = 2 * bcol;
+        const bool inside = pos < P.pp && bcol >= 0 && ix < P.w && a >= 0 && iy < P.h;
         if (U8) {
           la[u] = lb[u] = 0x80000000u;
           if (inside) {
