@@ -54,7 +54,8 @@ struct TcParams {
   int tap_phase[kMaxTaps];
   int tap_off[kMaxTaps];         // tap offset relative to dmin of its phase (>= 0)
   uint32_t lbo_p, phase_bytes, p_stage_bytes, w_slab_bytes, w_stage_bytes;
-  uint32_t smem_p, smem_w, smem_bar, smem_tab, smem_scl, smem_out, smem_res;  // offsets in dynamic smem
+  uint32_t smem_p, smem_w, smem_bar, smem_tab, smem_scl, smem_out, smem_res, smem_as;  // offsets in dynamic smem
+  int as_n;                      // samples whose activation scales are cached in shared memory (0: read from global)
   unsigned long long pitch_magic, rps_magic;   // ceil(2^40 / d): x / d == (x * magic) >> 40 for x * d < 2^40
 };
 
@@ -130,6 +131,13 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
       btab[j] = make_desc(b_addr + (uint32_t)(2 * h) * P.lbo_p, P.lbo_p, 128u);
     }
   }
+  // per-sample activation scales [planes][n]: a copy in shared memory (the epilogue looks two of them up per position
+  // and item; from global memory that dependent L2 round trip sat in front of every item's accumulator wait)
+  float* const as_tab = reinterpret_cast<float*>(smem + P.smem_as);
+  for (int i = threadIdx.x; i < P.as_n * P.npl; i += kTcThreads) {
+    const int pl = i / P.as_n, smp = i - pl * P.as_n;
+    as_tab[i] = __ldg(act_scales + (long long)pl * g.n + smp);
+  }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -198,8 +206,13 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
             const long long o2 = (p == lane) ? off : out_offset(ptile, ctile, pbase + p, smp);
             float2 s2 = make_float2(0.0f, 0.0f);
             if (o2 >= 0) {
-              s2.x = __ldg(act_scales + smp);
-              if (P.npl > 1) s2.y = __ldg(act_scales + g.n + smp);
+              if (P.as_n) {
+                s2.x = as_tab[smp];
+                if (P.npl > 1) s2.y = as_tab[P.as_n + smp];
+              } else {
+                s2.x = __ldg(act_scales + smp);
+                if (P.npl > 1) s2.y = __ldg(act_scales + g.n + smp);
+              }
             }
             scl[p] = s2;
           }
@@ -469,7 +482,9 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   const size_t bar_bytes = 512 + (kMaxWStages * 3 * 2 + kMaxPStages * kMaxTaps * 2) * 8, tab_bytes = (size_t)cout * 16;
   const size_t scl_bytes = (size_t)8 * (tp / (8 / (P.creal >> 5))) * sizeof(float2), out_bytes = 8 * 32 * kOutPitch * sizeof(float);
   const size_t slack = 0;
-  const size_t fixed = bar_bytes + tab_bytes + scl_bytes + out_bytes + slack;
+  P.as_n = (size_t)g->n * nplanes * sizeof(float) <= 8192 ? g->n : 0;       // up to 1024 samples x 2 planes
+  const size_t as_bytes = ((size_t)P.as_n * nplanes * sizeof(float) + 15) & ~(size_t)15;
+  const size_t fixed = bar_bytes + tab_bytes + scl_bytes + out_bytes + as_bytes + slack;
   // minimum: 2 patch stages (1 when there is a single channel block and nothing to overlap with is no option:
   // the next item's patch is built while this one is multiplied), 2 weight stages of one tap, 2 residual steps
   const size_t res_min = has_res ? (size_t)8 * 2 * 4096 : 0;
@@ -512,6 +527,7 @@ static bool tc_plan(const lsq_act_geom* g, int nplanes, int cout, bool has_res, 
   P.smem_scl = o; o += (uint32_t)scl_bytes;
   P.smem_out = o; o += (uint32_t)out_bytes;
   P.smem_res = o; o += has_res ? (uint32_t)(8 * P.r_stages * 4096) : 0u;
+  P.smem_as = o; o += (uint32_t)as_bytes;
   return o <= 227 * 1024;
 }
 
@@ -546,7 +562,7 @@ int bconv2d_tc_launch(const uint32_t* d_planes, const lsq_act_geom* g, int nplan
   const long long qspan = (long long)g->n * g->rows_per_sample * g->pitch;
   P.p_tiles = (int)((qspan + P.tp - 1) / P.tp);
   const int n_items = P.p_tiles * P.n_ctiles;
-  const size_t smem_bytes = (size_t)P.smem_res;
+  const size_t smem_bytes = (size_t)P.smem_as + (((size_t)P.as_n * P.npl * sizeof(float) + 15) & ~(size_t)15);
 
   // the weight image follows the bit image inside d_wpack (lsq_bconv.cu)
   const size_t bits_bytes = ((size_t)cout * g->kh * g->kw * g->cw * 4 + 1023) / 1024 * 1024;
