@@ -715,7 +715,9 @@ stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__
       const float* const xs = x + (U8 ? 0ll : (long long)s * 3 * plane);
       const unsigned char* const us = xu8 + (U8 ? (long long)s * 3 * plane : 0ll);
       float2 v[kB][3];                                   // fp32 route: pixel pairs of the three channels
-      uint32_t la[kB], lb[kB];                           // uint8 route: levels c0 | c1 << 8 | c2 << 16 of the px = 0 / px = 1 pixel; bit 31: outside
+      uint32_t ra[kB][3];                                // uint8 route: the raw pixel pair of each channel (x | y << 8), bit 31: outside,
+                                                         // bit 30: second pixel outside -- untouched until the slot wait below, so that
+                                                         // all loads of a tile are in flight together
 #pragma unroll
       for (int u = 0; u < kB; ++u) {
         const int pos = third * 32 + lane + 96 * u;
@@ -725,19 +727,19 @@ stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__
         const int iy = 2 * a + py, ix = 2 * bcol;
         const bool inside = pos < P.pp && bcol >= 0 && ix < P.w && a >= 0 && iy < P.h;
         if (U8) {
-          la[u] = lb[u] = 0x80000000u;
+          ra[u][0] = ra[u][1] = ra[u][2] = 0x80000000u;
           if (inside) {
             const unsigned char* up = us + (long long)iy * P.w + ix;
             if (pair_loads) {                            // w even: ix + 1 < w
-              uchar2 q[3];
 #pragma unroll
-              for (int c = 0; c < 3; ++c) q[c] = __ldg(reinterpret_cast<const uchar2*>(up + c * plane));
-              la[u] = (uint32_t)q[0].x | ((uint32_t)q[1].x << 8) | ((uint32_t)q[2].x << 16);
-              lb[u] = (uint32_t)q[0].y | ((uint32_t)q[1].y << 8) | ((uint32_t)q[2].y << 16);
+              for (int c = 0; c < 3; ++c) ra[u][c] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(up + c * plane));
             } else {
-              la[u] = (uint32_t)__ldg(up) | ((uint32_t)__ldg(up + plane) << 8) | ((uint32_t)__ldg(up + 2 * plane) << 16);
-              if (ix + 1 < P.w)
-                lb[u] = (uint32_t)__ldg(up + 1) | ((uint32_t)__ldg(up + plane + 1) << 8) | ((uint32_t)__ldg(up + 2 * plane + 1) << 16);
+              const bool second = ix + 1 < P.w;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                ra[u][c] = (uint32_t)__ldg(up + c * plane);
+                if (second) ra[u][c] |= (uint32_t)__ldg(up + c * plane + 1) << 8; else ra[u][c] |= 0x40000000u;
+              }
             }
           }
         } else {
@@ -769,10 +771,11 @@ stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__
           if (U8) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const uint32_t l = e == 0 ? la[u] : lb[u];
               q[e] = make_uint4(0u, 0u, 0u, 0u);         // outside the image: zero padding of the NORMALISED tensor
-              if (!(l & 0x80000000u)) {
-                const uint32_t e0 = lutp[l & 0xFFu], e1 = lutp[256 + ((l >> 8) & 0xFFu)], e2 = lutp[512 + ((l >> 16) & 0xFFu)];
+              const bool out = (ra[u][0] & 0x80000000u) != 0u || (e == 1 && (ra[u][0] & 0x40000000u) != 0u);
+              if (!out) {
+                const uint32_t e0 = lutp[(ra[u][0] >> (8 * e)) & 0xFFu], e1 = lutp[256 + ((ra[u][1] >> (8 * e)) & 0xFFu)],
+                               e2 = lutp[512 + ((ra[u][2] >> (8 * e)) & 0xFFu)];
                 q[e] = make_uint4((e0 & 0xFFFFu) | (e1 << 16), e2 & 0xFFFFu, (e0 >> 16) | (e1 & 0xFFFF0000u), e2 >> 16);
               }
             }
