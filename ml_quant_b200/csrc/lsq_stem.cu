@@ -546,7 +546,7 @@ stem_fused_kernel(const float* __restrict__ x, const unsigned char* __restrict__
     // pooled row -> global: float4 units when rows are 16-byte multiples, else a scalar walk
     // pooled row -> global: thread t stores channel t >> 3, 16-byte quads (t & 7) and (t & 7) + 8 of the row (rows are
     // 16-byte multiples and at most 16 quads wide), else a scalar walk
-    const bool vec_store = (wp & 3) == 0;
+    const bool vec_store = (wp & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const int wq = wp >> 2;
     const int st_q = (int)threadIdx.x & 7, st_ch = (int)threadIdx.x >> 3;
     const int so0 = st_ch * kSfPoolPitch + 4 * st_q;

@@ -335,6 +335,15 @@ def test_fused_stem_kernel_matches_torch():
         # per output channel as well (a channel with small weights must not inherit the error scale of a large one)
         errc = float(((got - want).abs().amax(dim=(0, 2, 3)) / want.abs().amax(dim=(0, 2, 3)).clamp_min(1e-20)).max())
         assert errc < 1e-5, (n, h, w, errc)
+    # an output buffer that is only 4-byte aligned (a C caller's sub-allocation): the pooled rows leave by the scalar walk
+    x = torch.randn(2, 3, 64, 64, device=DEV)
+    img = ops.stem_pack(wt)
+    want = ops.stem_fwd(x, img, b)
+    buf = torch.zeros(want.numel() + 1, device=DEV)
+    ws = torch.empty(64, device=DEV)
+    ops._C.check(L.lsq_stem_fwd(x.data_ptr(), 2, 64, 64, img.data_ptr(), b.data_ptr(), ws.data_ptr(), buf.data_ptr() + 4,
+                                torch.cuda.current_stream().cuda_stream), 'lsq_stem_fwd')
+    assert torch.equal(buf[1:].view_as(want), want)
     # out-of-range pixels are clamped to the fp16 range on the one-kernel route (documented domain): finite output
     x = torch.randn(1, 3, 32, 32, device=DEV)
     x[0, 0, 3, 3] = 1e30
