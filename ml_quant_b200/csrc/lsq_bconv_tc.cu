@@ -197,7 +197,7 @@ bconv_tc_kernel(const uint32_t* __restrict__ planes, TcParams P, const float* __
           const float* rp = epi.residual + (off >= 0 ? off + (long long)chb * cstride : 0);
           const long long st = off >= 0 ? cstride : 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) rs[i] = __ldg(rp + i * st);
+          for (int i = 0; i < 32; ++i) rs[i] = ldg_stream(rp + i * st);
         }
         if (step == 0) {
           // per-position activation scales of this warp's positions, per-thread channel constants

@@ -168,4 +168,19 @@ __host__ __device__ inline long long vpos(const ActGeom& g, int s, int a, int b)
   return (long long)g.lead + ((long long)s * g.rps + g.ph + a) * g.pitch + b;
 }
 
+// Streaming loads of the quantizer sweeps: read-only path with a 256-byte L2 prefetch hint (the sweeps are bound by the
+// number of outstanding requests per SM, not by bytes: fetching the neighbouring 128 bytes into L2 with the same request
+// measured -2 % on the 64 x 56 x 56 rows and -5 % on the 512 x 7 x 7 rows; adding L1::no_allocate cost 14 %, the
+// sampled sweep re-uses the lines it fetched)
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 }  // namespace lsq

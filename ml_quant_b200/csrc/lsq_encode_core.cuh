@@ -32,7 +32,7 @@ __device__ __forceinline__ void encode_group(const float* __restrict__ xp, long 
       const int cc = c0 + u;
       if (FULL || cc < cn) {
         if (VEC == 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(xp + (long long)cc * cstride));
+          const float4 t = ldg_stream4(reinterpret_cast<const float4*>(xp + (long long)cc * cstride));
           raw[u][0] = t.x; raw[u][1 % VEC] = t.y; raw[u][2 % VEC] = t.z; raw[u][3 % VEC] = t.w;
         } else {
           raw[u][0] = __ldg(xp + (long long)cc * cstride);

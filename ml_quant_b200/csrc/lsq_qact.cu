@@ -189,7 +189,7 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const long long idx = i0 + 3 * j;
-          raw[u][j] = (gi < g_hi && idx < qp.len) ? __ldg(xr + idx) : 0.0f;
+          raw[u][j] = (gi < g_hi && idx < qp.len) ? ldg_stream(xr + idx) : 0.0f;
         }
       }
 #pragma unroll
