@@ -213,3 +213,33 @@ def test_quantlinear_construction_and_fp_equivalence():
     assert torch.allclose(fp(x), F.linear(x, fp.weight, fp.bias), atol=1e-6)
     with pytest.raises(ValueError):
         fp(torch.randn(3, 15))
+
+
+def test_pixel_lut_is_the_host_transform():
+    """runtime.pixel_lut evaluates torchvision's ToTensor + Normalize once per pixel level with the host's own fp32 ops."""
+    import torch
+    from ml_quant_b200 import runtime
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    lut = runtime.pixel_lut(mean, std)
+    assert lut.shape == (3, 256) and lut.dtype == torch.float32
+    img = torch.arange(256, dtype=torch.uint8).view(1, 1, 16, 16).repeat(2, 3, 1, 1)
+    want = img.to(torch.float32).div(255).sub_(torch.tensor(mean).view(1, 3, 1, 1)).div_(torch.tensor(std).view(1, 3, 1, 1))
+    got = torch.stack([lut[c][img[:, c].long()] for c in range(3)], dim=1)
+    assert torch.equal(got, want)
+    assert runtime.pixel_lut((0.1307,), (0.3081,)).shape == (1, 256)
+
+
+def test_uint8_input_needs_a_pixel_table():
+    """A model that was not prepared with set_pixel_input must reject uint8 batches loudly (no silent cast)."""
+    import pytest
+    import torch
+    from ml_quant_b200 import runtime
+
+    class M(torch.nn.Module):
+        def forward(self, x):
+            return x
+
+    with pytest.raises(RuntimeError):
+        runtime._lut_on(M(), torch.device('cpu'))
+    m = runtime.set_pixel_input(M(), (0.5,), (0.5,))
+    assert tuple(runtime._lut_on(m, torch.device('cpu')).shape) == (1, 256)
