@@ -406,7 +406,7 @@ static bool stem_plan(int n, int h, int w, StemParams& P, size_t& smem_bytes) {
 //    the W_lo half of the accumulator is added through a shared-memory exchange between warp pairs first (the sum
 //    must precede the ReLU / max).  The pooled row (64 x wp) is transposed through shared memory and stored
 //    along px.
-constexpr int kSfXPitch = 20;                  // exchange tile: [32 channels][16 columns + left neighbour], float4 conflict-free
+constexpr int kSfXPitch = 20;                  // exchange tile: [32 channels][8 columns x 2 rows + 2 left neighbours], float4 conflict-free
 constexpr int kSfPoolPitch = 68;               // pooled tile: [64 channels][<= 64 px], rows 16-byte aligned for the float4 store
 constexpr int kSfProducerWarps = 6;
 constexpr int kSfThreads = (17 + kSfProducerWarps) * 32;     // 16 epilogue warps, MMA warp 16, producer warps 17-22
