@@ -94,6 +94,11 @@ LSQ_API int lsq_row_absmean_ex(const float* d_x, int64_t rows, int64_t len, floa
                        const float* d_scales, int nscales, float* d_out,
                        void* d_ws, size_t ws_bytes, const lsq_prologue* pro, void* stream);
 
+/* Global average pool of the classifier head (AdaptiveAvgPool2d((1, 1)) of quant/models/resnet.py in front of the linear
+ * layer; outside the quantized path, here because ATen's generic reduction is launch-shaped work on 7 x 7 planes):
+ * d_out[p] = mean(d_x[p][0 .. inner)), one warp per plane, fixed summation tree (deterministic, batch invariant). */
+LSQ_API int lsq_plane_mean(const float* d_x, int64_t planes, int inner, float* d_out, void* stream);
+
 /* Least-squares optimal v1 for the 2-bit (ternary = 0) or ternary (= 1) quantizer: replaces
  * opt_v1 / compute_mask / cost_function (quant/binary/optimal.py:16-155).  Only every `skip`-th
  * element of a row enters the solve (optimal.py:134).  d_diag (optional, int32[rows][16]) receives

@@ -17,7 +17,7 @@ EXPORTS = [
     'lsq_fakequant', 'lsq_ste_backward', 'lsq_act_geometry', 'lsq_act_planes_bytes', 'lsq_encode_act',
     'lsq_wpack_bytes', 'lsq_pack_weights', 'lsq_bconv2d_fwd', 'lsq_bconv2d_tc_supported',
     'lsq_row_absmean_ex', 'lsq_solve_v1_ex', 'lsq_encode_act_ex', 'lsq_bconv2d_fwd_ex', 'lsq_stem_fwd',
-    'lsq_stem_image_bytes', 'lsq_stem_workspace_bytes', 'lsq_stem_supported', 'lsq_stem_is_fused', 'lsq_stem_pack_weights', 'lsq_u8_expand', 'lsq_stem_fwd_u8',
+    'lsq_stem_image_bytes', 'lsq_stem_workspace_bytes', 'lsq_stem_supported', 'lsq_stem_is_fused', 'lsq_stem_pack_weights', 'lsq_u8_expand', 'lsq_stem_fwd_u8', 'lsq_plane_mean',
     'lsq_pwconv_supported', 'lsq_pwconv_image_bytes', 'lsq_pwconv_pack_weights', 'lsq_pwconv_fwd',
     'lsq_solve_v1_multi', 'lsq_row_absmean_multi', 'lsq_wbits_bytes', 'lsq_unpack_weights',
     'lsq_quantize_act_workspace_bytes', 'lsq_quantize_act',
@@ -90,6 +90,8 @@ def lib():
             L.lsq_stem_workspace_bytes.argtypes = [i32, i32, i32]
             L.lsq_stem_supported.restype = i32
             L.lsq_stem_is_fused.restype = i32
+            L.lsq_plane_mean.restype = i32
+            L.lsq_plane_mean.argtypes = [vp, i64, i32, vp, vp]
             L.lsq_u8_expand.restype = i32
             L.lsq_u8_expand.argtypes = [vp, i64, i32, i64, vp, vp, vp]
             L.lsq_stem_fwd_u8.restype = i32

@@ -228,6 +228,25 @@ row_absmean_multi_kernel(const __grid_constant__ MultiTab tab, float alpha) {
 
 using namespace lsq;
 
+// Global average pool of the classifier head (quant/models/resnet.py: AdaptiveAvgPool2d((1, 1)) in front of the linear
+// layer): out[p] = mean(x[p][0 .. inner)).  One warp per plane and trip: coalesced 128-byte reads, a fixed shuffle tree
+// (deterministic, batch invariant).  Short planes (7 x 7 = 49 values) make ATen's generic reduction launch-shaped work
+// (57 us for 51 MB at batch 512); this is the 51 MB read.
+__global__ void __launch_bounds__(256)
+plane_mean_kernel(const float* __restrict__ x, long long planes, int inner, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp0; p < planes; p += nwarps) {
+    const float* xp = x + p * inner;
+    float s = 0.0f;
+    for (int j = lane; j < inner; j += 32) s += ldg_stream(xp + j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[p] = __fdiv_rn(s, (float)inner);
+  }
+}
+
 extern "C" {
 
 int lsq_abi_version(void) { return LSQ_ABI_VERSION; }
@@ -242,6 +261,17 @@ size_t lsq_reduce_workspace_bytes(int64_t rows, int64_t len) {
 int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales,
                     int nscales, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
   return lsq_row_absmean_ex(d_x, rows, len, alpha, d_scales, nscales, d_out, d_ws, ws_bytes, nullptr, stream);
+}
+
+int lsq_plane_mean(const float* d_x, int64_t planes, int inner, float* d_out, void* stream) {
+  LSQ_CHECK_ARG(d_x && d_out, "lsq_plane_mean: null pointer");
+  LSQ_CHECK_ARG(planes > 0 && inner > 0, "lsq_plane_mean: bad shape planes=%lld inner=%d", (long long)planes, inner);
+  long long grid = (planes + 7) / 8;                    // 8 warps per block
+  const long long cap = (long long)device_sms() * 8;
+  if (grid > cap) grid = cap;
+  plane_mean_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_x, planes, inner, d_out);
+  LSQ_CUDA_LAUNCH_CHECK("plane_mean_kernel");
+  return LSQ_OK;
 }
 
 int lsq_row_absmean_ex(const float* d_x, int64_t rows, int64_t len, float alpha, const float* d_scales,

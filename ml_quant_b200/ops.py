@@ -389,6 +389,21 @@ def stem_fwd(x: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.
     return out
 
 
+def plane_mean(x: torch.Tensor) -> torch.Tensor:
+    """Global average pool [n, c, h, w] -> [n, c] (lsq_plane_mean: one warp per plane, fixed summation tree)."""
+    require_cuda(x, 'x')
+    if x.dim() != 4:
+        raise ValueError('plane_mean takes a [n, c, h, w] tensor')
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return out
+    with torch.cuda.device(x.device), _launch('plane_mean', 4.0 * x.numel()):
+        _C.check(_C.lib().lsq_plane_mean(x.data_ptr(), n * c, h * w, out.data_ptr(), _stream()), 'lsq_plane_mean')
+    return out
+
+
 def u8_expand(x: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
     """fp32 tensor lut[c][x] of a uint8 tensor [n, c, ...] (lsq_u8_expand): the caller's ToTensor + Normalize, evaluated
     once per pixel level in ``lut`` float[c][256], applied on the device."""

@@ -225,6 +225,20 @@ class _FusedStem(nn.Module):
         return F.relu_(self.pool(y).add_(b.view(1, -1, 1, 1)))
 
 
+def _classifier_fused(head: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """``linear_classifier`` of QResNet (AdaptiveAvgPool2d((1, 1)), Flatten, Linear ...; quant/models/resnet.py) with the global
+    average pool as one warp-per-plane kernel (lsq_plane_mean) when the head has that shape; anything else runs as it is."""
+    mods = list(head.children()) if isinstance(head, nn.Sequential) else []
+    if (len(mods) >= 2 and isinstance(mods[0], nn.AdaptiveAvgPool2d) and mods[0].output_size in (1, (1, 1))
+            and isinstance(mods[1], nn.Flatten) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+        from . import ops
+        x = ops.plane_mean(x)
+        for m in mods[2:]:
+            x = m(x)
+        return x
+    return head(x)
+
+
 def optimize_for_inference(model: nn.Module) -> nn.Module:
     """Rewrite the callers of the hot path for eval-mode inference: every XnorBasicBlock
     runs its two QuantConv2d through ``forward_fused`` and the stem uses a BatchNorm-folded convolution.
@@ -256,7 +270,7 @@ def optimize_for_inference(model: nn.Module) -> nn.Module:
             x = self._lsq_stem(x)
             for blk in list(self.blocks)[1:]:
                 x = blk(x)
-            return self.linear_classifier(x)
+            return _classifier_fused(self.linear_classifier, x)
         model.forward = types.MethodType(fwd, model)
     return model
 

@@ -58,5 +58,6 @@ with torch.no_grad():
     ops.solve_v1_multi(ws, False, 3)
     ops.solve_v1_multi(ws, True, 3)
     ops.row_absmean_multi(ws)
+    ops.plane_mean(torch.randn(3, 70, 7, 7, device=DEV))
 torch.cuda.synchronize()
 print('sanitize_small: all kernels ran')

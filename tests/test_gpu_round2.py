@@ -680,3 +680,20 @@ def test_reference_on_cuda_against_reference_on_cpu_second_witness():
         open(os.environ['LSQ_WITNESS_OUT'], 'w').write(line + '\n')
     for case in d['cases']:
         assert case['max_fp64_cost_ratio_minus_1'] <= 1e-5, case
+
+
+def test_plane_mean_matches_torch():
+    """lsq_plane_mean (the classifier head's global average pool) against x.mean((2, 3)): <= 1e-6 relative (different,
+    fixed summation order), deterministic and batch invariant."""
+    from ml_quant_b200 import ops
+    torch.manual_seed(51)
+    for n, c, h, w in [(512, 512, 7, 7), (3, 64, 4, 4), (2, 5, 1, 1), (2, 3, 33, 17), (256, 512, 4, 4)]:
+        x = torch.randn(n, c, h, w, device=DEV) + 0.5
+        got = ops.plane_mean(x)
+        want = x.double().mean(dim=(2, 3))
+        assert got.shape == (n, c)
+        assert float((got.double() - want).abs().max()) <= 1e-6 * float(want.abs().max()) + 1e-7
+        assert torch.equal(got, ops.plane_mean(x))
+        assert torch.equal(got[:1], ops.plane_mean(x[:1].contiguous()))
+    with pytest.raises(ValueError):
+        ops.plane_mean(torch.zeros(4, 4, device=DEV))
