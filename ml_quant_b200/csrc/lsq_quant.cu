@@ -237,6 +237,27 @@ plane_mean_kernel(const float* __restrict__ x, long long planes, int inner, floa
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  if (inner <= 64) {
+    // short planes: four planes per warp and trip, their (at most two) loads per lane all in flight together
+    for (long long p0 = warp0 * 4; p0 < planes; p0 += nwarps * 4) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = p0 + u < planes;
+        const float* xp = x + (p0 + u) * inner;
+        a[u] = (ok && lane < inner) ? ldg_stream(xp + lane) : 0.0f;
+        b[u] = (ok && lane + 32 < inner) ? ldg_stream(xp + lane + 32) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float s = a[u] + b[u];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && p0 + u < planes) out[p0 + u] = __fdiv_rn(s, (float)inner);
+      }
+    }
+    return;
+  }
   for (long long p = warp0; p < planes; p += nwarps) {
     const float* xp = x + p * inner;
     float s = 0.0f;
@@ -266,7 +287,7 @@ int lsq_row_absmean(const float* d_x, int64_t rows, int64_t len, float alpha, co
 int lsq_plane_mean(const float* d_x, int64_t planes, int inner, float* d_out, void* stream) {
   LSQ_CHECK_ARG(d_x && d_out, "lsq_plane_mean: null pointer");
   LSQ_CHECK_ARG(planes > 0 && inner > 0, "lsq_plane_mean: bad shape planes=%lld inner=%d", (long long)planes, inner);
-  long long grid = (planes + 7) / 8;                    // 8 warps per block
+  long long grid = (planes + 31) / 32;                  // 8 warps per block, up to 4 planes per warp and trip
   const long long cap = (long long)device_sms() * 8;
   if (grid > cap) grid = cap;
   plane_mean_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_x, planes, inner, d_out);
