@@ -143,6 +143,29 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
   if (timing) tprev = clock64();
 #define LSQ_QTICK(i) do { if (timing) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; } } while (0)
 
+  // this CTA's share of the row, and the loads of its first trip of sweep 1: requested before the setup below so that their
+  // latency passes under it (every later trip requests the next one's loads before it processes its own)
+  const uint32_t g_lo = (uint32_t)(((unsigned long long)qp.groups * (unsigned)rank) / (unsigned)cs);
+  const uint32_t g_hi = (uint32_t)(((unsigned long long)qp.groups * (unsigned)(rank + 1)) / (unsigned)cs);
+#ifndef LSQ_QACT_KU
+#define LSQ_QACT_KU 2
+#endif
+  constexpr int kU = LSQ_QACT_KU;   // groups per thread and trip: 4 independent loads each in flight
+  auto issue_trip = [&](uint32_t gb, float (&raw)[kU][4]) {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint32_t gi = gb + u * T;
+      const long long i0 = (long long)gi * 12;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long idx = i0 + 3 * j;
+        raw[u][j] = (gi < g_hi && idx < qp.len) ? ldg_stream(xr + idx) : 0.0f;
+      }
+    }
+  };
+  float nxt[kU][4];
+  issue_trip(g_lo + tid, nxt);
+
   // ---- setup --------------------------------------------------------------------------------------------------
   for (int b = tid; b < kQBins; b += T) { sm.hcnt[b] = 0u; sm.hrem[b] = 0u; }
   for (int c = tid; c < g.cw * 32; c += T) {
@@ -157,8 +180,6 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
   __syncthreads();
 
   // ---- sweep 1: histogram of the sampled keys of this CTA's share of the row -------------------------------------
-  const uint32_t g_lo = (uint32_t)(((unsigned long long)qp.groups * (unsigned)rank) / (unsigned)cs);
-  const uint32_t g_hi = (uint32_t)(((unsigned long long)qp.groups * (unsigned)(rank + 1)) / (unsigned)cs);
   {
     uint32_t kmn = kNoKey, kmx = 0u, cb = 0u;
     double lb = 0.0;
@@ -176,22 +197,13 @@ quant_act_kernel(const float* __restrict__ x, ActGeom g, float alpha, Prologue p
       ++cb; lb += (double)a;
       return kIdBelow;
     };
-#ifndef LSQ_QACT_KU
-#define LSQ_QACT_KU 2
-#endif
-    constexpr int kU = LSQ_QACT_KU;   // groups per thread and trip: 4 independent loads each in flight
     for (uint32_t gb = g_lo + tid; gb < g_hi; gb += kU * T) {
       float raw[kU][4];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const uint32_t gi = gb + u * T;
-        const long long i0 = (long long)gi * 12;
+      for (int u = 0; u < kU; ++u)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const long long idx = i0 + 3 * j;
-          raw[u][j] = (gi < g_hi && idx < qp.len) ? ldg_stream(xr + idx) : 0.0f;
-        }
-      }
+        for (int j = 0; j < 4; ++j) raw[u][j] = nxt[u][j];
+      if (gb + kU * T < g_hi) issue_trip(gb + kU * T, nxt);
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const uint32_t gi = gb + u * T;
